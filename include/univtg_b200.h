@@ -1,0 +1,108 @@
+/*
+ * univtg_b200 — C ABI of the B200-native UniVTG hot path (cross-modal encoder + heads).
+ *
+ * Drop-in boundary: the reference reaches this path through ONE Python plugin call,
+ *     importlib.import_module('model.' + opt.model_id).build_model(opt) -> (model, criterion)
+ *     (reference main/config.py:341-342), then model(**model_inputs) (main/inference_mr.py:101,
+ *     main/train_vlp_ddp.py:56) and criterion(outputs, targets) (main/train_vlp_ddp.py:57).
+ * The reference has no FFI of its own (it is pure Python on torch); the functions below are what a
+ * ctypes binding for that plugin binds (univtg_b200/_lib.py).  Plain pointers and
+ * sizes only: no torch types.  All pointers are DEVICE pointers unless stated otherwise, all tensors are
+ * row-major/contiguous, `stream` is a cudaStream_t passed as void*.  Every function returns 0 on success,
+ * non-zero on failure; univtg_last_error() then describes the failure (thread local).
+ * Nothing here allocates device memory: the caller owns `packed` and `workspace`.
+ */
+#ifndef UNIVTG_B200_H_
+#define UNIVTG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UNIVTG_ABI_VERSION 1
+
+/* Model hyper-parameters: the fields of `args` that reference model/univtg.py:409-450 (build_model),
+ * model/transformer_encoder_droppath.py:141-152 (build_transformer) and model/position_encoding.py:113-126 read. */
+typedef struct univtg_config {
+  int32_t hidden_dim;       /* args.hidden_dim  (d)            */
+  int32_t nheads;           /* args.nheads      (H), dh = d/H  */
+  int32_t dim_feedforward;  /* args.dim_feedforward            */
+  int32_t enc_layers;       /* args.enc_layers                 */
+  int32_t n_input_proj;     /* args.n_input_proj in {1,2,3}    */
+  int32_t v_feat_dim;       /* args.v_feat_dim (already +2 TEF)*/
+  int32_t t_feat_dim;       /* args.t_feat_dim                 */
+  int32_t operand_format;   /* 0 = fp16 MMA operands (default), 1 = bf16; accumulation/LN/softmax/heads are fp32 */
+} univtg_config;
+
+/* Problem shape of one batch (reference Model.forward arguments, model/univtg.py:105). */
+typedef struct univtg_shape {
+  int32_t batch;  /* B   */
+  int32_t l_vid;  /* L_v */
+  int32_t l_txt;  /* L_t */
+  int32_t training; /* 1: keep the activations backward needs (larger workspace) */
+} univtg_shape;
+
+typedef struct univtg_plan univtg_plan; /* opaque; host memory only (tensor maps + pointer table) */
+
+const char* univtg_last_error(void);
+int univtg_abi_version(void);
+
+/* Number of fp32 parameter tensors univtg_pack_weights expects, in this order (reference state_dict names):
+ *   for i < n_input_proj: input_vid_proj.i.{LayerNorm.weight, LayerNorm.bias, net.1.weight, net.1.bias}
+ *   for i < n_input_proj: input_txt_proj.i.{...same...}
+ *   token_type_embeddings.weight
+ *   for l < enc_layers: transformer.encoder.layers.l.{self_attn.in_proj_weight, self_attn.in_proj_bias,
+ *        self_attn.out_proj.weight, self_attn.out_proj.bias, linear1.weight, linear1.bias, linear2.weight,
+ *        linear2.bias, norm1.weight, norm1.bias, norm2.weight, norm2.bias}
+ *   span_embed.layers.{0,1,2}.{weight,bias}; class_embed.layers.{0,1,2}.{weight,bias}; weightedpool.weight */
+int univtg_num_params(const univtg_config* cfg);
+/* Bytes of the packed-weight buffer (16-bit K-padded GEMM operands + fp32 vectors). */
+size_t univtg_packed_bytes(const univtg_config* cfg);
+/* Convert/re-layout the fp32 parameters into `packed` (device). `params`: HOST array of device pointers. */
+int univtg_pack_weights(const univtg_config* cfg, const float* const* params, int32_t n_params, void* packed, void* stream);
+
+/* Workspace bytes for one (config, shape). */
+size_t univtg_workspace_bytes(const univtg_config* cfg, const univtg_shape* shape);
+/* Build a plan: tensor maps over `packed` and `workspace` (both must stay alive and must not move).
+ * `dim_t`: device fp32 [hidden_dim], the sine-embedding denominators temperature**(2*(j//2)/d)
+ * (reference model/position_encoding.py:75) evaluated by the caller.  Zero-fills the workspace on `stream`. */
+int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, const void* packed, void* workspace,
+                       const float* dim_t, void* stream, univtg_plan** out);
+void univtg_plan_destroy(univtg_plan* plan);
+
+/* Model.forward (reference model/univtg.py:105-155).
+ *   src_txt [B,Lt,Dt] f32, src_txt_mask [B,Lt] f32 (1 = valid), src_vid [B,Lv,Dv] f32, src_vid_mask [B,Lv] f32
+ *   droppath_scale: NULL (eval) or [2*enc_layers, B] f32 per-sample residual-branch scales
+ *                   floor(keep + u)/keep in the reference's draw order (transformer_encoder_droppath.py:154-167)
+ * outputs: pred_logits [B,Lv,1], pred_spans [B,Lv,2], vid_mem_proj [B,Lv,d], txt_mem_proj [B,1,d],
+ *          saliency_scores [B,Lv]  (all f32) */
+int univtg_forward(univtg_plan* plan, const float* src_txt, const float* src_txt_mask, const float* src_vid,
+                   const float* src_vid_mask, const float* droppath_scale, float* pred_logits, float* pred_spans,
+                   float* vid_mem_proj, float* txt_mem_proj, float* saliency_scores, void* stream);
+
+/* Number of kernels one univtg_forward launches (for bench accounting). */
+int univtg_forward_num_launches(const univtg_plan* plan);
+
+/* ---- single operators (unit tests / profiling; same kernels the plan uses) ---- */
+
+/* C[M,N] = act(A*B^T + bias) * alpha.  a: [M,K] (a_mn=0) or [K,M] (a_mn=1); b: [N,K] (b_mn=0) or [K,N] (b_mn=1),
+ * 16-bit operands in `fmt`; K and the leading dimensions must be multiples of 8 elements.  out32 [M,N] f32 and/or
+ * out16 [M,N] 16-bit.  bn in {128,256}; ksplit>1 accumulates atomically into a pre-zeroed out32. */
+int univtg_op_gemm(const void* a, const void* b, int32_t M, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn, int32_t fmt,
+                   int32_t bn, int32_t ksplit, const float* bias, int32_t act, float alpha, float* out32, void* out16,
+                   void* stream);
+/* LayerNorm rows: in [rows,d] f32 -> out32 [rows,d] f32 and/or out16 [rows,ld16] 16-bit (zero padded). */
+int univtg_op_layernorm(const float* in, int32_t rows, int32_t d, const float* gamma, const float* beta, float eps,
+                        int32_t fmt, float* out32, void* out16, int32_t ld16, void* stream);
+/* Attention core.  q,k: [B*L,d] 16-bit (q pre-scaled); vt: [B*d,Lp] 16-bit (Lp multiple of 8, >= L, zero padded);
+ * key_mask [B,L] f32; out [B*L,d] 16-bit; lse [B,H,L] f32 or NULL.  impl: 0 = tcgen05 (dh in {64,128}), 1 = SIMT. */
+int univtg_op_attention(const void* q, const void* k, const void* vt, const float* key_mask, void* out, float* lse,
+                        int32_t B, int32_t L, int32_t Lp, int32_t H, int32_t dh, int32_t fmt, int32_t impl, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIVTG_B200_H_ */

@@ -1,0 +1,170 @@
+#!/usr/bin/env python
+"""Operator-level self test on a real B200: each case runs in its own subprocess under a timeout so a hung
+kernel cannot take the whole run down.  Usage: python tools/gpu_selftest.py [case ...]  (writes gpurun_out/selftest.json)"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _t16(x, fmt):
+    import torch
+    return x.to(torch.bfloat16 if fmt else torch.float16)
+
+
+def case_gemm(M, N, K, a_mn, b_mn, fmt, bn, ksplit, act, use_bias):
+    import torch
+    from univtg_b200 import _lib
+    lib = _lib.load_library()
+    g = torch.Generator(device="cpu").manual_seed(1234 + M + N + K)
+    A = torch.randn(M, K, generator=g).cuda()
+    Bm = torch.randn(N, K, generator=g).cuda()
+    bias = torch.randn(N, generator=g).cuda() if use_bias else None
+    A16, B16 = _t16(A, fmt), _t16(Bm, fmt)
+    ref = A16.float() @ B16.float().t()
+    if bias is not None:
+        ref = ref + bias
+    if act == 1:
+        ref = torch.relu(ref)
+    elif act == 2:
+        ref = torch.nn.functional.gelu(ref)
+    ref = ref * 0.5
+    a_in = A16.t().contiguous() if a_mn else A16.contiguous()
+    b_in = B16.t().contiguous() if b_mn else B16.contiguous()
+    out32 = torch.zeros(M, N, device="cuda")
+    out16 = torch.zeros(M, N, device="cuda", dtype=A16.dtype) if ksplit == 1 else None
+    rc = lib.univtg_op_gemm(_lib.ptr(a_in), _lib.ptr(b_in), M, N, K, a_mn, b_mn, fmt, bn, ksplit, _lib.ptr(bias), act, 0.5,
+                            _lib.ptr(out32), _lib.ptr(out16), _lib.stream_ptr())
+    _lib.check(rc, "op_gemm")
+    torch.cuda.synchronize()
+    err = (out32 - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    res = {"max_abs_err": err, "ref_max": scale}
+    if out16 is not None:
+        res["err16"] = (out16.float() - ref).abs().max().item()
+    res["ok"] = bool(err <= 2e-3 * max(scale, 1.0) * (1 if K <= 4096 else 4))
+    if not res["ok"]:
+        bad = ((out32 - ref).abs() > 1e-2 * max(scale, 1.0)).nonzero()
+        res["n_bad"] = int(bad.shape[0])
+        res["first_bad"] = bad[:8].tolist()
+        res["sample"] = [out32[0, :4].tolist(), ref[0, :4].tolist()]
+    return res
+
+
+def case_layernorm(rows, d, ld16, fmt):
+    import torch
+    from univtg_b200 import _lib
+    lib = _lib.load_library()
+    g = torch.Generator(device="cpu").manual_seed(7)
+    x = (torch.randn(rows, d, generator=g) * 2 + 0.5).cuda()
+    w = torch.randn(d, generator=g).cuda()
+    b = torch.randn(d, generator=g).cuda()
+    out32 = torch.empty(rows, d, device="cuda")
+    out16 = torch.full((rows, ld16), 7.0, device="cuda", dtype=torch.bfloat16 if fmt else torch.float16)
+    rc = lib.univtg_op_layernorm(_lib.ptr(x), rows, d, _lib.ptr(w), _lib.ptr(b), 1e-5, fmt, _lib.ptr(out32), _lib.ptr(out16), ld16,
+                                 _lib.stream_ptr())
+    _lib.check(rc, "op_layernorm")
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x, (d,), w, b, 1e-5)
+    e32 = (out32 - ref).abs().max().item()
+    e16 = (out16[:, :d].float() - _t16(ref, fmt).float()).abs().max().item()
+    pad = out16[:, d:].float().abs().max().item() if ld16 > d else 0.0
+    return {"err32": e32, "err16": e16, "pad_max": pad, "ok": bool(e32 < 2e-5 and e16 < 2e-2 and pad == 0.0)}
+
+
+def case_attention(B, L, H, dh, fmt, impl):
+    import torch
+    from univtg_b200 import _lib
+    lib = _lib.load_library()
+    d = H * dh
+    Lp = (L + 63) // 64 * 64
+    g = torch.Generator(device="cpu").manual_seed(99)
+    q = (torch.randn(B, L, H, dh, generator=g) * (dh ** -0.5)).cuda()
+    k = torch.randn(B, L, H, dh, generator=g).cuda()
+    v = torch.randn(B, L, H, dh, generator=g).cuda()
+    lens = torch.randint(max(1, L // 3), L + 1, (B,), generator=g)
+    lens[0] = L
+    mask = (torch.arange(L)[None, :] < lens[:, None]).float().cuda()
+    q16, k16, v16 = _t16(q, fmt), _t16(k, fmt), _t16(v, fmt)
+    vt = torch.zeros(B, d, Lp, device="cuda", dtype=q16.dtype)
+    vt[:, :, :L] = v16.reshape(B, L, d).permute(0, 2, 1)
+    out = torch.zeros(B * L, d, device="cuda", dtype=q16.dtype)
+    lse = torch.zeros(B, H, L, device="cuda")
+    rc = lib.univtg_op_attention(_lib.ptr(q16.reshape(B * L, d).contiguous()), _lib.ptr(k16.reshape(B * L, d).contiguous()),
+                                 _lib.ptr(vt), _lib.ptr(mask), _lib.ptr(out), _lib.ptr(lse), B, L, Lp, H, dh, fmt, impl,
+                                 _lib.stream_ptr())
+    _lib.check(rc, "op_attention")
+    torch.cuda.synchronize()
+    s = torch.einsum("bihc,bjhc->bhij", q16.float(), k16.float())
+    s = s.masked_fill(mask[:, None, None, :] == 0, float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    ref = torch.einsum("bhij,bjhc->bihc", p, v16.float()).reshape(B * L, d)
+    ref_lse = torch.logsumexp(s, dim=-1)
+    err = (out.float() - ref).abs().max().item()
+    elz = (lse - ref_lse).abs().max().item()
+    res = {"max_abs_err": err, "lse_err": elz, "ref_max": ref.abs().max().item(), "ok": bool(err < 2e-2 and elz < 1e-3)}
+    if not res["ok"]:
+        res["sample"] = [out[0, :4].float().tolist(), ref[0, :4].tolist()]
+    return res
+
+
+CASES = {
+    # name: (fn, args)
+    "gemm_k_small_fp16_bn128": (case_gemm, (128, 128, 64, 0, 0, 0, 128, 1, 0, False)),
+    "gemm_k_small_fp16_bn256": (case_gemm, (128, 256, 64, 0, 0, 0, 256, 1, 0, False)),
+    "gemm_k_k256_fp16": (case_gemm, (128, 256, 256, 0, 0, 0, 256, 1, 0, True)),
+    "gemm_k_ragged_fp16": (case_gemm, (300, 384, 200, 0, 0, 0, 128, 1, 1, True)),
+    "gemm_k_ragged_bf16_bn256": (case_gemm, (300, 512, 200, 0, 0, 1, 256, 1, 2, True)),
+    "gemm_k_big_fp16": (case_gemm, (3424, 1024, 1024, 0, 0, 0, 256, 1, 2, True)),
+    "gemm_k_big_multi_wave": (case_gemm, (3424, 3072, 1024, 0, 0, 0, 256, 1, 0, True)),
+    "gemm_k_ksplit": (case_gemm, (1024, 1024, 3424, 0, 0, 0, 256, 4, 0, False)),
+    "gemm_amn": (case_gemm, (256, 256, 192, 1, 0, 0, 256, 1, 0, True)),
+    "gemm_bmn": (case_gemm, (256, 256, 192, 0, 1, 0, 256, 1, 0, True)),
+    "gemm_abmn_bn128": (case_gemm, (256, 384, 200, 1, 1, 0, 128, 1, 0, True)),
+    "gemm_abmn_big_ksplit": (case_gemm, (1024, 1024, 3424, 1, 1, 0, 256, 4, 0, False)),
+    "ln_1024": (case_layernorm, (3424, 1024, 1024, 0)),
+    "ln_256_bf16": (case_layernorm, (77, 256, 256, 1)),
+    "ln_2818": (case_layernorm, (300, 2818, 2880, 0)),
+    "ln_514": (case_layernorm, (33, 514, 576, 0)),
+    "attn_simt_dh32": (case_attention, (2, 27, 8, 32, 0, 1)),
+    "attn_simt_dh128": (case_attention, (2, 107, 2, 128, 0, 1)),
+    "attn_tc_dh128_L107": (case_attention, (3, 107, 4, 128, 0, 0)),
+    "attn_tc_dh128_L128": (case_attention, (2, 128, 2, 128, 0, 0)),
+    "attn_tc_dh128_L300": (case_attention, (2, 300, 2, 128, 0, 0)),
+    "attn_tc_dh64_L182_bf16": (case_attention, (2, 182, 4, 64, 1, 0)),
+    "attn_tc_dh128_L1277": (case_attention, (1, 1277, 8, 128, 0, 0)),
+}
+
+
+def main():
+    if len(sys.argv) >= 3 and sys.argv[1] == "--one":
+        name = sys.argv[2]
+        fn, args = CASES[name]
+        print("RESULT " + json.dumps(fn(*args)))
+        return
+    names = sys.argv[1:] or list(CASES)
+    results = {}
+    for name in names:
+        try:
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", name], capture_output=True, text=True,
+                               timeout=150)
+            line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
+            if line:
+                results[name] = json.loads(line[-1][7:])
+            else:
+                results[name] = {"ok": False, "rc": p.returncode, "stderr": p.stderr[-600:], "stdout": p.stdout[-300:]}
+        except subprocess.TimeoutExpired:
+            results[name] = {"ok": False, "timeout": True}
+        print(name, json.dumps(results[name]), flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "selftest.json"), "w") as f:
+        json.dump(results, f, indent=1)
+    n_ok = sum(1 for r in results.values() if r.get("ok"))
+    print(f"SELFTEST {n_ok}/{len(results)} ok")
+
+
+if __name__ == "__main__":
+    main()

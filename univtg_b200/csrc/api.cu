@@ -1,0 +1,910 @@
+// C-ABI layer (include/univtg_b200.h): weight packing, plan construction (tensor maps + launch descriptors)
+// and the forward orchestration of reference Model.forward (model/univtg.py:105-155).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/univtg_b200.h"
+#include "kernels.h"
+#include "ptx.cuh"
+#include "rowops.h"
+
+using namespace uv;
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int pad64(int k) { return (k + 63) / 64 * 64; }
+
+// ------------------------------------------------------------------------------------------------
+// packed-weight layout
+// ------------------------------------------------------------------------------------------------
+struct ProjPacked {
+  size_t ln_w, ln_b;  // fp32 [din]
+  size_t w16;         // 16-bit [d, kpad]
+  size_t bias;        // fp32 [d]  (last layer: linear bias + token-type embedding row)
+  int din, kpad;
+};
+struct LayerPacked {
+  size_t w_in;   // 16-bit [3d, d]  (rows: Wq, Wk, Wv)
+  size_t b_in;   // fp32 [3d]
+  size_t w_out;  // 16-bit [d, d]
+  size_t b_out;
+  size_t w1, b1;  // [ff, d], [ff]
+  size_t w2, b2;  // [d, ff], [d]
+  size_t n1w, n1b, n2w, n2b;
+};
+struct PackedLayout {
+  ProjPacked vid[3], txt[3];
+  LayerPacked layer[16];
+  size_t conv1_w, conv1_b;                     // fused first conv of both heads: 16-bit [2d, 3d] (rows: class, span), fp32 [2d]
+  size_t conv2c_w, conv2c_b, conv2s_w, conv2s_b;  // 16-bit [d, 3d], fp32 [d]
+  size_t conv3c_w, conv3c_b, conv3s_w, conv3s_b;  // fp32 [3][d], [1], [2][3][d], [2]
+  size_t pool_w;                                  // fp32 [d]
+  size_t total;
+};
+
+struct Cursor {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  }
+};
+
+bool check_cfg(const univtg_config* c) {
+  if (!c) {
+    set_error("null config");
+    return false;
+  }
+  if (c->hidden_dim <= 0 || c->hidden_dim % 64 != 0) {
+    set_error("hidden_dim %d must be a positive multiple of 64", c->hidden_dim);
+    return false;
+  }
+  if (c->nheads <= 0 || c->hidden_dim % c->nheads != 0) {
+    set_error("nheads %d must divide hidden_dim %d", c->nheads, c->hidden_dim);
+    return false;
+  }
+  if (c->dim_feedforward <= 0 || c->dim_feedforward % 64 != 0) {
+    set_error("dim_feedforward %d must be a positive multiple of 64", c->dim_feedforward);
+    return false;
+  }
+  if (c->enc_layers < 1 || c->enc_layers > 16) {
+    set_error("enc_layers %d out of range [1,16]", c->enc_layers);
+    return false;
+  }
+  if (c->n_input_proj < 1 || c->n_input_proj > 3) {
+    set_error("n_input_proj %d out of range [1,3]", c->n_input_proj);
+    return false;
+  }
+  if (c->v_feat_dim <= 0 || c->t_feat_dim <= 0) {
+    set_error("feature dims must be positive");
+    return false;
+  }
+  if (c->operand_format != 0 && c->operand_format != 1) {
+    set_error("operand_format %d must be 0 (fp16) or 1 (bf16)", c->operand_format);
+    return false;
+  }
+  return true;
+}
+
+PackedLayout make_layout(const univtg_config& c) {
+  PackedLayout L;
+  memset(&L, 0, sizeof(L));
+  Cursor cur;
+  const int d = c.hidden_dim, ff = c.dim_feedforward;
+  for (int s = 0; s < 2; ++s) {
+    ProjPacked* pp = s == 0 ? L.vid : L.txt;
+    int din = s == 0 ? c.v_feat_dim : c.t_feat_dim;
+    for (int i = 0; i < c.n_input_proj; ++i) {
+      pp[i].din = din;
+      pp[i].kpad = pad64(din);
+      pp[i].ln_w = cur.take((size_t)din * 4);
+      pp[i].ln_b = cur.take((size_t)din * 4);
+      pp[i].w16 = cur.take((size_t)d * pp[i].kpad * 2);
+      pp[i].bias = cur.take((size_t)d * 4);
+      din = d;
+    }
+  }
+  for (int l = 0; l < c.enc_layers; ++l) {
+    LayerPacked& lp = L.layer[l];
+    lp.w_in = cur.take((size_t)3 * d * d * 2);
+    lp.b_in = cur.take((size_t)3 * d * 4);
+    lp.w_out = cur.take((size_t)d * d * 2);
+    lp.b_out = cur.take((size_t)d * 4);
+    lp.w1 = cur.take((size_t)ff * d * 2);
+    lp.b1 = cur.take((size_t)ff * 4);
+    lp.w2 = cur.take((size_t)d * ff * 2);
+    lp.b2 = cur.take((size_t)d * 4);
+    lp.n1w = cur.take((size_t)d * 4);
+    lp.n1b = cur.take((size_t)d * 4);
+    lp.n2w = cur.take((size_t)d * 4);
+    lp.n2b = cur.take((size_t)d * 4);
+  }
+  L.conv1_w = cur.take((size_t)2 * d * 3 * d * 2);
+  L.conv1_b = cur.take((size_t)2 * d * 4);
+  L.conv2c_w = cur.take((size_t)d * 3 * d * 2);
+  L.conv2c_b = cur.take((size_t)d * 4);
+  L.conv2s_w = cur.take((size_t)d * 3 * d * 2);
+  L.conv2s_b = cur.take((size_t)d * 4);
+  L.conv3c_w = cur.take((size_t)3 * d * 4);
+  L.conv3c_b = cur.take(4);
+  L.conv3s_w = cur.take((size_t)2 * 3 * d * 4);
+  L.conv3s_b = cur.take(8);
+  L.pool_w = cur.take((size_t)d * 4);
+  L.total = cur.off;
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_rows_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int rows, int cols, int ld, int fmt) {
+  const size_t total = (size_t)rows * ld;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ld), c = (int)(i % ld);
+    dst[i] = c < cols ? cvt16(src[(size_t)r * cols + c], fmt) : (uint16_t)0;
+  }
+}
+// Conv1d weight [N, C, 3] -> 16-bit [N, 3*C] with dst[n, t*C + c] = src[n, c, t]
+__global__ void pack_conv_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int N, int C, int fmt) {
+  const size_t total = (size_t)N * 3 * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / (3 * C));
+    const int rem = (int)(i % (3 * C));
+    const int t = rem / C, c = rem % C;
+    dst[i] = cvt16(src[((size_t)n * C + c) * 3 + t], fmt);
+  }
+}
+// Conv1d weight [N, C, 3] -> fp32 [N, 3, C]
+__global__ void pack_conv_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int C) {
+  const size_t total = (size_t)N * 3 * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / (3 * C));
+    const int rem = (int)(i % (3 * C));
+    const int t = rem / C, c = rem % C;
+    dst[i] = src[((size_t)n * C + c) * 3 + t];
+  }
+}
+__global__ void copy_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ dst, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = a[i] + (b ? b[i] : 0.f);
+}
+
+inline int grid_for(size_t total) {
+  size_t g = (total + 255) / 256;
+  return (int)(g > 1184 ? 1184 : (g < 1 ? 1 : g));
+}
+
+struct Packer {
+  uint8_t* base;
+  int fmt;
+  cudaStream_t st;
+  void rows(const float* src, size_t off, int rows_, int cols, int ld) {
+    pack_rows_kernel<<<grid_for((size_t)rows_ * ld), 256, 0, st>>>(src, reinterpret_cast<uint16_t*>(base + off), rows_, cols, ld, fmt);
+  }
+  void conv(const float* src, size_t off, int N, int C) {
+    pack_conv_kernel<<<grid_for((size_t)N * 3 * C), 256, 0, st>>>(src, reinterpret_cast<uint16_t*>(base + off), N, C, fmt);
+  }
+  void conv_f32(const float* src, size_t off, int N, int C) {
+    pack_conv_f32_kernel<<<grid_for((size_t)N * 3 * C), 256, 0, st>>>(src, reinterpret_cast<float*>(base + off), N, C);
+  }
+  void vec(const float* src, size_t off, int n, const float* add = nullptr) {
+    copy_add_kernel<<<grid_for(n), 256, 0, st>>>(src, add, reinterpret_cast<float*>(base + off), n);
+  }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+struct univtg_plan {
+  univtg_config cfg;
+  univtg_shape shp;
+  PackedLayout lay;
+  const uint8_t* packed;
+  uint8_t* ws;
+  const float* dim_t;
+  int num_sms;
+  int B, Lv, Lt, L, Lp, d, ff, H, dh, M, Mv, Mt, Mh;
+  // workspace pointers
+  uint16_t *a_vid[3], *a_txt[3];  // LN'd 16-bit projector inputs
+  float *p_vid32, *p_txt32;       // fp32 projector hidden (between projector layers)
+  float* txtproj32;               // [Mt, d] projected text tokens (+type embedding)
+  float* pos;                     // [Mv, d]
+  float* key_mask;                // [B, L]
+  float *x32, *y32;               // residual stream / pre-LayerNorm sum
+  uint16_t *x16, *xpos16, *q16, *k16, *vt16, *attn16, *h16;
+  uint16_t *hA, *h1, *hc2, *hs2;  // conv-head buffers (separated layout)
+  // launch descriptors
+  GemmGroup g_proj[3];
+  GemmGroup g_qkv[16], g_out[16], g_ffn1[16], g_ffn2[16];
+  GemmGroup g_conv1, g_conv2;
+  AttnArgs attn[16];
+  int bn_proj[3], bn_main;
+  int launches;
+};
+
+namespace {
+
+void init_problem(GemmProblem& p) {
+  memset(&p, 0, sizeof(p));
+  p.taps = 1;
+  p.ksplit = 1;
+  p.alpha = 1.f;
+  // default coordinate rules: K-major A [M,K] and B [N,K]
+  p.ca = OperandCoord{0, 0, 0, 1, 0, 1, 0, 0};
+  p.cb = OperandCoord{0, 0, 0, 1, 0, 1, 0, 0};
+}
+
+// K-major linear problem: A [M, K] (pitch lda), W [N, K] (pitch ldw), K multiple of 64.
+int setup_linear(GemmProblem& p, const uint16_t* A, int M, int K, int lda, const uint16_t* W, int N, int ldw, int bn) {
+  init_problem(p);
+  p.M = M;
+  p.N = N;
+  p.kblk_per_tap = K / 64;
+  if (K % 64 != 0) {
+    set_error("setup_linear: K %d not a multiple of 64", K);
+    return 1;
+  }
+  if (make_tmap_2d(&p.tm_a, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM, 64)) return 1;
+  if (make_tmap_2d(&p.tm_b, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn, 64)) return 1;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* univtg_last_error(void) { return uv::last_error(); }
+int univtg_abi_version(void) { return UNIVTG_ABI_VERSION; }
+
+int univtg_num_params(const univtg_config* cfg) {
+  if (!check_cfg(cfg)) return -1;
+  return 8 * cfg->n_input_proj + 1 + 12 * cfg->enc_layers + 12 + 1;
+}
+
+size_t univtg_packed_bytes(const univtg_config* cfg) {
+  if (!check_cfg(cfg)) return 0;
+  return make_layout(*cfg).total;
+}
+
+int univtg_pack_weights(const univtg_config* cfg, const float* const* params, int32_t n_params, void* packed, void* stream) {
+  if (!check_cfg(cfg)) return 1;
+  const int expect = univtg_num_params(cfg);
+  if (n_params != expect || !params || !packed) {
+    set_error("univtg_pack_weights: expected %d parameter tensors, got %d", expect, n_params);
+    return 1;
+  }
+  for (int i = 0; i < n_params; ++i)
+    if (!params[i]) {
+      set_error("univtg_pack_weights: parameter %d is null", i);
+      return 1;
+    }
+  const PackedLayout L = make_layout(*cfg);
+  const int d = cfg->hidden_dim, ff = cfg->dim_feedforward;
+  Packer pk{reinterpret_cast<uint8_t*>(packed), cfg->operand_format, (cudaStream_t)stream};
+  int idx = 0;
+  const int type_idx = 8 * cfg->n_input_proj;  // token_type_embeddings.weight [2, d]
+  const float* type_emb = params[type_idx];
+  for (int s = 0; s < 2; ++s) {
+    const ProjPacked* pp = s == 0 ? L.vid : L.txt;
+    for (int i = 0; i < cfg->n_input_proj; ++i) {
+      pk.vec(params[idx + 0], pp[i].ln_w, pp[i].din);
+      pk.vec(params[idx + 1], pp[i].ln_b, pp[i].din);
+      pk.rows(params[idx + 2], pp[i].w16, d, pp[i].din, pp[i].kpad);
+      const bool last = (i == cfg->n_input_proj - 1);
+      // token_type_embeddings: index 1 for video tokens, 0 for text tokens (model/univtg.py:114-115)
+      pk.vec(params[idx + 3], pp[i].bias, d, last ? type_emb + (s == 0 ? d : 0) : nullptr);
+      idx += 4;
+    }
+  }
+  idx += 1;  // type embedding consumed above
+  for (int l = 0; l < cfg->enc_layers; ++l) {
+    const LayerPacked& lp = L.layer[l];
+    pk.rows(params[idx + 0], lp.w_in, 3 * d, d, d);
+    pk.vec(params[idx + 1], lp.b_in, 3 * d);
+    pk.rows(params[idx + 2], lp.w_out, d, d, d);
+    pk.vec(params[idx + 3], lp.b_out, d);
+    pk.rows(params[idx + 4], lp.w1, ff, d, d);
+    pk.vec(params[idx + 5], lp.b1, ff);
+    pk.rows(params[idx + 6], lp.w2, d, ff, ff);
+    pk.vec(params[idx + 7], lp.b2, d);
+    pk.vec(params[idx + 8], lp.n1w, d);
+    pk.vec(params[idx + 9], lp.n1b, d);
+    pk.vec(params[idx + 10], lp.n2w, d);
+    pk.vec(params[idx + 11], lp.n2b, d);
+    idx += 12;
+  }
+  // span_embed.layers.{0,1,2}, class_embed.layers.{0,1,2}
+  const float* const* sp = params + idx;
+  const float* const* cl = params + idx + 6;
+  // fused first conv: rows [0,d) = class_embed.layers.0, rows [d,2d) = span_embed.layers.0
+  pk.conv(cl[0], L.conv1_w, d, d);
+  pk.conv(sp[0], L.conv1_w + (size_t)d * 3 * d * 2, d, d);
+  pk.vec(cl[1], L.conv1_b, d);
+  pk.vec(sp[1], L.conv1_b + (size_t)d * 4, d);
+  pk.conv(cl[2], L.conv2c_w, d, d);
+  pk.vec(cl[3], L.conv2c_b, d);
+  pk.conv(sp[2], L.conv2s_w, d, d);
+  pk.vec(sp[3], L.conv2s_b, d);
+  pk.conv_f32(cl[4], L.conv3c_w, 1, d);
+  pk.vec(cl[5], L.conv3c_b, 1);
+  pk.conv_f32(sp[4], L.conv3s_w, 2, d);
+  pk.vec(sp[5], L.conv3s_b, 2);
+  idx += 12;
+  pk.vec(params[idx], L.pool_w, d);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("univtg_pack_weights: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+}  // extern "C"
+
+namespace {
+
+struct WsLayout {
+  size_t a_vid[3], a_txt[3], p_vid32, p_txt32, txtproj32, pos, key_mask, x32, y32, x16, xpos16, q16, k16, vt16, attn16, h16, hA,
+      h1, hc2, hs2, total;
+};
+
+WsLayout make_ws(const univtg_config& c, const univtg_shape& s, const PackedLayout& L) {
+  WsLayout w;
+  memset(&w, 0, sizeof(w));
+  Cursor cur;
+  const size_t d = c.hidden_dim, ff = c.dim_feedforward;
+  const size_t B = s.batch, Lv = s.l_vid, Lt = s.l_txt, Lc = Lv + Lt;
+  const size_t M = B * Lc, Mv = B * Lv, Mt = B * Lt, Mh = B * (Lv + 1);
+  const size_t Lp = (Lc + 63) / 64 * 64;
+  for (int i = 0; i < c.n_input_proj; ++i) {
+    w.a_vid[i] = cur.take(Mv * L.vid[i].kpad * 2);
+    w.a_txt[i] = cur.take(Mt * L.txt[i].kpad * 2);
+  }
+  w.p_vid32 = cur.take(Mv * d * 4);
+  w.p_txt32 = cur.take(Mt * d * 4);
+  w.txtproj32 = cur.take(Mt * d * 4);
+  w.pos = cur.take(Mv * d * 4);
+  w.key_mask = cur.take(B * Lc * 4);
+  w.x32 = cur.take(M * d * 4);
+  w.y32 = cur.take(M * d * 4);
+  w.x16 = cur.take(M * d * 2);
+  w.xpos16 = cur.take(M * d * 2);
+  w.q16 = cur.take(M * d * 2);
+  w.k16 = cur.take(M * d * 2);
+  w.vt16 = cur.take(B * d * Lp * 2);
+  w.attn16 = cur.take(M * d * 2);
+  w.h16 = cur.take(M * ff * 2);
+  w.hA = cur.take((Mh + 2) * d * 2);
+  w.h1 = cur.take((Mh + 2) * 2 * d * 2);
+  w.hc2 = cur.take((Mh + 2) * d * 2);
+  w.hs2 = cur.take((Mh + 2) * d * 2);
+  w.total = cur.off;
+  return w;
+}
+
+bool check_shape(const univtg_shape* s) {
+  if (!s || s->batch < 1 || s->l_vid < 1 || s->l_txt < 1) {
+    set_error("bad shape");
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t univtg_workspace_bytes(const univtg_config* cfg, const univtg_shape* shape) {
+  if (!check_cfg(cfg) || !check_shape(shape)) return 0;
+  return make_ws(*cfg, *shape, make_layout(*cfg)).total;
+}
+
+int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, const void* packed, void* workspace,
+                       const float* dim_t, void* stream, univtg_plan** out) {
+  if (!check_cfg(cfg) || !check_shape(shape)) return 1;
+  if (!packed || !workspace || !dim_t || !out) {
+    set_error("univtg_plan_create: null argument");
+    return 1;
+  }
+  univtg_plan* P = new (std::nothrow) univtg_plan;
+  if (!P) {
+    set_error("out of host memory");
+    return 1;
+  }
+  memset(static_cast<void*>(P), 0, sizeof(*P));
+  P->cfg = *cfg;
+  P->shp = *shape;
+  P->lay = make_layout(*cfg);
+  P->packed = reinterpret_cast<const uint8_t*>(packed);
+  P->ws = reinterpret_cast<uint8_t*>(workspace);
+  P->dim_t = dim_t;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&P->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (P->num_sms <= 0) P->num_sms = 148;
+  const int d = cfg->hidden_dim, ff = cfg->dim_feedforward;
+  P->B = shape->batch;
+  P->Lv = shape->l_vid;
+  P->Lt = shape->l_txt;
+  P->L = P->Lv + P->Lt;
+  P->Lp = (P->L + 63) / 64 * 64;
+  P->d = d;
+  P->ff = ff;
+  P->H = cfg->nheads;
+  P->dh = d / cfg->nheads;
+  P->M = P->B * P->L;
+  P->Mv = P->B * P->Lv;
+  P->Mt = P->B * P->Lt;
+  P->Mh = P->B * (P->Lv + 1);
+  const WsLayout w = make_ws(*cfg, *shape, P->lay);
+  cudaError_t ce = cudaMemsetAsync(workspace, 0, w.total, (cudaStream_t)stream);
+  if (ce != cudaSuccess) {
+    set_error("workspace memset: %s", cudaGetErrorString(ce));
+    delete P;
+    return 1;
+  }
+  uint8_t* ws = P->ws;
+  for (int i = 0; i < cfg->n_input_proj; ++i) {
+    P->a_vid[i] = reinterpret_cast<uint16_t*>(ws + w.a_vid[i]);
+    P->a_txt[i] = reinterpret_cast<uint16_t*>(ws + w.a_txt[i]);
+  }
+  P->p_vid32 = reinterpret_cast<float*>(ws + w.p_vid32);
+  P->p_txt32 = reinterpret_cast<float*>(ws + w.p_txt32);
+  P->txtproj32 = reinterpret_cast<float*>(ws + w.txtproj32);
+  P->pos = reinterpret_cast<float*>(ws + w.pos);
+  P->key_mask = reinterpret_cast<float*>(ws + w.key_mask);
+  P->x32 = reinterpret_cast<float*>(ws + w.x32);
+  P->y32 = reinterpret_cast<float*>(ws + w.y32);
+  P->x16 = reinterpret_cast<uint16_t*>(ws + w.x16);
+  P->xpos16 = reinterpret_cast<uint16_t*>(ws + w.xpos16);
+  P->q16 = reinterpret_cast<uint16_t*>(ws + w.q16);
+  P->k16 = reinterpret_cast<uint16_t*>(ws + w.k16);
+  P->vt16 = reinterpret_cast<uint16_t*>(ws + w.vt16);
+  P->attn16 = reinterpret_cast<uint16_t*>(ws + w.attn16);
+  P->h16 = reinterpret_cast<uint16_t*>(ws + w.h16);
+  P->hA = reinterpret_cast<uint16_t*>(ws + w.hA);
+  P->h1 = reinterpret_cast<uint16_t*>(ws + w.h1);
+  P->hc2 = reinterpret_cast<uint16_t*>(ws + w.hc2);
+  P->hs2 = reinterpret_cast<uint16_t*>(ws + w.hs2);
+
+  const PackedLayout& Lw = P->lay;
+  const uint8_t* pk = P->packed;
+  auto W16 = [&](size_t off) { return reinterpret_cast<const uint16_t*>(pk + off); };
+  auto F32 = [&](size_t off) { return reinterpret_cast<const float*>(pk + off); };
+  const int fmt = cfg->operand_format;
+  int rc = 0;
+  // tile width: 256 when the N extent has at least one full 256 tile, else 128
+  P->bn_main = (d % 256 == 0) ? 256 : 128;
+
+  // ---- input projectors: one grouped launch per projector depth (video + text problems) ----
+  for (int i = 0; i < cfg->n_input_proj && !rc; ++i) {
+    GemmGroup& g = P->g_proj[i];
+    memset(&g, 0, sizeof(g));
+    g.num = 2;
+    g.fmt = fmt;
+    const bool last = (i == cfg->n_input_proj - 1);
+    const int bn = P->bn_main;
+    P->bn_proj[i] = bn;
+    GemmProblem& pv = g.p[0];
+    GemmProblem& pt = g.p[1];
+    rc |= setup_linear(pv, P->a_vid[i], P->Mv, Lw.vid[i].kpad, Lw.vid[i].kpad, W16(Lw.vid[i].w16), d, Lw.vid[i].kpad, bn);
+    rc |= setup_linear(pt, P->a_txt[i], P->Mt, Lw.txt[i].kpad, Lw.txt[i].kpad, W16(Lw.txt[i].w16), d, Lw.txt[i].kpad, bn);
+    pv.bias = F32(Lw.vid[i].bias);
+    pt.bias = F32(Lw.txt[i].bias);
+    if (!last) {
+      pv.act = pt.act = ACT_RELU;
+      pv.out32 = P->p_vid32;
+      pt.out32 = P->p_txt32;
+      pv.ld32 = pt.ld32 = d;
+    } else {
+      // video tokens -> stream rows b*L + l; text tokens -> rows b*L + Lv + l   (cat on the sequence axis, univtg.py:119)
+      pv.rps_in = P->Lv;
+      pv.rps_out = P->L;
+      pv.row_off = 0;
+      pt.rps_in = P->Lt;
+      pt.rps_out = P->L;
+      pt.row_off = P->Lv;
+      pv.out32 = pt.out32 = P->x32;
+      pv.ld32 = pt.ld32 = d;
+      pv.out16 = pt.out16 = P->x16;
+      pv.out16p = pt.out16p = P->xpos16;
+      pv.ld16 = pt.ld16 = d;
+      pv.addtab = P->pos;
+      pv.ld_addtab = d;
+      pv.out32_id = nullptr;  // vid_mem_proj: set per call
+      pv.ld32_id = d;
+      pt.out32_id = P->txtproj32;
+      pt.ld32_id = d;
+    }
+  }
+  // ---- encoder layers ----
+  const float qscale = 1.0f / sqrtf((float)P->dh);
+  for (int l = 0; l < cfg->enc_layers && !rc; ++l) {
+    const LayerPacked& lp = Lw.layer[l];
+    {
+      GemmGroup& g = P->g_qkv[l];
+      memset(&g, 0, sizeof(g));
+      g.num = 3;
+      g.fmt = fmt;
+      rc |= setup_linear(g.p[0], P->xpos16, P->M, d, d, W16(lp.w_in), d, d, P->bn_main);
+      rc |= setup_linear(g.p[1], P->xpos16, P->M, d, d, W16(lp.w_in) + (size_t)d * d, d, d, P->bn_main);
+      rc |= setup_linear(g.p[2], P->x16, P->M, d, d, W16(lp.w_in) + (size_t)2 * d * d, d, d, P->bn_main);
+      g.p[0].bias = F32(lp.b_in);
+      g.p[0].alpha = qscale;  // torch MHA scales q (after bias) by 1/sqrt(dh)
+      g.p[0].out16 = P->q16;
+      g.p[0].ld16 = d;
+      g.p[1].bias = F32(lp.b_in) + d;
+      g.p[1].out16 = P->k16;
+      g.p[1].ld16 = d;
+      g.p[2].bias = F32(lp.b_in) + 2 * d;
+      g.p[2].out16t = P->vt16;
+      g.p[2].ldt = P->Lp;
+      g.p[2].rps_in = P->L;
+      g.p[2].rps_out = P->L;
+    }
+    {
+      AttnArgs& a = P->attn[l];
+      memset(&a, 0, sizeof(a));
+      a.key_mask = P->key_mask;
+      a.out = P->attn16;
+      a.lse = nullptr;
+      a.B = P->B;
+      a.L = P->L;
+      a.Lp = P->Lp;
+      a.H = P->H;
+      a.dh = P->dh;
+      a.d = d;
+      a.fmt = fmt;
+      if (P->dh == 64 || P->dh == 128) {
+        rc |= make_tmap_2d(&a.tm_q, P->q16, (uint64_t)P->M, (uint64_t)d, (uint64_t)d, 128, 64);
+        rc |= make_tmap_2d(&a.tm_k, P->k16, (uint64_t)P->M, (uint64_t)d, (uint64_t)d, 128, 64);
+        rc |= make_tmap_2d(&a.tm_vt, P->vt16, (uint64_t)P->B * d, (uint64_t)P->Lp, (uint64_t)P->Lp, (uint32_t)P->dh, 64);
+      }
+    }
+    {
+      GemmGroup& g = P->g_out[l];
+      memset(&g, 0, sizeof(g));
+      g.num = 1;
+      g.fmt = fmt;
+      rc |= setup_linear(g.p[0], P->attn16, P->M, d, d, W16(lp.w_out), d, d, P->bn_main);
+      g.p[0].bias = F32(lp.b_out);
+      g.p[0].rps_in = P->L;
+      g.p[0].rps_out = P->L;
+      g.p[0].resid = P->x32;
+      g.p[0].ld_resid = d;
+      g.p[0].out32 = P->y32;
+      g.p[0].ld32 = d;
+    }
+    {
+      GemmGroup& g = P->g_ffn1[l];
+      memset(&g, 0, sizeof(g));
+      g.num = 1;
+      g.fmt = fmt;
+      rc |= setup_linear(g.p[0], P->x16, P->M, d, d, W16(lp.w1), ff, d, (ff % 256 == 0) ? 256 : 128);
+      g.p[0].bias = F32(lp.b1);
+      g.p[0].act = ACT_GELU;
+      g.p[0].out16 = P->h16;
+      g.p[0].ld16 = ff;
+    }
+    {
+      GemmGroup& g = P->g_ffn2[l];
+      memset(&g, 0, sizeof(g));
+      g.num = 1;
+      g.fmt = fmt;
+      rc |= setup_linear(g.p[0], P->h16, P->M, ff, ff, W16(lp.w2), d, ff, P->bn_main);
+      g.p[0].bias = F32(lp.b2);
+      g.p[0].rps_in = P->L;
+      g.p[0].rps_out = P->L;
+      g.p[0].resid = P->x32;
+      g.p[0].ld_resid = d;
+      g.p[0].out32 = P->y32;
+      g.p[0].ld32 = d;
+    }
+  }
+  // ---- conv heads (k=3, pad=1) as 3-tap GEMMs over the separated layout ----
+  if (!rc) {
+    const int bn = P->bn_main;
+    auto conv_problem = [&](GemmProblem& p, const uint16_t* A, int lda, const uint16_t* W, int N, const float* bias,
+                            uint16_t* out, int ldo) -> int {
+      init_problem(p);
+      p.M = P->Mh;
+      p.N = N;
+      p.taps = 3;
+      p.kblk_per_tap = d / 64;
+      // A tile row for tap t: buffer row m0 + t  (buffer row = logical row + 1)
+      p.ca = OperandCoord{0, 0, 0, 1, 0, 1, 1, 0};
+      // W2 [N, 3d]: column tap*d + k
+      p.cb = OperandCoord{0, 0, d, 1, 0, 1, 0, 0};
+      int r = make_tmap_2d(&p.tm_a, A, (uint64_t)P->Mh + 2, (uint64_t)d, (uint64_t)lda, GEMM_BM, 64);
+      r |= make_tmap_2d(&p.tm_b, W, (uint64_t)N, (uint64_t)3 * d, (uint64_t)3 * d, (uint32_t)bn, 64);
+      p.bias = bias;
+      p.act = ACT_RELU;
+      p.rps_in = P->Lv + 1;
+      p.rps_out = P->Lv + 1;
+      p.row_off = 1;
+      p.zero_sep = 1;
+      p.out16 = out;
+      p.ld16 = ldo;
+      return r;
+    };
+    memset(&P->g_conv1, 0, sizeof(GemmGroup));
+    P->g_conv1.num = 1;
+    P->g_conv1.fmt = fmt;
+    rc |= conv_problem(P->g_conv1.p[0], P->hA, d, W16(Lw.conv1_w), 2 * d, F32(Lw.conv1_b), P->h1, 2 * d);
+    memset(&P->g_conv2, 0, sizeof(GemmGroup));
+    P->g_conv2.num = 2;
+    P->g_conv2.fmt = fmt;
+    rc |= conv_problem(P->g_conv2.p[0], P->h1, 2 * d, W16(Lw.conv2c_w), d, F32(Lw.conv2c_b), P->hc2, d);
+    rc |= conv_problem(P->g_conv2.p[1], P->h1 + d, 2 * d, W16(Lw.conv2s_w), d, F32(Lw.conv2s_b), P->hs2, d);
+  }
+  if (rc) {
+    delete P;
+    return 1;
+  }
+  P->launches = 1 + 3 * cfg->n_input_proj + 7 * cfg->enc_layers + 4;
+  *out = P;
+  return 0;
+}
+
+void univtg_plan_destroy(univtg_plan* plan) { delete plan; }
+
+int univtg_forward_num_launches(const univtg_plan* plan) { return plan ? plan->launches : -1; }
+
+int univtg_forward(univtg_plan* P, const float* src_txt, const float* src_txt_mask, const float* src_vid,
+                   const float* src_vid_mask, const float* droppath_scale, float* pred_logits, float* pred_spans,
+                   float* vid_mem_proj, float* txt_mem_proj, float* saliency_scores, void* stream) {
+  if (!P || !src_txt || !src_txt_mask || !src_vid || !src_vid_mask || !pred_logits || !pred_spans || !vid_mem_proj ||
+      !txt_mem_proj || !saliency_scores) {
+    set_error("univtg_forward: null argument");
+    return 1;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const univtg_config& c = P->cfg;
+  const PackedLayout& Lw = P->lay;
+  const uint8_t* pk = P->packed;
+  auto F32 = [&](size_t off) { return reinterpret_cast<const float*>(pk + off); };
+  const int d = P->d, fmt = c.operand_format;
+  int rc = 0;
+
+  rc = launch_sine_pos(src_vid_mask, src_txt_mask, P->dim_t, P->pos, P->key_mask, P->B, P->Lv, P->Lt, d, st);
+  if (rc) return rc;
+
+  // ---- input projectors (LinearLayer: LN -> Dropout(eval: identity) -> Linear -> ReLU) ----
+  for (int i = 0; i < c.n_input_proj; ++i) {
+    for (int s = 0; s < 2; ++s) {
+      const ProjPacked& pp = s == 0 ? Lw.vid[i] : Lw.txt[i];
+      LnArgs a;
+      memset(&a, 0, sizeof(a));
+      a.in = i == 0 ? (s == 0 ? src_vid : src_txt) : (s == 0 ? P->p_vid32 : P->p_txt32);
+      a.ld_in = pp.din;
+      a.rows = s == 0 ? P->Mv : P->Mt;
+      a.d = pp.din;
+      a.gamma = F32(pp.ln_w);
+      a.beta = F32(pp.ln_b);
+      a.eps = 1e-5f;
+      a.fmt = fmt;
+      a.out16 = s == 0 ? P->a_vid[i] : P->a_txt[i];
+      a.ld16 = pp.kpad;
+      rc = launch_layernorm(a, st);
+      if (rc) return rc;
+    }
+    GemmGroup g = P->g_proj[i];
+    if (i == c.n_input_proj - 1) g.p[0].out32_id = vid_mem_proj;
+    rc = launch_gemm_group(g, P->bn_proj[i], P->num_sms, st);
+    if (rc) return rc;
+  }
+
+  // ---- encoder layers (post-norm; TransformerEncoderLayer.forward_post) ----
+  for (int l = 0; l < c.enc_layers; ++l) {
+    const LayerPacked& lp = Lw.layer[l];
+    rc = launch_gemm_group(P->g_qkv[l], P->bn_main, P->num_sms, st);
+    if (rc) return rc;
+    if (P->dh == 64 || P->dh == 128) rc = launch_attention(P->attn[l], st);
+    else rc = launch_attention_simt(P->attn[l], P->q16, P->k16, P->vt16, st);
+    if (rc) return rc;
+    {
+      GemmGroup g = P->g_out[l];
+      g.p[0].row_scale = droppath_scale ? droppath_scale + (size_t)(2 * l) * P->B : nullptr;
+      rc = launch_gemm_group(g, P->bn_main, P->num_sms, st);
+      if (rc) return rc;
+    }
+    {
+      LnArgs a;
+      memset(&a, 0, sizeof(a));
+      a.in = P->y32;
+      a.ld_in = d;
+      a.rows = P->M;
+      a.d = d;
+      a.gamma = F32(lp.n1w);
+      a.beta = F32(lp.n1b);
+      a.eps = 1e-5f;
+      a.fmt = fmt;
+      a.out32 = P->x32;
+      a.out16 = P->x16;
+      a.ld16 = d;
+      rc = launch_layernorm(a, st);
+      if (rc) return rc;
+    }
+    rc = launch_gemm_group(P->g_ffn1[l], (P->ff % 256 == 0) ? 256 : 128, P->num_sms, st);
+    if (rc) return rc;
+    {
+      GemmGroup g = P->g_ffn2[l];
+      g.p[0].row_scale = droppath_scale ? droppath_scale + (size_t)(2 * l + 1) * P->B : nullptr;
+      rc = launch_gemm_group(g, P->bn_main, P->num_sms, st);
+      if (rc) return rc;
+    }
+    {
+      LnArgs a;
+      memset(&a, 0, sizeof(a));
+      a.in = P->y32;
+      a.ld_in = d;
+      a.rows = P->M;
+      a.d = d;
+      a.gamma = F32(lp.n2w);
+      a.beta = F32(lp.n2b);
+      a.eps = 1e-5f;
+      a.fmt = fmt;
+      a.L = P->L;
+      a.Lv = P->Lv;
+      a.out32 = P->x32;
+      a.out16 = P->x16;
+      a.out16p = P->xpos16;
+      a.ld16 = d;
+      a.pos = P->pos;
+      if (l == c.enc_layers - 1) a.outc = P->hA;  // vid_mem = memory[:, :Lv] feeds the conv heads
+      rc = launch_layernorm(a, st);
+      if (rc) return rc;
+    }
+  }
+
+  // ---- heads ----
+  rc = launch_gemm_group(P->g_conv1, P->bn_main, P->num_sms, st);
+  if (rc) return rc;
+  rc = launch_gemm_group(P->g_conv2, P->bn_main, P->num_sms, st);
+  if (rc) return rc;
+  {
+    HeadFinalArgs a;
+    a.h_cls = P->hc2;
+    a.h_span = P->hs2;
+    a.w_cls = F32(Lw.conv3c_w);
+    a.w_span = F32(Lw.conv3s_w);
+    a.b_cls = F32(Lw.conv3c_b);
+    a.b_span = F32(Lw.conv3s_b);
+    a.pred_logits = pred_logits;
+    a.pred_spans = pred_spans;
+    a.B = P->B;
+    a.Lv = P->Lv;
+    a.d = d;
+    a.fmt = fmt;
+    rc = launch_conv_head_final(a, st);
+    if (rc) return rc;
+  }
+  {
+    PoolSalArgs a;
+    a.x_txt = P->txtproj32;
+    a.x_vid = vid_mem_proj;
+    a.txt_mask = src_txt_mask;
+    a.vid_mask = src_vid_mask;
+    a.w = F32(Lw.pool_w);
+    a.pooled = txt_mem_proj;
+    a.saliency = saliency_scores;
+    a.alpha_out = nullptr;
+    a.B = P->B;
+    a.Lt = P->Lt;
+    a.Lv = P->Lv;
+    a.d = d;
+    rc = launch_pool_saliency(a, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// single operators
+// ------------------------------------------------------------------------------------------------
+int univtg_op_gemm(const void* a, const void* b, int32_t M, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn, int32_t fmt,
+                   int32_t bn, int32_t ksplit, const float* bias, int32_t act, float alpha, float* out32, void* out16,
+                   void* stream) {
+  if (!a || !b || M < 1 || N < 1 || K < 1 || (bn != 128 && bn != 256)) {
+    set_error("univtg_op_gemm: bad argument");
+    return 1;
+  }
+  GemmGroup g;
+  memset(&g, 0, sizeof(g));
+  g.num = 1;
+  g.fmt = fmt;
+  GemmProblem& p = g.p[0];
+  init_problem(p);
+  p.M = M;
+  p.N = N;
+  p.a_mn = a_mn;
+  p.b_mn = b_mn;
+  p.kblk_per_tap = (K + 63) / 64;
+  p.ksplit = ksplit < 1 ? 1 : ksplit;
+  int rc = 0;
+  if (!a_mn) {
+    rc |= make_tmap_2d(&p.tm_a, a, (uint64_t)M, (uint64_t)K, (uint64_t)K, GEMM_BM, 64);
+  } else {
+    rc |= make_tmap_2d(&p.tm_a, a, (uint64_t)K, (uint64_t)M, (uint64_t)M, 64, 64);
+    p.ca = OperandCoord{0, 1, 0, 0, 0, 0, 0, 1};  // c0 = m0, c1 = k
+  }
+  if (!b_mn) {
+    rc |= make_tmap_2d(&p.tm_b, b, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)bn, 64);
+  } else {
+    rc |= make_tmap_2d(&p.tm_b, b, (uint64_t)K, (uint64_t)N, (uint64_t)N, 64, 64);
+    p.cb = OperandCoord{0, 1, 0, 0, 0, 0, 0, 1};
+  }
+  if (rc) return rc;
+  p.bias = bias;
+  p.act = act;
+  p.alpha = alpha;
+  p.out32 = out32;
+  p.ld32 = N;
+  p.out16 = reinterpret_cast<uint16_t*>(out16);
+  p.ld16 = N;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return launch_gemm_group(g, bn, sms, (cudaStream_t)stream);
+}
+
+int univtg_op_layernorm(const float* in, int32_t rows, int32_t d, const float* gamma, const float* beta, float eps,
+                        int32_t fmt, float* out32, void* out16, int32_t ld16, void* stream) {
+  if (!in || !gamma || !beta || rows < 1 || d < 1) {
+    set_error("univtg_op_layernorm: bad argument");
+    return 1;
+  }
+  LnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in = in;
+  a.ld_in = d;
+  a.rows = rows;
+  a.d = d;
+  a.gamma = gamma;
+  a.beta = beta;
+  a.eps = eps;
+  a.fmt = fmt;
+  a.out32 = out32;
+  a.out16 = reinterpret_cast<uint16_t*>(out16);
+  a.ld16 = out16 ? ld16 : d;
+  return launch_layernorm(a, (cudaStream_t)stream);
+}
+
+int univtg_op_attention(const void* q, const void* k, const void* vt, const float* key_mask, void* out, float* lse,
+                        int32_t B, int32_t L, int32_t Lp, int32_t H, int32_t dh, int32_t fmt, int32_t impl, void* stream) {
+  if (!q || !k || !vt || !key_mask || !out) {
+    set_error("univtg_op_attention: null argument");
+    return 1;
+  }
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  const int d = H * dh;
+  a.key_mask = key_mask;
+  a.out = reinterpret_cast<uint16_t*>(out);
+  a.lse = lse;
+  a.B = B;
+  a.L = L;
+  a.Lp = Lp;
+  a.H = H;
+  a.dh = dh;
+  a.d = d;
+  a.fmt = fmt;
+  if (impl == 1)
+    return launch_attention_simt(a, reinterpret_cast<const uint16_t*>(q), reinterpret_cast<const uint16_t*>(k),
+                                 reinterpret_cast<const uint16_t*>(vt), (cudaStream_t)stream);
+  int rc = 0;
+  rc |= make_tmap_2d(&a.tm_q, q, (uint64_t)B * L, (uint64_t)d, (uint64_t)d, 128, 64);
+  rc |= make_tmap_2d(&a.tm_k, k, (uint64_t)B * L, (uint64_t)d, (uint64_t)d, 128, 64);
+  rc |= make_tmap_2d(&a.tm_vt, vt, (uint64_t)B * d, (uint64_t)Lp, (uint64_t)Lp, (uint32_t)dh, 64);
+  if (rc) return rc;
+  return launch_attention(a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+// Internal (C++) interface between the C-ABI layer (api.cu) and the kernel translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace uv {
+
+constexpr int GEMM_BM = 128;  // UMMA M (cta_group::1)
+constexpr int GEMM_BK = 64;   // one 128-byte swizzle span of 16-bit elements
+constexpr int GEMM_MAX_GROUP = 4;
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+// TMA coordinate rule of one operand for the k-block (tap, kk) of the output tile whose first
+// row (A) / first column (B) is `mn0`:
+//   c0 = base0 + mn0*mn0s + tap*tap0 + kk*64*k0s      (innermost / contiguous coordinate)
+//   c1 = base1 + mn0*mn1s + tap*tap1 + kk*64*k1s      (row coordinate)
+struct OperandCoord {
+  int base0, mn0s, tap0, k0s;
+  int base1, mn1s, tap1, k1s;
+};
+
+// One C[M,N] = epilogue(A[M,K] * B[N,K]^T) problem.  Up to GEMM_MAX_GROUP problems share one
+// persistent launch (tiles of all problems are interleaved over the SMs).
+struct GemmProblem {
+  // 16-bit operand maps, 128-byte swizzle.
+  //   K-major  operand (contraction contiguous): dims {K, rows},  box {64, 128 (A) | BN (B)}
+  //   MN-major operand (contraction is the row): dims {MN, Krows}, box {64, 64}, one box per 64 M/N elements
+  CUtensorMap tm_a;
+  CUtensorMap tm_b;
+  OperandCoord ca, cb;
+  int a_mn, b_mn;    // 1: operand is MN-major in memory
+  int M, N;
+  int taps;          // 1 = plain; 3 = k=3 conv expressed as 3 K segments
+  int kblk_per_tap;  // 64-wide k-blocks per tap
+  int ksplit;        // >=1; k-blocks are split over `ksplit` tiles that accumulate atomically into out32
+  // ---- epilogue:  v = act(acc + bias[n]) * alpha * row_scale[b(m)]  (+ resid[orow, n]) ----
+  const float* bias;
+  float alpha;
+  int act;
+  const float* row_scale;  // [num samples] or null
+  int rps_in;              // rows per sample in the M index space (0: single sample)
+  int rps_out;             // out row = (m / rps_in) * rps_out + (m % rps_in) + row_off
+  int row_off;
+  int zero_sep;            // rows with (m % rps_in) == rps_in-1 are stored as exact zeros (conv separator rows)
+  const float* resid;      // fp32, indexed by out row
+  int ld_resid;
+  const float* addtab;     // fp32 table indexed by m (sine position table); only used for out16p
+  int ld_addtab;
+  float* out32;            // fp32 at remapped rows
+  int ld32;
+  float* out32_id;         // fp32 at identity rows (m)
+  int ld32_id;
+  uint16_t* out16;         // 16-bit at remapped rows
+  uint16_t* out16p;        // 16-bit(v + addtab[m, n]) at remapped rows (same leading dim as out16)
+  int ld16;
+  uint16_t* out16t;        // transposed 16-bit store: out16t[(b*N + n) * ldt + l],  m = b*rps_in + l
+  int ldt;
+  int accumulate;          // out32 += v (atomic) instead of out32 = v
+};
+
+struct GemmGroup {
+  int num;
+  int fmt;  // 0 fp16, 1 bf16
+  GemmProblem p[GEMM_MAX_GROUP];
+};
+
+// bn in {128, 256}.  Returns cudaError_t as int.
+int launch_gemm_group(const GemmGroup& g, int bn, int num_sms, cudaStream_t stream);
+
+// Encode a 2-D tensor map over a row-major 16-bit matrix [rows, cols] with row pitch `ld` elements,
+// box {box_cols, box_rows}, 128-byte swizzle, zero fill out of bounds.  Returns 0 on success.
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
+                 uint32_t box_cols);
+
+const char* last_error();
+void set_error(const char* fmt, ...);
+
+}  // namespace uv

@@ -1,0 +1,319 @@
+// Bandwidth-bound row kernels of the UniVTG hot path (HBM roofline; 128-bit coalesced accesses, warp reductions):
+//   * layernorm_rows     - nn.LayerNorm (eps 1e-5, biased variance) of LinearLayer (model/univtg.py:392,401) and of
+//                          norm1/norm2 (model/transformer_encoder_droppath.py:99-100,121,125); emits the fp32 residual
+//                          stream plus the 16-bit GEMM operands x and x+pos (q = k = x + pos, :117).
+//   * sine_pos_table     - PositionEmbeddingSine.forward (model/position_encoding.py:60-83)
+//   * pool_saliency      - WeightedPool.forward (model/univtg.py:43-49) + cosine saliency (:146-147)
+//   * conv_head_final    - third Conv1d (k=3) of class_embed / span_embed + sigmoid + (-1,+1) sign (model/univtg.py:129-136)
+#include <math.h>
+
+#include "kernels.h"
+#include "ptx.cuh"
+#include "rowops.h"
+
+namespace uv {
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over rows.  One warp per row.
+// ------------------------------------------------------------------------------------------------
+struct LnStore {
+  const LnArgs& a;
+  int row, b, l;
+  bool has_pos;
+  size_t prow, crow;
+  __device__ LnStore(const LnArgs& a_, int row_) : a(a_), row(row_) {
+    b = 0;
+    l = row;
+    if (a.L > 0) {
+      b = row / a.L;
+      l = row - b * a.L;
+    }
+    has_pos = (a.pos != nullptr) && (a.L > 0) && (l < a.Lv);
+    prow = (size_t)b * a.Lv + l;
+    crow = (size_t)1 + (size_t)b * (a.Lv + 1) + l;
+  }
+  __device__ __forceinline__ void store4(int j, float4 v) const {
+    if (a.out32) *reinterpret_cast<float4*>(a.out32 + (size_t)row * a.d + j) = v;
+    uint2 pk;
+    pk.x = cvt16x2(v.x, v.y, a.fmt);
+    pk.y = cvt16x2(v.z, v.w, a.fmt);
+    if (a.out16) *reinterpret_cast<uint2*>(a.out16 + (size_t)row * a.ld16 + j) = pk;
+    if (a.out16p) {
+      uint2 pp = pk;
+      if (has_pos) {
+        const float4 p = *reinterpret_cast<const float4*>(a.pos + prow * a.d + j);
+        pp.x = cvt16x2(v.x + p.x, v.y + p.y, a.fmt);
+        pp.y = cvt16x2(v.z + p.z, v.w + p.w, a.fmt);
+      }
+      *reinterpret_cast<uint2*>(a.out16p + (size_t)row * a.ld16 + j) = pp;
+    }
+    if (a.outc && a.L > 0 && l < a.Lv) *reinterpret_cast<uint2*>(a.outc + crow * a.d + j) = pk;
+  }
+  __device__ __forceinline__ void store1(int j, float v) const {
+    if (a.out32) a.out32[(size_t)row * a.d + j] = v;
+    const uint16_t h = cvt16(v, a.fmt);
+    if (a.out16) a.out16[(size_t)row * a.ld16 + j] = h;
+    if (a.out16p) a.out16p[(size_t)row * a.ld16 + j] = has_pos ? cvt16(v + a.pos[prow * a.d + j], a.fmt) : h;
+    if (a.outc && a.L > 0 && l < a.Lv) a.outc[crow * a.d + j] = h;
+  }
+};
+
+// d == NV * 128: the row lives in registers (NV float4 per lane), one global read.
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_rows_vec_kernel(const LnArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= a.rows) return;
+  const float* x = a.in + (size_t)warp * a.ld_in;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = *reinterpret_cast<const float4*>(x + (i * 32 + lane) * 4);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) / (float)a.d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+  const float var = warp_sum(q) / (float)a.d;
+  const float rstd = rsqrtf(var + a.eps);
+  if (lane == 0) {
+    if (a.mean_out) a.mean_out[warp] = mean;
+    if (a.rstd_out) a.rstd_out[warp] = rstd;
+  }
+  const LnStore st(a, warp);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = (i * 32 + lane) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(a.gamma + j);
+    const float4 be = *reinterpret_cast<const float4*>(a.beta + j);
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + be.x;
+    o.y = (v[i].y - mean) * rstd * g.y + be.y;
+    o.z = (v[i].z - mean) * rstd * g.z + be.z;
+    o.w = (v[i].w - mean) * rstd * g.w + be.w;
+    st.store4(j, o);
+  }
+}
+
+// arbitrary d (e.g. 2818 = SlowFast+CLIP+TEF): three passes over the row, later passes hit L1/L2.
+__global__ void __launch_bounds__(256) layernorm_rows_generic_kernel(const LnArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= a.rows) return;
+  const float* x = a.in + (size_t)warp * a.ld_in;
+  float s = 0.f;
+  for (int j = lane; j < a.d; j += 32) s += x[j];
+  const float mean = warp_sum(s) / (float)a.d;
+  float q = 0.f;
+  for (int j = lane; j < a.d; j += 32) {
+    const float dx = x[j] - mean;
+    q += dx * dx;
+  }
+  const float var = warp_sum(q) / (float)a.d;
+  const float rstd = rsqrtf(var + a.eps);
+  if (lane == 0) {
+    if (a.mean_out) a.mean_out[warp] = mean;
+    if (a.rstd_out) a.rstd_out[warp] = rstd;
+  }
+  const LnStore st(a, warp);
+  for (int j = lane; j < a.d; j += 32) st.store1(j, (x[j] - mean) * rstd * a.gamma[j] + a.beta[j]);
+  // zero the K padding of the 16-bit operand row (columns d .. ld16)
+  if (a.out16)
+    for (int j = a.d + lane; j < a.ld16; j += 32) a.out16[(size_t)warp * a.ld16 + j] = 0;
+}
+
+int launch_layernorm(const LnArgs& a, cudaStream_t stream) {
+  if (a.rows <= 0) return 0;
+  const int threads = 256;
+  const int blocks = (a.rows * 32 + threads - 1) / threads;
+  const bool vec_ok = (a.ld_in % 4 == 0) && (a.ld16 == a.d) && ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0);
+  if (vec_ok && a.d == 1024) layernorm_rows_vec_kernel<8><<<blocks, threads, 0, stream>>>(a);
+  else if (vec_ok && a.d == 512) layernorm_rows_vec_kernel<4><<<blocks, threads, 0, stream>>>(a);
+  else if (vec_ok && a.d == 256) layernorm_rows_vec_kernel<2><<<blocks, threads, 0, stream>>>(a);
+  else layernorm_rows_generic_kernel<<<blocks, threads, 0, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) set_error("layernorm launch failed: %s", cudaGetErrorString(e));
+  return (int)e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sine position table  pos[b, l, j]  (fp32, [B*Lv, d])
+//   c = cumsum(mask); e = c / (c_last + 1e-6) * 2pi; pos = sin(e / dim_t[j]) (j even) | cos(e / dim_t[j]) (j odd)
+// dim_t is supplied by the host (computed once with the reference's own fp32 expression).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sine_pos_table_kernel(const float* __restrict__ mask, const float* __restrict__ txt_mask,
+                                                            const float* __restrict__ dim_t, float* __restrict__ pos,
+                                                            float* __restrict__ key_mask, int Lv, int Lt, int d) {
+  extern __shared__ float s_e[];  // [Lv]
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    float c = 0.f;
+    for (int l = 0; l < Lv; ++l) {
+      c += mask[(size_t)b * Lv + l];
+      s_e[l] = c;
+    }
+    const float denom = c + 1e-6f;
+    const float scale = 6.283185307179586f;  // float32(2*math.pi)
+    for (int l = 0; l < Lv; ++l) s_e[l] = s_e[l] / denom * scale;
+  }
+  // concatenated key mask [B, Lv+Lt] (mask = cat([src_vid_mask, src_txt_mask]), model/univtg.py:120)
+  if (key_mask != nullptr) {
+    const int L = Lv + Lt;
+    for (int l = threadIdx.x; l < L; l += blockDim.x)
+      key_mask[(size_t)b * L + l] = (l < Lv) ? mask[(size_t)b * Lv + l] : txt_mask[(size_t)b * Lt + (l - Lv)];
+  }
+  __syncthreads();
+  const int total = Lv * d;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int l = i / d;
+    const int j = i - l * d;
+    const float arg = s_e[l] / dim_t[j];
+    pos[((size_t)b * Lv + l) * d + j] = (j & 1) ? cosf(arg) : sinf(arg);
+  }
+}
+
+int launch_sine_pos(const float* mask, const float* txt_mask, const float* dim_t, float* pos, float* key_mask, int B, int Lv,
+                    int Lt, int d, cudaStream_t stream) {
+  sine_pos_table_kernel<<<B, 256, Lv * sizeof(float), stream>>>(mask, txt_mask, dim_t, pos, key_mask, Lv, Lt, d);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) set_error("sine_pos launch failed: %s", cudaGetErrorString(e));
+  return (int)e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// WeightedPool + cosine saliency.  One CTA per sample.
+//   alpha = softmax_l(x_t . w + (1 - m_t) * -1e30);  pooled = sum_l alpha_l x_t[l]
+//   sal[l] = cos(x_v[l], pooled) + log(m_v[l] + 1e-45)      (denormal-sensitive: no FTZ / fast-math)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pool_saliency_kernel(const PoolSalArgs a) {
+  extern __shared__ float sm[];
+  float* s_alpha = sm;            // [Lt]
+  float* s_pool = sm + a.Lt;      // [d]
+  __shared__ float s_red[8];
+  __shared__ float s_pn;
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const float* xt = a.x_txt + (size_t)b * a.Lt * a.d;
+  const float* xv = a.x_vid + (size_t)b * a.Lv * a.d;
+  for (int l = warp; l < a.Lt; l += nw) {
+    float s = 0.f;
+    for (int j = lane; j < a.d; j += 32) s += xt[(size_t)l * a.d + j] * a.w[j];
+    s = warp_sum(s);
+    if (lane == 0) s_alpha[l] = s + (1.0f - a.txt_mask[(size_t)b * a.Lt + l]) * (-1e30f);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float mx = -INFINITY;
+    for (int l = lane; l < a.Lt; l += 32) mx = fmaxf(mx, s_alpha[l]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int l = lane; l < a.Lt; l += 32) {
+      const float e = expf(s_alpha[l] - mx);
+      s_alpha[l] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    for (int l = lane; l < a.Lt; l += 32) s_alpha[l] = s_alpha[l] / sum;
+  }
+  __syncthreads();
+  if (a.alpha_out)
+    for (int l = threadIdx.x; l < a.Lt; l += blockDim.x) a.alpha_out[(size_t)b * a.Lt + l] = s_alpha[l];
+  float pn = 0.f;
+  for (int j = threadIdx.x; j < a.d; j += blockDim.x) {
+    float p = 0.f;
+    for (int l = 0; l < a.Lt; ++l) p += xt[(size_t)l * a.d + j] * s_alpha[l];
+    s_pool[j] = p;
+    a.pooled[(size_t)b * a.d + j] = p;
+    pn += p * p;
+  }
+  pn = warp_sum(pn);
+  if (lane == 0) s_red[warp] = pn;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < nw; ++i) t += s_red[i];
+    s_pn = sqrtf(t);
+  }
+  __syncthreads();
+  const float pnorm = fmaxf(s_pn, 1e-8f);
+  for (int l = warp; l < a.Lv; l += nw) {
+    float dot = 0.f, nn = 0.f;
+    for (int j = lane; j < a.d; j += 32) {
+      const float v = xv[(size_t)l * a.d + j];
+      dot += v * s_pool[j];
+      nn += v * v;
+    }
+    dot = warp_sum(dot);
+    nn = warp_sum(nn);
+    if (lane == 0) {
+      const float vn = fmaxf(sqrtf(nn), 1e-8f);
+      const float cosv = dot / (vn * pnorm);
+      a.saliency[(size_t)b * a.Lv + l] = cosv + logf(a.vid_mask[(size_t)b * a.Lv + l] + 1e-45f);
+    }
+  }
+}
+
+int launch_pool_saliency(const PoolSalArgs& a, cudaStream_t stream) {
+  const size_t smem = (size_t)(a.Lt + a.d) * sizeof(float);
+  pool_saliency_kernel<<<a.B, 256, smem, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) set_error("pool_saliency launch failed: %s", cudaGetErrorString(e));
+  return (int)e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Final conv layer of both heads (out channels 1 and 2) + sigmoid + sign.  One warp per (b, l).
+// Hidden activations are 16-bit in the separated conv layout: row 1 + b*(Lv+1) + l, zero separator rows.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_head_final_kernel(const HeadFinalArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= a.B * a.Lv) return;
+  const int b = warp / a.Lv, l = warp - b * a.Lv;
+  const size_t row = (size_t)1 + (size_t)b * (a.Lv + 1) + l;  // centre row in the +1-offset buffer
+  float acc_c = 0.f, acc_s0 = 0.f, acc_s1 = 0.f;
+  for (int t = 0; t < 3; ++t) {
+    const uint16_t* hc = a.h_cls + (row + t - 1) * a.d;
+    const uint16_t* hs = a.h_span + (row + t - 1) * a.d;
+    const float* wc = a.w_cls + (size_t)t * a.d;            // [3][d]
+    const float* ws0 = a.w_span + (size_t)t * a.d;          // [2][3][d]
+    const float* ws1 = a.w_span + (size_t)(3 + t) * a.d;
+    for (int j = lane * 2; j < a.d; j += 64) {
+      const uint32_t c2 = *reinterpret_cast<const uint32_t*>(hc + j);
+      const uint32_t s2 = *reinterpret_cast<const uint32_t*>(hs + j);
+      const float c0 = ld16((uint16_t)(c2 & 0xffff), a.fmt), c1 = ld16((uint16_t)(c2 >> 16), a.fmt);
+      const float s0 = ld16((uint16_t)(s2 & 0xffff), a.fmt), s1 = ld16((uint16_t)(s2 >> 16), a.fmt);
+      acc_c += c0 * wc[j] + c1 * wc[j + 1];
+      acc_s0 += s0 * ws0[j] + s1 * ws0[j + 1];
+      acc_s1 += s0 * ws1[j] + s1 * ws1[j + 1];
+    }
+  }
+  acc_c = warp_sum(acc_c);
+  acc_s0 = warp_sum(acc_s0);
+  acc_s1 = warp_sum(acc_s1);
+  if (lane == 0) {
+    const float zc = acc_c + a.b_cls[0];
+    const float z0 = acc_s0 + a.b_span[0];
+    const float z1 = acc_s1 + a.b_span[1];
+    a.pred_logits[warp] = 1.f / (1.f + expf(-zc));
+    a.pred_spans[(size_t)warp * 2 + 0] = -(1.f / (1.f + expf(-z0)));
+    a.pred_spans[(size_t)warp * 2 + 1] = 1.f / (1.f + expf(-z1));
+  }
+}
+
+int launch_conv_head_final(const HeadFinalArgs& a, cudaStream_t stream) {
+  const int rows = a.B * a.Lv;
+  const int threads = 256;
+  const int blocks = (rows * 32 + threads - 1) / threads;
+  conv_head_final_kernel<<<blocks, threads, 0, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) set_error("conv_head_final launch failed: %s", cudaGetErrorString(e));
+  return (int)e;
+}
+
+}  // namespace uv
