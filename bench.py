@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the UniVTG hot path on B200 (contract in the task statement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+A "step" is one pass of the hot path over one synthetic batch:
+  cfg2_fwd   BASELINE.json configs[1]: B=32, L_v=75, L_t=32, d=1024, 4 layers, forward (inference)       [default]
+  cfg5_fwd   configs[4]: B=8, L_v=1200, L_t=77, 6 layers, forward
+Metric: video-query pairs/sec (whole job, all ranks).  `value` is measured with inputs resident in HBM; `e2e` through the
+public plugin API (`model(**inputs)`) with pinned HOST inputs, H2D + D2H inside the timed region.
+N>1: one process per GPU (torchrun), each rank runs its own replica on its own batch (the path shards by sample; inference
+needs no collective) -> "scaling": "weak".
+--impl reference: the CPU arm (the oracle port of the reference's fp32 PyTorch path, all host threads), rank 0 only.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from univtg_b200 import synth  # noqa: E402
+
+WORKLOADS = {
+    "cfg2_fwd": dict(cfg="cfg2", mode="fwd"),
+    "cfg4_fwd": dict(cfg="cfg4", mode="fwd"),
+    "cfg5_fwd": dict(cfg="cfg5", mode="fwd"),
+}
+SMI_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        z = json.load(open(p))
+        return dict(hbm_gbs=z["hbm_gbs"], tflops_burst=z["bf16_tflops"], tflops_sustained=z["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms during the timed region."""
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={SMI_QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path).read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def gemm_flops_forward(cfg):
+    """Algorithmic FLOPs of everything the tcgen05 GEMM kernel executes in one forward (projectors, QKV/out/FFN, conv 1-2)."""
+    d, ff, N = cfg["hidden_dim"], cfg["dim_feedforward"], cfg["enc_layers"]
+    B, Lv, Lt = cfg["batch"], cfg["l_vid"], cfg["l_txt"]
+    L = Lv + Lt
+    enc = N * (8 * L * d * d + 4 * L * d * ff)
+    proj = 2 * Lv * (cfg["v_feat_dim"] * d + d * d) + 2 * Lt * (cfg["t_feat_dim"] * d + d * d)
+    conv = 8 * Lv * 3 * d * d
+    return B * (enc + proj + conv)
+
+
+def run_reference_arm(args, wl, cfg):
+    """CPU arm: the oracle port of the reference's fp32 path on all host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import univtg_oracle as O  # the second place bench.py may execute oracle/
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.make_state_dict(cfg, seed=0)
+    sd = {k: v.float() for k, v in sd.items()}
+    inp = synth.make_inputs(cfg, seed=1)
+    B = cfg["batch"]
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 2))):
+            O.forward(sd, cfg, **inp, dtype=torch.float32)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.forward(sd, cfg, **inp, dtype=torch.float32)
+        dt = time.perf_counter() - t0
+    val = B * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "video-query pairs/sec", "value": val, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "batch": B, "l_vid": cfg["l_vid"], "l_txt": cfg["l_txt"],
+                   "hidden_dim": cfg["hidden_dim"], "enc_layers": cfg["enc_layers"]},
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full batches (B={B}) of {args.workload}, oracle/univtg_oracle.py fp32, "
+                                   f"torch {torch.__version__} CPU, {cores} threads"},
+        "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2_fwd", choices=sorted(WORKLOADS))
+    ap.add_argument("--operand-format", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    wl = WORKLOADS[args.workload]
+    cfg = synth.CONFIGS[wl["cfg"]]
+
+    if args.impl == "reference":
+        run_reference_arm(args, wl, cfg)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a GPU (no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    from univtg_b200 import build_model
+
+    model, _ = build_model(synth.reference_args(cfg, device=str(dev), operand_format=args.operand_format))
+    model.load_state_dict(synth.make_state_dict(cfg, seed=0), strict=True)
+    model.to(dev).eval()
+    B, Lv, Lt, d = cfg["batch"], cfg["l_vid"], cfg["l_txt"], cfg["hidden_dim"]
+
+    # Rotating set of distinct input batches whose total size exceeds the 126 MB L2 (no L2-resident inputs between steps).
+    per_batch = B * (Lv * cfg["v_feat_dim"] + Lt * cfg["t_feat_dim"] + Lv + Lt) * 4
+    n_rot = max(2, int(160e6 // per_batch) + 1)
+    host_batches = []
+    for i in range(n_rot):
+        inp = synth.make_inputs(cfg, seed=1 + 7 * rank + i)
+        host_batches.append({k: v.pin_memory() for k, v in inp.items()})
+    dev_batches = [{k: v.to(dev) for k, v in hb.items()} for hb in host_batches]
+    launches_per_step = model.num_forward_launches(B, Lv, Lt)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ------------------------------------------------ device-resident timing ------------------------------------------------
+    with torch.no_grad():
+        for i in range(args.warmup):
+            model(**dev_batches[i % n_rot])
+        sync_all()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        for i in range(args.steps):
+            model(**dev_batches[i % n_rot])
+        e1.record()
+        sync_all()
+        ms_total = e0.elapsed_time(e1)
+
+        # -------------------------------------------- end-to-end through the public API ------------------------------------
+        out_host = {"pred_logits": torch.empty(B, Lv, 1).pin_memory(), "pred_spans": torch.empty(B, Lv, 2).pin_memory(),
+                    "saliency_scores": torch.empty(B, Lv).pin_memory()}
+        stage = {k: torch.empty_like(v, device=dev) for k, v in host_batches[0].items()}
+
+        def e2e_step(i):
+            hb = host_batches[i % n_rot]
+            for k in stage:
+                stage[k].copy_(hb[k], non_blocking=True)
+            out = model(**stage)
+            for k, hbuf in out_host.items():
+                hbuf.copy_(out[k], non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the caller consumes the step's result on the host
+
+        for i in range(3):
+            e2e_step(i)
+        sync_all()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(args.steps):
+            e2e_step(i)
+        f1.record()
+        sync_all()
+        ms_e2e = f0.elapsed_time(f1)
+        clocks = sampler.stop() if rank == 0 else None
+
+        # ------------------------------- per-kernel-class durations (CUDA events between launches) -----------------------
+        kind_ms = {0: [], 1: [], 2: []}
+        n_kind = {0: 0, 1: 0, 2: 0}
+        prof_steps = 5
+        for i in range(prof_steps):
+            tl = model.profile_forward(dev_batches[i % n_rot])
+            acc = {0: 0.0, 1: 0.0, 2: 0.0}
+            n_kind = {0: 0, 1: 0, 2: 0}
+            for kind, ms in tl:
+                acc[kind] += ms
+                n_kind[kind] += 1
+            for k in acc:
+                kind_ms[k].append(acc[k])
+        gemm_ms = statistics.median(kind_ms[1])
+        attn_ms = statistics.median(kind_ms[2])
+        row_ms = statistics.median(kind_ms[0])
+
+    # max over ranks
+    t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks = load_peaks()
+        pairs = B * args.steps * n_gpus
+        value = pairs / (ms_total * 1e-3)
+        e2e_value = pairs / (ms_e2e * 1e-3)
+        total_flops, enc_flops = synth.flops_forward(cfg)
+        gflops = gemm_flops_forward(cfg)
+        n_gemm = max(1, n_kind[1])
+        achieved_tf = gflops / (gemm_ms * 1e-3) / 1e12
+        h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+        d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+        line = {
+            "metric": "video-query pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16" if args.operand_format == "fp16" else "bf16", "data": "synthetic",
+            "config": {"workload": args.workload, "batch_per_gpu": B, "global_batch": B * n_gpus, "l_vid": Lv, "l_txt": Lt,
+                       "hidden_dim": d, "nheads": cfg["nheads"], "dim_feedforward": cfg["dim_feedforward"],
+                       "enc_layers": cfg["enc_layers"], "v_feat_dim": cfg["v_feat_dim"], "t_feat_dim": cfg["t_feat_dim"],
+                       "accumulate": "f32", "parallelism": f"replicas x{n_gpus} (shard by sample, no collective)",
+                       "l2_policy": f"{n_rot} rotating input batches ({n_rot * per_batch / 1e6:.0f} MB > 126 MB L2)",
+                       "clips_per_s": value * Lv},
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "launches_per_step": launches_per_step,
+            "clocks": clocks,
+            "tflops_algorithmic": total_flops / (ms_total / args.steps * 1e-3) / 1e12,
+            "encoder_tflops_pct_of_sustained_peak": 100.0 * enc_flops / (ms_total / args.steps * 1e-3) / 1e12 / peaks["tflops_sustained"],
+            "roofline": {"kernel": "gemm_tcgen05_kernel", "bound": "tensor", "achieved": achieved_tf,
+                         "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["tflops_sustained"],
+                         "traffic": None, "peak_source": peaks["source"] + ", sustained (kernel timed inside a step)",
+                         "launches_per_step": n_gemm, "avg_launch_us": gemm_ms / n_gemm * 1e3,
+                         "flops_per_launch": gflops / n_gemm,
+                         "step_share": {"gemm_ms": gemm_ms, "attention_ms": attn_ms, "row_kernels_ms": row_ms}},
+        }
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(cfg, args.workload)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(cfg, workload):
+    """Oracle port of the reference fp32 path on the host cores, bounded sample (~10-30 s of CPU work)."""
+    from oracle import univtg_oracle as O  # checker/baseline leg only
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {k: v.float() for k, v in synth.make_state_dict(cfg, seed=0).items()}
+    sample_b = min(cfg["batch"], 8)
+    inp = synth.make_inputs(cfg, seed=1, batch=sample_b)
+    with torch.no_grad():
+        O.forward(sd, cfg, **inp, dtype=torch.float32)
+        t0 = time.perf_counter()
+        n = 0
+        while True:
+            O.forward(sd, cfg, **inp, dtype=torch.float32)
+            n += 1
+            dt = time.perf_counter() - t0
+            if dt > 10.0 or n >= 50:
+                break
+    return {"value": sample_b * n / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": f"{n} forwards of B={sample_b} ({workload} shape), oracle/univtg_oracle.py fp32 on {cores} torch threads"}
+
+
+if __name__ == "__main__":
+    main()

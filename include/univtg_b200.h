@@ -86,6 +86,12 @@ int univtg_forward(univtg_plan* plan, const float* src_txt, const float* src_txt
 /* Number of kernels one univtg_forward launches (for bench accounting). */
 int univtg_forward_num_launches(const univtg_plan* plan);
 
+/* Optional per-launch CUDA-event timeline of univtg_forward (bench / profiling only; adds event records to the stream).
+ * read_profile returns the number of launches of the last forward and fills ms[i] / kinds[i]
+ * (kind 0 = bandwidth-bound row kernel, 1 = tcgen05 GEMM, 2 = attention); it synchronises on the last event. */
+int univtg_plan_set_profiling(univtg_plan* plan, int32_t enable);
+int univtg_plan_read_profile(univtg_plan* plan, float* ms, int32_t* kinds, int32_t cap);
+
 /* ---- single operators (unit tests / profiling; same kernels the plan uses) ---- */
 
 /* C[M,N] = act(A*B^T + bias) * alpha.  a: [M,K] (a_mn=0) or [K,M] (a_mn=1); b: [N,K] (b_mn=0) or [K,N] (b_mn=1),

@@ -49,6 +49,8 @@ SIGNATURES = {
     "univtg_plan_destroy": (None, [c_void_p]),
     "univtg_forward": (c_int, [c_void_p] * 12),
     "univtg_forward_num_launches": (c_int, [c_void_p]),
+    "univtg_plan_set_profiling": (c_int, [c_void_p, c_int]),
+    "univtg_plan_read_profile": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "univtg_op_gemm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                c_float, c_void_p, c_void_p, c_void_p]),
     "univtg_op_layernorm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_int,

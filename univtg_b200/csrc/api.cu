@@ -227,7 +227,31 @@ struct univtg_plan {
   AttnArgs attn[16];
   int bn_proj[3], bn_main;
   int launches;
+  // optional per-launch CUDA-event timeline (bench / profiling only)
+  int profiling;
+  int n_marks;
+  cudaEvent_t marks[160];
+  int mark_kind[160];  // kind of the launch that ENDS at mark i (i >= 1): 0 row kernel, 1 tcgen05 GEMM, 2 attention
 };
+
+namespace {
+inline void prof_begin(univtg_plan* P, cudaStream_t st) {
+  if (!P->profiling) return;
+  P->n_marks = 0;
+  if (!P->marks[0]) cudaEventCreate(&P->marks[0]);
+  cudaEventRecord(P->marks[0], st);
+  P->mark_kind[0] = -1;
+  P->n_marks = 1;
+}
+inline void prof_mark(univtg_plan* P, cudaStream_t st, int kind) {
+  if (!P->profiling || P->n_marks >= 160) return;
+  const int i = P->n_marks;
+  if (!P->marks[i]) cudaEventCreate(&P->marks[i]);
+  cudaEventRecord(P->marks[i], st);
+  P->mark_kind[i] = kind;
+  P->n_marks = i + 1;
+}
+}  // namespace
 
 namespace {
 
@@ -653,7 +677,35 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
   return 0;
 }
 
-void univtg_plan_destroy(univtg_plan* plan) { delete plan; }
+void univtg_plan_destroy(univtg_plan* plan) {
+  if (!plan) return;
+  for (int i = 0; i < 160; ++i)
+    if (plan->marks[i]) cudaEventDestroy(plan->marks[i]);
+  delete plan;
+}
+
+int univtg_plan_set_profiling(univtg_plan* plan, int32_t enable) {
+  if (!plan) return 1;
+  plan->profiling = enable ? 1 : 0;
+  plan->n_marks = 0;
+  return 0;
+}
+
+int univtg_plan_read_profile(univtg_plan* plan, float* ms, int32_t* kinds, int32_t cap) {
+  if (!plan || !ms || !kinds) return -1;
+  if (plan->n_marks < 2) return 0;
+  cudaError_t e = cudaEventSynchronize(plan->marks[plan->n_marks - 1]);
+  if (e != cudaSuccess) {
+    set_error("profile sync: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  int n = 0;
+  for (int i = 1; i < plan->n_marks && n < cap; ++i, ++n) {
+    cudaEventElapsedTime(&ms[n], plan->marks[i - 1], plan->marks[i]);
+    kinds[n] = plan->mark_kind[i];
+  }
+  return n;
+}
 
 int univtg_forward_num_launches(const univtg_plan* plan) { return plan ? plan->launches : -1; }
 
@@ -672,9 +724,11 @@ int univtg_forward(univtg_plan* P, const float* src_txt, const float* src_txt_ma
   auto F32 = [&](size_t off) { return reinterpret_cast<const float*>(pk + off); };
   const int d = P->d, fmt = c.operand_format;
   int rc = 0;
+  prof_begin(P, st);
 
   rc = launch_sine_pos(src_vid_mask, src_txt_mask, P->dim_t, P->pos, P->key_mask, P->B, P->Lv, P->Lt, d, st);
   if (rc) return rc;
+  prof_mark(P, st, 0);
 
   // ---- input projectors (LinearLayer: LN -> Dropout(eval: identity) -> Linear -> ReLU) ----
   for (int i = 0; i < c.n_input_proj; ++i) {
@@ -694,11 +748,13 @@ int univtg_forward(univtg_plan* P, const float* src_txt, const float* src_txt_ma
       a.ld16 = pp.kpad;
       rc = launch_layernorm(a, st);
       if (rc) return rc;
+      prof_mark(P, st, 0);
     }
     GemmGroup g = P->g_proj[i];
     if (i == c.n_input_proj - 1) g.p[0].out32_id = vid_mem_proj;
     rc = launch_gemm_group(g, P->bn_proj[i], P->num_sms, st);
     if (rc) return rc;
+    prof_mark(P, st, 1);
   }
 
   // ---- encoder layers (post-norm; TransformerEncoderLayer.forward_post) ----
@@ -706,14 +762,17 @@ int univtg_forward(univtg_plan* P, const float* src_txt, const float* src_txt_ma
     const LayerPacked& lp = Lw.layer[l];
     rc = launch_gemm_group(P->g_qkv[l], P->bn_main, P->num_sms, st);
     if (rc) return rc;
+    prof_mark(P, st, 1);
     if (P->dh == 64 || P->dh == 128) rc = launch_attention(P->attn[l], st);
     else rc = launch_attention_simt(P->attn[l], P->q16, P->k16, P->vt16, st);
     if (rc) return rc;
+    prof_mark(P, st, 2);
     {
       GemmGroup g = P->g_out[l];
       g.p[0].row_scale = droppath_scale ? droppath_scale + (size_t)(2 * l) * P->B : nullptr;
       rc = launch_gemm_group(g, P->bn_main, P->num_sms, st);
       if (rc) return rc;
+      prof_mark(P, st, 1);
     }
     {
       LnArgs a;
@@ -731,14 +790,17 @@ int univtg_forward(univtg_plan* P, const float* src_txt, const float* src_txt_ma
       a.ld16 = d;
       rc = launch_layernorm(a, st);
       if (rc) return rc;
+      prof_mark(P, st, 0);
     }
     rc = launch_gemm_group(P->g_ffn1[l], (P->ff % 256 == 0) ? 256 : 128, P->num_sms, st);
     if (rc) return rc;
+    prof_mark(P, st, 1);
     {
       GemmGroup g = P->g_ffn2[l];
       g.p[0].row_scale = droppath_scale ? droppath_scale + (size_t)(2 * l + 1) * P->B : nullptr;
       rc = launch_gemm_group(g, P->bn_main, P->num_sms, st);
       if (rc) return rc;
+      prof_mark(P, st, 1);
     }
     {
       LnArgs a;
@@ -761,14 +823,17 @@ int univtg_forward(univtg_plan* P, const float* src_txt, const float* src_txt_ma
       if (l == c.enc_layers - 1) a.outc = P->hA;  // vid_mem = memory[:, :Lv] feeds the conv heads
       rc = launch_layernorm(a, st);
       if (rc) return rc;
+      prof_mark(P, st, 0);
     }
   }
 
   // ---- heads ----
   rc = launch_gemm_group(P->g_conv1, P->bn_main, P->num_sms, st);
   if (rc) return rc;
+  prof_mark(P, st, 1);
   rc = launch_gemm_group(P->g_conv2, P->bn_main, P->num_sms, st);
   if (rc) return rc;
+  prof_mark(P, st, 1);
   {
     HeadFinalArgs a;
     a.h_cls = P->hc2;
@@ -785,6 +850,7 @@ int univtg_forward(univtg_plan* P, const float* src_txt, const float* src_txt_ma
     a.fmt = fmt;
     rc = launch_conv_head_final(a, st);
     if (rc) return rc;
+    prof_mark(P, st, 0);
   }
   {
     PoolSalArgs a;
@@ -802,6 +868,7 @@ int univtg_forward(univtg_plan* P, const float* src_txt, const float* src_txt_ma
     a.d = d;
     rc = launch_pool_saliency(a, st);
     if (rc) return rc;
+    prof_mark(P, st, 0);
   }
   return 0;
 }

@@ -1,0 +1,372 @@
+"""Host-side mirror of the reference plugin boundary for the UniVTG hot path.
+
+    build_model(args) -> (model, criterion)          reference model/univtg.py:409-450
+    model(src_txt=, src_txt_mask=, src_vid=, src_vid_mask=) -> dict   reference model/univtg.py:105-155
+
+Same `args` fields, same forward signature, same output-dict keys, same `state_dict` keys/shapes (reference checkpoints load
+with strict=True).  PyTorch is used for parameters, device memory and streams only: all arithmetic runs in the CUDA library
+behind include/univtg_b200.h (univtg_b200/_lib.py).  There is no eager / CPU fallback: without the library or a GPU the
+forward raises.
+"""
+import ctypes
+import math
+
+import torch
+from torch import nn
+
+from . import _lib
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# parameter containers that reproduce the reference's state_dict key names
+# ------------------------------------------------------------------------------------------------------------------
+class _Params(nn.Module):
+    """A bag of named parameters (stands in for nn.Linear / nn.LayerNorm / nn.Conv1d / nn.Embedding key layouts)."""
+
+    def __init__(self, **shapes):
+        super().__init__()
+        for name, shape in shapes.items():
+            self.register_parameter(name, nn.Parameter(torch.zeros(shape)))
+
+
+class _Attn(nn.Module):  # keys of nn.MultiheadAttention
+    def __init__(self, d):
+        super().__init__()
+        self.in_proj_weight = nn.Parameter(torch.zeros(3 * d, d))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * d))
+        self.out_proj = _Params(weight=(d, d), bias=(d,))
+
+
+class _EncoderLayer(nn.Module):  # keys of TransformerEncoderLayer (transformer_encoder_droppath.py:88-106)
+    def __init__(self, d, ff):
+        super().__init__()
+        self.self_attn = _Attn(d)
+        self.linear1 = _Params(weight=(ff, d), bias=(ff,))
+        self.linear2 = _Params(weight=(d, ff), bias=(d,))
+        self.norm1 = _Params(weight=(d,), bias=(d,))
+        self.norm2 = _Params(weight=(d,), bias=(d,))
+
+
+class _Encoder(nn.Module):
+    def __init__(self, d, ff, n):
+        super().__init__()
+        self.layers = nn.ModuleList([_EncoderLayer(d, ff) for _ in range(n)])
+
+
+class _Transformer(nn.Module):
+    def __init__(self, d, ff, n, nhead):
+        super().__init__()
+        self.encoder = _Encoder(d, ff, n)
+        self.d_model = d
+        self.nhead = nhead
+
+
+class _TxtPos(nn.Module):  # TrainablePositionalEncoding keys (unused unless --use_txt_pos; never receives gradients)
+    def __init__(self, max_q_l, d):
+        super().__init__()
+        self.position_embeddings = _Params(weight=(max_q_l, d))
+        self.LayerNorm = _Params(weight=(d,), bias=(d,))
+
+
+class _ConvHead(nn.Module):  # Conv (model/univtg.py:367-382): 3 x Conv1d(k=3)
+    def __init__(self, d, out_dim):
+        super().__init__()
+        self.layers = nn.ModuleList([_Params(weight=(d, d, 3), bias=(d,)), _Params(weight=(d, d, 3), bias=(d,)),
+                                     _Params(weight=(out_dim, d, 3), bias=(out_dim,))])
+
+
+class _LinearLayer(nn.Module):  # LinearLayer (model/univtg.py:384-406): LayerNorm + Sequential(Dropout, Linear)
+    def __init__(self, din, dout):
+        super().__init__()
+        self.LayerNorm = _Params(weight=(din,), bias=(din,))
+        self.net = nn.ModuleList([nn.Identity(), _Params(weight=(dout, din), bias=(dout,))])
+
+
+def _uniform_(t, bound):
+    with torch.no_grad():
+        t.uniform_(-bound, bound)
+
+
+class _PlanEntry:
+    __slots__ = ("handle", "workspace", "shape")
+
+
+class Model(nn.Module):
+    """B200-native UniVTG model: the reference `Model` (model/univtg.py:51-155) behind the same interface."""
+
+    def __init__(self, args):
+        super().__init__()
+        d = int(args.hidden_dim)
+        self.hidden_dim = d
+        self.nheads = int(args.nheads)
+        self.dim_feedforward = int(args.dim_feedforward)
+        self.enc_layers = int(args.enc_layers)
+        self.n_input_proj = int(args.n_input_proj)
+        self.txt_dim = int(args.t_feat_dim)
+        self.vid_dim = int(args.v_feat_dim)
+        self.input_dropout = float(args.input_dropout)
+        self.droppath = float(args.droppath)
+        self.attn_dropout = float(args.dropout)
+        self.span_loss_type = args.span_loss_type
+        self.use_txt_pos = bool(args.use_txt_pos)
+        self.max_v_l = int(getattr(args, "max_v_l", 75))
+        self.operand_format = {"fp16": 0, "bf16": 1}[getattr(args, "operand_format", "fp16")]
+        if bool(getattr(args, "pre_norm", False)):
+            # the reference raises AttributeError here (forward_pre is not defined, transformer_encoder_droppath.py:128-134)
+            raise NotImplementedError("pre_norm is not supported by the UniVTG encoder (reference has no forward_pre)")
+        if args.position_embedding not in ("v2", "sine"):
+            raise ValueError(f"not supported {args.position_embedding}")
+        if not 1 <= self.n_input_proj <= 3:
+            raise ValueError("n_input_proj must be 1, 2 or 3")
+        if self.use_txt_pos:
+            raise NotImplementedError("use_txt_pos=True (learned text positions) is outside the accelerated path")
+
+        # registration order == reference Model.__init__ (keeps state_dict / optimizer parameter order identical)
+        self.transformer = _Transformer(d, self.dim_feedforward, self.enc_layers, self.nheads)
+        self.txt_position_embed = _TxtPos(int(args.max_q_l), d)
+        self.token_type_embeddings = _Params(weight=(2, d))
+        self.span_embed = _ConvHead(d, 2 if self.span_loss_type == "l1" else self.max_v_l * 2)
+        self.class_embed = _ConvHead(d, 1)
+        dims_t = [self.txt_dim] + [d] * 3
+        dims_v = [self.vid_dim] + [d] * 3
+        self.input_txt_proj = nn.ModuleList([_LinearLayer(dims_t[i], d) for i in range(self.n_input_proj)])
+        self.input_vid_proj = nn.ModuleList([_LinearLayer(dims_v[i], d) for i in range(self.n_input_proj)])
+        self.weightedpool = _Params(weight=(d, 1))
+        self.reset_parameters()
+
+        self._packed = None
+        self._packed_key = None
+        self._plans = {}
+        self._dim_t = None
+        self._cfg = _lib.Config(d, self.nheads, self.dim_feedforward, self.enc_layers, self.n_input_proj, self.vid_dim,
+                                self.txt_dim, self.operand_format)
+
+    # ---- initialisation with the reference's distributions --------------------------------------------------------
+    def reset_parameters(self):
+        with torch.no_grad():
+            for name, p in self.named_parameters():
+                if name.startswith("transformer."):
+                    if p.dim() > 1:  # Transformer._reset_parameters: xavier-uniform on every matrix
+                        nn.init.xavier_uniform_(p)
+                    elif name.endswith(("norm1.weight", "norm2.weight")):
+                        p.fill_(1.0)
+                    elif name.endswith(("linear1.bias", "linear2.bias")):
+                        fan_in = self.hidden_dim if "linear1" in name else self.dim_feedforward
+                        _uniform_(p, 1.0 / math.sqrt(fan_in))
+                    else:
+                        p.zero_()  # in_proj_bias, out_proj.bias, LayerNorm biases
+                elif name.endswith("LayerNorm.weight"):
+                    p.fill_(1.0)
+                elif name.endswith("LayerNorm.bias"):
+                    p.zero_()
+                elif name == "token_type_embeddings.weight":
+                    p.normal_(0.0, 0.02)
+                elif name == "txt_position_embed.position_embeddings.weight":
+                    p.normal_(0.0, 1.0)
+                elif name == "weightedpool.weight":
+                    nn.init.xavier_uniform_(p)
+                elif p.dim() >= 2:  # nn.Linear / nn.Conv1d default: kaiming_uniform(a=sqrt(5)) == U(+-1/sqrt(fan_in))
+                    fan_in = p.shape[1] * (p.shape[2] if p.dim() == 3 else 1)
+                    _uniform_(p, 1.0 / math.sqrt(fan_in))
+                else:  # their biases
+                    owner = dict(self.named_parameters())[name[:-4] + "weight"]
+                    fan_in = owner.shape[1] * (owner.shape[2] if owner.dim() == 3 else 1)
+                    _uniform_(p, 1.0 / math.sqrt(fan_in))
+
+    # ---- C-ABI plumbing -----------------------------------------------------------------------------------------------
+    def _abi_params(self):
+        """Parameters in the order include/univtg_b200.h documents for univtg_pack_weights."""
+        ps = []
+        for proj in (self.input_vid_proj, self.input_txt_proj):
+            for layer in proj:
+                ps += [layer.LayerNorm.weight, layer.LayerNorm.bias, layer.net[1].weight, layer.net[1].bias]
+        ps.append(self.token_type_embeddings.weight)
+        for lyr in self.transformer.encoder.layers:
+            ps += [lyr.self_attn.in_proj_weight, lyr.self_attn.in_proj_bias, lyr.self_attn.out_proj.weight,
+                   lyr.self_attn.out_proj.bias, lyr.linear1.weight, lyr.linear1.bias, lyr.linear2.weight, lyr.linear2.bias,
+                   lyr.norm1.weight, lyr.norm1.bias, lyr.norm2.weight, lyr.norm2.bias]
+        for head in (self.span_embed, self.class_embed):
+            for c in head.layers:
+                ps += [c.weight, c.bias]
+        ps.append(self.weightedpool.weight)
+        return ps
+
+    def _device(self):
+        return self.weightedpool.weight.device
+
+    def _ensure_packed(self):
+        """(Re)pack the fp32 parameters into the 16-bit operand buffer when any parameter changed."""
+        lib = _lib.load_library()
+        params = self._abi_params()
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("univtg_b200: the model must live on a CUDA device (no CPU path); call model.to('cuda')")
+        key = (dev.index,) + tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is not None and key == self._packed_key:
+            return
+        for p in params:
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("univtg_b200: parameters must be contiguous float32 tensors")
+        nbytes = lib.univtg_packed_bytes(ctypes.byref(self._cfg))
+        if nbytes == 0:
+            raise RuntimeError("univtg_b200: " + _lib.last_error())
+        if self._packed is None or self._packed.device != dev or self._packed.numel() != nbytes:
+            self._packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._drop_plans()  # plans hold tensor maps into the old buffer
+        arr = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
+        _lib.check(lib.univtg_pack_weights(ctypes.byref(self._cfg), arr, len(params), _lib.ptr(self._packed), _lib.stream_ptr()),
+                   "univtg_pack_weights")
+        self._packed_key = key
+
+    def _drop_plans(self):
+        lib = _lib.load_library()
+        for e in self._plans.values():
+            lib.univtg_plan_destroy(e.handle)
+        self._plans = {}
+
+    def __del__(self):
+        try:
+            self._drop_plans()
+        except Exception:
+            pass
+
+    def _get_dim_t(self, dev):
+        if self._dim_t is None or self._dim_t.device != dev:
+            # PositionEmbeddingSine (model/position_encoding.py:72-75), evaluated with the same fp32 torch expression
+            dim_t = torch.arange(self.hidden_dim, dtype=torch.float32, device=dev)
+            self._dim_t = (10000 ** (2 * torch.div(dim_t, 2).int() / self.hidden_dim)).contiguous()
+        return self._dim_t
+
+    def _get_plan(self, B, Lv, Lt, training):
+        key = (B, Lv, Lt, int(training))
+        e = self._plans.get(key)
+        if e is not None:
+            return e
+        lib = _lib.load_library()
+        if len(self._plans) >= 8:  # bounded cache of shape buckets (collate pads to the batch maximum, so shapes vary)
+            old = next(iter(self._plans))
+            lib.univtg_plan_destroy(self._plans.pop(old).handle)
+        dev = self._device()
+        shp = _lib.Shape(B, Lv, Lt, int(training))
+        nbytes = lib.univtg_workspace_bytes(ctypes.byref(self._cfg), ctypes.byref(shp))
+        if nbytes == 0:
+            raise RuntimeError("univtg_b200: " + _lib.last_error())
+        e = _PlanEntry()
+        e.shape = shp
+        e.workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        handle = ctypes.c_void_p()
+        _lib.check(lib.univtg_plan_create(ctypes.byref(self._cfg), ctypes.byref(shp), _lib.ptr(self._packed), _lib.ptr(e.workspace),
+                                          _lib.ptr(self._get_dim_t(dev)), _lib.stream_ptr(), ctypes.byref(handle)),
+                   "univtg_plan_create")
+        e.handle = handle
+        self._plans[key] = e
+        return e
+
+    # ---- forward ------------------------------------------------------------------------------------------------------
+    def forward(self, src_txt, src_txt_mask, src_vid, src_vid_mask, src_cls=None, src_cls_mask=None):
+        """
+        Args (reference model/univtg.py:105; masks are float32 or bool with 1 = valid, inputs right-padded with zeros):
+            src_txt [B, Lt, Dt], src_txt_mask [B, Lt], src_vid [B, Lv, Dv], src_vid_mask [B, Lv]
+        Returns dict: pred_logits [B,Lv,1], pred_spans [B,Lv,2], src_vid_mask (passthrough), vid_mem_proj [B,Lv,d],
+            txt_mem_proj [B,1,d], saliency_scores [B,Lv]
+        """
+        if src_cls is not None:
+            raise NotImplementedError("src_cls (TAL class prompts, 'tal' train_path) is outside the accelerated path")
+        if self.span_loss_type != "l1":
+            raise NotImplementedError  # same behaviour as the reference (model/univtg.py:138)
+        if src_vid.dim() != 3 or src_txt.dim() != 3 or src_vid.shape[0] != src_txt.shape[0]:
+            raise ValueError("src_vid / src_txt must be [B, L, D] with the same batch size")
+        if src_vid.shape[2] != self.vid_dim or src_txt.shape[2] != self.txt_dim:
+            raise ValueError(f"feature dims ({src_vid.shape[2]}, {src_txt.shape[2]}) != model ({self.vid_dim}, {self.txt_dim})")
+        dev = self._device()
+        if src_vid.device != dev:
+            raise RuntimeError(f"inputs on {src_vid.device}, model on {dev}")
+        B, Lv, _ = src_vid.shape
+        Lt = src_txt.shape[1]
+        if tuple(src_vid_mask.shape) != (B, Lv) or tuple(src_txt_mask.shape) != (B, Lt):
+            raise ValueError("mask shapes do not match the features")
+        training = self.training and torch.is_grad_enabled()
+        if training:
+            from .autograd import forward_train  # backward kernels live in the same library
+
+            return forward_train(self, src_txt, src_txt_mask, src_vid, src_vid_mask)
+        return self._forward_inference(src_txt, src_txt_mask, src_vid, src_vid_mask)
+
+    def _forward_inference(self, src_txt, src_txt_mask, src_vid, src_vid_mask, droppath_scale=None):
+        lib = _lib.load_library()
+        dev = self._device()
+        B, Lv, _ = src_vid.shape
+        Lt = src_txt.shape[1]
+        d = self.hidden_dim
+        with torch.cuda.device(dev):
+            self._ensure_packed()
+            plan = self._get_plan(B, Lv, Lt, False)
+            txt = src_txt.detach().to(torch.float32).contiguous()
+            vid = src_vid.detach().to(torch.float32).contiguous()
+            tmask = src_txt_mask.detach().to(torch.float32).contiguous()
+            vmask = src_vid_mask.detach().to(torch.float32).contiguous()
+            pred_logits = torch.empty(B, Lv, 1, device=dev)
+            pred_spans = torch.empty(B, Lv, 2, device=dev)
+            vid_mem_proj = torch.empty(B, Lv, d, device=dev)
+            txt_mem_proj = torch.empty(B, 1, d, device=dev)
+            saliency = torch.empty(B, Lv, device=dev)
+            _lib.check(lib.univtg_forward(plan.handle, _lib.ptr(txt), _lib.ptr(tmask), _lib.ptr(vid), _lib.ptr(vmask),
+                                          _lib.ptr(droppath_scale), _lib.ptr(pred_logits), _lib.ptr(pred_spans),
+                                          _lib.ptr(vid_mem_proj), _lib.ptr(txt_mem_proj), _lib.ptr(saliency), _lib.stream_ptr()),
+                       "univtg_forward")
+        return {"pred_logits": pred_logits, "pred_spans": pred_spans, "src_vid_mask": src_vid_mask,
+                "vid_mem_proj": vid_mem_proj, "txt_mem_proj": txt_mem_proj, "saliency_scores": saliency}
+
+    def profile_forward(self, inputs):
+        """Run one inference forward with the per-launch CUDA-event timeline on; returns [(kind, ms), ...]
+        (kind 0 = row kernel, 1 = tcgen05 GEMM, 2 = attention)."""
+        lib = _lib.load_library()
+        B, Lv, _ = inputs["src_vid"].shape
+        Lt = inputs["src_txt"].shape[1]
+        with torch.cuda.device(self._device()):
+            self._ensure_packed()
+            plan = self._get_plan(B, Lv, Lt, False)
+            lib.univtg_plan_set_profiling(plan.handle, 1)
+            try:
+                self._forward_inference(**inputs)
+                ms = (ctypes.c_float * 160)()
+                kinds = (ctypes.c_int32 * 160)()
+                n = lib.univtg_plan_read_profile(plan.handle, ms, kinds, 160)
+            finally:
+                lib.univtg_plan_set_profiling(plan.handle, 0)
+        if n < 0:
+            raise RuntimeError("univtg_b200: " + _lib.last_error())
+        return [(int(kinds[i]), float(ms[i])) for i in range(n)]
+
+    def num_forward_launches(self, B, Lv, Lt):
+        lib = _lib.load_library()
+        with torch.cuda.device(self._device()):
+            self._ensure_packed()
+            return int(lib.univtg_forward_num_launches(self._get_plan(B, Lv, Lt, False).handle))
+
+
+def build_model(args):
+    """Same contract as reference model/univtg.py:409-450: returns (model, criterion); reads the same `args` fields."""
+    from .criterion import SetCriterion
+
+    try:
+        device = torch.device(args.device)  # reference: torch.device(args.device); criterion.to(device)
+    except (TypeError, RuntimeError):
+        device = None
+    model = Model(args)
+    weight_dict = {"loss_b": args.b_loss_coef, "loss_g": args.g_loss_coef, "loss_f": args.f_loss_coef,
+                   "loss_s_intra": args.s_loss_intra_coef, "loss_s_inter": args.s_loss_inter_coef}
+    if args.dset_type in ["mr", "vlp"]:
+        if "tal" not in args.train_path:
+            losses = ["spans", "labels", "saliency"]
+        else:
+            losses = ["spans", "labels", "saliency_cls"]
+    elif args.dset_type in ["hl", "vs"]:
+        losses = ["labels", "saliency"]
+    else:
+        raise ValueError(f"unknown dset_type {args.dset_type}")
+    criterion = SetCriterion(weight_dict=weight_dict, losses=losses, eos_coef=args.eos_coef, temperature=args.temperature,
+                             span_loss_type=args.span_loss_type, max_v_l=args.max_v_l, saliency_margin=args.saliency_margin)
+    if device is not None:
+        criterion.to(device)
+    return model, criterion
