@@ -103,10 +103,11 @@ int univtg_op_gemm(const void* a, const void* b, int32_t M, int32_t N, int32_t K
 /* LayerNorm rows: in [rows,d] f32 -> out32 [rows,d] f32 and/or out16 [rows,ld16] 16-bit (zero padded). */
 int univtg_op_layernorm(const float* in, int32_t rows, int32_t d, const float* gamma, const float* beta, float eps,
                         int32_t fmt, float* out32, void* out16, int32_t ld16, void* stream);
-/* Attention core.  q,k: [B*L,d] 16-bit (q pre-scaled); vt: [B*d,Lp] 16-bit (Lp multiple of 8, >= L, zero padded);
- * key_mask [B,L] f32; out [B*L,d] 16-bit; lse [B,H,L] f32 or NULL.  impl: 0 = tcgen05 (dh in {64,128}), 1 = SIMT. */
-int univtg_op_attention(const void* q, const void* k, const void* vt, const float* key_mask, void* out, float* lse,
-                        int32_t B, int32_t L, int32_t Lp, int32_t H, int32_t dh, int32_t fmt, int32_t impl, void* stream);
+/* Attention core.  qkv: [B*L, 3d] 16-bit, column blocks Q | K | V (heads are dh-wide sub-blocks), d = H*dh; scores are
+ * scaled by 1/sqrt(dh); key_mask [B,L] f32 (1 = valid key); out [B*L,d] 16-bit; lse [B,H,L] f32 or NULL.
+ * impl: 0 = tcgen05 (dh in {64,128}), 1 = SIMT (any dh). */
+int univtg_op_attention(const void* qkv, const float* key_mask, void* out, float* lse, int32_t B, int32_t L, int32_t H,
+                        int32_t dh, int32_t fmt, int32_t impl, void* stream);
 
 #ifdef __cplusplus
 }

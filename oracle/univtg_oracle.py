@@ -79,11 +79,10 @@ def multi_head_attention(xq, xv, key_valid, w_in, b_in, w_out, b_out, nheads, op
     q = mm(xq, w_in[:d], opq, b_in[:d])
     k = mm(xq, w_in[d:2 * d], opq, b_in[d:2 * d])
     v = mm(xv, w_in[2 * d:], opq, b_in[2 * d:])
-    q = q * (1.0 / math.sqrt(dh))
     q = opq(q).reshape(B, L, nheads, dh).permute(0, 2, 1, 3).contiguous()
     k = opq(k).reshape(B, L, nheads, dh).permute(0, 2, 3, 1).contiguous()
     v = opq(v).reshape(B, L, nheads, dh).permute(0, 2, 1, 3).contiguous()
-    s = q @ k
+    s = (q @ k) * (1.0 / math.sqrt(dh))  # torch scales q before the product; the CUDA path scales the fp32 scores
     s = s.masked_fill(~key_valid[:, None, None, :], float("-inf"))
     s = s - s.amax(dim=-1, keepdim=True)
     p = torch.exp(s)

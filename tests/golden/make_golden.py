@@ -85,7 +85,7 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
     run_case("tiny_ragged", "tiny", seed=10, ragged=True)
-    run_case("tiny_full", "tiny", seed=20, ragged=False, head_gain=8.0)
+    run_case("tiny_full", "tiny", seed=20, ragged=False, head_gain=4.0)
     run_case("cfg1_demo", "cfg1", seed=30, ragged=False, demo=True)
     run_case("cfg2_b4_ragged", "cfg2", seed=40, ragged=True, batch=4)
     run_case("cfg2_full", "cfg2", seed=50, ragged=False, with_grads=False)

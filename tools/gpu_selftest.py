@@ -80,25 +80,22 @@ def case_attention(B, L, H, dh, fmt, impl):
     from univtg_b200 import _lib
     lib = _lib.load_library()
     d = H * dh
-    Lp = (L + 63) // 64 * 64
     g = torch.Generator(device="cpu").manual_seed(99)
-    q = (torch.randn(B, L, H, dh, generator=g) * (dh ** -0.5)).cuda()
+    q = torch.randn(B, L, H, dh, generator=g).cuda()
     k = torch.randn(B, L, H, dh, generator=g).cuda()
     v = torch.randn(B, L, H, dh, generator=g).cuda()
     lens = torch.randint(max(1, L // 3), L + 1, (B,), generator=g)
     lens[0] = L
     mask = (torch.arange(L)[None, :] < lens[:, None]).float().cuda()
     q16, k16, v16 = _t16(q, fmt), _t16(k, fmt), _t16(v, fmt)
-    vt = torch.zeros(B, d, Lp, device="cuda", dtype=q16.dtype)
-    vt[:, :, :L] = v16.reshape(B, L, d).permute(0, 2, 1)
+    qkv = torch.cat([q16.reshape(B * L, d), k16.reshape(B * L, d), v16.reshape(B * L, d)], dim=1).contiguous()
     out = torch.zeros(B * L, d, device="cuda", dtype=q16.dtype)
     lse = torch.zeros(B, H, L, device="cuda")
-    rc = lib.univtg_op_attention(_lib.ptr(q16.reshape(B * L, d).contiguous()), _lib.ptr(k16.reshape(B * L, d).contiguous()),
-                                 _lib.ptr(vt), _lib.ptr(mask), _lib.ptr(out), _lib.ptr(lse), B, L, Lp, H, dh, fmt, impl,
+    rc = lib.univtg_op_attention(_lib.ptr(qkv), _lib.ptr(mask), _lib.ptr(out), _lib.ptr(lse), B, L, H, dh, fmt, impl,
                                  _lib.stream_ptr())
     _lib.check(rc, "op_attention")
     torch.cuda.synchronize()
-    s = torch.einsum("bihc,bjhc->bhij", q16.float(), k16.float())
+    s = torch.einsum("bihc,bjhc->bhij", q16.float(), k16.float()) * (dh ** -0.5)
     s = s.masked_fill(mask[:, None, None, :] == 0, float("-inf"))
     p = torch.softmax(s, dim=-1)
     ref = torch.einsum("bhij,bjhc->bihc", p, v16.float()).reshape(B * L, d)

@@ -55,8 +55,8 @@ SIGNATURES = {
                                c_float, c_void_p, c_void_p, c_void_p]),
     "univtg_op_layernorm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_int,
                                     c_void_p]),
-    "univtg_op_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                    c_int, c_int, c_int, c_void_p]),
+    "univtg_op_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    c_void_p]),
 }
 
 

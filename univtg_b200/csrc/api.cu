@@ -210,7 +210,7 @@ struct univtg_plan {
   uint8_t* ws;
   const float* dim_t;
   int num_sms;
-  int B, Lv, Lt, L, Lp, d, ff, H, dh, M, Mv, Mt, Mh;
+  int B, Lv, Lt, L, d, ff, H, dh, M, Mv, Mt, Mh;
   // workspace pointers
   uint16_t *a_vid[3], *a_txt[3];  // LN'd 16-bit projector inputs
   float *p_vid32, *p_txt32;       // fp32 projector hidden (between projector layers)
@@ -218,7 +218,7 @@ struct univtg_plan {
   float* pos;                     // [Mv, d]
   float* key_mask;                // [B, L]
   float *x32, *y32;               // residual stream / pre-LayerNorm sum
-  uint16_t *x16, *xpos16, *q16, *k16, *vt16, *attn16, *h16;
+  uint16_t *x16, *xpos16, *qkv16, *attn16, *h16;
   uint16_t *hA, *h1, *hc2, *hs2;  // conv-head buffers (separated layout)
   // launch descriptors
   GemmGroup g_proj[3];
@@ -375,7 +375,7 @@ int univtg_pack_weights(const univtg_config* cfg, const float* const* params, in
 namespace {
 
 struct WsLayout {
-  size_t a_vid[3], a_txt[3], p_vid32, p_txt32, txtproj32, pos, key_mask, x32, y32, x16, xpos16, q16, k16, vt16, attn16, h16, hA,
+  size_t a_vid[3], a_txt[3], p_vid32, p_txt32, txtproj32, pos, key_mask, x32, y32, x16, xpos16, qkv16, attn16, h16, hA,
       h1, hc2, hs2, total;
 };
 
@@ -386,7 +386,6 @@ WsLayout make_ws(const univtg_config& c, const univtg_shape& s, const PackedLayo
   const size_t d = c.hidden_dim, ff = c.dim_feedforward;
   const size_t B = s.batch, Lv = s.l_vid, Lt = s.l_txt, Lc = Lv + Lt;
   const size_t M = B * Lc, Mv = B * Lv, Mt = B * Lt, Mh = B * (Lv + 1);
-  const size_t Lp = (Lc + 63) / 64 * 64;
   for (int i = 0; i < c.n_input_proj; ++i) {
     w.a_vid[i] = cur.take(Mv * L.vid[i].kpad * 2);
     w.a_txt[i] = cur.take(Mt * L.txt[i].kpad * 2);
@@ -400,9 +399,7 @@ WsLayout make_ws(const univtg_config& c, const univtg_shape& s, const PackedLayo
   w.y32 = cur.take(M * d * 4);
   w.x16 = cur.take(M * d * 2);
   w.xpos16 = cur.take(M * d * 2);
-  w.q16 = cur.take(M * d * 2);
-  w.k16 = cur.take(M * d * 2);
-  w.vt16 = cur.take(B * d * Lp * 2);
+  w.qkv16 = cur.take(M * 3 * d * 2);
   w.attn16 = cur.take(M * d * 2);
   w.h16 = cur.take(M * ff * 2);
   w.hA = cur.take((Mh + 2) * d * 2);
@@ -458,7 +455,6 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
   P->Lv = shape->l_vid;
   P->Lt = shape->l_txt;
   P->L = P->Lv + P->Lt;
-  P->Lp = (P->L + 63) / 64 * 64;
   P->d = d;
   P->ff = ff;
   P->H = cfg->nheads;
@@ -488,9 +484,7 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
   P->y32 = reinterpret_cast<float*>(ws + w.y32);
   P->x16 = reinterpret_cast<uint16_t*>(ws + w.x16);
   P->xpos16 = reinterpret_cast<uint16_t*>(ws + w.xpos16);
-  P->q16 = reinterpret_cast<uint16_t*>(ws + w.q16);
-  P->k16 = reinterpret_cast<uint16_t*>(ws + w.k16);
-  P->vt16 = reinterpret_cast<uint16_t*>(ws + w.vt16);
+  P->qkv16 = reinterpret_cast<uint16_t*>(ws + w.qkv16);
   P->attn16 = reinterpret_cast<uint16_t*>(ws + w.attn16);
   P->h16 = reinterpret_cast<uint16_t*>(ws + w.h16);
   P->hA = reinterpret_cast<uint16_t*>(ws + w.hA);
@@ -555,23 +549,17 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
     {
       GemmGroup& g = P->g_qkv[l];
       memset(&g, 0, sizeof(g));
-      g.num = 3;
+      g.num = 2;
       g.fmt = fmt;
-      rc |= setup_linear(g.p[0], P->xpos16, P->M, d, d, W16(lp.w_in), d, d, P->bn_main);
-      rc |= setup_linear(g.p[1], P->xpos16, P->M, d, d, W16(lp.w_in) + (size_t)d * d, d, d, P->bn_main);
-      rc |= setup_linear(g.p[2], P->x16, P->M, d, d, W16(lp.w_in) + (size_t)2 * d * d, d, d, P->bn_main);
+      // q = k = x + pos -> columns [0, 2d) of qkv16; v = x -> columns [2d, 3d)   (in_proj rows: Wq, Wk, Wv)
+      rc |= setup_linear(g.p[0], P->xpos16, P->M, d, d, W16(lp.w_in), 2 * d, d, P->bn_main);
+      rc |= setup_linear(g.p[1], P->x16, P->M, d, d, W16(lp.w_in) + (size_t)2 * d * d, d, d, P->bn_main);
       g.p[0].bias = F32(lp.b_in);
-      g.p[0].alpha = qscale;  // torch MHA scales q (after bias) by 1/sqrt(dh)
-      g.p[0].out16 = P->q16;
-      g.p[0].ld16 = d;
-      g.p[1].bias = F32(lp.b_in) + d;
-      g.p[1].out16 = P->k16;
-      g.p[1].ld16 = d;
-      g.p[2].bias = F32(lp.b_in) + 2 * d;
-      g.p[2].out16t = P->vt16;
-      g.p[2].ldt = P->Lp;
-      g.p[2].rps_in = P->L;
-      g.p[2].rps_out = P->L;
+      g.p[0].out16 = P->qkv16;
+      g.p[0].ld16 = 3 * d;
+      g.p[1].bias = F32(lp.b_in) + 2 * d;
+      g.p[1].out16 = P->qkv16 + 2 * d;
+      g.p[1].ld16 = 3 * d;
     }
     {
       AttnArgs& a = P->attn[l];
@@ -579,18 +567,15 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
       a.key_mask = P->key_mask;
       a.out = P->attn16;
       a.lse = nullptr;
+      a.scale = qscale;  // torch MHA: q * dh**-0.5 before q k^T
       a.B = P->B;
       a.L = P->L;
-      a.Lp = P->Lp;
       a.H = P->H;
       a.dh = P->dh;
       a.d = d;
       a.fmt = fmt;
-      if (P->dh == 64 || P->dh == 128) {
-        rc |= make_tmap_2d(&a.tm_q, P->q16, (uint64_t)P->M, (uint64_t)d, (uint64_t)d, 128, 64);
-        rc |= make_tmap_2d(&a.tm_k, P->k16, (uint64_t)P->M, (uint64_t)d, (uint64_t)d, 128, 64);
-        rc |= make_tmap_2d(&a.tm_vt, P->vt16, (uint64_t)P->B * d, (uint64_t)P->Lp, (uint64_t)P->Lp, (uint32_t)P->dh, 64);
-      }
+      if (P->dh == 64 || P->dh == 128)
+        rc |= make_tmap_2d(&a.tm_qkv, P->qkv16, (uint64_t)P->M, (uint64_t)3 * d, (uint64_t)3 * d, 128, 64);
     }
     {
       GemmGroup& g = P->g_out[l];
@@ -764,7 +749,7 @@ int univtg_forward(univtg_plan* P, const float* src_txt, const float* src_txt_ma
     if (rc) return rc;
     prof_mark(P, st, 1);
     if (P->dh == 64 || P->dh == 128) rc = launch_attention(P->attn[l], st);
-    else rc = launch_attention_simt(P->attn[l], P->q16, P->k16, P->vt16, st);
+    else rc = launch_attention_simt(P->attn[l], P->qkv16, st);
     if (rc) return rc;
     prof_mark(P, st, 2);
     {
@@ -944,9 +929,9 @@ int univtg_op_layernorm(const float* in, int32_t rows, int32_t d, const float* g
   return launch_layernorm(a, (cudaStream_t)stream);
 }
 
-int univtg_op_attention(const void* q, const void* k, const void* vt, const float* key_mask, void* out, float* lse,
-                        int32_t B, int32_t L, int32_t Lp, int32_t H, int32_t dh, int32_t fmt, int32_t impl, void* stream) {
-  if (!q || !k || !vt || !key_mask || !out) {
+int univtg_op_attention(const void* qkv, const float* key_mask, void* out, float* lse, int32_t B, int32_t L, int32_t H,
+                        int32_t dh, int32_t fmt, int32_t impl, void* stream) {
+  if (!qkv || !key_mask || !out) {
     set_error("univtg_op_attention: null argument");
     return 1;
   }
@@ -956,21 +941,15 @@ int univtg_op_attention(const void* q, const void* k, const void* vt, const floa
   a.key_mask = key_mask;
   a.out = reinterpret_cast<uint16_t*>(out);
   a.lse = lse;
+  a.scale = 1.0f / sqrtf((float)dh);
   a.B = B;
   a.L = L;
-  a.Lp = Lp;
   a.H = H;
   a.dh = dh;
   a.d = d;
   a.fmt = fmt;
-  if (impl == 1)
-    return launch_attention_simt(a, reinterpret_cast<const uint16_t*>(q), reinterpret_cast<const uint16_t*>(k),
-                                 reinterpret_cast<const uint16_t*>(vt), (cudaStream_t)stream);
-  int rc = 0;
-  rc |= make_tmap_2d(&a.tm_q, q, (uint64_t)B * L, (uint64_t)d, (uint64_t)d, 128, 64);
-  rc |= make_tmap_2d(&a.tm_k, k, (uint64_t)B * L, (uint64_t)d, (uint64_t)d, 128, 64);
-  rc |= make_tmap_2d(&a.tm_vt, vt, (uint64_t)B * d, (uint64_t)Lp, (uint64_t)Lp, (uint32_t)dh, 64);
-  if (rc) return rc;
+  if (impl == 1) return launch_attention_simt(a, reinterpret_cast<const uint16_t*>(qkv), (cudaStream_t)stream);
+  if (make_tmap_2d(&a.tm_qkv, qkv, (uint64_t)B * L, (uint64_t)3 * d, (uint64_t)3 * d, 128, 64)) return 1;
   return launch_attention(a, (cudaStream_t)stream);
 }
 

@@ -1,6 +1,7 @@
 // Multi-head attention core of the encoder layer (torch MHA semantics, SURVEY.md §A.3;
 // call site model/transformer_encoder_droppath.py:118):
-//     S = Q K^T (Q pre-scaled by 1/sqrt(dh)) + key-padding(-inf);  P = softmax_j(S);  O = P V
+//     S = (Q K^T) / sqrt(dh) + key-padding(-inf);  P = softmax_j(S);  O = P V
+// Q, K, V are the three d-wide column blocks of one [B*L, 3d] 16-bit matrix written by the in-projection GEMM.
 // Flash-style: S and P never touch HBM.  tcgen05 path (dh in {64,128}):
 //   CTA = one (batch, head, 128-query tile); loop over 128-key tiles with online softmax.
 //   warp 0 lane 0 : TMA producer + tcgen05.mma issuer (S = Q K^T into TMEM cols [0,128); O_j = P V into [128,128+dh))
@@ -20,7 +21,7 @@ struct AttnCfg {
   static constexpr int kQBytes = 128 * DH * 2;   // DH/64 boxes of [128 rows x 64]
   static constexpr int kKBytes = 128 * DH * 2;   // K tile; re-used for P: 2 boxes of [128 rows x 64] = 32 KB
   static constexpr int kKPBytes = (kKBytes > 32768) ? kKBytes : 32768;
-  static constexpr int kVBytes = DH * 128 * 2;   // 2 boxes of [DH rows x 64 kv]
+  static constexpr int kVBytes = 128 * DH * 2;   // DH/64 boxes of [128 kv rows x 64]: MN-major B operand of P V
   static constexpr int kSmemBytes = 1024 + kQBytes + kKPBytes + kVBytes + 128 * 4 + 128;
   static constexpr uint32_t kTmemCols = 256;     // S: 128 cols, O: DH cols
 };
@@ -52,9 +53,7 @@ __global__ void __launch_bounds__(160, 2) attention_tcgen05_kernel(const __grid_
   const int num_kv = (L + 127) / 128;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&a.tm_q);
-    tma_prefetch_desc(&a.tm_k);
-    tma_prefetch_desc(&a.tm_vt);
+    tma_prefetch_desc(&a.tm_qkv);
     mbar_init(q_full, 1);
     mbar_init(k_full, 1);
     mbar_init(v_full, 1);
@@ -74,21 +73,21 @@ __global__ void __launch_bounds__(160, 2) attention_tcgen05_kernel(const __grid_
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_f16(128, 128, a.fmt, 0, 0);
-      const uint32_t idesc_o = make_idesc_f16(128, DH, a.fmt, 0, 0);
+      const uint32_t idesc_o = make_idesc_f16(128, DH, a.fmt, 0, 1);  // B = V is MN-major (dh contiguous)
       mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
 #pragma unroll
-      for (int kb = 0; kb < DH / 64; ++kb) tma_load_2d(sQ + kb * 16384, &a.tm_q, q_full, h * DH + kb * 64, b * L + q0);
+      for (int kb = 0; kb < DH / 64; ++kb) tma_load_2d(sQ + kb * 16384, &a.tm_qkv, q_full, h * DH + kb * 64, b * L + q0);
       for (int j = 0; j < num_kv; ++j) {
         const uint32_t ph = j & 1;
         if (j > 0) mbar_wait(o_full, ph ^ 1);  // previous PV retired: K/P and V buffers are free
         mbar_arrive_expect_tx(k_full, Cfg::kKBytes);
 #pragma unroll
         for (int kb = 0; kb < DH / 64; ++kb)
-          tma_load_2d(sKP + kb * 16384, &a.tm_k, k_full, h * DH + kb * 64, b * L + j * 128);
+          tma_load_2d(sKP + kb * 16384, &a.tm_qkv, k_full, a.d + h * DH + kb * 64, b * L + j * 128);
         mbar_arrive_expect_tx(v_full, Cfg::kVBytes);
 #pragma unroll
-        for (int vb = 0; vb < 2; ++vb)
-          tma_load_2d(sV + vb * (DH * 128), &a.tm_vt, v_full, j * 128 + vb * 64, b * a.d + h * DH);
+        for (int vb = 0; vb < DH / 64; ++vb)
+          tma_load_2d(sV + vb * 16384, &a.tm_qkv, v_full, 2 * a.d + h * DH + vb * 64, b * L + j * 128);
         if (j == 0) mbar_wait(q_full, 0);
         mbar_wait(k_full, ph);
         tc_fence_after();
@@ -105,9 +104,9 @@ __global__ void __launch_bounds__(160, 2) attention_tcgen05_kernel(const __grid_
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
           const uint32_t offp = (ks / 4) * 16384 + (ks % 4) * 32;
-          const uint32_t offv = (ks / 4) * (DH * 128) + (ks % 4) * 32;
+          // V tile: 64-wide dh blocks of [128 kv rows x 128 B]; 16 kv rows = two 1024 B swizzle atoms
           umma_f16_ss(tmem_o, make_smem_desc_sw128(smem_u32(sKP) + offp, 16, 1024),
-                      make_smem_desc_sw128(smem_u32(sV) + offv, 16, 1024), idesc_o, ks > 0 ? 1u : 0u);
+                      make_smem_desc_sw128(smem_u32(sV) + ks * 2048, 16384, 1024), idesc_o, ks > 0 ? 1u : 0u);
         }
         umma_commit(o_full);
       }
@@ -118,7 +117,7 @@ __global__ void __launch_bounds__(160, 2) attention_tcgen05_kernel(const __grid_
     const int row = wq * 32 + lane;     // query row inside the tile
     const int tid = threadIdx.x - 32;   // 0..127
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-    constexpr float kLog2e = 1.4426950408889634f;
+    const float kLog2e = 1.4426950408889634f * a.scale;  // scores are scaled by 1/sqrt(dh) inside the exponent
     float m_run = -INFINITY, l_run = 0.f;
     float acc[DH];
 #pragma unroll
@@ -143,11 +142,11 @@ __global__ void __launch_bounds__(160, 2) attention_tcgen05_kernel(const __grid_
         tmem_ld_32x32b_x32(tmem_s + lane_addr + c * 32, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]) + s_bias[c * 32 + i]);
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]) * kLog2e + s_bias[c * 32 + i]);
       }
-      const float m_new = fmaxf(m_run, mx);
+      const float m_new = fmaxf(m_run, mx);  // running max of scaled scores in log2 units
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = exp2f((m_run - m_use) * kLog2e);  // m_run = -inf -> 0
+      const float alpha = exp2f(m_run - m_use);  // m_run = -inf -> 0
       // pass B: probabilities -> 16-bit P tile (A operand of the PV product), K-major SW128
       float psum = 0.f;
 #pragma unroll
@@ -158,8 +157,8 @@ __global__ void __launch_bounds__(160, 2) attention_tcgen05_kernel(const __grid_
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = exp2f((__uint_as_float(r[i]) + s_bias[c * 32 + i] - m_use) * kLog2e);
-          const float p1 = exp2f((__uint_as_float(r[i + 1]) + s_bias[c * 32 + i + 1] - m_use) * kLog2e);
+          const float p0 = exp2f(__uint_as_float(r[i]) * kLog2e + s_bias[c * 32 + i] - m_use);
+          const float p1 = exp2f(__uint_as_float(r[i + 1]) * kLog2e + s_bias[c * 32 + i + 1] - m_use);
           psum += p0 + p1;
           pk[i / 2] = cvt16x2(p0, p1, a.fmt);
         }
@@ -203,7 +202,7 @@ __global__ void __launch_bounds__(160, 2) attention_tcgen05_kernel(const __grid_
         v.w = cvt16x2(acc[c + 6] * inv, acc[c + 7] * inv, a.fmt);
         *reinterpret_cast<uint4*>(dst + c) = v;
       }
-      if (a.lse) a.lse[((size_t)b * a.H + h) * L + qi] = m_run + logf(l_run);
+      if (a.lse) a.lse[((size_t)b * a.H + h) * L + qi] = m_run * 0.6931471805599453f + logf(l_run);
     }
   }
   tc_fence_before();
@@ -219,13 +218,12 @@ __global__ void __launch_bounds__(160, 2) attention_tcgen05_kernel(const __grid_
 // One warp per (b, h, query row); scores staged in shared memory.
 // ------------------------------------------------------------------------------------------------
 struct AttnSimtArgs {
-  const uint16_t* q;
-  const uint16_t* k;
-  const uint16_t* vt;
+  const uint16_t* qkv;  // [B*L, 3d]
   const float* key_mask;
   uint16_t* out;
   float* lse;
-  int B, L, Lp, H, dh, d, fmt;
+  float scale;
+  int B, L, H, dh, d, fmt;
 };
 
 __global__ void __launch_bounds__(128) attention_simt_kernel(const AttnSimtArgs a) {
@@ -237,14 +235,16 @@ __global__ void __launch_bounds__(128) attention_simt_kernel(const AttnSimtArgs 
   const int h = (gw / a.L) % a.H;
   const int b = gw / (a.L * a.H);
   float* sc = s_sc + warp * a.L;
-  const uint16_t* qrow = a.q + ((size_t)b * a.L + i) * a.d + h * a.dh;
+  const size_t ld = (size_t)3 * a.d;
+  const uint16_t* qrow = a.qkv + ((size_t)b * a.L + i) * ld + h * a.dh;
   float mx = -INFINITY;
   for (int j = lane; j < a.L; j += 32) {
     float s = -INFINITY;
     if (a.key_mask[(size_t)b * a.L + j] != 0.f) {
-      const uint16_t* krow = a.k + ((size_t)b * a.L + j) * a.d + h * a.dh;
+      const uint16_t* krow = a.qkv + ((size_t)b * a.L + j) * ld + a.d + h * a.dh;
       s = 0.f;
       for (int c = 0; c < a.dh; ++c) s += ld16(qrow[c], a.fmt) * ld16(krow[c], a.fmt);
+      s *= a.scale;
     }
     sc[j] = s;
     mx = fmaxf(mx, s);
@@ -260,9 +260,9 @@ __global__ void __launch_bounds__(128) attention_simt_kernel(const AttnSimtArgs 
   sum = warp_sum(sum);
   __syncwarp();
   for (int c = lane; c < a.dh; c += 32) {
-    const uint16_t* vrow = a.vt + ((size_t)b * a.d + h * a.dh + c) * a.Lp;
+    const uint16_t* vcol = a.qkv + (size_t)b * a.L * ld + 2 * a.d + h * a.dh + c;
     float o = 0.f;
-    for (int j = 0; j < a.L; ++j) o += sc[j] * ld16(vrow[j], a.fmt);
+    for (int j = 0; j < a.L; ++j) o += sc[j] * ld16(vcol[(size_t)j * ld], a.fmt);
     a.out[((size_t)b * a.L + i) * a.d + h * a.dh + c] = cvt16(o / sum, a.fmt);
   }
   if (lane == 0 && a.lse) a.lse[((size_t)b * a.H + h) * a.L + i] = mx + logf(sum);
@@ -288,8 +288,8 @@ static int launch_tc(const AttnArgs& a, cudaStream_t stream) {
   return (int)e;
 }
 
-int launch_attention_simt(const AttnArgs& a, const uint16_t* q, const uint16_t* k, const uint16_t* vt, cudaStream_t stream) {
-  AttnSimtArgs s{q, k, vt, a.key_mask, a.out, a.lse, a.B, a.L, a.Lp, a.H, a.dh, a.d, a.fmt};
+int launch_attention_simt(const AttnArgs& a, const uint16_t* qkv, cudaStream_t stream) {
+  AttnSimtArgs s{qkv, a.key_mask, a.out, a.lse, a.scale, a.B, a.L, a.H, a.dh, a.d, a.fmt};
   const int warps = a.B * a.H * a.L;
   const size_t smem = (size_t)4 * a.L * sizeof(float);
   if (smem > 48 * 1024) {

@@ -7,11 +7,11 @@
 // in-projections + out-projection (torch MHA called at model/transformer_encoder_droppath.py:118), the FFN
 // (:122) and the k=3 Conv1d heads (model/univtg.py:378-382) expressed as three row-shifted K segments.
 //
-// Roles (256 threads, 1 CTA / SM, persistent over a static round-robin tile schedule):
+// Roles (384 threads, 1 CTA / SM, persistent over a static round-robin tile schedule):
 //   warp 0 lane 0 : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier expect_tx)
 //   warp 1 lane 0 : MMA issuer     (tcgen05.mma cta_group::1, M=128, N=BN, K=16 x4 per 64-wide k-block)
 //   warp 2        : TMEM allocator (2 accumulator stages of BN fp32 columns)
-//   warps 4..7    : epilogue       (tcgen05.ld 32x32b -> smem transpose -> coalesced global stores)
+//   warps 4..11   : epilogue       (tcgen05.ld 32x32b -> smem transpose -> 128-bit coalesced global loads/stores)
 #include <stdarg.h>
 #include <stdio.h>
 
@@ -26,8 +26,8 @@ struct GemmCfg {
   static constexpr int kABytes = GEMM_BM * 128;          // 128 rows x 64 x 2 B
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;  // multiple of 1024
-  static constexpr int kEpiFloats = 4 * 32 * 33;         // per-warp 32x32 transpose buffers (padded)
-  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kEpiFloats * 4 + 4 * 32 * 8 + 256;
+  static constexpr int kEpiFloats = 8 * 32 * 16;         // per-warp 32x16 fp32 transpose buffers (XOR-swizzled quads)
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kEpiFloats * 4 + 8 * 32 * 8 + 256;
   static constexpr uint32_t kTmemCols = 2 * BN;          // 256 or 512 (power of two)
 };
 
@@ -59,7 +59,7 @@ __device__ __forceinline__ bool decode_tile(const GemmGroup& g, int bn, int t, T
 }
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmGroup g) {
+__global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmGroup g) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -67,9 +67,9 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
 
   uint8_t* stage_base = smem;
   float* epi_buf = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  int* s_orow = reinterpret_cast<int*>(epi_buf + Cfg::kEpiFloats);        // [4][32]
-  float* s_rscale = reinterpret_cast<float*>(s_orow + 4 * 32);            // [4][32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rscale + 4 * 32);
+  int* s_orow = reinterpret_cast<int*>(epi_buf + Cfg::kEpiFloats);        // [8][32]
+  float* s_rscale = reinterpret_cast<float*>(s_orow + 8 * 32);            // [8][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rscale + 8 * 32);
   uint64_t* full_bar = bars;                        // [kStages]
   uint64_t* empty_bar = bars + Cfg::kStages;        // [kStages]
   uint64_t* tmem_full = bars + 2 * Cfg::kStages;    // [2]
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], 8);
     }
     fence_barrier_init();
   }
@@ -186,92 +186,140 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
     }
   } else if (warp >= 4) {
     // ========================================= epilogue =========================================
-    const int wq = warp & 3;  // TMEM lane quarter this warp may access
-    float* buf = epi_buf + wq * (32 * 33);
-    int* orow_s = s_orow + wq * 32;
-    float* rscale_s = s_rscale + wq * 32;
+    // 8 warps: warp w may only touch TMEM lanes [32*(w%4), +32); the two warps of a lane quarter split the columns.
+    const int wq = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int ew = warp - 4;
+    float* buf = epi_buf + ew * (32 * 16);
+    int* orow_s = s_orow + ew * 32;
+    float* rscale_s = s_rscale + ew * 32;
     const int fmt = g.fmt;
+    const int rsub = lane >> 2;  // row inside a group of 8
+    const int cq = lane & 3;     // which 4-column quad of the 16-column chunk
     int as = 0;
     uint32_t aphase = 0;
     TileInfo ti;
     for (int t = blockIdx.x; decode_tile(g, BN, t, ti); t += gridDim.x) {
       const GemmProblem& pr = g.p[ti.p];
+      // hoist the problem description into registers (the struct lives in the constant bank)
+      const int pM = pr.M, pN = pr.N, rps_in = pr.rps_in, rps_out = pr.rps_out, row_off = pr.row_off;
+      const int act = pr.act;
+      const float* __restrict__ bias = (ti.split == 0) ? pr.bias : nullptr;
+      const float* __restrict__ resid = pr.resid;
+      const float* __restrict__ addtab = pr.addtab;
+      float* __restrict__ out32 = pr.out32;
+      float* __restrict__ out32_id = pr.out32_id;
+      uint16_t* __restrict__ out16 = pr.out16;
+      uint16_t* __restrict__ out16p = pr.out16p;
+      const int ld_resid = pr.ld_resid, ld_addtab = pr.ld_addtab, ld32 = pr.ld32, ld32_id = pr.ld32_id, ld16 = pr.ld16;
+      const bool atomic = (pr.accumulate != 0) || (pr.ksplit > 1);
+      const bool vec = pr.vec_ok != 0;
+
       const int m0 = ti.m_blk * GEMM_BM + wq * 32;
-      const int n_base = ti.n_blk * BN;
+      const int n_base = ti.n_blk * BN + half * (BN / 2);
       // ---- per-row bookkeeping (thread = row) ----
-      const int m = m0 + lane;
-      int b = 0, l = m;
-      if (pr.rps_in > 0) {
-        b = m / pr.rps_in;
-        l = m - b * pr.rps_in;
+      {
+        const int m = m0 + lane;
+        int b = 0, l = m;
+        if (rps_in > 0) {
+          b = m / rps_in;
+          l = m - b * rps_in;
+        }
+        const bool valid = m < pM;
+        const bool sep = pr.zero_sep && (l == rps_in - 1);
+        float rsc = pr.alpha;
+        if (pr.row_scale != nullptr && valid) rsc *= pr.row_scale[b];
+        if (sep) rsc = 0.f;
+        orow_s[lane] = valid ? ((rps_in > 0 ? b * rps_out + l : m) + row_off) : -1;
+        rscale_s[lane] = rsc;
       }
-      const bool valid = m < pr.M;
-      const bool sep = pr.zero_sep && (l == pr.rps_in - 1);
-      const int orow = (pr.rps_in > 0 ? b * pr.rps_out + l : m) + pr.row_off;
-      float rsc = pr.alpha;
-      if (pr.row_scale != nullptr && valid) rsc *= pr.row_scale[b];
-      if (sep) rsc = 0.f;
-      orow_s[lane] = valid ? orow : -1;
-      rscale_s[lane] = rsc;
       __syncwarp();
 
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + as * BN;
-      const bool add_bias = (pr.bias != nullptr) && (ti.split == 0);
-      const bool atomic = (pr.accumulate != 0) || (pr.ksplit > 1);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + as * BN + half * (BN / 2);
 
       for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = n_base + c * 32;
-        if (n0 >= pr.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_addr + c * 32, r);
+        const int n0 = n_base + c * 16;
+        if (n0 >= pN) break;  // warp-uniform
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_addr + c * 16, r);
         tmem_ld_wait();
-        if (pr.out16t != nullptr) {
-          // transposed store (V^T for the attention PV product): thread = row, registers = columns
-          if (valid) {
+        // ---- transpose through smem: thread = row writes 16 columns as 4 quads; afterwards 4 lanes cover one row.
+        //      quad q of row r lives at physical quad q ^ ((r >> 1) & 3): conflict-free for both access patterns ----
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int n = n0 + j;
-              if (n < pr.N) {
-                float v = __uint_as_float(r[j]);
-                if (add_bias) v += __ldg(pr.bias + n);
-                if (pr.act == ACT_RELU) v = fmaxf(v, 0.f);
-                else if (pr.act == ACT_GELU) v = gelu_erf(v);
-                v *= rsc;
-                pr.out16t[((size_t)b * pr.N + n) * pr.ldt + l] = cvt16(v, fmt);
-              }
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(buf + lane * 16 + 4 * (q ^ ((lane >> 1) & 3))) =
+              make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+        __syncwarp();
+        const int n = n0 + 4 * cq;
+        if (n < pN) {
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias != nullptr) {
+            if (vec) bv = __ldg(reinterpret_cast<const float4*>(bias + n));
+            else {
+              bv.x = __ldg(bias + n);
+              if (n + 1 < pN) bv.y = __ldg(bias + n + 1);
+              if (n + 2 < pN) bv.z = __ldg(bias + n + 2);
+              if (n + 3 < pN) bv.w = __ldg(bias + n + 3);
             }
           }
-          continue;
-        }
-        // ---- transpose through smem: afterwards lane = column, loop index = row ----
 #pragma unroll
-        for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = __uint_as_float(r[j]);
-        __syncwarp();
-        const int n = n0 + lane;
-        const bool ncol = n < pr.N;
-        const float bias_v = (add_bias && ncol) ? __ldg(pr.bias + n) : 0.f;
-#pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
-          const int orr = orow_s[rr];
-          if (orr < 0 || !ncol) continue;
-          float v = buf[rr * 33 + lane] + bias_v;
-          if (pr.act == ACT_RELU) v = fmaxf(v, 0.f);
-          else if (pr.act == ACT_GELU) v = gelu_erf(v);
-          v *= rscale_s[rr];
-          if (pr.resid != nullptr) v += pr.resid[(size_t)orr * pr.ld_resid + n];
-          if (pr.out32 != nullptr) {
-            float* dst = pr.out32 + (size_t)orr * pr.ld32 + n;
-            if (atomic) atomicAdd(dst, v);
-            else *dst = v;
-          }
-          const int mrow = m0 + rr;
-          if (pr.out32_id != nullptr) pr.out32_id[(size_t)mrow * pr.ld32_id + n] = v;
-          if (pr.out16 != nullptr) pr.out16[(size_t)orr * pr.ld16 + n] = cvt16(v, fmt);
-          if (pr.out16p != nullptr) {
-            const float pv = (pr.addtab != nullptr) ? pr.addtab[(size_t)mrow * pr.ld_addtab + n] : 0.f;
-            pr.out16p[(size_t)orr * pr.ld16 + n] = cvt16(v + pv, fmt);
+          for (int i = 0; i < 4; ++i) {
+            const int rr = rsub + 8 * i;
+            const int orr = orow_s[rr];
+            if (orr < 0) continue;
+            float4 v = *reinterpret_cast<const float4*>(buf + rr * 16 + 4 * (cq ^ ((rr >> 1) & 3)));
+            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+            if (act == ACT_RELU) {
+              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            } else if (act == ACT_GELU) {
+              v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+            }
+            const float rs = rscale_s[rr];
+            v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
+            const int mrow = m0 + rr;
+            if (vec) {
+              if (resid != nullptr) {
+                const float4 rv = *reinterpret_cast<const float4*>(resid + (size_t)orr * ld_resid + n);
+                v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+              }
+              if (out32 != nullptr) {
+                float* dst = out32 + (size_t)orr * ld32 + n;
+                if (atomic) {
+                  atomicAdd(dst, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
+                } else {
+                  *reinterpret_cast<float4*>(dst) = v;
+                }
+              }
+              if (out32_id != nullptr) *reinterpret_cast<float4*>(out32_id + (size_t)mrow * ld32_id + n) = v;
+              if (out16 != nullptr)
+                *reinterpret_cast<uint2*>(out16 + (size_t)orr * ld16 + n) = make_uint2(cvt16x2(v.x, v.y, fmt), cvt16x2(v.z, v.w, fmt));
+              if (out16p != nullptr) {
+                float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (addtab != nullptr) pv = *reinterpret_cast<const float4*>(addtab + (size_t)mrow * ld_addtab + n);
+                *reinterpret_cast<uint2*>(out16p + (size_t)orr * ld16 + n) =
+                    make_uint2(cvt16x2(v.x + pv.x, v.y + pv.y, fmt), cvt16x2(v.z + pv.z, v.w + pv.w, fmt));
+              }
+            } else {
+              // unaligned leading dimensions (e.g. the [d, 2818] projector weight gradient): scalar stores
+              const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (n + e >= pN) break;
+                float x = vv[e];
+                if (resid != nullptr) x += resid[(size_t)orr * ld_resid + n + e];
+                if (out32 != nullptr) {
+                  float* dst = out32 + (size_t)orr * ld32 + n + e;
+                  if (atomic) atomicAdd(dst, x);
+                  else *dst = x;
+                }
+                if (out32_id != nullptr) out32_id[(size_t)mrow * ld32_id + n + e] = x;
+                if (out16 != nullptr) out16[(size_t)orr * ld16 + n + e] = cvt16(x, fmt);
+                if (out16p != nullptr)
+                  out16p[(size_t)orr * ld16 + n + e] = cvt16(x + (addtab ? addtab[(size_t)mrow * ld_addtab + n + e] : 0.f), fmt);
+              }
+            }
           }
         }
         __syncwarp();
@@ -349,7 +397,7 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 }
 
 template <int BN>
-static int launch_bn(const GemmGroup& g, int num_sms, cudaStream_t stream) {
+static int launch_bn(GemmGroup& g, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -374,10 +422,17 @@ static int launch_bn(const GemmGroup& g, int num_sms, cudaStream_t stream) {
       return (int)cudaErrorInvalidValue;
     }
     total += ((pr.M + GEMM_BM - 1) / GEMM_BM) * ((pr.N + BN - 1) / BN) * pr.ksplit;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    GemmProblem& w = g.p[p];
+    w.vec_ok = (pr.N % 4 == 0) && al16(pr.bias) && (!pr.resid || (al16(pr.resid) && pr.ld_resid % 4 == 0)) &&
+               (!pr.addtab || (al16(pr.addtab) && pr.ld_addtab % 4 == 0)) && (!pr.out32 || (al16(pr.out32) && pr.ld32 % 4 == 0)) &&
+               (!pr.out32_id || (al16(pr.out32_id) && pr.ld32_id % 4 == 0)) &&
+               ((!pr.out16 && !pr.out16p) || (pr.ld16 % 4 == 0 && (reinterpret_cast<uintptr_t>(pr.out16) & 7) == 0 &&
+                                              (reinterpret_cast<uintptr_t>(pr.out16p) & 7) == 0));
   }
   if (total == 0) return 0;
   const int grid = total < num_sms ? total : num_sms;
-  gemm_tcgen05_kernel<BN><<<grid, 256, Cfg::kSmemBytes, stream>>>(g);
+  gemm_tcgen05_kernel<BN><<<grid, 384, Cfg::kSmemBytes, stream>>>(g);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("gemm launch failed: %s", cudaGetErrorString(e));
@@ -386,7 +441,7 @@ static int launch_bn(const GemmGroup& g, int num_sms, cudaStream_t stream) {
   return 0;
 }
 
-int launch_gemm_group(const GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
+int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
   if (g.num < 1 || g.num > GEMM_MAX_GROUP) {
     set_error("gemm group size %d out of range", g.num);
     return (int)cudaErrorInvalidValue;

@@ -55,9 +55,8 @@ struct GemmProblem {
   uint16_t* out16;         // 16-bit at remapped rows
   uint16_t* out16p;        // 16-bit(v + addtab[m, n]) at remapped rows (same leading dim as out16)
   int ld16;
-  uint16_t* out16t;        // transposed 16-bit store: out16t[(b*N + n) * ldt + l],  m = b*rps_in + l
-  int ldt;
   int accumulate;          // out32 += v (atomic) instead of out32 = v
+  int vec_ok;              // set by launch_gemm_group: every pointer / leading dimension allows 128-bit accesses
 };
 
 struct GemmGroup {
@@ -67,7 +66,7 @@ struct GemmGroup {
 };
 
 // bn in {128, 256}.  Returns cudaError_t as int.
-int launch_gemm_group(const GemmGroup& g, int bn, int num_sms, cudaStream_t stream);
+int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream);
 
 // Encode a 2-D tensor map over a row-major 16-bit matrix [rows, cols] with row pitch `ld` elements,
 // box {box_cols, box_rows}, 128-byte swizzle, zero fill out of bounds.  Returns 0 on success.

@@ -127,6 +127,57 @@ __global__ void __launch_bounds__(256) layernorm_rows_generic_kernel(const LnArg
     for (int j = a.d + lane; j < a.ld16; j += 32) a.out16[(size_t)warp * a.ld16 + j] = 0;
 }
 
+// arbitrary d <= 128*EPT: one 128-thread block per row, the row lives in registers (single HBM read).
+template <int EPT>
+__global__ void __launch_bounds__(128) layernorm_rows_block_kernel(const LnArgs a) {
+  __shared__ float s_red[4];
+  __shared__ float s_stat[2];
+  const int row = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* x = a.in + (size_t)row * a.ld_in;
+  float v[EPT];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    const int j = tid + 128 * i;
+    v[i] = j < a.d ? x[j] : 0.f;
+    s += v[i];
+  }
+  s = warp_sum(s);
+  if (lane == 0) s_red[warp] = s;
+  __syncthreads();
+  if (tid == 0) s_stat[0] = (s_red[0] + s_red[1] + s_red[2] + s_red[3]) / (float)a.d;
+  __syncthreads();
+  const float mean = s_stat[0];
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    const int j = tid + 128 * i;
+    const float dx = j < a.d ? v[i] - mean : 0.f;
+    q += dx * dx;
+  }
+  q = warp_sum(q);
+  __syncthreads();
+  if (lane == 0) s_red[warp] = q;
+  __syncthreads();
+  if (tid == 0) {
+    const float var = (s_red[0] + s_red[1] + s_red[2] + s_red[3]) / (float)a.d;
+    s_stat[1] = rsqrtf(var + a.eps);
+    if (a.mean_out) a.mean_out[row] = mean;
+    if (a.rstd_out) a.rstd_out[row] = s_stat[1];
+  }
+  __syncthreads();
+  const float rstd = s_stat[1];
+  const LnStore st(a, row);
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    const int j = tid + 128 * i;
+    if (j < a.d) st.store1(j, (v[i] - mean) * rstd * a.gamma[j] + a.beta[j]);
+  }
+  if (a.out16)
+    for (int j = a.d + tid; j < a.ld16; j += 128) a.out16[(size_t)row * a.ld16 + j] = 0;
+}
+
 int launch_layernorm(const LnArgs& a, cudaStream_t stream) {
   if (a.rows <= 0) return 0;
   const int threads = 256;
@@ -135,6 +186,8 @@ int launch_layernorm(const LnArgs& a, cudaStream_t stream) {
   if (vec_ok && a.d == 1024) layernorm_rows_vec_kernel<8><<<blocks, threads, 0, stream>>>(a);
   else if (vec_ok && a.d == 512) layernorm_rows_vec_kernel<4><<<blocks, threads, 0, stream>>>(a);
   else if (vec_ok && a.d == 256) layernorm_rows_vec_kernel<2><<<blocks, threads, 0, stream>>>(a);
+  else if (a.d <= 128 * 8) layernorm_rows_block_kernel<8><<<a.rows, 128, 0, stream>>>(a);
+  else if (a.d <= 128 * 24) layernorm_rows_block_kernel<24><<<a.rows, 128, 0, stream>>>(a);
   else layernorm_rows_generic_kernel<<<blocks, threads, 0, stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("layernorm launch failed: %s", cudaGetErrorString(e));
@@ -149,27 +202,45 @@ int launch_layernorm(const LnArgs& a, cudaStream_t stream) {
 __global__ void __launch_bounds__(256) sine_pos_table_kernel(const float* __restrict__ mask, const float* __restrict__ txt_mask,
                                                             const float* __restrict__ dim_t, float* __restrict__ pos,
                                                             float* __restrict__ key_mask, int Lv, int Lt, int d) {
-  extern __shared__ float s_e[];  // [Lv]
+  extern __shared__ float s_e[];  // [Lv] cumulative position, then the normalised angle
+  __shared__ float s_part[256];
   const int b = blockIdx.x;
-  if (threadIdx.x == 0) {
-    float c = 0.f;
-    for (int l = 0; l < Lv; ++l) {
-      c += mask[(size_t)b * Lv + l];
-      s_e[l] = c;
-    }
-    const float denom = c + 1e-6f;
-    const float scale = 6.283185307179586f;  // float32(2*math.pi)
-    for (int l = 0; l < Lv; ++l) s_e[l] = s_e[l] / denom * scale;
+  const int tid = threadIdx.x;
+  // block-wide inclusive scan of the 0/1 mask (sums of small integers: exact in fp32 in any order)
+  const int per = (Lv + 255) / 256;
+  const int l0 = tid * per;
+  float run = 0.f;
+  for (int l = l0; l < min(Lv, l0 + per); ++l) {
+    run += mask[(size_t)b * Lv + l];
+    s_e[l] = run;
   }
+  s_part[tid] = run;
+  __syncthreads();
+  if (tid == 0) {
+    float acc = 0.f;
+    for (int i = 0; i < 256; ++i) {
+      const float t = s_part[i];
+      s_part[i] = acc;
+      acc += t;
+    }
+  }
+  __syncthreads();
+  const float off = s_part[tid];
+  for (int l = l0; l < min(Lv, l0 + per); ++l) s_e[l] += off;
+  __syncthreads();
+  const float denom = s_e[Lv - 1] + 1e-6f;
+  const float scale = 6.283185307179586f;  // float32(2*math.pi)
+  __syncthreads();
+  for (int l = tid; l < Lv; l += 256) s_e[l] = s_e[l] / denom * scale;
   // concatenated key mask [B, Lv+Lt] (mask = cat([src_vid_mask, src_txt_mask]), model/univtg.py:120)
-  if (key_mask != nullptr) {
+  if (key_mask != nullptr && blockIdx.y == 0) {
     const int L = Lv + Lt;
-    for (int l = threadIdx.x; l < L; l += blockDim.x)
+    for (int l = tid; l < L; l += 256)
       key_mask[(size_t)b * L + l] = (l < Lv) ? mask[(size_t)b * Lv + l] : txt_mask[(size_t)b * Lt + (l - Lv)];
   }
   __syncthreads();
   const int total = Lv * d;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+  for (int i = blockIdx.y * 256 + tid; i < total; i += gridDim.y * 256) {
     const int l = i / d;
     const int j = i - l * d;
     const float arg = s_e[l] / dim_t[j];
@@ -179,7 +250,10 @@ __global__ void __launch_bounds__(256) sine_pos_table_kernel(const float* __rest
 
 int launch_sine_pos(const float* mask, const float* txt_mask, const float* dim_t, float* pos, float* key_mask, int B, int Lv,
                     int Lt, int d, cudaStream_t stream) {
-  sine_pos_table_kernel<<<B, 256, Lv * sizeof(float), stream>>>(mask, txt_mask, dim_t, pos, key_mask, Lv, Lt, d);
+  int chunks = (Lv * d + 8191) / 8192;
+  if (chunks < 1) chunks = 1;
+  if (chunks > 64) chunks = 64;
+  sine_pos_table_kernel<<<dim3(B, chunks), 256, Lv * sizeof(float), stream>>>(mask, txt_mask, dim_t, pos, key_mask, Lv, Lt, d);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("sine_pos launch failed: %s", cudaGetErrorString(e));
   return (int)e;
@@ -190,16 +264,12 @@ int launch_sine_pos(const float* mask, const float* txt_mask, const float* dim_t
 //   alpha = softmax_l(x_t . w + (1 - m_t) * -1e30);  pooled = sum_l alpha_l x_t[l]
 //   sal[l] = cos(x_v[l], pooled) + log(m_v[l] + 1e-45)      (denormal-sensitive: no FTZ / fast-math)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pool_saliency_kernel(const PoolSalArgs a) {
+__global__ void __launch_bounds__(256) weighted_pool_kernel(const PoolSalArgs a) {
   extern __shared__ float sm[];
-  float* s_alpha = sm;            // [Lt]
-  float* s_pool = sm + a.Lt;      // [d]
-  __shared__ float s_red[8];
-  __shared__ float s_pn;
+  float* s_alpha = sm;  // [Lt]
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const float* xt = a.x_txt + (size_t)b * a.Lt * a.d;
-  const float* xv = a.x_vid + (size_t)b * a.Lv * a.d;
   for (int l = warp; l < a.Lt; l += nw) {
     float s = 0.f;
     for (int j = lane; j < a.d; j += 32) s += xt[(size_t)l * a.d + j] * a.w[j];
@@ -223,44 +293,43 @@ __global__ void __launch_bounds__(256) pool_saliency_kernel(const PoolSalArgs a)
   __syncthreads();
   if (a.alpha_out)
     for (int l = threadIdx.x; l < a.Lt; l += blockDim.x) a.alpha_out[(size_t)b * a.Lt + l] = s_alpha[l];
-  float pn = 0.f;
   for (int j = threadIdx.x; j < a.d; j += blockDim.x) {
     float p = 0.f;
     for (int l = 0; l < a.Lt; ++l) p += xt[(size_t)l * a.d + j] * s_alpha[l];
-    s_pool[j] = p;
     a.pooled[(size_t)b * a.d + j] = p;
-    pn += p * p;
   }
+}
+
+// one warp per (b, l): cos(x_v[b,l], pooled[b]) + log(mask + 1e-45)
+__global__ void __launch_bounds__(256) cosine_saliency_kernel(const PoolSalArgs a) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= a.B * a.Lv) return;
+  const int b = gw / a.Lv;
+  const float* xv = a.x_vid + (size_t)gw * a.d;
+  const float* pl = a.pooled + (size_t)b * a.d;
+  float dot = 0.f, nn = 0.f, pn = 0.f;
+  for (int j = lane * 4; j < a.d; j += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xv + j);
+    const float4 p = *reinterpret_cast<const float4*>(pl + j);
+    dot += v.x * p.x + v.y * p.y + v.z * p.z + v.w * p.w;
+    nn += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    pn += p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w;
+  }
+  dot = warp_sum(dot);
+  nn = warp_sum(nn);
   pn = warp_sum(pn);
-  if (lane == 0) s_red[warp] = pn;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int i = 0; i < nw; ++i) t += s_red[i];
-    s_pn = sqrtf(t);
-  }
-  __syncthreads();
-  const float pnorm = fmaxf(s_pn, 1e-8f);
-  for (int l = warp; l < a.Lv; l += nw) {
-    float dot = 0.f, nn = 0.f;
-    for (int j = lane; j < a.d; j += 32) {
-      const float v = xv[(size_t)l * a.d + j];
-      dot += v * s_pool[j];
-      nn += v * v;
-    }
-    dot = warp_sum(dot);
-    nn = warp_sum(nn);
-    if (lane == 0) {
-      const float vn = fmaxf(sqrtf(nn), 1e-8f);
-      const float cosv = dot / (vn * pnorm);
-      a.saliency[(size_t)b * a.Lv + l] = cosv + logf(a.vid_mask[(size_t)b * a.Lv + l] + 1e-45f);
-    }
+  if (lane == 0) {
+    const float vn = fmaxf(sqrtf(nn), 1e-8f);
+    const float pnorm = fmaxf(sqrtf(pn), 1e-8f);
+    a.saliency[gw] = dot / (vn * pnorm) + logf(a.vid_mask[gw] + 1e-45f);
   }
 }
 
 int launch_pool_saliency(const PoolSalArgs& a, cudaStream_t stream) {
-  const size_t smem = (size_t)(a.Lt + a.d) * sizeof(float);
-  pool_saliency_kernel<<<a.B, 256, smem, stream>>>(a);
+  weighted_pool_kernel<<<a.B, 256, (size_t)a.Lt * sizeof(float), stream>>>(a);
+  const int rows = a.B * a.Lv;
+  cosine_saliency_kernel<<<(rows * 32 + 255) / 256, 256, 0, stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("pool_saliency launch failed: %s", cudaGetErrorString(e));
   return (int)e;

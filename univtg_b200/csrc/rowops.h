@@ -58,16 +58,16 @@ struct HeadFinalArgs {
 int launch_conv_head_final(const HeadFinalArgs& a, cudaStream_t stream);
 
 struct AttnArgs {
-  // Q, K: [B*L, d] 16-bit row-major (heads are contiguous dh-wide column blocks); Q pre-scaled by 1/sqrt(dh).
-  // Vt : [B*d, Lp] 16-bit, Vt[(b*d + h*dh + c), j] = V[b, j, h, c]; columns L..Lp are zero.
-  CUtensorMap tm_q, tm_k, tm_vt;
+  // qkv: [B*L, 3d] 16-bit row-major; column blocks [0,d) = Q, [d,2d) = K, [2d,3d) = V (heads = dh-wide sub-blocks).
+  CUtensorMap tm_qkv;  // box {64, 128}, 128B swizzle
+  float scale;         // 1/sqrt(dh), applied to Q K^T inside the softmax exponent
   const float* key_mask;  // [B, L] 1 = valid key (src_key_padding_mask is its negation)
   uint16_t* out;          // [B*L, d] 16-bit attention output (heads concatenated)
   float* lse;             // [B, H, L] log-sum-exp per query row (training) or null
-  int B, L, Lp, H, dh, d, fmt;
+  int B, L, H, dh, d, fmt;
 };
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
-// SIMT variant for head sizes outside {64,128}; reads q/k/vt through plain pointers.
-int launch_attention_simt(const AttnArgs& a, const uint16_t* q, const uint16_t* k, const uint16_t* vt, cudaStream_t stream);
+// SIMT variant for head sizes outside {64,128}; reads qkv through a plain pointer.
+int launch_attention_simt(const AttnArgs& a, const uint16_t* qkv, cudaStream_t stream);
 
 }  // namespace uv
