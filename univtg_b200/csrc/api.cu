@@ -217,6 +217,7 @@ struct univtg_plan {
   float* txtproj32;               // [Mt, d] projected text tokens (+type embedding)
   float* pos;                     // [Mv, d]
   float* key_mask;                // [B, L]
+  float* pool_logits;             // [B, Lt]
   float *x32, *y32;               // residual stream / pre-LayerNorm sum
   uint16_t *x16, *xpos16, *qkv16, *attn16, *h16;
   uint16_t *hA, *h1, *hc2, *hs2;  // conv-head buffers (separated layout)
@@ -260,6 +261,7 @@ void init_problem(GemmProblem& p) {
   p.taps = 1;
   p.ksplit = 1;
   p.alpha = 1.f;
+  p.a_fmt = p.b_fmt = p.out_fmt = -1;
   // default coordinate rules: K-major A [M,K] and B [N,K]
   p.ca = OperandCoord{0, 0, 0, 1, 0, 1, 0, 0};
   p.cb = OperandCoord{0, 0, 0, 1, 0, 1, 0, 0};
@@ -375,7 +377,7 @@ int univtg_pack_weights(const univtg_config* cfg, const float* const* params, in
 namespace {
 
 struct WsLayout {
-  size_t a_vid[3], a_txt[3], p_vid32, p_txt32, txtproj32, pos, key_mask, x32, y32, x16, xpos16, qkv16, attn16, h16, hA,
+  size_t a_vid[3], a_txt[3], p_vid32, p_txt32, txtproj32, pos, key_mask, pool_logits, x32, y32, x16, xpos16, qkv16, attn16, h16, hA,
       h1, hc2, hs2, total;
 };
 
@@ -395,6 +397,7 @@ WsLayout make_ws(const univtg_config& c, const univtg_shape& s, const PackedLayo
   w.txtproj32 = cur.take(Mt * d * 4);
   w.pos = cur.take(Mv * d * 4);
   w.key_mask = cur.take(B * Lc * 4);
+  w.pool_logits = cur.take(B * Lt * 4);
   w.x32 = cur.take(M * d * 4);
   w.y32 = cur.take(M * d * 4);
   w.x16 = cur.take(M * d * 2);
@@ -480,6 +483,7 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
   P->txtproj32 = reinterpret_cast<float*>(ws + w.txtproj32);
   P->pos = reinterpret_cast<float*>(ws + w.pos);
   P->key_mask = reinterpret_cast<float*>(ws + w.key_mask);
+  P->pool_logits = reinterpret_cast<float*>(ws + w.pool_logits);
   P->x32 = reinterpret_cast<float*>(ws + w.x32);
   P->y32 = reinterpret_cast<float*>(ws + w.y32);
   P->x16 = reinterpret_cast<uint16_t*>(ws + w.x16);
@@ -657,7 +661,7 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
     delete P;
     return 1;
   }
-  P->launches = 1 + 3 * cfg->n_input_proj + 7 * cfg->enc_layers + 4;
+  P->launches = 1 + 3 * cfg->n_input_proj + 7 * cfg->enc_layers + 6;
   *out = P;
   return 0;
 }
@@ -847,6 +851,7 @@ int univtg_forward(univtg_plan* P, const float* src_txt, const float* src_txt_ma
     a.pooled = txt_mem_proj;
     a.saliency = saliency_scores;
     a.alpha_out = nullptr;
+    a.logits_ws = P->pool_logits;
     a.B = P->B;
     a.Lt = P->Lt;
     a.Lv = P->Lv;

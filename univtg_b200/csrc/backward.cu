@@ -1,0 +1,467 @@
+// Bandwidth-bound backward kernels of the UniVTG hot path: LayerNorm backward, 16-bit conversion with
+// bias-gradient column sums, the last conv layer of the heads, weighted-pool backward and stream-gradient assembly.
+// Gradients that feed tensor-core GEMMs are emitted as bf16 (fp16 would underflow), statistics stay fp32.
+#include <math.h>
+
+#include "backward.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace uv {
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward.  128 threads walk one row at a time (columns j = tid + 128 i, row in registers);
+// each block owns a strided set of rows and keeps dgamma / dbeta / colsum partials in registers.
+// ------------------------------------------------------------------------------------------------
+template <int EPT>
+__global__ void __launch_bounds__(128) layernorm_bwd_kernel(const LnBwdArgs a) {
+  __shared__ float s_red[2][4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float acc_g[EPT], acc_b[EPT], acc_c[EPT];
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) acc_g[i] = acc_b[i] = acc_c[i] = 0.f;
+  const float inv_d = 1.0f / (float)a.d;
+
+  for (int row = blockIdx.x; row < a.rows; row += gridDim.x) {
+    const float mean = a.mean[row], rstd = a.rstd[row];
+    const float* dout = a.dout + (size_t)row * a.ld_dout;
+    const float* y = a.y + (size_t)row * a.ld_y;
+    float xh[EPT], g[EPT];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const int j = tid + 128 * i;
+      xh[i] = 0.f;
+      g[i] = 0.f;
+      if (j < a.d) {
+        const float dj = dout[j];
+        xh[i] = (y[j] - mean) * rstd;
+        g[i] = dj * a.gamma[j];
+        acc_g[i] += dj * xh[i];
+        acc_b[i] += dj;
+        s1 += g[i];
+        s2 += g[i] * xh[i];
+      }
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    __syncthreads();  // previous iteration's readers are done
+    if (lane == 0) {
+      s_red[0][warp] = s1;
+      s_red[1][warp] = s2;
+    }
+    __syncthreads();
+    const float c1 = (s_red[0][0] + s_red[0][1] + s_red[0][2] + s_red[0][3]) * inv_d;
+    const float c2 = (s_red[1][0] + s_red[1][1] + s_red[1][2] + s_red[1][3]) * inv_d;
+    float rs = 1.f;
+    if (a.row_scale != nullptr) rs = a.row_scale[a.L > 0 ? row / a.L : 0];
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const int j = tid + 128 * i;
+      if (j < a.d) {
+        float dy = rstd * (g[i] - c1 - xh[i] * c2);
+        if (a.relu_mask_y && !(y[j] > 0.f)) dy = 0.f;
+        if (a.dy32) a.dy32[(size_t)row * a.d + j] = dy;
+        const float br = dy * rs;
+        acc_c[i] += br;
+        if (a.dbr16) a.dbr16[(size_t)row * a.ld16 + j] = cvt16(br, a.fmt16);
+      }
+    }
+    if (a.dbr16)
+      for (int j = a.d + tid; j < a.ld16; j += 128) a.dbr16[(size_t)row * a.ld16 + j] = 0;
+  }
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    const int j = tid + 128 * i;
+    if (j < a.d) {
+      if (a.dgamma) atomicAdd(a.dgamma + j, acc_g[i]);
+      if (a.dbeta) atomicAdd(a.dbeta + j, acc_b[i]);
+      if (a.colsum) atomicAdd(a.colsum + j, acc_c[i]);
+    }
+  }
+}
+
+int launch_layernorm_bwd(const LnBwdArgs& a, cudaStream_t stream) {
+  if (a.rows <= 0) return 0;
+  const int grid = a.rows < 592 ? a.rows : 592;  // 4 blocks per SM; each block keeps register partials over its rows
+  if (a.d <= 128 * 8) layernorm_bwd_kernel<8><<<grid, 128, 0, stream>>>(a);
+  else if (a.d <= 128 * 24) layernorm_bwd_kernel<24><<<grid, 128, 0, stream>>>(a);
+  else {
+    set_error("layernorm_bwd: d %d > 3072 not supported", a.d);
+    return (int)cudaErrorInvalidValue;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) set_error("layernorm_bwd launch failed: %s", cudaGetErrorString(e));
+  return (int)e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> 16-bit conversion with optional column sums.  Block = 256 threads x 32 rows; thread = 4 columns.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cvt16_colsum_kernel(const float* __restrict__ in32, int ld_in, uint16_t* __restrict__ out16,
+                                                          int ld_out, int rows, int cols, int fmt, float* __restrict__ colsum) {
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (c >= cols) return;
+  const int r0 = blockIdx.y * 32;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = r0; r < min(rows, r0 + 32); ++r) {
+    const float4 v = *reinterpret_cast<const float4*>(in32 + (size_t)r * ld_in + c);
+    *reinterpret_cast<uint2*>(out16 + (size_t)r * ld_out + c) = make_uint2(cvt16x2(v.x, v.y, fmt), cvt16x2(v.z, v.w, fmt));
+    s.x += v.x;
+    s.y += v.y;
+    s.z += v.z;
+    s.w += v.w;
+  }
+  if (colsum) {
+    atomicAdd(colsum + c, s.x);
+    atomicAdd(colsum + c + 1, s.y);
+    atomicAdd(colsum + c + 2, s.z);
+    atomicAdd(colsum + c + 3, s.w);
+  }
+}
+
+int launch_cvt16_colsum(const float* in32, int ld_in, uint16_t* out16, int ld_out, int rows, int cols, int fmt, float* colsum,
+                        cudaStream_t stream) {
+  if (cols % 4 != 0 || ld_in % 4 != 0 || ld_out % 4 != 0) {
+    set_error("cvt16_colsum: dims must be multiples of 4");
+    return (int)cudaErrorInvalidValue;
+  }
+  dim3 grid((cols / 4 + 255) / 256, (rows + 31) / 32);
+  cvt16_colsum_kernel<<<grid, 256, 0, stream>>>(in32, ld_in, out16, ld_out, rows, cols, fmt, colsum);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) set_error("cvt16_colsum launch failed: %s", cudaGetErrorString(e));
+  return (int)e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// delta[b,h,i] = rowsum(dO * O) per head.  One warp per token row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attn_delta_kernel(const uint16_t* __restrict__ dO, int fmt_do, const uint16_t* __restrict__ O,
+                                                        int fmt_o, float* __restrict__ delta, int B, int L, int H, int dh) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B * L) return;
+  const int b = row / L, i = row - b * L;
+  const int d = H * dh;
+  for (int h = 0; h < H; ++h) {
+    float s = 0.f;
+    for (int c = lane; c < dh; c += 32) {
+      const size_t idx = (size_t)row * d + h * dh + c;
+      s += ld16(dO[idx], fmt_do) * ld16(O[idx], fmt_o);
+    }
+    s = warp_sum(s);
+    if (lane == 0) delta[((size_t)b * H + h) * L + i] = s;
+  }
+}
+
+int launch_attn_delta(const uint16_t* dO, int fmt_do, const uint16_t* O, int fmt_o, float* delta, int B, int L, int H, int dh,
+                      cudaStream_t stream) {
+  const int rows = B * L;
+  attn_delta_kernel<<<(rows * 32 + 255) / 256, 256, 0, stream>>>(dO, fmt_do, O, fmt_o, delta, B, L, H, dh);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) set_error("attn_delta launch failed: %s", cudaGetErrorString(e));
+  return (int)e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT attention backward (any head size).  One warp per (b, h, query i); dK / dV / dQ accumulate atomically in fp32.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attention_bwd_simt_kernel(const AttnBwdArgs a) {
+  extern __shared__ float s_buf[];  // [4 warps][2][L]: p and ds
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * 4 + warp;
+  if (gw >= a.B * a.H * a.L) return;
+  const int i = gw % a.L;
+  const int h = (gw / a.L) % a.H;
+  const int b = gw / (a.L * a.H);
+  float* p_s = s_buf + (size_t)warp * 2 * a.L;
+  float* ds_s = p_s + a.L;
+  const size_t ld = (size_t)3 * a.d;
+  const uint16_t* qrow = a.qkv + ((size_t)b * a.L + i) * ld + h * a.dh;
+  const uint16_t* dorow = a.dO + ((size_t)b * a.L + i) * a.d + h * a.dh;
+  const float lse = a.lse[((size_t)b * a.H + h) * a.L + i];
+  const float dlt = a.delta[((size_t)b * a.H + h) * a.L + i];
+  for (int j = lane; j < a.L; j += 32) {
+    float p = 0.f, ds = 0.f;
+    if (a.key_mask[(size_t)b * a.L + j] != 0.f) {
+      const uint16_t* krow = a.qkv + ((size_t)b * a.L + j) * ld + a.d + h * a.dh;
+      const uint16_t* vrow = a.qkv + ((size_t)b * a.L + j) * ld + 2 * a.d + h * a.dh;
+      float s = 0.f, dp = 0.f;
+      for (int c = 0; c < a.dh; ++c) {
+        s += ld16(qrow[c], a.fmt_act) * ld16(krow[c], a.fmt_act);
+        dp += ld16(dorow[c], a.fmt_grad) * ld16(vrow[c], a.fmt_act);
+      }
+      p = expf(s * a.scale - lse);
+      ds = p * (dp - dlt) * a.scale;
+    }
+    p_s[j] = p;
+    ds_s[j] = ds;
+  }
+  __syncwarp();
+  for (int c = lane; c < a.dh; c += 32) {
+    const float qc = ld16(qrow[c], a.fmt_act);
+    const float doc = ld16(dorow[c], a.fmt_grad);
+    float dq = 0.f;
+    for (int j = 0; j < a.L; ++j) {
+      const float ds = ds_s[j], p = p_s[j];
+      if (p == 0.f && ds == 0.f) continue;
+      const size_t kbase = ((size_t)b * a.L + j) * ld;
+      dq += ds * ld16(a.qkv[kbase + a.d + h * a.dh + c], a.fmt_act);
+      atomicAdd(a.dqkv32 + kbase + a.d + h * a.dh + c, ds * qc);
+      atomicAdd(a.dqkv32 + kbase + 2 * a.d + h * a.dh + c, p * doc);
+    }
+    atomicAdd(a.dqkv32 + ((size_t)b * a.L + i) * ld + h * a.dh + c, dq);
+  }
+}
+
+int launch_attention_bwd_simt(const AttnBwdArgs& a, cudaStream_t stream) {
+  const int warps = a.B * a.H * a.L;
+  const size_t smem = (size_t)4 * 2 * a.L * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("attention_bwd_simt smem %zu: %s", smem, cudaGetErrorString(e));
+      return (int)e;
+    }
+  }
+  attention_bwd_simt_kernel<<<(warps + 3) / 4, 128, smem, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) set_error("attention_bwd_simt launch failed: %s", cudaGetErrorString(e));
+  return (int)e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Heads, last conv layer backward.
+//   z_o[m] = b_o + sum_t sum_c W[o, c, t] h[m + t - 1, c];  pred = (+-) sigmoid(z)
+// kernel 1: dz (pre-sigmoid gradients) per clip, conv layout, separators zero
+// kernel 2: dh[m', c] = relu'(h[m', c]) * sum_t sum_o dz_o[m' - t + 1] W[o, c, t]   (+ column sums)
+// kernel 3: dW[o, c, t] = sum_m dz_o[m] h[m + t - 1, c],  db[o] = sum_m dz_o[m]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_dz_kernel(const HeadFinalBwdArgs a) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int rows = a.B * (a.Lv + 1) + 2;
+  if (idx >= rows) return;
+  float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int m = idx - 1;  // logical conv row
+  if (m >= 0 && m < a.B * (a.Lv + 1)) {
+    const int b = m / (a.Lv + 1), l = m - b * (a.Lv + 1);
+    if (l < a.Lv) {
+      const size_t k = (size_t)b * a.Lv + l;
+      const float pc = a.pred_logits[k];
+      const float s0 = -a.pred_spans[2 * k];  // sigmoid value of the left offset (stored negated)
+      const float s1 = a.pred_spans[2 * k + 1];
+      out.x = a.g_logits[k] * pc * (1.f - pc);
+      out.y = -a.g_spans[2 * k] * s0 * (1.f - s0);
+      out.z = a.g_spans[2 * k + 1] * s1 * (1.f - s1);
+    }
+  }
+  *reinterpret_cast<float4*>(a.dz + (size_t)idx * 4) = out;
+}
+
+__global__ void __launch_bounds__(256) head_dh_kernel(const HeadFinalBwdArgs a) {
+  // one warp per buffer row (1 .. B*(Lv+1)); lanes over channels
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int Mh = a.B * (a.Lv + 1);
+  if (gw >= Mh) return;
+  const size_t row = (size_t)gw + 1;  // buffer row of logical row m' = gw
+  const int l = gw % (a.Lv + 1);
+  const bool sep = (l == a.Lv);
+  // dz of logical rows m' - t + 1 for t = 0, 1, 2  -> buffer rows row + 1 - t
+  float dzc[3], dz0[3], dz1[3];
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const float4 v = *reinterpret_cast<const float4*>(a.dz + (row + 1 - t) * 4);
+    dzc[t] = v.x;
+    dz0[t] = v.y;
+    dz1[t] = v.z;
+  }
+  for (int c = lane * 2; c < a.d; c += 64) {
+    float gc[2] = {0.f, 0.f}, gs[2] = {0.f, 0.f};
+    if (!sep) {
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          gc[e] += dzc[t] * a.w_cls[(size_t)t * a.d + c + e];
+          gs[e] += dz0[t] * a.w_span[(size_t)t * a.d + c + e] + dz1[t] * a.w_span[(size_t)(3 + t) * a.d + c + e];
+        }
+      }
+      const uint32_t hc = *reinterpret_cast<const uint32_t*>(a.h_cls + row * a.d + c);
+      const uint32_t hs = *reinterpret_cast<const uint32_t*>(a.h_span + row * a.d + c);
+      if (!pos16((uint16_t)(hc & 0xffff))) gc[0] = 0.f;
+      if (!pos16((uint16_t)(hc >> 16))) gc[1] = 0.f;
+      if (!pos16((uint16_t)(hs & 0xffff))) gs[0] = 0.f;
+      if (!pos16((uint16_t)(hs >> 16))) gs[1] = 0.f;
+    }
+    *reinterpret_cast<uint32_t*>(a.dh_cls + row * a.d + c) = cvt16x2(gc[0], gc[1], a.fmt_grad);
+    *reinterpret_cast<uint32_t*>(a.dh_span + row * a.d + c) = cvt16x2(gs[0], gs[1], a.fmt_grad);
+  }
+}
+
+__global__ void __launch_bounds__(256) head_dw_kernel(const HeadFinalBwdArgs a) {
+  // thread = channel c (blockIdx.x * 256 + tid); blockIdx.y = slab of 64 logical rows
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  const int Mh = a.B * (a.Lv + 1);
+  const int m0 = blockIdx.y * 64;
+  if (c >= a.d) return;
+  float wc[3] = {0.f, 0.f, 0.f}, w0[3] = {0.f, 0.f, 0.f}, w1[3] = {0.f, 0.f, 0.f};
+  float cs_c = 0.f, cs_s = 0.f;
+  for (int m = m0; m < min(Mh, m0 + 64); ++m) {
+    const size_t row = (size_t)m + 1;
+    const float4 dz = *reinterpret_cast<const float4*>(a.dz + row * 4);
+    if (a.cs_cls) {
+      cs_c += ld16(a.dh_cls[row * a.d + c], a.fmt_grad);
+      cs_s += ld16(a.dh_span[row * a.d + c], a.fmt_grad);
+    }
+    if (dz.x == 0.f && dz.y == 0.f && dz.z == 0.f) continue;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const float hc = ld16(a.h_cls[(row + t - 1) * a.d + c], a.fmt_act);
+      const float hs = ld16(a.h_span[(row + t - 1) * a.d + c], a.fmt_act);
+      wc[t] += dz.x * hc;
+      w0[t] += dz.y * hs;
+      w1[t] += dz.z * hs;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    atomicAdd(a.gw_cls + (size_t)c * 3 + t, wc[t]);
+    atomicAdd(a.gw_span + (size_t)c * 3 + t, w0[t]);
+    atomicAdd(a.gw_span + ((size_t)a.d + c) * 3 + t, w1[t]);
+  }
+  if (a.cs_cls) {
+    atomicAdd(a.cs_cls + c, cs_c);
+    atomicAdd(a.cs_span + c, cs_s);
+  }
+  if (c == 0) {  // bias gradients: sum of dz over this slab
+    float bc = 0.f, b0 = 0.f, b1 = 0.f;
+    for (int m = m0; m < min(Mh, m0 + 64); ++m) {
+      const float4 dz = *reinterpret_cast<const float4*>(a.dz + ((size_t)m + 1) * 4);
+      bc += dz.x;
+      b0 += dz.y;
+      b1 += dz.z;
+    }
+    atomicAdd(a.gb_cls, bc);
+    atomicAdd(a.gb_span, b0);
+    atomicAdd(a.gb_span + 1, b1);
+  }
+}
+
+int launch_head_final_bwd(const HeadFinalBwdArgs& a, cudaStream_t stream) {
+  const int Mh = a.B * (a.Lv + 1);
+  head_dz_kernel<<<(Mh + 2 + 255) / 256, 256, 0, stream>>>(a);
+  head_dh_kernel<<<(Mh * 32 + 255) / 256, 256, 0, stream>>>(a);
+  head_dw_kernel<<<dim3((a.d + 255) / 256, (Mh + 63) / 64), 256, 0, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) set_error("head_final_bwd launch failed: %s", cudaGetErrorString(e));
+  return (int)e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weighted pool backward.  pooled = sum_l alpha_l x_l, alpha = softmax(x . w + mask bias).  One CTA per sample.
+//   dalpha_l = g . x_l;  dlogit_l = alpha_l (dalpha_l - sum_k alpha_k dalpha_k)
+//   dx_l = alpha_l g + dlogit_l w;  dw += sum_l dlogit_l x_l
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pool_bwd_kernel(const PoolBwdArgs a) {
+  extern __shared__ float sm[];
+  float* s_da = sm;              // [Lt] dalpha, then dlogit
+  __shared__ float s_dot;
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const float* xt = a.x_txt + (size_t)b * a.Lt * a.d;
+  const float* g = a.g_pooled + (size_t)b * a.d;
+  const float* al = a.alpha + (size_t)b * a.Lt;
+  for (int l = warp; l < a.Lt; l += nw) {
+    float s = 0.f;
+    for (int j = lane; j < a.d; j += 32) s += g[j] * xt[(size_t)l * a.d + j];
+    s = warp_sum(s);
+    if (lane == 0) s_da[l] = s;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float s = 0.f;
+    for (int l = lane; l < a.Lt; l += 32) s += al[l] * s_da[l];
+    s = warp_sum(s);
+    if (lane == 0) s_dot = s;
+  }
+  __syncthreads();
+  const float dot = s_dot;
+  for (int l = threadIdx.x; l < a.Lt; l += blockDim.x) s_da[l] = al[l] * (s_da[l] - dot);
+  __syncthreads();
+  for (int j = threadIdx.x; j < a.d; j += blockDim.x) {
+    const float gj = g[j], wj = a.w[j];
+    float dw = 0.f;
+    for (int l = 0; l < a.Lt; ++l) {
+      const float dl = s_da[l];
+      a.dx_txt[((size_t)b * a.Lt + l) * a.d + j] = al[l] * gj + dl * wj;
+      dw += dl * xt[(size_t)l * a.d + j];
+    }
+    atomicAdd(a.gw + j, dw);
+  }
+}
+
+int launch_pool_bwd(const PoolBwdArgs& a, cudaStream_t stream) {
+  pool_bwd_kernel<<<a.B, 256, (size_t)a.Lt * sizeof(float), stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) set_error("pool_bwd launch failed: %s", cudaGetErrorString(e));
+  return (int)e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Projector-output gradient assembly: rows of one modality gathered from the stream gradient + the direct
+// (saliency-loss) gradient, emitted as a 16-bit GEMM operand with column sums.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stream_gather_kernel(const float* __restrict__ dx, int L, int off, const float* __restrict__ extra,
+                                                           uint16_t* __restrict__ out16, float* __restrict__ colsum, int B, int Ls,
+                                                           int d, int fmt) {
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (c >= d) return;
+  const int r0 = blockIdx.y * 32;
+  const int rows = B * Ls;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = r0; r < min(rows, r0 + 32); ++r) {
+    const int b = r / Ls, l = r - b * Ls;
+    float4 v = *reinterpret_cast<const float4*>(dx + ((size_t)b * L + off + l) * d + c);
+    if (extra) {
+      const float4 e = *reinterpret_cast<const float4*>(extra + (size_t)r * d + c);
+      v.x += e.x;
+      v.y += e.y;
+      v.z += e.z;
+      v.w += e.w;
+    }
+    *reinterpret_cast<uint2*>(out16 + (size_t)r * d + c) = make_uint2(cvt16x2(v.x, v.y, fmt), cvt16x2(v.z, v.w, fmt));
+    s.x += v.x;
+    s.y += v.y;
+    s.z += v.z;
+    s.w += v.w;
+  }
+  if (colsum) {
+    atomicAdd(colsum + c, s.x);
+    atomicAdd(colsum + c + 1, s.y);
+    atomicAdd(colsum + c + 2, s.z);
+    atomicAdd(colsum + c + 3, s.w);
+  }
+}
+
+int launch_stream_gather(const float* dx_stream, int L, int off, const float* extra, uint16_t* out16, float* colsum, int B, int Ls,
+                         int d, int fmt, cudaStream_t stream) {
+  dim3 grid((d / 4 + 255) / 256, (B * Ls + 31) / 32);
+  stream_gather_kernel<<<grid, 256, 0, stream>>>(dx_stream, L, off, extra, out16, colsum, B, Ls, d, fmt);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) set_error("stream_gather launch failed: %s", cudaGetErrorString(e));
+  return (int)e;
+}
+
+__global__ void __launch_bounds__(256) axpy_kernel(float* __restrict__ y, const float* __restrict__ x, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] += x[i];
+}
+int launch_axpy(float* y, const float* x, size_t n, cudaStream_t stream) {
+  size_t g = (n + 255) / 256;
+  axpy_kernel<<<(int)(g > 1184 ? 1184 : g), 256, 0, stream>>>(y, x, n);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) set_error("axpy launch failed: %s", cudaGetErrorString(e));
+  return (int)e;
+}
+
+}  // namespace uv

@@ -11,7 +11,7 @@
 //   warp 0 lane 0 : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier expect_tx)
 //   warp 1 lane 0 : MMA issuer     (tcgen05.mma cta_group::1, M=128, N=BN, K=16 x4 per 64-wide k-block)
 //   warp 2        : TMEM allocator (2 accumulator stages of BN fp32 columns)
-//   warps 4..11   : epilogue       (tcgen05.ld 32x32b -> smem transpose -> 128-bit coalesced global loads/stores)
+//   warps 4..11   : epilogue       (tcgen05.ld 32x32b; thread = row owns whole 32 B sectors -> 128-bit global loads/stores)
 #include <stdarg.h>
 #include <stdio.h>
 
@@ -26,8 +26,8 @@ struct GemmCfg {
   static constexpr int kABytes = GEMM_BM * 128;          // 128 rows x 64 x 2 B
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;  // multiple of 1024
-  static constexpr int kEpiFloats = 8 * 32 * 16;         // per-warp 32x16 fp32 transpose buffers (XOR-swizzled quads)
-  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kEpiFloats * 4 + 8 * 32 * 8 + 256;
+  static constexpr int kEpiFloats = 8 * (BN / 2);         // per-epilogue-warp bias slice
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kEpiFloats * 4 + 256;
   static constexpr uint32_t kTmemCols = 2 * BN;          // 256 or 512 (power of two)
 };
 
@@ -67,9 +67,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
 
   uint8_t* stage_base = smem;
   float* epi_buf = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  int* s_orow = reinterpret_cast<int*>(epi_buf + Cfg::kEpiFloats);        // [8][32]
-  float* s_rscale = reinterpret_cast<float*>(s_orow + 8 * 32);            // [8][32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rscale + 8 * 32);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + Cfg::kEpiFloats);
   uint64_t* full_bar = bars;                        // [kStages]
   uint64_t* empty_bar = bars + Cfg::kStages;        // [kStages]
   uint64_t* tmem_full = bars + 2 * Cfg::kStages;    // [2]
@@ -152,7 +150,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       TileInfo ti;
       for (int t = blockIdx.x; decode_tile(g, BN, t, ti); t += gridDim.x) {
         const GemmProblem& pr = g.p[ti.p];
-        const uint32_t idesc = make_idesc_f16(GEMM_BM, BN, g.fmt, pr.a_mn, pr.b_mn);
+        const uint32_t idesc = make_idesc_f16_ab(GEMM_BM, BN, pr.a_fmt < 0 ? g.fmt : pr.a_fmt, pr.b_fmt < 0 ? g.fmt : pr.b_fmt, pr.a_mn, pr.b_mn);
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -187,22 +185,20 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
   } else if (warp >= 4) {
     // ========================================= epilogue =========================================
     // 8 warps: warp w may only touch TMEM lanes [32*(w%4), +32); the two warps of a lane quarter split the columns.
+    // thread = output row: every thread owns 16 consecutive columns per step = 32 B (16-bit) / 64 B (fp32) of one row,
+    // i.e. whole 32-byte sectors, so loads and stores go straight from/to registers with 128-bit accesses.
     const int wq = warp & 3;
     const int half = (warp - 4) >> 2;
     const int ew = warp - 4;
-    float* buf = epi_buf + ew * (32 * 16);
-    int* orow_s = s_orow + ew * 32;
-    float* rscale_s = s_rscale + ew * 32;
+    float* bias_s = epi_buf + ew * (BN / 2);
     const int fmt = g.fmt;
-    const int rsub = lane >> 2;  // row inside a group of 8
-    const int cq = lane & 3;     // which 4-column quad of the 16-column chunk
     int as = 0;
     uint32_t aphase = 0;
     TileInfo ti;
     for (int t = blockIdx.x; decode_tile(g, BN, t, ti); t += gridDim.x) {
       const GemmProblem& pr = g.p[ti.p];
       // hoist the problem description into registers (the struct lives in the constant bank)
-      const int pM = pr.M, pN = pr.N, rps_in = pr.rps_in, rps_out = pr.rps_out, row_off = pr.row_off;
+      const int pM = pr.M, pN = pr.N, rps_in = pr.rps_in;
       const int act = pr.act;
       const float* __restrict__ bias = (ti.split == 0) ? pr.bias : nullptr;
       const float* __restrict__ resid = pr.resid;
@@ -211,27 +207,45 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       float* __restrict__ out32_id = pr.out32_id;
       uint16_t* __restrict__ out16 = pr.out16;
       uint16_t* __restrict__ out16p = pr.out16p;
-      const int ld_resid = pr.ld_resid, ld_addtab = pr.ld_addtab, ld32 = pr.ld32, ld32_id = pr.ld32_id, ld16 = pr.ld16;
       const bool atomic = (pr.accumulate != 0) || (pr.ksplit > 1);
       const bool vec = pr.vec_ok != 0;
+      const int ofmt = pr.out_fmt < 0 ? fmt : pr.out_fmt;
+      const float* __restrict__ aux32 = pr.aux32;
+      const int aux_mode = pr.aux_mode;
+      const uint16_t* __restrict__ mask16 = pr.mask16;
+      float* __restrict__ colsum = pr.colsum;
+      const int cs32 = pr.cs32 > 1 ? pr.cs32 : 1;
 
       const int m0 = ti.m_blk * GEMM_BM + wq * 32;
       const int n_base = ti.n_blk * BN + half * (BN / 2);
-      // ---- per-row bookkeeping (thread = row) ----
-      {
-        const int m = m0 + lane;
-        int b = 0, l = m;
-        if (rps_in > 0) {
-          b = m / rps_in;
-          l = m - b * rps_in;
-        }
-        const bool valid = m < pM;
-        const bool sep = pr.zero_sep && (l == rps_in - 1);
-        float rsc = pr.alpha;
-        if (pr.row_scale != nullptr && valid) rsc *= pr.row_scale[b];
-        if (sep) rsc = 0.f;
-        orow_s[lane] = valid ? ((rps_in > 0 ? b * rps_out + l : m) + row_off) : -1;
-        rscale_s[lane] = rsc;
+      // ---- this thread's row ----
+      const int m = m0 + lane;
+      int b = 0, l = m;
+      if (rps_in > 0) {
+        b = m / rps_in;
+        l = m - b * rps_in;
+      }
+      const bool is_sep = (rps_in > 0) && (l == rps_in - 1);
+      const bool valid = (m < pM) && !(pr.skip_sep && is_sep);
+      float rsc = pr.alpha;
+      if (pr.row_scale != nullptr && m < pM) rsc *= pr.row_scale[b];
+      if (pr.zero_sep && is_sep) rsc = 0.f;
+      const size_t orow = (size_t)((rps_in > 0 ? b * pr.rps_out + l : m) + pr.row_off);
+      const float* resid_row = resid ? resid + orow * pr.ld_resid : nullptr;
+      const float* aux_row = aux32 ? aux32 + orow * pr.ld_aux : nullptr;
+      const uint16_t* mask_row = mask16 ? mask16 + orow * pr.ld_mask : nullptr;
+      const float* add_row = addtab ? addtab + (size_t)m * pr.ld_addtab : nullptr;
+      float* o32_row = out32 ? out32 + orow * pr.ld32 : nullptr;
+      float* o32i_row = out32_id ? out32_id + (size_t)m * pr.ld32_id : nullptr;
+      uint16_t* o16_row = out16 ? out16 + orow * pr.ld16 : nullptr;
+      uint16_t* o16p_row = out16p ? out16p + orow * pr.ld16 : nullptr;
+
+      // bias slice of this warp's columns -> smem (broadcast reads in the column loop)
+      __syncwarp();
+#pragma unroll
+      for (int j = lane; j < BN / 2; j += 32) {
+        const int n = n_base + j;
+        bias_s[j] = (bias != nullptr && n < pN) ? __ldg(bias + n) : 0.f;
       }
       __syncwarp();
 
@@ -244,85 +258,127 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
         if (n0 >= pN) break;  // warp-uniform
         uint32_t r[16];
         tmem_ld_32x32b_x16(t_addr + c * 16, r);
-        tmem_ld_wait();
-        // ---- transpose through smem: thread = row writes 16 columns as 4 quads; afterwards 4 lanes cover one row.
-        //      quad q of row r lives at physical quad q ^ ((r >> 1) & 3): conflict-free for both access patterns ----
+        float rv[16];
+        if (vec && valid && resid_row != nullptr) {  // issue the residual loads before waiting on TMEM
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(buf + lane * 16 + 4 * (q ^ ((lane >> 1) & 3))) =
-              make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
-        __syncwarp();
-        const int n = n0 + 4 * cq;
-        if (n < pN) {
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (bias != nullptr) {
-            if (vec) bv = __ldg(reinterpret_cast<const float4*>(bias + n));
-            else {
-              bv.x = __ldg(bias + n);
-              if (n + 1 < pN) bv.y = __ldg(bias + n + 1);
-              if (n + 2 < pN) bv.z = __ldg(bias + n + 2);
-              if (n + 3 < pN) bv.w = __ldg(bias + n + 3);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rr = rsub + 8 * i;
-            const int orr = orow_s[rr];
-            if (orr < 0) continue;
-            float4 v = *reinterpret_cast<const float4*>(buf + rr * 16 + 4 * (cq ^ ((rr >> 1) & 3)));
-            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-            if (act == ACT_RELU) {
-              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-            } else if (act == ACT_GELU) {
-              v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
-            }
-            const float rs = rscale_s[rr];
-            v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
-            const int mrow = m0 + rr;
-            if (vec) {
-              if (resid != nullptr) {
-                const float4 rv = *reinterpret_cast<const float4*>(resid + (size_t)orr * ld_resid + n);
-                v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-              }
-              if (out32 != nullptr) {
-                float* dst = out32 + (size_t)orr * ld32 + n;
-                if (atomic) {
-                  atomicAdd(dst, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
-                } else {
-                  *reinterpret_cast<float4*>(dst) = v;
-                }
-              }
-              if (out32_id != nullptr) *reinterpret_cast<float4*>(out32_id + (size_t)mrow * ld32_id + n) = v;
-              if (out16 != nullptr)
-                *reinterpret_cast<uint2*>(out16 + (size_t)orr * ld16 + n) = make_uint2(cvt16x2(v.x, v.y, fmt), cvt16x2(v.z, v.w, fmt));
-              if (out16p != nullptr) {
-                float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (addtab != nullptr) pv = *reinterpret_cast<const float4*>(addtab + (size_t)mrow * ld_addtab + n);
-                *reinterpret_cast<uint2*>(out16p + (size_t)orr * ld16 + n) =
-                    make_uint2(cvt16x2(v.x + pv.x, v.y + pv.y, fmt), cvt16x2(v.z + pv.z, v.w + pv.w, fmt));
-              }
-            } else {
-              // unaligned leading dimensions (e.g. the [d, 2818] projector weight gradient): scalar stores
-              const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (n + e >= pN) break;
-                float x = vv[e];
-                if (resid != nullptr) x += resid[(size_t)orr * ld_resid + n + e];
-                if (out32 != nullptr) {
-                  float* dst = out32 + (size_t)orr * ld32 + n + e;
-                  if (atomic) atomicAdd(dst, x);
-                  else *dst = x;
-                }
-                if (out32_id != nullptr) out32_id[(size_t)mrow * ld32_id + n + e] = x;
-                if (out16 != nullptr) out16[(size_t)orr * ld16 + n + e] = cvt16(x, fmt);
-                if (out16p != nullptr)
-                  out16p[(size_t)orr * ld16 + n + e] = cvt16(x + (addtab ? addtab[(size_t)mrow * ld_addtab + n + e] : 0.f), fmt);
-              }
-            }
+          for (int q = 0; q < 4; ++q) {
+            const float4 t4 = *reinterpret_cast<const float4*>(resid_row + n0 + 4 * q);
+            rv[4 * q] = t4.x; rv[4 * q + 1] = t4.y; rv[4 * q + 2] = t4.z; rv[4 * q + 3] = t4.w;
           }
         }
-        __syncwarp();
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float x = __uint_as_float(r[j]) + bias_s[c * 16 + j];
+          if (act == ACT_RELU) x = fmaxf(x, 0.f);
+          else if (act == ACT_GELU) x = gelu_erf(x);
+          v[j] = x * rsc;
+        }
+        if (vec) {
+          if (valid) {
+            if (resid_row != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] += rv[j];
+            }
+            if (aux_row != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 a4 = *reinterpret_cast<const float4*>(aux_row + n0 + 4 * q);
+                if (aux_mode == 1) {
+                  v[4 * q] *= gelu_erf_grad(a4.x); v[4 * q + 1] *= gelu_erf_grad(a4.y);
+                  v[4 * q + 2] *= gelu_erf_grad(a4.z); v[4 * q + 3] *= gelu_erf_grad(a4.w);
+                } else {
+                  v[4 * q] *= a4.x; v[4 * q + 1] *= a4.y; v[4 * q + 2] *= a4.z; v[4 * q + 3] *= a4.w;
+                }
+              }
+            }
+            if (mask_row != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const uint4 mk = *reinterpret_cast<const uint4*>(mask_row + n0 + 8 * q);
+                const uint32_t w4[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (!pos16((uint16_t)(w4[e] & 0xffff))) v[8 * q + 2 * e] = 0.f;
+                  if (!pos16((uint16_t)(w4[e] >> 16))) v[8 * q + 2 * e + 1] = 0.f;
+                }
+              }
+            }
+            if (o32_row != nullptr) {
+              if (atomic) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) atomicAdd(o32_row + n0 + j, v[j]);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  *reinterpret_cast<float4*>(o32_row + n0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              }
+            }
+            if (o32i_row != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(o32i_row + n0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+            if (o16_row != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 2; ++q)
+                *reinterpret_cast<uint4*>(o16_row + n0 + 8 * q) =
+                    make_uint4(cvt16x2(v[8 * q], v[8 * q + 1], ofmt), cvt16x2(v[8 * q + 2], v[8 * q + 3], ofmt),
+                               cvt16x2(v[8 * q + 4], v[8 * q + 5], ofmt), cvt16x2(v[8 * q + 6], v[8 * q + 7], ofmt));
+            }
+            if (o16p_row != nullptr) {
+              float p[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) p[j] = v[j];
+              if (add_row != nullptr) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 a4 = *reinterpret_cast<const float4*>(add_row + n0 + 4 * q);
+                  p[4 * q] += a4.x; p[4 * q + 1] += a4.y; p[4 * q + 2] += a4.z; p[4 * q + 3] += a4.w;
+                }
+              }
+#pragma unroll
+              for (int q = 0; q < 2; ++q)
+                *reinterpret_cast<uint4*>(o16p_row + n0 + 8 * q) =
+                    make_uint4(cvt16x2(p[8 * q], p[8 * q + 1], ofmt), cvt16x2(p[8 * q + 2], p[8 * q + 3], ofmt),
+                               cvt16x2(p[8 * q + 4], p[8 * q + 5], ofmt), cvt16x2(p[8 * q + 6], p[8 * q + 7], ofmt));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.f;  // invalid rows contribute nothing to the column sums
+          }
+        } else {
+          // unaligned leading dimensions / ragged N (e.g. the [d, 2818] projector weight gradient): scalar accesses
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = n0 + j;
+            float x = v[j];
+            if (valid && n < pN) {
+              if (resid_row != nullptr) x += resid_row[n];
+              if (aux_row != nullptr) x *= (aux_mode == 1) ? gelu_erf_grad(aux_row[n]) : aux_row[n];
+              if (mask_row != nullptr && !pos16(mask_row[n])) x = 0.f;
+              if (o32_row != nullptr) {
+                float* dst = o32_row + (size_t)n * cs32;
+                if (atomic) atomicAdd(dst, x);
+                else *dst = x;
+              }
+              if (o32i_row != nullptr) o32i_row[n] = x;
+              if (o16_row != nullptr) o16_row[n] = cvt16(x, ofmt);
+              if (o16p_row != nullptr) o16p_row[n] = cvt16(x + (add_row ? add_row[n] : 0.f), ofmt);
+            } else {
+              x = 0.f;
+            }
+            v[j] = x;
+          }
+        }
+        if (colsum != nullptr) {  // warp-uniform: column sums over this warp's 32 rows, one atomic per column
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float sj = warp_sum(v[j]);
+            if (lane == j && n0 + j < pN) atomicAdd(colsum + n0 + j, sj);
+          }
+        }
       }
       // release the accumulator stage
       tc_fence_before();
@@ -424,11 +480,11 @@ static int launch_bn(GemmGroup& g, int num_sms, cudaStream_t stream) {
     total += ((pr.M + GEMM_BM - 1) / GEMM_BM) * ((pr.N + BN - 1) / BN) * pr.ksplit;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     GemmProblem& w = g.p[p];
-    w.vec_ok = (pr.N % 4 == 0) && al16(pr.bias) && (!pr.resid || (al16(pr.resid) && pr.ld_resid % 4 == 0)) &&
+    w.vec_ok = (pr.N % 16 == 0) && (pr.cs32 <= 1) && (!pr.aux32 || (al16(pr.aux32) && pr.ld_aux % 4 == 0)) &&
+               (!pr.mask16 || (al16(pr.mask16) && pr.ld_mask % 8 == 0)) && (!pr.resid || (al16(pr.resid) && pr.ld_resid % 4 == 0)) &&
                (!pr.addtab || (al16(pr.addtab) && pr.ld_addtab % 4 == 0)) && (!pr.out32 || (al16(pr.out32) && pr.ld32 % 4 == 0)) &&
                (!pr.out32_id || (al16(pr.out32_id) && pr.ld32_id % 4 == 0)) &&
-               ((!pr.out16 && !pr.out16p) || (pr.ld16 % 4 == 0 && (reinterpret_cast<uintptr_t>(pr.out16) & 7) == 0 &&
-                                              (reinterpret_cast<uintptr_t>(pr.out16p) & 7) == 0));
+               ((!pr.out16 && !pr.out16p) || (pr.ld16 % 8 == 0 && al16(pr.out16) && al16(pr.out16p)));
   }
   if (total == 0) return 0;
   const int grid = total < num_sms ? total : num_sms;

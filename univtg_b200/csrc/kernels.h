@@ -56,6 +56,17 @@ struct GemmProblem {
   uint16_t* out16p;        // 16-bit(v + addtab[m, n]) at remapped rows (same leading dim as out16)
   int ld16;
   int accumulate;          // out32 += v (atomic) instead of out32 = v
+  // ---- backward-pass extras (all optional) ----
+  int a_fmt, b_fmt;        // per-operand 16-bit format override (-1: group fmt); gradients travel as bf16, activations as fp16
+  int out_fmt;             // format of out16 / out16p (-1: group fmt)
+  const float* aux32;      // fp32 matrix indexed like out32 (remapped rows)
+  int ld_aux;
+  int aux_mode;            // 1: v *= gelu'(aux)   2: v *= aux (e.g. a dropout mask incl. its 1/(1-p) scale)
+  const uint16_t* mask16;  // 16-bit activation indexed like out16: v = 0 where mask16 <= 0 (ReLU backward)
+  int ld_mask;
+  float* colsum;           // fp32 [N]: atomically accumulates the column sums of the stored values (bias gradients)
+  int cs32;                // column stride of out32 (0/1: dense); 3 writes a Conv1d weight-gradient tap in [n, c, 3] layout
+  int skip_sep;            // rows with (m % rps_in) == rps_in-1 are not stored at all
   int vec_ok;              // set by launch_gemm_group: every pointer / leading dimension allows 128-bit accesses
 };
 

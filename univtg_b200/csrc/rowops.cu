@@ -239,20 +239,24 @@ __global__ void __launch_bounds__(256) sine_pos_table_kernel(const float* __rest
       key_mask[(size_t)b * L + l] = (l < Lv) ? mask[(size_t)b * Lv + l] : txt_mask[(size_t)b * Lt + (l - Lv)];
   }
   __syncthreads();
-  const int total = Lv * d;
+  // dim_t[2k] == dim_t[2k+1]: one division and one sincos give the (sin, cos) pair of columns 2k, 2k+1
+  const int half = d >> 1;
+  const int total = Lv * half;
   for (int i = blockIdx.y * 256 + tid; i < total; i += gridDim.y * 256) {
-    const int l = i / d;
-    const int j = i - l * d;
-    const float arg = s_e[l] / dim_t[j];
-    pos[((size_t)b * Lv + l) * d + j] = (j & 1) ? cosf(arg) : sinf(arg);
+    const int l = i / half;
+    const int k = i - l * half;
+    const float arg = s_e[l] / dim_t[2 * k];
+    float sv, cv;
+    sincosf(arg, &sv, &cv);
+    *reinterpret_cast<float2*>(pos + ((size_t)b * Lv + l) * d + 2 * k) = make_float2(sv, cv);
   }
 }
 
 int launch_sine_pos(const float* mask, const float* txt_mask, const float* dim_t, float* pos, float* key_mask, int B, int Lv,
                     int Lt, int d, cudaStream_t stream) {
-  int chunks = (Lv * d + 8191) / 8192;
+  int chunks = (Lv * d + 4095) / 4096;
   if (chunks < 1) chunks = 1;
-  if (chunks > 64) chunks = 64;
+  if (chunks > 128) chunks = 128;
   sine_pos_table_kernel<<<dim3(B, chunks), 256, Lv * sizeof(float), stream>>>(mask, txt_mask, dim_t, pos, key_mask, Lv, Lt, d);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("sine_pos launch failed: %s", cudaGetErrorString(e));
@@ -264,38 +268,55 @@ int launch_sine_pos(const float* mask, const float* txt_mask, const float* dim_t
 //   alpha = softmax_l(x_t . w + (1 - m_t) * -1e30);  pooled = sum_l alpha_l x_t[l]
 //   sal[l] = cos(x_v[l], pooled) + log(m_v[l] + 1e-45)      (denormal-sensitive: no FTZ / fast-math)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) weighted_pool_kernel(const PoolSalArgs a) {
-  extern __shared__ float sm[];
-  float* s_alpha = sm;  // [Lt]
-  const int b = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  const float* xt = a.x_txt + (size_t)b * a.Lt * a.d;
-  for (int l = warp; l < a.Lt; l += nw) {
-    float s = 0.f;
-    for (int j = lane; j < a.d; j += 32) s += xt[(size_t)l * a.d + j] * a.w[j];
-    s = warp_sum(s);
-    if (lane == 0) s_alpha[l] = s + (1.0f - a.txt_mask[(size_t)b * a.Lt + l]) * (-1e30f);
+// logits[b, l] = x_t[b, l] . w + (1 - mask) * -1e30: one warp per text token
+__global__ void __launch_bounds__(256) pool_logits_kernel(const PoolSalArgs a, float* __restrict__ logits) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= a.B * a.Lt) return;
+  const float* x = a.x_txt + (size_t)gw * a.d;
+  float s = 0.f;
+  for (int j = lane * 4; j < a.d; j += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(x + j);
+    const float4 w = *reinterpret_cast<const float4*>(a.w + j);
+    s += v.x * w.x + v.y * w.y + v.z * w.z + v.w * w.w;
   }
-  __syncthreads();
+  s = warp_sum(s);
+  if (lane == 0) logits[gw] = s + (1.0f - a.txt_mask[gw]) * (-1e30f);
+}
+
+// softmax over the tokens (recomputed per block, Lt is small) and pooled[b, j] for a 128-column slab
+__global__ void __launch_bounds__(128) weighted_pool_kernel(const PoolSalArgs a, const float* __restrict__ logits) {
+  extern __shared__ float s_alpha[];  // [Lt]
+  __shared__ float s_stat[2];
+  const int b = blockIdx.x;
+  const int j = blockIdx.y * 128 + threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) {
     float mx = -INFINITY;
-    for (int l = lane; l < a.Lt; l += 32) mx = fmaxf(mx, s_alpha[l]);
+    for (int l = lane; l < a.Lt; l += 32) mx = fmaxf(mx, logits[(size_t)b * a.Lt + l]);
     mx = warp_max(mx);
     float sum = 0.f;
     for (int l = lane; l < a.Lt; l += 32) {
-      const float e = expf(s_alpha[l] - mx);
+      const float e = expf(logits[(size_t)b * a.Lt + l] - mx);
       s_alpha[l] = e;
       sum += e;
     }
     sum = warp_sum(sum);
-    for (int l = lane; l < a.Lt; l += 32) s_alpha[l] = s_alpha[l] / sum;
+    if (lane == 0) s_stat[0] = sum;
   }
   __syncthreads();
-  if (a.alpha_out)
-    for (int l = threadIdx.x; l < a.Lt; l += blockDim.x) a.alpha_out[(size_t)b * a.Lt + l] = s_alpha[l];
-  for (int j = threadIdx.x; j < a.d; j += blockDim.x) {
+  const float inv = s_stat[0];
+  for (int l = threadIdx.x; l < a.Lt; l += 128) {
+    const float al = s_alpha[l] / inv;
+    __syncwarp();
+    s_alpha[l] = al;
+    if (a.alpha_out && blockIdx.y == 0) a.alpha_out[(size_t)b * a.Lt + l] = al;
+  }
+  __syncthreads();
+  if (j < a.d) {
+    const float* xt = a.x_txt + (size_t)b * a.Lt * a.d + j;
     float p = 0.f;
-    for (int l = 0; l < a.Lt; ++l) p += xt[(size_t)l * a.d + j] * s_alpha[l];
+    for (int l = 0; l < a.Lt; ++l) p += xt[(size_t)l * a.d] * s_alpha[l];
     a.pooled[(size_t)b * a.d + j] = p;
   }
 }
@@ -327,7 +348,8 @@ __global__ void __launch_bounds__(256) cosine_saliency_kernel(const PoolSalArgs 
 }
 
 int launch_pool_saliency(const PoolSalArgs& a, cudaStream_t stream) {
-  weighted_pool_kernel<<<a.B, 256, (size_t)a.Lt * sizeof(float), stream>>>(a);
+  pool_logits_kernel<<<(a.B * a.Lt * 32 + 255) / 256, 256, 0, stream>>>(a, a.logits_ws);
+  weighted_pool_kernel<<<dim3(a.B, (a.d + 127) / 128), 128, (size_t)a.Lt * sizeof(float), stream>>>(a, a.logits_ws);
   const int rows = a.B * a.Lv;
   cosine_saliency_kernel<<<(rows * 32 + 255) / 256, 256, 0, stream>>>(a);
   cudaError_t e = cudaGetLastError();

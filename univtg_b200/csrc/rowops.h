@@ -40,6 +40,7 @@ struct PoolSalArgs {
   float* pooled;          // [B, d]   (txt_mem_proj)
   float* saliency;        // [B, Lv]
   float* alpha_out;       // [B, Lt] softmax weights (training) or null
+  float* logits_ws;       // [B, Lt] scratch
   int B, Lt, Lv, d;
 };
 int launch_pool_saliency(const PoolSalArgs& a, cudaStream_t stream);
