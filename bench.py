@@ -32,7 +32,12 @@ WORKLOADS = {
     "cfg2_fwd": dict(cfg="cfg2", mode="fwd"),
     "cfg4_fwd": dict(cfg="cfg4", mode="fwd"),
     "cfg5_fwd": dict(cfg="cfg5", mode="fwd"),
+    # BASELINE.json configs[2]: cfg2 shapes, criterion (5 losses) + backward + grad-clip + AdamW (train_vlp_ddp.py:56-68)
+    "cfg3_train": dict(cfg="cfg2", mode="train"),
+    # configs[3]: per-rank shard (B=32, L_v=150) of the vlp_ddp pre-training batch; N ranks -> global batch 32 N
+    "cfg4_train": dict(cfg="cfg4", mode="train"),
 }
+DEFAULT_WORKLOAD = "cfg2_fwd"
 SMI_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -102,39 +107,101 @@ def gemm_flops_forward(cfg):
     return B * (enc + proj + conv)
 
 
+def oracle_step_fn(cfg, mode, batch):
+    """One CPU step of the oracle port: forward (mode fwd) or forward + criterion + backward + grad-clip + AdamW (mode train)."""
+    from oracle import univtg_oracle as O  # bench.py may execute oracle/ only in the CPU legs
+
+    sd = {k: v.float() for k, v in synth.make_state_dict(cfg, seed=0).items()}
+    inp = synth.make_inputs(cfg, seed=1, batch=batch)
+    if mode == "fwd":
+        def step():
+            with torch.no_grad():
+                O.forward(sd, cfg, **inp, dtype=torch.float32)
+        return step
+    tgt = synth.make_targets(inp, seed=2)
+    leaves = {k: v.clone().requires_grad_(not k.startswith("txt_position_embed")) for k, v in sd.items()}
+    params = [v for v in leaves.values() if v.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-4)
+    wd = {"loss_b": 10.0, "loss_g": 1.0, "loss_f": 10.0, "loss_s_intra": 0.1, "loss_s_inter": 0.1}
+
+    def step():
+        out = O.forward(leaves, cfg, **inp, dtype=torch.float32)
+        total = O.weighted_total(O.criterion(out, tgt), wd)
+        opt.zero_grad()
+        total.backward()
+        torch.nn.utils.clip_grad_norm_(params, 0.1)
+        opt.step()
+        return float(total)
+    return step
+
+
 def run_reference_arm(args, wl, cfg):
-    """CPU arm: the oracle port of the reference's fp32 path on all host cores (rank 0 only)."""
+    """CPU arm: the oracle port of the reference's fp32 path on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import univtg_oracle as O  # the second place bench.py may execute oracle/
-
-    sd = synth.make_state_dict(cfg, seed=0)
-    sd = {k: v.float() for k, v in sd.items()}
-    inp = synth.make_inputs(cfg, seed=1)
     B = cfg["batch"]
-    small = synth.make_inputs(cfg, seed=1, batch=min(B, 4))
-    cores = pick_threads(lambda: O.forward(sd, cfg, **small, dtype=torch.float32))
-    with torch.no_grad():
-        for _ in range(max(1, min(args.warmup, 2))):
-            O.forward(sd, cfg, **inp, dtype=torch.float32)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            O.forward(sd, cfg, **inp, dtype=torch.float32)
-        dt = time.perf_counter() - t0
+    cores = pick_threads(oracle_step_fn(cfg, wl["mode"], min(B, 4)))
+    step = oracle_step_fn(cfg, wl["mode"], B)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
     val = B * args.steps / dt
     line = {
         "impl": "reference", "metric": "video-query pairs/sec", "value": val, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "batch": B, "l_vid": cfg["l_vid"], "l_txt": cfg["l_txt"],
+        "config": {"workload": args.workload, "mode": wl["mode"], "batch": B, "l_vid": cfg["l_vid"], "l_txt": cfg["l_txt"],
                    "hidden_dim": cfg["hidden_dim"], "enc_layers": cfg["enc_layers"]},
         "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} full batches (B={B}) of {args.workload}, oracle/univtg_oracle.py fp32, "
+                         "sample": f"{args.steps} full steps (B={B}) of {args.workload}, oracle/univtg_oracle.py fp32, "
                                    f"torch {torch.__version__} CPU, {cores} threads"},
         "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def pick_threads(fn):
+    """All host cores the process may use, unless over-subscription (cgroup quota < visible cores) makes fewer threads
+    faster: time one call at a few thread counts and keep the best."""
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    cands = sorted({c for c in (avail, 32, 8) if 1 <= c <= avail}, reverse=True)
+    best, best_t = cands[-1], None
+    for c in sorted(cands):  # small counts first: a crawling 128-thread run must not eat the time budget
+        torch.set_num_threads(c)
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = c, dt
+        if dt > 20.0:
+            break
+    torch.set_num_threads(best)
+    return best
+
+
+def cpu_baseline(cfg, wl, workload):
+    """Oracle port of the reference fp32 path on the host cores, bounded sample (~10-30 s of CPU work)."""
+    sample_b = min(cfg["batch"], 8)
+    step = oracle_step_fn(cfg, wl["mode"], sample_b)
+    cores = pick_threads(step)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        step()
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > 10.0 or n >= 50:
+            break
+    return {"value": sample_b * n / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": f"{n} steps of B={sample_b} ({workload} shape, mode {wl['mode']}), oracle/univtg_oracle.py fp32 on {cores} "
+                      f"torch threads"}
 
 
 def main():
@@ -143,13 +210,14 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2_fwd", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--operand-format", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     wl = WORKLOADS[args.workload]
     cfg = synth.CONFIGS[wl["cfg"]]
+    train = wl["mode"] == "train"
 
     if args.impl == "reference":
         run_reference_arm(args, wl, cfg)
@@ -170,21 +238,35 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
-    from univtg_b200 import build_model
+    from univtg_b200 import build_model, ddp
 
-    model, _ = build_model(synth.reference_args(cfg, device=str(dev), operand_format=args.operand_format))
+    model, crit = build_model(synth.reference_args(cfg, device=str(dev), operand_format=args.operand_format))
     model.load_state_dict(synth.make_state_dict(cfg, seed=0), strict=True)
-    model.to(dev).eval()
+    model.to(dev)
+    crit.to(dev)
     B, Lv, Lt, d = cfg["batch"], cfg["l_vid"], cfg["l_txt"], cfg["hidden_dim"]
+    opt = None
+    if train:
+        model.train()
+        crit.train()
+        opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-4)
+        if dist is not None:
+            ddp.broadcast_parameters(model)
+            ddp.attach_flat_allreduce(model)  # ONE NCCL all-reduce of the flat gradient buffer per step
+    else:
+        model.eval()
 
     # Rotating set of distinct input batches whose total size exceeds the 126 MB L2 (no L2-resident inputs between steps).
     per_batch = B * (Lv * cfg["v_feat_dim"] + Lt * cfg["t_feat_dim"] + Lv + Lt) * 4
     n_rot = max(2, int(160e6 // per_batch) + 1)
-    host_batches = []
+    host_batches, host_targets = [], []
     for i in range(n_rot):
         inp = synth.make_inputs(cfg, seed=1 + 7 * rank + i)
         host_batches.append({k: v.pin_memory() for k, v in inp.items()})
+        if train:
+            host_targets.append({k: v.pin_memory() for k, v in synth.make_targets(inp, seed=100 + 7 * rank + i).items()})
     dev_batches = [{k: v.to(dev) for k, v in hb.items()} for hb in host_batches]
+    dev_targets = [{k: v.to(dev) for k, v in ht.items()} for ht in host_targets]
     launches_per_step = model.num_forward_launches(B, Lv, Lt)
 
     def sync_all():
@@ -193,54 +275,83 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ------------------------------------------------ device-resident timing ------------------------------------------------
-    with torch.no_grad():
-        for i in range(args.warmup):
-            model(**dev_batches[i % n_rot])
-        sync_all()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sync_all()
-        e0.record()
-        for i in range(args.steps):
-            model(**dev_batches[i % n_rot])
-        e1.record()
-        sync_all()
-        ms_total = e0.elapsed_time(e1)
+    def train_step(inputs, targets):
+        out = model(**inputs)
+        ld = crit(out, targets)
+        total = sum(ld[k] * crit.weight_dict[k] for k in ld if k in crit.weight_dict)
+        opt.zero_grad(set_to_none=True)
+        total.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)  # reference --grad_clip 0.1
+        opt.step()
+        return total
 
-        # -------------------------------------------- end-to-end through the public API ------------------------------------
+    def device_step(i):
+        if train:
+            return train_step(dev_batches[i % n_rot], dev_targets[i % n_rot])
+        with torch.no_grad():
+            return model(**dev_batches[i % n_rot])
+
+    # ------------------------------------------------ device-resident timing ------------------------------------------------
+    for i in range(args.warmup):
+        device_step(i)
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for i in range(args.steps):
+        device_step(i)
+    e1.record()
+    sync_all()
+    ms_total = e0.elapsed_time(e1)
+
+    # -------------------------------------------- end-to-end through the public API ------------------------------------
+    stage = {k: torch.empty_like(v, device=dev) for k, v in host_batches[0].items()}
+    stage_t = {k: torch.empty_like(v, device=dev) for k, v in host_targets[0].items()} if train else {}
+    if train:
+        out_host = {"loss": torch.empty(()).pin_memory()}
+    else:
         out_host = {"pred_logits": torch.empty(B, Lv, 1).pin_memory(), "pred_spans": torch.empty(B, Lv, 2).pin_memory(),
                     "saliency_scores": torch.empty(B, Lv).pin_memory()}
-        stage = {k: torch.empty_like(v, device=dev) for k, v in host_batches[0].items()}
 
-        def e2e_step(i):
-            hb = host_batches[i % n_rot]
-            for k in stage:
-                stage[k].copy_(hb[k], non_blocking=True)
-            out = model(**stage)
+    def e2e_step(i):
+        hb = host_batches[i % n_rot]
+        for k in stage:
+            stage[k].copy_(hb[k], non_blocking=True)
+        if train:
+            ht = host_targets[i % n_rot]
+            for k in stage_t:
+                stage_t[k].copy_(ht[k], non_blocking=True)
+            total = train_step(stage, stage_t)
+            out_host["loss"].copy_(total.detach(), non_blocking=True)  # the reference logs float(losses) every step
+        else:
+            with torch.no_grad():
+                out = model(**stage)
             for k, hbuf in out_host.items():
                 hbuf.copy_(out[k], non_blocking=True)
-            torch.cuda.current_stream().synchronize()  # the caller consumes the step's result on the host
+        torch.cuda.current_stream().synchronize()  # the caller consumes the step's result on the host
 
-        for i in range(3):
-            e2e_step(i)
-        sync_all()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for i in range(args.steps):
-            e2e_step(i)
-        f1.record()
-        sync_all()
-        ms_e2e = f0.elapsed_time(f1)
-        clocks = sampler.stop() if rank == 0 else None
+    for i in range(3):
+        e2e_step(i)
+    sync_all()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    f1.record()
+    sync_all()
+    ms_e2e = f0.elapsed_time(f1)
+    clocks = sampler.stop() if rank == 0 else None
 
-        # ------------------------------- per-kernel-class durations (CUDA events between launches) -----------------------
-        kind_ms = {0: [], 1: [], 2: []}
-        n_kind = {0: 0, 1: 0, 2: 0}
-        prof_steps = 5
-        for i in range(prof_steps):
+    # ------------------- per-kernel-class durations of the forward (CUDA events between launches) ---------------------
+    kind_ms = {0: [], 1: [], 2: []}
+    n_kind = {0: 0, 1: 0, 2: 0}
+    was_training = model.training
+    model.eval()
+    with torch.no_grad():
+        for i in range(5):
             tl = model.profile_forward(dev_batches[i % n_rot])
             acc = {0: 0.0, 1: 0.0, 2: 0.0}
             n_kind = {0: 0, 1: 0, 2: 0}
@@ -249,9 +360,10 @@ def main():
                 n_kind[kind] += 1
             for k in acc:
                 kind_ms[k].append(acc[k])
-        gemm_ms = statistics.median(kind_ms[1])
-        attn_ms = statistics.median(kind_ms[2])
-        row_ms = statistics.median(kind_ms[0])
+    model.train(was_training)
+    gemm_ms = statistics.median(kind_ms[1])
+    attn_ms = statistics.median(kind_ms[2])
+    row_ms = statistics.median(kind_ms[0])
 
     # max over ranks
     t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
@@ -265,85 +377,51 @@ def main():
         value = pairs / (ms_total * 1e-3)
         e2e_value = pairs / (ms_e2e * 1e-3)
         total_flops, enc_flops = synth.flops_forward(cfg)
+        if train:
+            total_flops, enc_flops = 3 * total_flops, 3 * enc_flops  # dgrad + wgrad
         gflops = gemm_flops_forward(cfg)
         n_gemm = max(1, n_kind[1])
         achieved_tf = gflops / (gemm_ms * 1e-3) / 1e12
         h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+        if train:
+            h2d += sum(v.numel() * v.element_size() for v in host_targets[0].values())
         d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+        step_ms = ms_total / args.steps
         line = {
-            "metric": "video-query pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": n_gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16" if args.operand_format == "fp16" else "bf16", "data": "synthetic",
-            "config": {"workload": args.workload, "batch_per_gpu": B, "global_batch": B * n_gpus, "l_vid": Lv, "l_txt": Lt,
-                       "hidden_dim": d, "nheads": cfg["nheads"], "dim_feedforward": cfg["dim_feedforward"],
+            "metric": "video-query pairs/sec" + (" (fwd+bwd)" if train else " (fwd)"), "value": value, "unit": "pairs/s",
+            "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.operand_format == "fp16" else "bf16",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "mode": wl["mode"], "batch_per_gpu": B, "global_batch": B * n_gpus, "l_vid": Lv,
+                       "l_txt": Lt, "hidden_dim": d, "nheads": cfg["nheads"], "dim_feedforward": cfg["dim_feedforward"],
                        "enc_layers": cfg["enc_layers"], "v_feat_dim": cfg["v_feat_dim"], "t_feat_dim": cfg["t_feat_dim"],
-                       "accumulate": "f32", "parallelism": f"replicas x{n_gpus} (shard by sample, no collective)",
+                       "operands": "fp16 activations/weights, bf16 gradients, f32 accumulate + statistics",
+                       "step": ("forward + criterion + backward + clip_grad_norm(0.1) + AdamW" if train else "forward"),
+                       "parallelism": (f"dp{n_gpus}: shard by sample, one flat-gradient NCCL all-reduce per step" if train
+                                       else f"replicas x{n_gpus} (shard by sample, no collective)"),
                        "l2_policy": f"{n_rot} rotating input batches ({n_rot * per_batch / 1e6:.0f} MB > 126 MB L2)",
                        "clips_per_s": value * Lv},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches_per_step * args.steps,
-            "launches_per_step": launches_per_step,
+            "gpu_launches": launches_per_step * args.steps * (3 if train else 1),
+            "launches_per_step": launches_per_step * (3 if train else 1),
             "clocks": clocks,
-            "tflops_algorithmic": total_flops / (ms_total / args.steps * 1e-3) / 1e12,
-            "encoder_tflops_pct_of_sustained_peak": 100.0 * enc_flops / (ms_total / args.steps * 1e-3) / 1e12 / peaks["tflops_sustained"],
+            "tflops_algorithmic": total_flops / (step_ms * 1e-3) / 1e12,
+            "encoder_tflops_pct_of_sustained_peak": 100.0 * enc_flops / (step_ms * 1e-3) / 1e12 / peaks["tflops_sustained"],
             "roofline": {"kernel": "gemm_tcgen05_kernel", "bound": "tensor", "achieved": achieved_tf,
                          "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["tflops_sustained"],
                          "traffic": None, "peak_source": peaks["source"] + ", sustained (kernel timed inside a step)",
+                         "scope": "forward launches of the kernel (CUDA events between launches)",
                          "launches_per_step": n_gemm, "avg_launch_us": gemm_ms / n_gemm * 1e3,
                          "flops_per_launch": gflops / n_gemm,
                          "step_share": {"gemm_ms": gemm_ms, "attention_ms": attn_ms, "row_kernels_ms": row_ms}},
         }
         if n_gpus == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(cfg, args.workload)
+            line["cpu_baseline"] = cpu_baseline(cfg, wl, args.workload)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
-
-
-def pick_threads(fn):
-    """All host cores the process may use, unless over-subscription (cgroup quota < visible cores) makes fewer threads
-    faster: time one call at a few thread counts and keep the best."""
-    try:
-        avail = len(os.sched_getaffinity(0))
-    except AttributeError:
-        avail = os.cpu_count() or 1
-    cands = sorted({c for c in (avail, avail // 2, 32, 16, 8) if 1 <= c <= avail}, reverse=True)
-    best, best_t = cands[0], None
-    with torch.no_grad():
-        for c in cands:
-            torch.set_num_threads(c)
-            fn()
-            t0 = time.perf_counter()
-            fn()
-            dt = time.perf_counter() - t0
-            if best_t is None or dt < best_t:
-                best, best_t = c, dt
-    torch.set_num_threads(best)
-    return best
-
-
-def cpu_baseline(cfg, workload):
-    """Oracle port of the reference fp32 path on the host cores, bounded sample (~10-30 s of CPU work)."""
-    from oracle import univtg_oracle as O  # checker/baseline leg only
-
-    sd = {k: v.float() for k, v in synth.make_state_dict(cfg, seed=0).items()}
-    sample_b = min(cfg["batch"], 8)
-    inp = synth.make_inputs(cfg, seed=1, batch=sample_b)
-    cores = pick_threads(lambda: O.forward(sd, cfg, **inp, dtype=torch.float32))
-    with torch.no_grad():
-        O.forward(sd, cfg, **inp, dtype=torch.float32)
-        t0 = time.perf_counter()
-        n = 0
-        while True:
-            O.forward(sd, cfg, **inp, dtype=torch.float32)
-            n += 1
-            dt = time.perf_counter() - t0
-            if dt > 10.0 or n >= 50:
-                break
-    return {"value": sample_b * n / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
-            "sample": f"{n} forwards of B={sample_b} ({workload} shape), oracle/univtg_oracle.py fp32 on {cores} torch threads"}
 
 
 if __name__ == "__main__":

@@ -83,6 +83,38 @@ int univtg_forward(univtg_plan* plan, const float* src_txt, const float* src_txt
                    const float* src_vid_mask, const float* droppath_scale, float* pred_logits, float* pred_spans,
                    float* vid_mem_proj, float* txt_mem_proj, float* saliency_scores, void* stream);
 
+/* ---- training (reference main/train_vlp_ddp.py:56-64: model(**inputs); criterion(outputs, targets); losses.backward()) ---- */
+
+/* Bytes of the training workspace (saved activations + backward scratch) for one (config, shape). */
+size_t univtg_train_workspace_bytes(const univtg_config* cfg, const univtg_shape* shape);
+/* Model.forward in training mode: same outputs as univtg_forward, keeps what backward needs in `train_ws`.
+ *   droppath_scale: NULL or [2*enc_layers, B] (see univtg_forward)
+ *   drop_masks: NULL or HOST array of 2*n_input_proj device pointers (video layers, then text layers): fp32 [rows, din_i]
+ *               input-dropout multipliers (0 or 1/(1-p)) drawn by the caller in the reference's order; entries may be NULL. */
+int univtg_forward_train(univtg_plan* plan, void* train_ws, const float* src_txt, const float* src_txt_mask,
+                         const float* src_vid, const float* src_vid_mask, const float* droppath_scale,
+                         const float* const* drop_masks, float* pred_logits, float* pred_spans, float* vid_mem_proj,
+                         float* txt_mem_proj, float* saliency_scores, void* stream);
+/* Backward of the last univtg_forward_train on (plan, train_ws).  g_*: upstream gradients of pred_logits [B,Lv,1],
+ * pred_spans [B,Lv,2], vid_mem_proj [B,Lv,d], txt_mem_proj [B,1,d] (NULL = zero).  grads: HOST array of device pointers,
+ * one ZERO-FILLED fp32 tensor per parameter in univtg_pack_weights order and in the parameter's own layout. */
+int univtg_backward(univtg_plan* plan, void* train_ws, const float* src_txt, const float* src_vid, const float* droppath_scale,
+                    const float* const* drop_masks, const float* g_logits, const float* g_spans, const float* g_vid_mem_proj,
+                    const float* g_txt_mem_proj, float* const* grads, int32_t n_grads, void* stream);
+
+/* SetCriterion for model_id=univtg (reference model/univtg.py:195-282): losses5 = {loss_b, loss_g, loss_f, loss_s_inter,
+ * loss_s_intra}.  targets as main/dataset.py:1078-1098 builds them (all f32 except saliency_pos_idx = saliency_pos_labels[:,0],
+ * int64, NULL when absent).  `scratch` (univtg_loss_scratch_bytes) carries per-loss gradients to univtg_loss_backward. */
+size_t univtg_loss_scratch_bytes(int32_t B, int32_t Lv);
+int univtg_loss_forward(const float* pred_logits, const float* pred_spans, const float* vid_mem_proj, const float* txt_mem_proj,
+                        const float* timestamp, const float* timestamp_mask, const float* timestamp_window,
+                        const float* span_labels_nn, const float* saliency_scores, const int64_t* saliency_pos_idx, int32_t B,
+                        int32_t Lv, int32_t d, float eos_coef, float temperature, float* losses5, void* scratch, void* stream);
+/* w5: device fp32 [5] = dL/d(loss_k).  Writes the gradients of the four model outputs. */
+int univtg_loss_backward(const float* w5, const float* vid_mem_proj, const float* txt_mem_proj, const int64_t* saliency_pos_idx,
+                         int32_t B, int32_t Lv, int32_t d, const void* scratch, float* d_logits, float* d_spans,
+                         float* d_vid_mem_proj, float* d_txt_mem_proj, void* stream);
+
 /* Number of kernels one univtg_forward launches (for bench accounting). */
 int univtg_forward_num_launches(const univtg_plan* plan);
 

@@ -114,14 +114,16 @@ def test_padding_invariance():
 
 def test_long_video_config5_shape_runs():
     """cfg5 (L = 1277, 6 layers): multi-tile online-softmax attention path; checked against the fp16-emulating oracle on a
-    2-sample slice (the oracle needs ~10 s for it)."""
+    1-sample slice (the oracle needs a few seconds for it)."""
     from oracle import univtg_oracle as O
 
     cfg = synth.CONFIGS["cfg5"]
     sd = synth.make_state_dict(cfg, seed=60)
-    inp = synth.make_inputs(cfg, seed=61, ragged=True, batch=2)
+    inp = synth.make_inputs(cfg, seed=61, ragged=False, batch=1)
+    inp["src_vid_mask"][0, 1100:] = 0  # some padded clips
+    inp["src_vid"][0, 1100:] = 0
     out = _run(_model(cfg, sd), inp)
-    emu = O.forward(sd, cfg, **inp, opq=O.round_fp16)
+    emu = O.forward(sd, cfg, **inp, opq=O.round_fp16, dtype=torch.float32)
     for k in ("pred_logits", "pred_spans", "saliency_scores"):
         torch.testing.assert_close(out[k].double().cpu(), emu[k], rtol=3e-4, atol=1e-4, msg=lambda m: f"cfg5/{k}: {m}")
 

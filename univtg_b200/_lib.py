@@ -49,6 +49,15 @@ SIGNATURES = {
     "univtg_plan_destroy": (None, [c_void_p]),
     "univtg_forward": (c_int, [c_void_p] * 12),
     "univtg_forward_num_launches": (c_int, [c_void_p]),
+    "univtg_train_workspace_bytes": (c_size_t, [ctypes.POINTER(Config), ctypes.POINTER(Shape)]),
+    "univtg_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "univtg_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_void_p, c_void_p,
+                                c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_int, c_void_p]),
+    "univtg_loss_scratch_bytes": (c_size_t, [c_int, c_int]),
+    "univtg_loss_forward": (c_int, [c_void_p] * 10 + [c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "univtg_loss_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p]),
     "univtg_plan_set_profiling": (c_int, [c_void_p, c_int]),
     "univtg_plan_read_profile": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "univtg_op_gemm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,

@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       const uint16_t* __restrict__ mask16 = pr.mask16;
       float* __restrict__ colsum = pr.colsum;
       const int cs32 = pr.cs32 > 1 ? pr.cs32 : 1;
+      float* __restrict__ pre32 = pr.pre32;
 
       const int m0 = ti.m_blk * GEMM_BM + wq * 32;
       const int n_base = ti.n_blk * BN + half * (BN / 2);
@@ -239,6 +240,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       float* o32i_row = out32_id ? out32_id + (size_t)m * pr.ld32_id : nullptr;
       uint16_t* o16_row = out16 ? out16 + orow * pr.ld16 : nullptr;
       uint16_t* o16p_row = out16p ? out16p + orow * pr.ld16 : nullptr;
+      float* pre_row = pre32 ? pre32 + orow * pr.ld_pre : nullptr;
 
       // bias slice of this warp's columns -> smem (broadcast reads in the column loop)
       __syncwarp();
@@ -268,6 +270,14 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
         }
         tmem_ld_wait();
         float v[16];
+        if (pre_row != nullptr && valid) {  // training: keep the pre-activation (needs N % 4 == 0, checked on the host)
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (n0 + 4 * q < pN)
+              *reinterpret_cast<float4*>(pre_row + n0 + 4 * q) = make_float4(
+                  __uint_as_float(r[4 * q]) + bias_s[c * 16 + 4 * q], __uint_as_float(r[4 * q + 1]) + bias_s[c * 16 + 4 * q + 1],
+                  __uint_as_float(r[4 * q + 2]) + bias_s[c * 16 + 4 * q + 2], __uint_as_float(r[4 * q + 3]) + bias_s[c * 16 + 4 * q + 3]);
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float x = __uint_as_float(r[j]) + bias_s[c * 16 + j];

@@ -64,6 +64,8 @@ struct GemmProblem {
   int aux_mode;            // 1: v *= gelu'(aux)   2: v *= aux (e.g. a dropout mask incl. its 1/(1-p) scale)
   const uint16_t* mask16;  // 16-bit activation indexed like out16: v = 0 where mask16 <= 0 (ReLU backward)
   int ld_mask;
+  float* pre32;            // fp32 (acc + bias) BEFORE the activation, indexed like out32 (saved for GELU backward)
+  int ld_pre;
   float* colsum;           // fp32 [N]: atomically accumulates the column sums of the stored values (bias gradients)
   int cs32;                // column stride of out32 (0/1: dense); 3 writes a Conv1d weight-gradient tap in [n, c, 3] layout
   int skip_sep;            // rows with (m % rps_in) == rps_in-1 are not stored at all

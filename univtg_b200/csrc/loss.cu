@@ -1,0 +1,343 @@
+// SetCriterion of the reference for model_id = univtg (model/univtg.py:195-282, 338-351; utils/span_utils.py:46-122):
+//   loss_b  smooth-L1 of (timestamp + pred_spans) vs span_labels_nn on foreground clips
+//   loss_g  1 - generalised temporal IoU on foreground clips (only the diagonal of the reference's N x N matrix is used)
+//   loss_f  weighted binary cross-entropy of pred_logits (foreground weight 1, valid background eos_coef)
+//   loss_s_inter / loss_s_intra  two InfoNCE terms on cosine similarities (temperature 0.07)
+// Forward computes the five losses AND the per-loss gradients w.r.t. the small model outputs; the backward kernel turns
+// the cosine-matrix gradients into gradients of vid_mem_proj / txt_mem_proj for given loss weights.
+#include <math.h>
+
+#include "kernels.h"
+#include "loss.h"
+#include "ptx.cuh"
+
+namespace uv {
+
+// ------------------------------------------------------------------------------------------------
+// kernel 1: cosines.  warps [0, B*Lv): cos_in[b,l] = cos(xv[b,l], xt[b]) and |xv[b,l]|;
+//           warps [B*Lv, B*Lv + B*B): sim[b,b'] = cos(xv[b,pos_b], xt[b'])
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) loss_cos_kernel(const LossArgs a) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_in = a.B * a.Lv;
+  if (gw >= n_in + a.B * a.B) return;
+  int bv, lv, bt;
+  if (gw < n_in) {
+    bv = gw / a.Lv;
+    lv = gw - bv * a.Lv;
+    bt = bv;
+  } else {
+    const int k = gw - n_in;
+    bv = k / a.B;
+    bt = k - bv * a.B;
+    lv = (int)a.pos_idx[bv];
+  }
+  const float* u = a.xv + ((size_t)bv * a.Lv + lv) * a.d;
+  const float* v = a.xt + (size_t)bt * a.d;
+  float dot = 0.f, nu = 0.f, nv = 0.f;
+  for (int j = lane * 4; j < a.d; j += 128) {
+    const float4 x = *reinterpret_cast<const float4*>(u + j);
+    const float4 y = *reinterpret_cast<const float4*>(v + j);
+    dot += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+    nu += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+    nv += y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
+  }
+  dot = warp_sum(dot);
+  nu = warp_sum(nu);
+  nv = warp_sum(nv);
+  if (lane == 0) {
+    const float un = fmaxf(sqrtf(nu), 1e-8f), vn = fmaxf(sqrtf(nv), 1e-8f);
+    const float c = dot / (un * vn);
+    if (gw < n_in) {
+      a.cos_in[gw] = c;
+      a.vnorm[gw] = un;
+      if (lv == 0) a.tnorm[bv] = vn;
+    } else {
+      a.sim[gw - n_in] = c;
+    }
+  }
+}
+
+// block-wide sum of one float per thread (256 threads)
+__device__ __forceinline__ float block_sum(float v, float* s_red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += s_red[i];
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 2 (single block): all five losses + gradients w.r.t. pred_spans / pred_logits / cos_in / sim.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) loss_finish_kernel(const LossArgs a) {
+  extern __shared__ float sm[];
+  float* s_rowlse = sm;                // [B]   logsumexp over l of z[b, :]
+  float* s_collse = s_rowlse + a.B;    // [B]   logsumexp over b' of z[b', pos_b]  (column pos_b)
+  float* s_irow = s_collse + a.B;      // [B]   inter: logsumexp over b' of sim[b, b'] / tau
+  float* s_icol = s_irow + a.B;        // [B]   inter: logsumexp over b of sim[b, b'] / tau
+  __shared__ float s_red[8];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int B = a.B, Lv = a.Lv, n = B * Lv;
+  const float inv_tau = 1.0f / a.temperature;
+
+  // ---- counts ----
+  float c_fg = 0.f, c_valid = 0.f, c_sal = 0.f;
+  for (int i = tid; i < n; i += nt) {
+    c_fg += (a.window[i] != 0.f) ? 1.f : 0.f;
+    c_valid += (a.tmask[i] != 0.f) ? 1.f : 0.f;
+    c_sal += a.sal[i];
+  }
+  const float n_fg = block_sum(c_fg, s_red);
+  const float n_valid = block_sum(c_valid, s_red);
+  const float sal_sum = block_sum(c_sal, s_red);
+
+  // ---- spans (loss_b, loss_g) and labels (loss_f) ----
+  float lb = 0.f, lg = 0.f, lf = 0.f;
+  for (int i = tid; i < n; i += nt) {
+    const float w = a.window[i];
+    const bool fg = w != 0.f;
+    float gb0 = 0.f, gb1 = 0.f, gg0 = 0.f, gg1 = 0.f;
+    const float s1 = a.timestamp[2 * i] + a.pred_spans[2 * i];
+    const float e1 = a.timestamp[2 * i + 1] + a.pred_spans[2 * i + 1];
+    const float s2 = a.span_gt[2 * i], e2 = a.span_gt[2 * i + 1];
+    {  // smooth L1 (beta = 1) * window, normalised by the foreground count
+      const float d0 = s1 - s2, d1 = e1 - e2;
+      const float a0 = fabsf(d0), a1 = fabsf(d1);
+      lb += ((a0 < 1.f ? 0.5f * d0 * d0 : a0 - 0.5f) + (a1 < 1.f ? 0.5f * d1 * d1 : a1 - 0.5f)) * w;
+      gb0 = (a0 < 1.f ? d0 : (d0 > 0.f ? 1.f : -1.f)) * w / n_fg;
+      gb1 = (a1 < 1.f ? d1 : (d1 > 0.f ? 1.f : -1.f)) * w / n_fg;
+    }
+    if (fg) {  // generalised IoU of (s1, e1) vs (s2, e2)
+      const float lo_i = fmaxf(s1, s2), hi_i = fminf(e1, e2);
+      const float inter_raw = hi_i - lo_i;
+      const float inter = fmaxf(inter_raw, 0.f);
+      const float uni = (e1 - s1) + (e2 - s2) - inter;
+      const float lo_e = fminf(s1, s2), hi_e = fmaxf(e1, e2);
+      const float enc_raw = hi_e - lo_e;
+      const float enc = fmaxf(enc_raw, 0.f);
+      const float giou = inter / uni - (enc - uni) / enc;
+      lg += 1.f - giou;
+      // torch tie rules: max/min split evenly on ties; clamp(min=0) passes the gradient where x >= 0
+      const float act_i = inter_raw >= 0.f ? 1.f : 0.f;
+      const float dmax_s1 = s1 > s2 ? 1.f : (s1 == s2 ? 0.5f : 0.f);   // d max(s1,s2)/d s1
+      const float dmin_e1 = e1 < e2 ? 1.f : (e1 == e2 ? 0.5f : 0.f);   // d min(e1,e2)/d e1
+      const float di_s = -act_i * dmax_s1, di_e = act_i * dmin_e1;
+      const float du_s = -1.f - di_s, du_e = 1.f - di_e;
+      const float act_e = enc_raw >= 0.f ? 1.f : 0.f;
+      const float dmin_s1 = s1 < s2 ? 1.f : (s1 == s2 ? 0.5f : 0.f);
+      const float dmax_e1 = e1 > e2 ? 1.f : (e1 == e2 ? 0.5f : 0.f);
+      const float de_s = -act_e * dmin_s1, de_e = act_e * dmax_e1;
+      // giou = inter/uni - 1 + uni/enc
+      const float dg_s = (di_s * uni - inter * du_s) / (uni * uni) + (du_s * enc - uni * de_s) / (enc * enc);
+      const float dg_e = (di_e * uni - inter * du_e) / (uni * uni) + (du_e * enc - uni * de_e) / (enc * enc);
+      gg0 = -dg_s / n_fg;
+      gg1 = -dg_e / n_fg;
+    }
+    a.g_spans_b[2 * i] = gb0;
+    a.g_spans_b[2 * i + 1] = gb1;
+    a.g_spans_g[2 * i] = gg0;
+    a.g_spans_g[2 * i + 1] = gg1;
+    {  // weighted BCE
+      const float p = a.pred_logits[i];
+      const bool valid = a.tmask[i] != 0.f;
+      const float wt = fg ? 1.f : (valid ? a.eos_coef : 0.f);
+      const float y = fg ? 1.f : 0.f;
+      float gf = 0.f;
+      if (valid) {
+        const float lp = fmaxf(logf(p), -100.f), l1p = fmaxf(logf(1.f - p), -100.f);
+        lf += -(y * lp + (1.f - y) * l1p) * wt;
+        gf = wt * (p - y) / fmaxf(p * (1.f - p), 1e-12f) / n_valid;
+      }
+      a.g_logits_f[i] = gf;
+    }
+  }
+  lb = block_sum(lb, s_red);
+  lg = block_sum(lg, s_red);
+  lf = block_sum(lf, s_red);
+  if (tid == 0) {
+    a.losses[0] = lb / n_fg;
+    a.losses[1] = lg / n_fg;
+    a.losses[2] = lf / n_valid;
+  }
+
+  // ---- saliency ----
+  if (a.pos_idx == nullptr || sal_sum == 0.f) {  // reference returns 0. for both terms
+    for (int i = tid; i < n; i += nt) a.g_cos_in[i] = 0.f;
+    for (int i = tid; i < B * B; i += nt) a.g_sim[i] = 0.f;
+    if (tid == 0) {
+      a.losses[3] = 0.f;
+      a.losses[4] = 0.f;
+    }
+    return;
+  }
+  // inter-video: sim [B, B]
+  for (int r = tid; r < 2 * B; r += nt) {
+    const int b = r % B;
+    const bool col = r >= B;
+    float mx = -INFINITY;
+    for (int k = 0; k < B; ++k) mx = fmaxf(mx, (col ? a.sim[k * B + b] : a.sim[b * B + k]) * inv_tau);
+    float s = 0.f;
+    for (int k = 0; k < B; ++k) s += expf((col ? a.sim[k * B + b] : a.sim[b * B + k]) * inv_tau - mx);
+    (col ? s_icol : s_irow)[b] = mx + logf(s);
+  }
+  __syncthreads();
+  float l_inter = 0.f;
+  for (int b = tid; b < B; b += nt) l_inter += 2.f * a.sim[b * B + b] * inv_tau - s_irow[b] - s_icol[b];
+  l_inter = block_sum(l_inter, s_red);
+  for (int i = tid; i < B * B; i += nt) {
+    const int b = i / B, k = i - b * B;
+    const float z = a.sim[i] * inv_tau;
+    const float dlt = (b == k) ? 2.f : 0.f;
+    a.g_sim[i] = -(dlt - expf(z - s_irow[b]) - expf(z - s_icol[k])) * inv_tau / (float)B;
+  }
+  // intra-video: z[b,l] = (cos_in[b,l] + log(keep + 1e-45)) / tau
+  //   keep[b,l] = ((sal[b,l] < sal[b,pos_b]) or l == pos_b) and tmask[b,l]
+  auto zval = [&](int b, int l) -> float {
+    const int p = (int)a.pos_idx[b];
+    const bool keep = ((a.sal[b * Lv + l] < a.sal[b * Lv + p]) || (l == p)) && (a.tmask[b * Lv + l] != 0.f);
+    return (a.cos_in[b * Lv + l] + logf((keep ? 1.f : 0.f) + 1e-45f)) * inv_tau;
+  };
+  for (int r = tid; r < 2 * B; r += nt) {
+    const int b = r % B;
+    if (r < B) {  // row b: over l
+      float mx = -INFINITY;
+      for (int l = 0; l < Lv; ++l) mx = fmaxf(mx, zval(b, l));
+      float s = 0.f;
+      for (int l = 0; l < Lv; ++l) s += expf(zval(b, l) - mx);
+      s_rowlse[b] = mx + logf(s);
+    } else {  // column pos_b: over samples b'
+      const int p = (int)a.pos_idx[b];
+      float mx = -INFINITY;
+      for (int k = 0; k < B; ++k) mx = fmaxf(mx, zval(k, p));
+      float s = 0.f;
+      for (int k = 0; k < B; ++k) s += expf(zval(k, p) - mx);
+      s_collse[b] = mx + logf(s);
+    }
+  }
+  __syncthreads();
+  float l_intra = 0.f;
+  for (int b = tid; b < B; b += nt) {
+    const float zp = zval(b, (int)a.pos_idx[b]);
+    l_intra += 2.f * zp - s_rowlse[b] - s_collse[b];
+  }
+  l_intra = block_sum(l_intra, s_red);
+  for (int i = tid; i < n; i += nt) {
+    const int b = i / Lv, l = i - b * Lv;
+    const float z = zval(b, l);
+    // d/dz[b,l] of -(1/B) sum_b'' [ z[b'',p''] - rowlse[b''] + z[b'',p''] - collse(p'')[b''] ]
+    float g = -expf(z - s_rowlse[b]);
+    if (l == (int)a.pos_idx[b]) g += 2.f;
+    for (int k = 0; k < B; ++k)
+      if ((int)a.pos_idx[k] == l) g -= expf(z - s_collse[k]);
+    a.g_cos_in[i] = -g * inv_tau / (float)B;
+  }
+  if (tid == 0) {
+    a.losses[3] = -l_inter / (float)B;
+    a.losses[4] = -l_intra / (float)B;
+  }
+}
+
+int launch_loss_forward(const LossArgs& a, cudaStream_t stream) {
+  if (a.pos_idx != nullptr) {
+    const int warps = a.B * a.Lv + a.B * a.B;
+    loss_cos_kernel<<<(warps * 32 + 255) / 256, 256, 0, stream>>>(a);
+  }
+  loss_finish_kernel<<<1, 256, (size_t)4 * a.B * sizeof(float), stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) set_error("loss forward launch failed: %s", cudaGetErrorString(e));
+  return (int)e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: weights w[5] (dL/d loss_k) -> gradients of the model outputs.
+//   d cos(u, v)/du = v / (|u||v|) - cos * u / |u|^2
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) loss_bwd_small_kernel(const LossBwdArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = a.B * a.Lv;
+  if (i >= n) return;
+  const float wb = a.w[0], wg = a.w[1], wf = a.w[2];
+  a.d_logits[i] = wf * a.g_logits_f[i];
+  a.d_spans[2 * i] = wb * a.g_spans_b[2 * i] + wg * a.g_spans_g[2 * i];
+  a.d_spans[2 * i + 1] = wb * a.g_spans_b[2 * i + 1] + wg * a.g_spans_g[2 * i + 1];
+}
+
+// one warp per (b, l): d xv[b, l, :]
+__global__ void __launch_bounds__(256) loss_bwd_vid_kernel(const LossBwdArgs a) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= a.B * a.Lv) return;
+  const int b = gw / a.Lv, l = gw - b * a.Lv;
+  const float w_inter = a.w[3], w_intra = a.w[4];
+  const float un = a.vnorm[gw];
+  const float gi = w_intra * a.g_cos_in[gw];
+  const float ci = a.cos_in[gw];
+  const bool is_pos = a.pos_idx != nullptr && (int)a.pos_idx[b] == l;
+  const float* u = a.xv + (size_t)gw * a.d;
+  float* out = a.d_xv + (size_t)gw * a.d;
+  for (int j = lane * 4; j < a.d; j += 128) {
+    const float4 x = *reinterpret_cast<const float4*>(u + j);
+    const float4 t = *reinterpret_cast<const float4*>(a.xt + (size_t)b * a.d + j);
+    const float s1 = gi / (un * a.tnorm[b]);
+    float s2 = gi * ci / (un * un);
+    float4 o = make_float4(s1 * t.x, s1 * t.y, s1 * t.z, s1 * t.w);
+    if (is_pos) {
+      for (int k = 0; k < a.B; ++k) {
+        const float gx = w_inter * a.g_sim[b * a.B + k];
+        const float4 tk = *reinterpret_cast<const float4*>(a.xt + (size_t)k * a.d + j);
+        const float c1 = gx / (un * a.tnorm[k]);
+        o.x += c1 * tk.x;
+        o.y += c1 * tk.y;
+        o.z += c1 * tk.z;
+        o.w += c1 * tk.w;
+        s2 += gx * a.sim[b * a.B + k] / (un * un);
+      }
+    }
+    o.x -= s2 * x.x;
+    o.y -= s2 * x.y;
+    o.z -= s2 * x.z;
+    o.w -= s2 * x.w;
+    *reinterpret_cast<float4*>(out + j) = o;
+  }
+}
+
+// one block per sample b: d xt[b, :]
+__global__ void __launch_bounds__(256) loss_bwd_txt_kernel(const LossBwdArgs a) {
+  const int b = blockIdx.x;
+  const float w_inter = a.w[3], w_intra = a.w[4];
+  const float tn = a.tnorm[b];
+  for (int j = threadIdx.x; j < a.d; j += blockDim.x) {
+    const float tj = a.xt[(size_t)b * a.d + j];
+    float o = 0.f;
+    for (int l = 0; l < a.Lv; ++l) {
+      const int i = b * a.Lv + l;
+      const float g = w_intra * a.g_cos_in[i];
+      if (g != 0.f) o += g * (a.xv[(size_t)i * a.d + j] / (a.vnorm[i] * tn) - a.cos_in[i] * tj / (tn * tn));
+    }
+    if (a.pos_idx != nullptr) {
+      for (int k = 0; k < a.B; ++k) {
+        const float g = w_inter * a.g_sim[k * a.B + b];
+        const int i = k * a.Lv + (int)a.pos_idx[k];
+        o += g * (a.xv[(size_t)i * a.d + j] / (a.vnorm[i] * tn) - a.sim[k * a.B + b] * tj / (tn * tn));
+      }
+    }
+    a.d_xt[(size_t)b * a.d + j] = o;
+  }
+}
+
+int launch_loss_backward(const LossBwdArgs& a, cudaStream_t stream) {
+  const int n = a.B * a.Lv;
+  loss_bwd_small_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a);
+  loss_bwd_vid_kernel<<<(n * 32 + 255) / 256, 256, 0, stream>>>(a);
+  loss_bwd_txt_kernel<<<a.B, 256, 0, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) set_error("loss backward launch failed: %s", cudaGetErrorString(e));
+  return (int)e;
+}
+
+}  // namespace uv

@@ -1,0 +1,336 @@
+// Shared between api.cu (inference orchestration) and train.cu (training forward/backward): packed-weight layout,
+// workspace layout and the plan object behind the opaque univtg_plan handle.
+#pragma once
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/univtg_b200.h"
+#include "backward.h"
+#include "kernels.h"
+#include "loss.h"
+#include "ptx.cuh"
+#include "rowops.h"
+
+using namespace uv;
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int pad64(int k) { return (k + 63) / 64 * 64; }
+
+// ------------------------------------------------------------------------------------------------
+// packed-weight layout
+// ------------------------------------------------------------------------------------------------
+struct ProjPacked {
+  size_t ln_w, ln_b;  // fp32 [din]
+  size_t w16;         // 16-bit [d, kpad]
+  size_t bias;        // fp32 [d]  (last layer: linear bias + token-type embedding row)
+  int din, kpad;
+};
+struct LayerPacked {
+  size_t w_in;   // 16-bit [3d, d]  (rows: Wq, Wk, Wv)
+  size_t b_in;   // fp32 [3d]
+  size_t w_out;  // 16-bit [d, d]
+  size_t b_out;
+  size_t w1, b1;  // [ff, d], [ff]
+  size_t w2, b2;  // [d, ff], [d]
+  size_t n1w, n1b, n2w, n2b;
+};
+struct PackedLayout {
+  ProjPacked vid[3], txt[3];
+  LayerPacked layer[16];
+  size_t conv1_w, conv1_b;                     // fused first conv of both heads: 16-bit [2d, 3d] (rows: class, span), fp32 [2d]
+  size_t conv2c_w, conv2c_b, conv2s_w, conv2s_b;  // 16-bit [d, 3d], fp32 [d]
+  size_t conv3c_w, conv3c_b, conv3s_w, conv3s_b;  // fp32 [3][d], [1], [2][3][d], [2]
+  size_t pool_w;                                  // fp32 [d]
+  size_t total;
+};
+
+struct Cursor {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  }
+};
+
+bool check_cfg(const univtg_config* c) {
+  if (!c) {
+    set_error("null config");
+    return false;
+  }
+  if (c->hidden_dim <= 0 || c->hidden_dim % 64 != 0) {
+    set_error("hidden_dim %d must be a positive multiple of 64", c->hidden_dim);
+    return false;
+  }
+  if (c->nheads <= 0 || c->hidden_dim % c->nheads != 0) {
+    set_error("nheads %d must divide hidden_dim %d", c->nheads, c->hidden_dim);
+    return false;
+  }
+  if (c->dim_feedforward <= 0 || c->dim_feedforward % 64 != 0) {
+    set_error("dim_feedforward %d must be a positive multiple of 64", c->dim_feedforward);
+    return false;
+  }
+  if (c->enc_layers < 1 || c->enc_layers > 16) {
+    set_error("enc_layers %d out of range [1,16]", c->enc_layers);
+    return false;
+  }
+  if (c->n_input_proj < 1 || c->n_input_proj > 3) {
+    set_error("n_input_proj %d out of range [1,3]", c->n_input_proj);
+    return false;
+  }
+  if (c->v_feat_dim <= 0 || c->t_feat_dim <= 0) {
+    set_error("feature dims must be positive");
+    return false;
+  }
+  if (c->operand_format != 0 && c->operand_format != 1) {
+    set_error("operand_format %d must be 0 (fp16) or 1 (bf16)", c->operand_format);
+    return false;
+  }
+  return true;
+}
+
+PackedLayout make_layout(const univtg_config& c) {
+  PackedLayout L;
+  memset(&L, 0, sizeof(L));
+  Cursor cur;
+  const int d = c.hidden_dim, ff = c.dim_feedforward;
+  for (int s = 0; s < 2; ++s) {
+    ProjPacked* pp = s == 0 ? L.vid : L.txt;
+    int din = s == 0 ? c.v_feat_dim : c.t_feat_dim;
+    for (int i = 0; i < c.n_input_proj; ++i) {
+      pp[i].din = din;
+      pp[i].kpad = pad64(din);
+      pp[i].ln_w = cur.take((size_t)din * 4);
+      pp[i].ln_b = cur.take((size_t)din * 4);
+      pp[i].w16 = cur.take((size_t)d * pp[i].kpad * 2);
+      pp[i].bias = cur.take((size_t)d * 4);
+      din = d;
+    }
+  }
+  for (int l = 0; l < c.enc_layers; ++l) {
+    LayerPacked& lp = L.layer[l];
+    lp.w_in = cur.take((size_t)3 * d * d * 2);
+    lp.b_in = cur.take((size_t)3 * d * 4);
+    lp.w_out = cur.take((size_t)d * d * 2);
+    lp.b_out = cur.take((size_t)d * 4);
+    lp.w1 = cur.take((size_t)ff * d * 2);
+    lp.b1 = cur.take((size_t)ff * 4);
+    lp.w2 = cur.take((size_t)d * ff * 2);
+    lp.b2 = cur.take((size_t)d * 4);
+    lp.n1w = cur.take((size_t)d * 4);
+    lp.n1b = cur.take((size_t)d * 4);
+    lp.n2w = cur.take((size_t)d * 4);
+    lp.n2b = cur.take((size_t)d * 4);
+  }
+  L.conv1_w = cur.take((size_t)2 * d * 3 * d * 2);
+  L.conv1_b = cur.take((size_t)2 * d * 4);
+  L.conv2c_w = cur.take((size_t)d * 3 * d * 2);
+  L.conv2c_b = cur.take((size_t)d * 4);
+  L.conv2s_w = cur.take((size_t)d * 3 * d * 2);
+  L.conv2s_b = cur.take((size_t)d * 4);
+  L.conv3c_w = cur.take((size_t)3 * d * 4);
+  L.conv3c_b = cur.take(4);
+  L.conv3s_w = cur.take((size_t)2 * 3 * d * 4);
+  L.conv3s_b = cur.take(8);
+  L.pool_w = cur.take((size_t)d * 4);
+  L.total = cur.off;
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_rows_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int rows, int cols, int ld, int fmt) {
+  const size_t total = (size_t)rows * ld;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ld), c = (int)(i % ld);
+    dst[i] = c < cols ? cvt16(src[(size_t)r * cols + c], fmt) : (uint16_t)0;
+  }
+}
+// Conv1d weight [N, C, 3] -> 16-bit [N, 3*C] with dst[n, t*C + c] = src[n, c, t]
+__global__ void pack_conv_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int N, int C, int fmt) {
+  const size_t total = (size_t)N * 3 * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / (3 * C));
+    const int rem = (int)(i % (3 * C));
+    const int t = rem / C, c = rem % C;
+    dst[i] = cvt16(src[((size_t)n * C + c) * 3 + t], fmt);
+  }
+}
+// Conv1d weight [N, C, 3] -> fp32 [N, 3, C]
+__global__ void pack_conv_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int C) {
+  const size_t total = (size_t)N * 3 * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / (3 * C));
+    const int rem = (int)(i % (3 * C));
+    const int t = rem / C, c = rem % C;
+    dst[i] = src[((size_t)n * C + c) * 3 + t];
+  }
+}
+__global__ void copy_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ dst, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = a[i] + (b ? b[i] : 0.f);
+}
+
+inline int grid_for(size_t total) {
+  size_t g = (total + 255) / 256;
+  return (int)(g > 1184 ? 1184 : (g < 1 ? 1 : g));
+}
+
+struct Packer {
+  uint8_t* base;
+  int fmt;
+  cudaStream_t st;
+  void rows(const float* src, size_t off, int rows_, int cols, int ld) {
+    pack_rows_kernel<<<grid_for((size_t)rows_ * ld), 256, 0, st>>>(src, reinterpret_cast<uint16_t*>(base + off), rows_, cols, ld, fmt);
+  }
+  void conv(const float* src, size_t off, int N, int C) {
+    pack_conv_kernel<<<grid_for((size_t)N * 3 * C), 256, 0, st>>>(src, reinterpret_cast<uint16_t*>(base + off), N, C, fmt);
+  }
+  void conv_f32(const float* src, size_t off, int N, int C) {
+    pack_conv_f32_kernel<<<grid_for((size_t)N * 3 * C), 256, 0, st>>>(src, reinterpret_cast<float*>(base + off), N, C);
+  }
+  void vec(const float* src, size_t off, int n, const float* add = nullptr) {
+    copy_add_kernel<<<grid_for(n), 256, 0, st>>>(src, add, reinterpret_cast<float*>(base + off), n);
+  }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+struct univtg_plan {
+  univtg_config cfg;
+  univtg_shape shp;
+  PackedLayout lay;
+  const uint8_t* packed;
+  uint8_t* ws;
+  const float* dim_t;
+  int num_sms;
+  int B, Lv, Lt, L, d, ff, H, dh, M, Mv, Mt, Mh;
+  // workspace pointers
+  uint16_t *a_vid[3], *a_txt[3];  // LN'd 16-bit projector inputs
+  float *p_vid32, *p_txt32;       // fp32 projector hidden (between projector layers)
+  float* txtproj32;               // [Mt, d] projected text tokens (+type embedding)
+  float* pos;                     // [Mv, d]
+  float* key_mask;                // [B, L]
+  float* pool_logits;             // [B, Lt]
+  float *x32, *y32;               // residual stream / pre-LayerNorm sum
+  uint16_t *x16, *xpos16, *qkv16, *attn16, *h16;
+  uint16_t *hA, *h1, *hc2, *hs2;  // conv-head buffers (separated layout)
+  // launch descriptors
+  GemmGroup g_proj[3];
+  GemmGroup g_qkv[16], g_out[16], g_ffn1[16], g_ffn2[16];
+  GemmGroup g_conv1, g_conv2;
+  AttnArgs attn[16];
+  int bn_proj[3], bn_main;
+  int launches;
+  // optional per-launch CUDA-event timeline (bench / profiling only)
+  int profiling;
+  int n_marks;
+  cudaEvent_t marks[160];
+  int mark_kind[160];  // kind of the launch that ENDS at mark i (i >= 1): 0 row kernel, 1 tcgen05 GEMM, 2 attention
+};
+
+namespace {
+inline void prof_begin(univtg_plan* P, cudaStream_t st) {
+  if (!P->profiling) return;
+  P->n_marks = 0;
+  if (!P->marks[0]) cudaEventCreate(&P->marks[0]);
+  cudaEventRecord(P->marks[0], st);
+  P->mark_kind[0] = -1;
+  P->n_marks = 1;
+}
+inline void prof_mark(univtg_plan* P, cudaStream_t st, int kind) {
+  if (!P->profiling || P->n_marks >= 160) return;
+  const int i = P->n_marks;
+  if (!P->marks[i]) cudaEventCreate(&P->marks[i]);
+  cudaEventRecord(P->marks[i], st);
+  P->mark_kind[i] = kind;
+  P->n_marks = i + 1;
+}
+}  // namespace
+
+namespace {
+
+void init_problem(GemmProblem& p) {
+  memset(&p, 0, sizeof(p));
+  p.taps = 1;
+  p.ksplit = 1;
+  p.alpha = 1.f;
+  p.a_fmt = p.b_fmt = p.out_fmt = -1;
+  // default coordinate rules: K-major A [M,K] and B [N,K]
+  p.ca = OperandCoord{0, 0, 0, 1, 0, 1, 0, 0};
+  p.cb = OperandCoord{0, 0, 0, 1, 0, 1, 0, 0};
+}
+
+// K-major linear problem: A [M, K] (pitch lda), W [N, K] (pitch ldw), K multiple of 64.
+int setup_linear(GemmProblem& p, const uint16_t* A, int M, int K, int lda, const uint16_t* W, int N, int ldw, int bn) {
+  init_problem(p);
+  p.M = M;
+  p.N = N;
+  p.kblk_per_tap = K / 64;
+  if (K % 64 != 0) {
+    set_error("setup_linear: K %d not a multiple of 64", K);
+    return 1;
+  }
+  if (make_tmap_2d(&p.tm_a, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM, 64)) return 1;
+  if (make_tmap_2d(&p.tm_b, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn, 64)) return 1;
+  return 0;
+}
+
+}  // namespace
+
+
+namespace {
+
+struct WsLayout {
+  size_t a_vid[3], a_txt[3], p_vid32, p_txt32, txtproj32, pos, key_mask, pool_logits, x32, y32, x16, xpos16, qkv16, attn16, h16, hA,
+      h1, hc2, hs2, total;
+};
+
+WsLayout make_ws(const univtg_config& c, const univtg_shape& s, const PackedLayout& L) {
+  WsLayout w;
+  memset(&w, 0, sizeof(w));
+  Cursor cur;
+  const size_t d = c.hidden_dim, ff = c.dim_feedforward;
+  const size_t B = s.batch, Lv = s.l_vid, Lt = s.l_txt, Lc = Lv + Lt;
+  const size_t M = B * Lc, Mv = B * Lv, Mt = B * Lt, Mh = B * (Lv + 1);
+  for (int i = 0; i < c.n_input_proj; ++i) {
+    w.a_vid[i] = cur.take(Mv * L.vid[i].kpad * 2);
+    w.a_txt[i] = cur.take(Mt * L.txt[i].kpad * 2);
+  }
+  w.p_vid32 = cur.take(Mv * d * 4);
+  w.p_txt32 = cur.take(Mt * d * 4);
+  w.txtproj32 = cur.take(Mt * d * 4);
+  w.pos = cur.take(Mv * d * 4);
+  w.key_mask = cur.take(B * Lc * 4);
+  w.pool_logits = cur.take(B * Lt * 4);
+  w.x32 = cur.take(M * d * 4);
+  w.y32 = cur.take(M * d * 4);
+  w.x16 = cur.take(M * d * 2);
+  w.xpos16 = cur.take(M * d * 2);
+  w.qkv16 = cur.take(M * 3 * d * 2);
+  w.attn16 = cur.take(M * d * 2);
+  w.h16 = cur.take(M * ff * 2);
+  w.hA = cur.take((Mh + 2) * d * 2);
+  w.h1 = cur.take((Mh + 2) * 2 * d * 2);
+  w.hc2 = cur.take((Mh + 2) * d * 2);
+  w.hs2 = cur.take((Mh + 2) * d * 2);
+  w.total = cur.off;
+  return w;
+}
+
+bool check_shape(const univtg_shape* s) {
+  if (!s || s->batch < 1 || s->l_vid < 1 || s->l_txt < 1) {
+    set_error("bad shape");
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+

@@ -34,6 +34,10 @@ struct LnStore {
   }
   __device__ __forceinline__ void store4(int j, float4 v) const {
     if (a.out32) *reinterpret_cast<float4*>(a.out32 + (size_t)row * a.d + j) = v;
+    if (a.mul32) {
+      const float4 m = *reinterpret_cast<const float4*>(a.mul32 + (size_t)row * a.d + j);
+      v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+    }
     uint2 pk;
     pk.x = cvt16x2(v.x, v.y, a.fmt);
     pk.y = cvt16x2(v.z, v.w, a.fmt);
@@ -51,6 +55,7 @@ struct LnStore {
   }
   __device__ __forceinline__ void store1(int j, float v) const {
     if (a.out32) a.out32[(size_t)row * a.d + j] = v;
+    if (a.mul32) v *= a.mul32[(size_t)row * a.d + j];
     const uint16_t h = cvt16(v, a.fmt);
     if (a.out16) a.out16[(size_t)row * a.ld16 + j] = h;
     if (a.out16p) a.out16p[(size_t)row * a.ld16 + j] = has_pos ? cvt16(v + a.pos[prow * a.d + j], a.fmt) : h;

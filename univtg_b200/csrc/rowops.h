@@ -22,6 +22,7 @@ struct LnArgs {
   int ld16;
   const float* pos;    // [B*Lv, d] fp32 sine table (row b*Lv + l)
   uint16_t* outc;      // conv-head layout: row 1 + b*(Lv+1) + l of a [B*(Lv+1)+2, d] buffer (video rows only)
+  const float* mul32;  // [rows, d] multiplier applied to the 16-bit outputs only (input-dropout mask incl. 1/(1-p)), or null
   float* mean_out;     // [rows] (training)
   float* rstd_out;     // [rows]
 };

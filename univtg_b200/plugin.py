@@ -230,6 +230,38 @@ class Model(nn.Module):
         except Exception:
             pass
 
+    def _get_train_ws(self, B, Lv, Lt):
+        """Training workspace (saved activations + backward scratch), one per shape bucket, zero-filled once."""
+        lib = _lib.load_library()
+        key = (B, Lv, Lt)
+        cache = self.__dict__.setdefault("_train_ws", {})
+        ws = cache.get(key)
+        if ws is None:
+            if len(cache) >= 4:
+                cache.pop(next(iter(cache)))
+            shp = _lib.Shape(B, Lv, Lt, 1)
+            nbytes = lib.univtg_train_workspace_bytes(ctypes.byref(self._cfg), ctypes.byref(shp))
+            if nbytes == 0:
+                raise RuntimeError("univtg_b200: " + _lib.last_error())
+            ws = torch.zeros(nbytes, dtype=torch.uint8, device=self._device())
+            cache[key] = ws
+        return ws
+
+    def _grad_buffer(self):
+        """One flat fp32 gradient buffer with a view per parameter (C-ABI order); also the all-reduce payload."""
+        params = self._abi_params()
+        buf = self.__dict__.get("_flat_grad")
+        total = sum(p.numel() for p in params)
+        if buf is None or buf[0].device != self._device() or buf[0].numel() != total:
+            flat = torch.zeros(total, dtype=torch.float32, device=self._device())
+            views, off = [], 0
+            for p in params:
+                views.append(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            buf = (flat, views)
+            self.__dict__["_flat_grad"] = buf
+        return buf
+
     def _get_dim_t(self, dev):
         if self._dim_t is None or self._dim_t.device != dev:
             # PositionEmbeddingSine (model/position_encoding.py:72-75), evaluated with the same fp32 torch expression
