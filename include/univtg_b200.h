@@ -141,6 +141,12 @@ int univtg_op_layernorm(const float* in, int32_t rows, int32_t d, const float* g
 int univtg_op_attention(const void* qkv, const float* key_mask, void* out, float* lse, int32_t B, int32_t L, int32_t H,
                         int32_t dh, int32_t fmt, int32_t impl, void* stream);
 
+/* Attention core backward.  qkv as above; dO [B*L,d] bf16 gradient of `out`; O = forward output (16-bit, fmt_act);
+ * lse from the forward; delta_ws [B,H,L] f32 scratch; dqkv32 [B*L,3d] f32 receives dQ | dK | dV.  impl: 0 tcgen05, 1 SIMT. */
+int univtg_op_attention_bwd(const void* qkv, const void* dO, const void* O, const float* key_mask, const float* lse,
+                            float* delta_ws, float* dqkv32, int32_t B, int32_t L, int32_t H, int32_t dh, int32_t fmt_act,
+                            int32_t impl, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -108,6 +108,45 @@ def case_attention(B, L, H, dh, fmt, impl):
     return res
 
 
+def case_attention_bwd(B, L, H, dh, fmt, impl):
+    import torch
+    from univtg_b200 import _lib
+    lib = _lib.load_library()
+    d = H * dh
+    g = torch.Generator(device="cpu").manual_seed(321)
+    q = torch.randn(B, L, H, dh, generator=g).cuda()
+    k = torch.randn(B, L, H, dh, generator=g).cuda()
+    v = torch.randn(B, L, H, dh, generator=g).cuda()
+    dO = (torch.randn(B, L, H, dh, generator=g) * 1e-3).cuda()
+    lens = torch.randint(max(1, L // 3), L + 1, (B,), generator=g)
+    lens[0] = L
+    mask = (torch.arange(L)[None, :] < lens[:, None]).float().cuda()
+    q16, k16, v16 = _t16(q, fmt), _t16(k, fmt), _t16(v, fmt)
+    dO16 = dO.to(torch.bfloat16)
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q16, k16, v16))
+    s = torch.einsum("bihc,bjhc->bhij", qf, kf) * (dh ** -0.5)
+    s = s.masked_fill(mask[:, None, None, :] == 0, float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    o = torch.einsum("bhij,bjhc->bihc", p, vf)
+    o.backward(dO16.float())
+    lse = torch.logsumexp(s, dim=-1).detach().contiguous()
+    qkv = torch.cat([q16.reshape(B * L, d), k16.reshape(B * L, d), v16.reshape(B * L, d)], dim=1).contiguous()
+    O16 = _t16(o.detach(), fmt).reshape(B * L, d).contiguous()
+    delta = torch.zeros(B, H, L, device="cuda")
+    dqkv = torch.full((B * L, 3 * d), float("nan"), device="cuda")
+    rc = lib.univtg_op_attention_bwd(_lib.ptr(qkv), _lib.ptr(dO16.reshape(B * L, d).contiguous()), _lib.ptr(O16), _lib.ptr(mask),
+                                     _lib.ptr(lse), _lib.ptr(delta), _lib.ptr(dqkv), B, L, H, dh, fmt, impl, _lib.stream_ptr())
+    _lib.check(rc, "op_attention_bwd")
+    torch.cuda.synchronize()
+    res = {"ok": True}
+    for name, ref, got in (("dq", qf.grad, dqkv[:, :d]), ("dk", kf.grad, dqkv[:, d:2 * d]), ("dv", vf.grad, dqkv[:, 2 * d:])):
+        ref = ref.reshape(B * L, d)
+        rel = ((got - ref).norm() / ref.norm()).item()
+        res[name + "_rel"] = rel
+        res["ok"] = bool(res["ok"] and rel < 2e-2 and bool(torch.isfinite(got).all()))
+    return res
+
+
 CASES = {
     # name: (fn, args)
     "gemm_k_small_fp16_bn128": (case_gemm, (128, 128, 64, 0, 0, 0, 128, 1, 0, False)),
@@ -133,6 +172,11 @@ CASES = {
     "attn_tc_dh128_L300": (case_attention, (2, 300, 2, 128, 0, 0)),
     "attn_tc_dh64_L182_bf16": (case_attention, (2, 182, 4, 64, 1, 0)),
     "attn_tc_dh128_L1277": (case_attention, (1, 1277, 8, 128, 0, 0)),
+    "attnbwd_simt_dh32": (case_attention_bwd, (2, 27, 4, 32, 0, 1)),
+    "attnbwd_simt_dh128": (case_attention_bwd, (2, 107, 2, 128, 0, 1)),
+    "attnbwd_tc_dh128_L107": (case_attention_bwd, (3, 107, 4, 128, 0, 0)),
+    "attnbwd_tc_dh128_L182": (case_attention_bwd, (2, 182, 2, 128, 0, 0)),
+    "attnbwd_tc_dh64_L300_bf16": (case_attention_bwd, (2, 300, 4, 64, 1, 0)),
 }
 
 

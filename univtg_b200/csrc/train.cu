@@ -934,6 +934,43 @@ LossScratch make_loss_scratch(int B, int Lv, uint8_t* base) {
 }
 }  // namespace
 
+int univtg_op_attention_bwd(const void* qkv, const void* dO, const void* O, const float* key_mask, const float* lse,
+                            float* delta_ws, float* dqkv32, int32_t B, int32_t L, int32_t H, int32_t dh, int32_t fmt_act,
+                            int32_t impl, void* stream) {
+  if (!qkv || !dO || !O || !key_mask || !lse || !delta_ws || !dqkv32) {
+    set_error("univtg_op_attention_bwd: null argument");
+    return 1;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int d = H * dh, M = B * L;
+  int rc = launch_attn_delta(reinterpret_cast<const uint16_t*>(dO), FMT_BF16, reinterpret_cast<const uint16_t*>(O), fmt_act,
+                             delta_ws, B, L, H, dh, st);
+  if (rc) return rc;
+  AttnBwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.qkv = reinterpret_cast<const uint16_t*>(qkv);
+  a.dO = reinterpret_cast<const uint16_t*>(dO);
+  a.key_mask = key_mask;
+  a.lse = lse;
+  a.delta = delta_ws;
+  a.dqkv32 = dqkv32;
+  a.scale = 1.0f / sqrtf((float)dh);
+  a.B = B;
+  a.L = L;
+  a.H = H;
+  a.dh = dh;
+  a.d = d;
+  a.fmt_act = fmt_act;
+  a.fmt_grad = FMT_BF16;
+  const bool tc = impl == 0;
+  a.dq_atomic = (!tc || (L + 127) / 128 > 1) ? 1 : 0;
+  if (a.dq_atomic) cudaMemsetAsync(dqkv32, 0, (size_t)M * 3 * d * 4, st);
+  if (!tc) return launch_attention_bwd_simt(a, st);
+  if (make_tmap_2d(&a.tm_qkv, qkv, (uint64_t)M, (uint64_t)3 * d, (uint64_t)3 * d, 128, 64)) return 1;
+  if (make_tmap_2d(&a.tm_do, dO, (uint64_t)M, (uint64_t)d, (uint64_t)d, 128, 64)) return 1;
+  return launch_attention_bwd(a, st);
+}
+
 size_t univtg_loss_scratch_bytes(int32_t B, int32_t Lv) { return make_loss_scratch(B, Lv, nullptr).total; }
 
 int univtg_loss_forward(const float* pred_logits, const float* pred_spans, const float* vid_mem_proj, const float* txt_mem_proj,
