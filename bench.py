@@ -308,38 +308,59 @@ def main():
     ms_total = e0.elapsed_time(e1)
 
     # -------------------------------------------- end-to-end through the public API ------------------------------------
-    stage = {k: torch.empty_like(v, device=dev) for k, v in host_batches[0].items()}
-    stage_t = {k: torch.empty_like(v, device=dev) for k, v in host_targets[0].items()} if train else {}
+    # Every step copies ITS inputs from pinned host memory and reads ITS result back on the host.  The H2D copy of step
+    # i+1 is issued on a side stream while step i computes (two staging slots) - the pipelining any input loop would do.
+    n_slot = 2
+    stage = [{k: torch.empty_like(v, device=dev) for k, v in host_batches[0].items()} for _ in range(n_slot)]
+    stage_t = [{k: torch.empty_like(v, device=dev) for k, v in host_targets[0].items()} if train else {} for _ in range(n_slot)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in range(n_slot)]   # staging slot filled
+    freed = [torch.cuda.Event() for _ in range(n_slot)]   # staging slot consumed by compute
     if train:
         out_host = {"loss": torch.empty(()).pin_memory()}
     else:
         out_host = {"pred_logits": torch.empty(B, Lv, 1).pin_memory(), "pred_spans": torch.empty(B, Lv, 2).pin_memory(),
                     "saliency_scores": torch.empty(B, Lv).pin_memory()}
 
-    def e2e_step(i):
-        hb = host_batches[i % n_rot]
-        for k in stage:
-            stage[k].copy_(hb[k], non_blocking=True)
-        if train:
-            ht = host_targets[i % n_rot]
-            for k in stage_t:
-                stage_t[k].copy_(ht[k], non_blocking=True)
-            total = train_step(stage, stage_t)
-            out_host["loss"].copy_(total.detach(), non_blocking=True)  # the reference logs float(losses) every step
-        else:
-            with torch.no_grad():
-                out = model(**stage)
-            for k, hbuf in out_host.items():
-                hbuf.copy_(out[k], non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller consumes the step's result on the host
+    def issue_copy(i):
+        slot = i % n_slot
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[slot])
+            hb = host_batches[i % n_rot]
+            for k in stage[slot]:
+                stage[slot][k].copy_(hb[k], non_blocking=True)
+            if train:
+                ht = host_targets[i % n_rot]
+                for k in stage_t[slot]:
+                    stage_t[slot][k].copy_(ht[k], non_blocking=True)
+            ready[slot].record(copy_stream)
 
-    for i in range(3):
-        e2e_step(i)
+    def e2e_run(n):
+        main = torch.cuda.current_stream()
+        for s_ in range(n_slot):
+            freed[s_].record(main)
+        issue_copy(0)
+        for i in range(n):
+            slot = i % n_slot
+            if i + 1 < n:
+                issue_copy(i + 1)
+            main.wait_event(ready[slot])
+            if train:
+                total = train_step(stage[slot], stage_t[slot])
+                out_host["loss"].copy_(total.detach(), non_blocking=True)  # the reference logs float(losses) every step
+            else:
+                with torch.no_grad():
+                    out = model(**stage[slot])
+                for k, hbuf in out_host.items():
+                    hbuf.copy_(out[k], non_blocking=True)
+            freed[slot].record(main)
+            main.synchronize()  # the caller consumes the step's result on the host
+
+    e2e_run(3)
     sync_all()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for i in range(args.steps):
-        e2e_step(i)
+    e2e_run(args.steps)
     f1.record()
     sync_all()
     ms_e2e = f0.elapsed_time(f1)

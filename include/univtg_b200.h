@@ -88,6 +88,7 @@ int univtg_forward(univtg_plan* plan, const float* src_txt, const float* src_txt
 /* Bytes of the training workspace (saved activations + backward scratch) for one (config, shape). */
 size_t univtg_train_workspace_bytes(const univtg_config* cfg, const univtg_shape* shape);
 /* Model.forward in training mode: same outputs as univtg_forward, keeps what backward needs in `train_ws`.
+ * Training plans must be created with operand_format = 1 (bf16 activations, weights and gradients).
  *   droppath_scale: NULL or [2*enc_layers, B] (see univtg_forward)
  *   drop_masks: NULL or HOST array of 2*n_input_proj device pointers (video layers, then text layers): fp32 [rows, din_i]
  *               input-dropout multipliers (0 or 1/(1-p)) drawn by the caller in the reference's order; entries may be NULL. */
@@ -142,7 +143,8 @@ int univtg_op_attention(const void* qkv, const float* key_mask, void* out, float
                         int32_t dh, int32_t fmt, int32_t impl, void* stream);
 
 /* Attention core backward.  qkv as above; dO [B*L,d] bf16 gradient of `out`; O = forward output (16-bit, fmt_act);
- * lse from the forward; delta_ws [B,H,L] f32 scratch; dqkv32 [B*L,3d] f32 receives dQ | dK | dV.  impl: 0 tcgen05, 1 SIMT. */
+ * lse from the forward; delta_ws [B,H,L] f32 scratch; dqkv32 [B*L,3d] f32 receives dQ | dK | dV.  impl: 0 tcgen05 (needs
+ * fmt_act = 1: one tcgen05.mma takes both operands in one 16-bit format), 1 SIMT. */
 int univtg_op_attention_bwd(const void* qkv, const void* dO, const void* O, const float* key_mask, const float* lse,
                             float* delta_ws, float* dqkv32, int32_t B, int32_t L, int32_t H, int32_t dh, int32_t fmt_act,
                             int32_t impl, void* stream);

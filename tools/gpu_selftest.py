@@ -174,8 +174,8 @@ CASES = {
     "attn_tc_dh128_L1277": (case_attention, (1, 1277, 8, 128, 0, 0)),
     "attnbwd_simt_dh32": (case_attention_bwd, (2, 27, 4, 32, 0, 1)),
     "attnbwd_simt_dh128": (case_attention_bwd, (2, 107, 2, 128, 0, 1)),
-    "attnbwd_tc_dh128_L107": (case_attention_bwd, (3, 107, 4, 128, 0, 0)),
-    "attnbwd_tc_dh128_L182": (case_attention_bwd, (2, 182, 2, 128, 0, 0)),
+    "attnbwd_tc_dh128_L107": (case_attention_bwd, (3, 107, 4, 128, 1, 0)),
+    "attnbwd_tc_dh128_L182": (case_attention_bwd, (2, 182, 2, 128, 1, 0)),
     "attnbwd_tc_dh64_L300_bf16": (case_attention_bwd, (2, 300, 4, 64, 1, 0)),
 }
 

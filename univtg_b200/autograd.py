@@ -47,7 +47,7 @@ class _UniVTGFunction(torch.autograd.Function):
         Lt = src_txt.shape[1]
         d = model.hidden_dim
         with torch.cuda.device(dev):
-            model._ensure_packed()
+            model._ensure_packed(training=True)
             plan = model._get_plan(B, Lv, Lt, True)
             ws = model._get_train_ws(B, Lv, Lt)
             txt = src_txt.detach().to(torch.float32).contiguous()

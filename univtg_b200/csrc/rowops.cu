@@ -311,9 +311,8 @@ __global__ void __launch_bounds__(128) weighted_pool_kernel(const PoolSalArgs a,
   }
   __syncthreads();
   const float inv = s_stat[0];
-  for (int l = threadIdx.x; l < a.Lt; l += 128) {
+  for (int l = threadIdx.x; l < a.Lt; l += 128) {  // each element is read and written by the same thread
     const float al = s_alpha[l] / inv;
-    __syncwarp();
     s_alpha[l] = al;
     if (a.alpha_out && blockIdx.y == 0) a.alpha_out[(size_t)b * a.Lt + l] = al;
   }

@@ -162,6 +162,10 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
   }
   cudaStream_t st = (cudaStream_t)stream;
   const univtg_config& c = P->cfg;
+  if (c.operand_format != FMT_BF16) {
+    set_error("training plans must use operand_format = 1 (bf16): gradients are bf16 and one tcgen05.mma takes A and B in one format");
+    return 1;
+  }
   const PackedLayout& Lw = P->lay;
   const uint8_t* pk = P->packed;
   auto F32 = [&](size_t off) { return reinterpret_cast<const float*>(pk + off); };
@@ -455,6 +459,10 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     return 1;
   }
   const univtg_config& c = P->cfg;
+  if (c.operand_format != FMT_BF16) {
+    set_error("training plans must use operand_format = 1 (bf16)");
+    return 1;
+  }
   if (n_grads != univtg_num_params(&c)) {
     set_error("univtg_backward: expected %d gradient tensors, got %d", univtg_num_params(&c), n_grads);
     return 1;
@@ -963,6 +971,10 @@ int univtg_op_attention_bwd(const void* qkv, const void* dO, const void* O, cons
   a.fmt_act = fmt_act;
   a.fmt_grad = FMT_BF16;
   const bool tc = impl == 0;
+  if (tc && fmt_act != FMT_BF16) {
+    set_error("univtg_op_attention_bwd: the tensor-core path needs bf16 activations (A and B of one MMA share a format)");
+    return 1;
+  }
   a.dq_atomic = (!tc || (L + 127) / 128 > 1) ? 1 : 0;
   if (a.dq_atomic) cudaMemsetAsync(dqkv32, 0, (size_t)M * 3 * d * 4, st);
   if (!tc) return launch_attention_bwd_simt(a, st);

@@ -134,12 +134,16 @@ class Model(nn.Module):
         self.weightedpool = _Params(weight=(d, 1))
         self.reset_parameters()
 
-        self._packed = None
-        self._packed_key = None
+        # eval: fp16 operands by default (11-bit significand keeps the north-star tolerance); training: bf16 operands for
+        # activations, weights AND gradients (fp16 gradients underflow, and one tcgen05.mma takes A and B in one format).
+        self._packed = {}
+        self._packed_key = {}
         self._plans = {}
         self._dim_t = None
-        self._cfg = _lib.Config(d, self.nheads, self.dim_feedforward, self.enc_layers, self.n_input_proj, self.vid_dim,
-                                self.txt_dim, self.operand_format)
+        self._cfgs = {
+            fmt: _lib.Config(d, self.nheads, self.dim_feedforward, self.enc_layers, self.n_input_proj, self.vid_dim, self.txt_dim, fmt)
+            for fmt in (0, 1)}
+        self._cfg = self._cfgs[self.operand_format]
 
     # ---- initialisation with the reference's distributions --------------------------------------------------------
     def reset_parameters(self):
@@ -194,29 +198,35 @@ class Model(nn.Module):
     def _device(self):
         return self.weightedpool.weight.device
 
-    def _ensure_packed(self):
-        """(Re)pack the fp32 parameters into the 16-bit operand buffer when any parameter changed."""
+    def _fmt(self, training):
+        return 1 if training else self.operand_format
+
+    def _ensure_packed(self, training=False):
+        """(Re)pack the fp32 parameters into the 16-bit operand buffer of the mode's format when any parameter changed."""
         lib = _lib.load_library()
+        fmt = self._fmt(training)
+        cfg = self._cfgs[fmt]
         params = self._abi_params()
         dev = self._device()
         if dev.type != "cuda":
             raise RuntimeError("univtg_b200: the model must live on a CUDA device (no CPU path); call model.to('cuda')")
         key = (dev.index,) + tuple((p.data_ptr(), p._version) for p in params)
-        if self._packed is not None and key == self._packed_key:
+        if self._packed.get(fmt) is not None and key == self._packed_key.get(fmt):
             return
         for p in params:
             if p.dtype != torch.float32 or not p.is_contiguous():
                 raise RuntimeError("univtg_b200: parameters must be contiguous float32 tensors")
-        nbytes = lib.univtg_packed_bytes(ctypes.byref(self._cfg))
+        nbytes = lib.univtg_packed_bytes(ctypes.byref(cfg))
         if nbytes == 0:
             raise RuntimeError("univtg_b200: " + _lib.last_error())
-        if self._packed is None or self._packed.device != dev or self._packed.numel() != nbytes:
-            self._packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        buf = self._packed.get(fmt)
+        if buf is None or buf.device != dev or buf.numel() != nbytes:
+            self._packed[fmt] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             self._drop_plans()  # plans hold tensor maps into the old buffer
         arr = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
-        _lib.check(lib.univtg_pack_weights(ctypes.byref(self._cfg), arr, len(params), _lib.ptr(self._packed), _lib.stream_ptr()),
+        _lib.check(lib.univtg_pack_weights(ctypes.byref(cfg), arr, len(params), _lib.ptr(self._packed[fmt]), _lib.stream_ptr()),
                    "univtg_pack_weights")
-        self._packed_key = key
+        self._packed_key[fmt] = key
 
     def _drop_plans(self):
         lib = _lib.load_library()
@@ -240,7 +250,7 @@ class Model(nn.Module):
             if len(cache) >= 4:
                 cache.pop(next(iter(cache)))
             shp = _lib.Shape(B, Lv, Lt, 1)
-            nbytes = lib.univtg_train_workspace_bytes(ctypes.byref(self._cfg), ctypes.byref(shp))
+            nbytes = lib.univtg_train_workspace_bytes(ctypes.byref(self._cfgs[1]), ctypes.byref(shp))
             if nbytes == 0:
                 raise RuntimeError("univtg_b200: " + _lib.last_error())
             ws = torch.zeros(nbytes, dtype=torch.uint8, device=self._device())
@@ -279,15 +289,17 @@ class Model(nn.Module):
             old = next(iter(self._plans))
             lib.univtg_plan_destroy(self._plans.pop(old).handle)
         dev = self._device()
+        cfg = self._cfgs[self._fmt(training)]
         shp = _lib.Shape(B, Lv, Lt, int(training))
-        nbytes = lib.univtg_workspace_bytes(ctypes.byref(self._cfg), ctypes.byref(shp))
+        nbytes = lib.univtg_workspace_bytes(ctypes.byref(cfg), ctypes.byref(shp))
         if nbytes == 0:
             raise RuntimeError("univtg_b200: " + _lib.last_error())
         e = _PlanEntry()
         e.shape = shp
         e.workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         handle = ctypes.c_void_p()
-        _lib.check(lib.univtg_plan_create(ctypes.byref(self._cfg), ctypes.byref(shp), _lib.ptr(self._packed), _lib.ptr(e.workspace),
+        _lib.check(lib.univtg_plan_create(ctypes.byref(cfg), ctypes.byref(shp), _lib.ptr(self._packed[self._fmt(training)]),
+                                          _lib.ptr(e.workspace),
                                           _lib.ptr(self._get_dim_t(dev)), _lib.stream_ptr(), ctypes.byref(handle)),
                    "univtg_plan_create")
         e.handle = handle
