@@ -88,7 +88,7 @@ int univtg_forward(univtg_plan* plan, const float* src_txt, const float* src_txt
 /* Bytes of the training workspace (saved activations + backward scratch) for one (config, shape). */
 size_t univtg_train_workspace_bytes(const univtg_config* cfg, const univtg_shape* shape);
 /* Model.forward in training mode: same outputs as univtg_forward, keeps what backward needs in `train_ws`.
- * Training plans must be created with operand_format = 1 (bf16 activations, weights and gradients).
+
  *   droppath_scale: NULL or [2*enc_layers, B] (see univtg_forward)
  *   drop_masks: NULL or HOST array of 2*n_input_proj device pointers (video layers, then text layers): fp32 [rows, din_i]
  *               input-dropout multipliers (0 or 1/(1-p)) drawn by the caller in the reference's order; entries may be NULL. */
@@ -98,10 +98,14 @@ int univtg_forward_train(univtg_plan* plan, void* train_ws, const float* src_txt
                          float* txt_mem_proj, float* saliency_scores, void* stream);
 /* Backward of the last univtg_forward_train on (plan, train_ws).  g_*: upstream gradients of pred_logits [B,Lv,1],
  * pred_spans [B,Lv,2], vid_mem_proj [B,Lv,d], txt_mem_proj [B,1,d] (NULL = zero).  grads: HOST array of device pointers,
- * one ZERO-FILLED fp32 tensor per parameter in univtg_pack_weights order and in the parameter's own layout. */
+ * one ZERO-FILLED fp32 tensor per parameter in univtg_pack_weights order and in the parameter's own layout.
+ * grad_scale: power-of-two loss scale S > 0.  Gradient GEMM operands share the plan's 16-bit format (one tcgen05.mma takes
+ * A and B in one format); with fp16 operands the intermediate gradients are carried multiplied by S so they do not
+ * underflow, and every parameter gradient is multiplied by 1/S where it is written (the results are unscaled).  Use 1 for
+ * bf16 plans. */
 int univtg_backward(univtg_plan* plan, void* train_ws, const float* src_txt, const float* src_vid, const float* droppath_scale,
                     const float* const* drop_masks, const float* g_logits, const float* g_spans, const float* g_vid_mem_proj,
-                    const float* g_txt_mem_proj, float* const* grads, int32_t n_grads, void* stream);
+                    const float* g_txt_mem_proj, float grad_scale, float* const* grads, int32_t n_grads, void* stream);
 
 /* SetCriterion for model_id=univtg (reference model/univtg.py:195-282): losses5 = {loss_b, loss_g, loss_f, loss_s_inter,
  * loss_s_intra}.  targets as main/dataset.py:1078-1098 builds them (all f32 except saliency_pos_idx = saliency_pos_labels[:,0],
@@ -133,6 +137,10 @@ int univtg_plan_read_profile(univtg_plan* plan, float* ms, int32_t* kinds, int32
 int univtg_op_gemm(const void* a, const void* b, int32_t M, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn, int32_t fmt,
                    int32_t bn, int32_t ksplit, const float* bias, int32_t act, float alpha, float* out32, void* out16,
                    void* stream);
+/* Profiling aid: when `buf` (device, >= 148*8 uint64) is non-NULL every following GEMM launch stamps %globaltimer per CTA:
+ * [0] entry, [1] setup done, [2] all TMA issued, [3] first stage landed, [4] last MMA issued, [5] accumulator ready,
+ * [6] epilogue done, [7] exit.  Pass NULL to switch it off. */
+int univtg_debug_gemm_timeline(void* buf);
 /* LayerNorm rows: in [rows,d] f32 -> out32 [rows,d] f32 and/or out16 [rows,ld16] 16-bit (zero padded). */
 int univtg_op_layernorm(const float* in, int32_t rows, int32_t d, const float* gamma, const float* beta, float eps,
                         int32_t fmt, float* out32, void* out16, int32_t ld16, void* stream);
@@ -142,9 +150,9 @@ int univtg_op_layernorm(const float* in, int32_t rows, int32_t d, const float* g
 int univtg_op_attention(const void* qkv, const float* key_mask, void* out, float* lse, int32_t B, int32_t L, int32_t H,
                         int32_t dh, int32_t fmt, int32_t impl, void* stream);
 
-/* Attention core backward.  qkv as above; dO [B*L,d] bf16 gradient of `out`; O = forward output (16-bit, fmt_act);
- * lse from the forward; delta_ws [B,H,L] f32 scratch; dqkv32 [B*L,3d] f32 receives dQ | dK | dV.  impl: 0 tcgen05 (needs
- * fmt_act = 1: one tcgen05.mma takes both operands in one 16-bit format), 1 SIMT. */
+/* Attention core backward.  qkv as above; dO [B*L,d] 16-bit gradient of `out`; O = forward output (16-bit, fmt_act);
+ * (same 16-bit format as qkv); lse from the forward; delta_ws [B,H,L] f32 scratch; dqkv32 [B*L,3d] f32 receives
+ * dQ | dK | dV.  impl: 0 tcgen05, 1 SIMT. */
 int univtg_op_attention_bwd(const void* qkv, const void* dO, const void* O, const float* key_mask, const float* lse,
                             float* delta_ws, float* dqkv32, int32_t B, int32_t L, int32_t H, int32_t dh, int32_t fmt_act,
                             int32_t impl, void* stream);

@@ -125,7 +125,7 @@ def test_long_video_config5_shape_runs():
     out = _run(_model(cfg, sd), inp)
     emu = O.forward(sd, cfg, **inp, opq=O.round_fp16, dtype=torch.float32)
     for k in ("pred_logits", "pred_spans", "saliency_scores"):
-        torch.testing.assert_close(out[k].double().cpu(), emu[k], rtol=3e-4, atol=1e-4, msg=lambda m: f"cfg5/{k}: {m}")
+        torch.testing.assert_close(out[k].double().cpu(), emu[k].double(), rtol=3e-4, atol=1e-4, msg=lambda m: f"cfg5/{k}: {m}")
 
 
 def test_state_dict_roundtrip_and_repack_on_update():

@@ -54,6 +54,43 @@ def case_gemm(M, N, K, a_mn, b_mn, fmt, bn, ksplit, act, use_bias):
     return res
 
 
+def case_gemm_timeline(M, N, K, act, want32, want16, bn):
+    """Per-CTA phase timeline (ns) of one GEMM launch: where does the time go?"""
+    import torch
+    from univtg_b200 import _lib
+    lib = _lib.load_library()
+    A = torch.randn(M, K, device="cuda").half()
+    Bm = torch.randn(N, K, device="cuda").half()
+    bias = torch.randn(N, device="cuda")
+    out32 = torch.zeros(M, N, device="cuda") if want32 else None
+    out16 = torch.zeros(M, N, device="cuda", dtype=torch.float16) if want16 else None
+    buf = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
+
+    def run():
+        _lib.check(lib.univtg_op_gemm(_lib.ptr(A), _lib.ptr(Bm), M, N, K, 0, 0, 0, bn, 1, _lib.ptr(bias), act, 1.0, _lib.ptr(out32),
+                                      _lib.ptr(out16), _lib.stream_ptr()), "op_gemm")
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    lib.univtg_debug_gemm_timeline(_lib.ptr(buf))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run()
+    e1.record()
+    torch.cuda.synchronize()
+    lib.univtg_debug_gemm_timeline(None)
+    t = buf.view(148, 8).cpu()
+    used = t[:, 0] > 0
+    t = t[used]
+    t0 = int(t[:, 0].min())
+    rel = (t - t0).float() / 1000.0  # us
+    names = ["entry", "setup", "tma_issued", "first_stage", "last_mma", "acc_ready", "epi_done", "exit"]
+    res = {"event_us": e0.elapsed_time(e1) * 1e3, "ctas": int(used.sum()), "ok": True}
+    for i, n in enumerate(names):
+        res[n] = [round(float(rel[:, i].min()), 2), round(float(rel[:, i].median()), 2), round(float(rel[:, i].max()), 2)]
+    return res
+
+
 def case_layernorm(rows, d, ld16, fmt):
     import torch
     from univtg_b200 import _lib
@@ -122,7 +159,7 @@ def case_attention_bwd(B, L, H, dh, fmt, impl):
     lens[0] = L
     mask = (torch.arange(L)[None, :] < lens[:, None]).float().cuda()
     q16, k16, v16 = _t16(q, fmt), _t16(k, fmt), _t16(v, fmt)
-    dO16 = dO.to(torch.bfloat16)
+    dO16 = _t16(dO * 1024.0, fmt)  # loss-scaled gradient in the activations' format
     qf, kf, vf = (t.float().requires_grad_(True) for t in (q16, k16, v16))
     s = torch.einsum("bihc,bjhc->bhij", qf, kf) * (dh ** -0.5)
     s = s.masked_fill(mask[:, None, None, :] == 0, float("-inf"))
@@ -139,7 +176,9 @@ def case_attention_bwd(B, L, H, dh, fmt, impl):
     _lib.check(rc, "op_attention_bwd")
     torch.cuda.synchronize()
     res = {"ok": True}
-    for name, ref, got in (("dq", qf.grad, dqkv[:, :d]), ("dk", kf.grad, dqkv[:, d:2 * d]), ("dv", vf.grad, dqkv[:, 2 * d:])):
+    dqkv = dqkv / 1024.0
+    for name, ref, got in (("dq", qf.grad / 1024.0, dqkv[:, :d]), ("dk", kf.grad / 1024.0, dqkv[:, d:2 * d]),
+                           ("dv", vf.grad / 1024.0, dqkv[:, 2 * d:])):
         ref = ref.reshape(B * L, d)
         rel = ((got - ref).norm() / ref.norm()).item()
         res[name + "_rel"] = rel
@@ -161,6 +200,10 @@ CASES = {
     "gemm_bmn": (case_gemm, (256, 256, 192, 0, 1, 0, 256, 1, 0, True)),
     "gemm_abmn_bn128": (case_gemm, (256, 384, 200, 1, 1, 0, 128, 1, 0, True)),
     "gemm_abmn_big_ksplit": (case_gemm, (1024, 1024, 3424, 1, 1, 0, 256, 4, 0, False)),
+    "tl_ffn1": (case_gemm_timeline, (3424, 1024, 1024, 2, False, True, 256)),
+    "tl_outproj": (case_gemm_timeline, (3424, 1024, 1024, 0, True, False, 256)),
+    "tl_qkv_bn256": (case_gemm_timeline, (3424, 3072, 1024, 0, False, True, 256)),
+    "tl_ffn1_bn128": (case_gemm_timeline, (3424, 1024, 1024, 2, False, True, 128)),
     "ln_1024": (case_layernorm, (3424, 1024, 1024, 0)),
     "ln_256_bf16": (case_layernorm, (77, 256, 256, 1)),
     "ln_2818": (case_layernorm, (300, 2818, 2880, 0)),
@@ -174,8 +217,8 @@ CASES = {
     "attn_tc_dh128_L1277": (case_attention, (1, 1277, 8, 128, 0, 0)),
     "attnbwd_simt_dh32": (case_attention_bwd, (2, 27, 4, 32, 0, 1)),
     "attnbwd_simt_dh128": (case_attention_bwd, (2, 107, 2, 128, 0, 1)),
-    "attnbwd_tc_dh128_L107": (case_attention_bwd, (3, 107, 4, 128, 1, 0)),
-    "attnbwd_tc_dh128_L182": (case_attention_bwd, (2, 182, 2, 128, 1, 0)),
+    "attnbwd_tc_dh128_L107": (case_attention_bwd, (3, 107, 4, 128, 0, 0)),
+    "attnbwd_tc_dh128_L182": (case_attention_bwd, (2, 182, 2, 128, 0, 0)),
     "attnbwd_tc_dh64_L300_bf16": (case_attention_bwd, (2, 300, 4, 64, 1, 0)),
 }
 

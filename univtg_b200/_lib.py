@@ -53,7 +53,7 @@ SIGNATURES = {
     "univtg_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "univtg_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_void_p, c_void_p,
-                                c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_int, c_void_p]),
+                                c_void_p, c_void_p, c_float, ctypes.POINTER(c_void_p), c_int, c_void_p]),
     "univtg_loss_scratch_bytes": (c_size_t, [c_int, c_int]),
     "univtg_loss_forward": (c_int, [c_void_p] * 10 + [c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "univtg_loss_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
@@ -62,6 +62,7 @@ SIGNATURES = {
     "univtg_plan_read_profile": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "univtg_op_gemm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                c_float, c_void_p, c_void_p, c_void_p]),
+    "univtg_debug_gemm_timeline": (c_int, [c_void_p]),
     "univtg_op_layernorm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_int,
                                     c_void_p]),
     "univtg_op_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,

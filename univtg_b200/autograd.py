@@ -96,8 +96,8 @@ class _UniVTGFunction(torch.autograd.Function):
                 g_spans = g_spans if g_spans is not None else torch.zeros(B, Lv, 2, device=dev)
             arr = (ctypes.c_void_p * len(views))(*[v.data_ptr() for v in views])
             _lib.check(lib.univtg_backward(ctx.plan.handle, _lib.ptr(ctx.ws), _lib.ptr(txt), _lib.ptr(vid), _lib.ptr(scales),
-                                           mask_arr, _lib.ptr(g_logits), _lib.ptr(g_spans), _lib.ptr(g_vmp), _lib.ptr(g_tmp), arr,
-                                           len(views), _lib.stream_ptr()), "univtg_backward")
+                                           mask_arr, _lib.ptr(g_logits), _lib.ptr(g_spans), _lib.ptr(g_vmp), _lib.ptr(g_tmp),
+                                           float(model.grad_scale), arr, len(views), _lib.stream_ptr()), "univtg_backward")
             hook = getattr(model, "_flat_grad_hook", None)
             if hook is not None:
                 hook(flat)  # e.g. the single NCCL all-reduce of univtg_b200.ddp

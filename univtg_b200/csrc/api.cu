@@ -589,6 +589,11 @@ int univtg_op_gemm(const void* a, const void* b, int32_t M, int32_t N, int32_t K
   return launch_gemm_group(g, bn, sms, (cudaStream_t)stream);
 }
 
+int univtg_debug_gemm_timeline(void* buf) {
+  uv::set_gemm_timeline_buffer(reinterpret_cast<unsigned long long*>(buf));
+  return 0;
+}
+
 int univtg_op_layernorm(const float* in, int32_t rows, int32_t d, const float* gamma, const float* beta, float eps,
                         int32_t fmt, float* out32, void* out16, int32_t ld16, void* stream) {
   if (!in || !gamma || !beta || rows < 1 || d < 1) {

@@ -74,9 +74,9 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const LnBwdArgs a) {
   for (int i = 0; i < EPT; ++i) {
     const int j = tid + 128 * i;
     if (j < a.d) {
-      if (a.dgamma) atomicAdd(a.dgamma + j, acc_g[i]);
-      if (a.dbeta) atomicAdd(a.dbeta + j, acc_b[i]);
-      if (a.colsum) atomicAdd(a.colsum + j, acc_c[i]);
+      if (a.dgamma) atomicAdd(a.dgamma + j, acc_g[i] * a.pgrad_scale);
+      if (a.dbeta) atomicAdd(a.dbeta + j, acc_b[i] * a.pgrad_scale);
+      if (a.colsum) atomicAdd(a.colsum + j, acc_c[i] * a.pgrad_scale);
     }
   }
 }
@@ -99,7 +99,7 @@ int launch_layernorm_bwd(const LnBwdArgs& a, cudaStream_t stream) {
 // fp32 -> 16-bit conversion with optional column sums.  Block = 256 threads x 32 rows; thread = 4 columns.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) cvt16_colsum_kernel(const float* __restrict__ in32, int ld_in, uint16_t* __restrict__ out16,
-                                                          int ld_out, int rows, int cols, int fmt, float* __restrict__ colsum) {
+                                                          int ld_out, int rows, int cols, int fmt, float* __restrict__ colsum, float cscale) {
   const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
   if (c >= cols) return;
   const int r0 = blockIdx.y * 32;
@@ -113,21 +113,21 @@ __global__ void __launch_bounds__(256) cvt16_colsum_kernel(const float* __restri
     s.w += v.w;
   }
   if (colsum) {
-    atomicAdd(colsum + c, s.x);
-    atomicAdd(colsum + c + 1, s.y);
-    atomicAdd(colsum + c + 2, s.z);
-    atomicAdd(colsum + c + 3, s.w);
+    atomicAdd(colsum + c, s.x * cscale);
+    atomicAdd(colsum + c + 1, s.y * cscale);
+    atomicAdd(colsum + c + 2, s.z * cscale);
+    atomicAdd(colsum + c + 3, s.w * cscale);
   }
 }
 
 int launch_cvt16_colsum(const float* in32, int ld_in, uint16_t* out16, int ld_out, int rows, int cols, int fmt, float* colsum,
-                        cudaStream_t stream) {
+                        float colsum_scale, cudaStream_t stream) {
   if (cols % 4 != 0 || ld_in % 4 != 0 || ld_out % 4 != 0) {
     set_error("cvt16_colsum: dims must be multiples of 4");
     return (int)cudaErrorInvalidValue;
   }
   dim3 grid((cols / 4 + 255) / 256, (rows + 31) / 32);
-  cvt16_colsum_kernel<<<grid, 256, 0, stream>>>(in32, ld_in, out16, ld_out, rows, cols, fmt, colsum);
+  cvt16_colsum_kernel<<<grid, 256, 0, stream>>>(in32, ld_in, out16, ld_out, rows, cols, fmt, colsum, colsum_scale);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("cvt16_colsum launch failed: %s", cudaGetErrorString(e));
   return (int)e;
@@ -250,9 +250,9 @@ __global__ void __launch_bounds__(256) head_dz_kernel(const HeadFinalBwdArgs a) 
       const float pc = a.pred_logits[k];
       const float s0 = -a.pred_spans[2 * k];  // sigmoid value of the left offset (stored negated)
       const float s1 = a.pred_spans[2 * k + 1];
-      out.x = a.g_logits[k] * pc * (1.f - pc);
-      out.y = -a.g_spans[2 * k] * s0 * (1.f - s0);
-      out.z = a.g_spans[2 * k + 1] * s1 * (1.f - s1);
+      out.x = a.in_scale * a.g_logits[k] * pc * (1.f - pc);
+      out.y = -a.in_scale * a.g_spans[2 * k] * s0 * (1.f - s0);
+      out.z = a.in_scale * a.g_spans[2 * k + 1] * s1 * (1.f - s1);
     }
   }
   *reinterpret_cast<float4*>(a.dz + (size_t)idx * 4) = out;
@@ -326,13 +326,13 @@ __global__ void __launch_bounds__(256) head_dw_kernel(const HeadFinalBwdArgs a) 
   }
 #pragma unroll
   for (int t = 0; t < 3; ++t) {
-    atomicAdd(a.gw_cls + (size_t)c * 3 + t, wc[t]);
-    atomicAdd(a.gw_span + (size_t)c * 3 + t, w0[t]);
-    atomicAdd(a.gw_span + ((size_t)a.d + c) * 3 + t, w1[t]);
+    atomicAdd(a.gw_cls + (size_t)c * 3 + t, wc[t] * a.pgrad_scale);
+    atomicAdd(a.gw_span + (size_t)c * 3 + t, w0[t] * a.pgrad_scale);
+    atomicAdd(a.gw_span + ((size_t)a.d + c) * 3 + t, w1[t] * a.pgrad_scale);
   }
   if (a.cs_cls) {
-    atomicAdd(a.cs_cls + c, cs_c);
-    atomicAdd(a.cs_span + c, cs_s);
+    atomicAdd(a.cs_cls + c, cs_c * a.pgrad_scale);
+    atomicAdd(a.cs_span + c, cs_s * a.pgrad_scale);
   }
   if (c == 0) {  // bias gradients: sum of dz over this slab
     float bc = 0.f, b0 = 0.f, b1 = 0.f;
@@ -342,9 +342,9 @@ __global__ void __launch_bounds__(256) head_dw_kernel(const HeadFinalBwdArgs a) 
       b0 += dz.y;
       b1 += dz.z;
     }
-    atomicAdd(a.gb_cls, bc);
-    atomicAdd(a.gb_span, b0);
-    atomicAdd(a.gb_span + 1, b1);
+    atomicAdd(a.gb_cls, bc * a.pgrad_scale);
+    atomicAdd(a.gb_span, b0 * a.pgrad_scale);
+    atomicAdd(a.gb_span + 1, b1 * a.pgrad_scale);
   }
 }
 
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const PoolBwdArgs a) {
     float dw = 0.f;
     for (int l = 0; l < a.Lt; ++l) {
       const float dl = s_da[l];
-      a.dx_txt[((size_t)b * a.Lt + l) * a.d + j] = al[l] * gj + dl * wj;
+      a.dx_txt[((size_t)b * a.Lt + l) * a.d + j] = (al[l] * gj + dl * wj) * a.out_scale;
       dw += dl * xt[(size_t)l * a.d + j];
     }
     atomicAdd(a.gw + j, dw);
@@ -413,8 +413,8 @@ int launch_pool_bwd(const PoolBwdArgs& a, cudaStream_t stream) {
 // (saliency-loss) gradient, emitted as a 16-bit GEMM operand with column sums.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) stream_gather_kernel(const float* __restrict__ dx, int L, int off, const float* __restrict__ extra,
-                                                           uint16_t* __restrict__ out16, float* __restrict__ colsum, int B, int Ls,
-                                                           int d, int fmt) {
+                                                           float extra_scale, uint16_t* __restrict__ out16,
+                                                           float* __restrict__ colsum, float cscale, int B, int Ls, int d, int fmt) {
   const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
   if (c >= d) return;
   const int r0 = blockIdx.y * 32;
@@ -425,10 +425,10 @@ __global__ void __launch_bounds__(256) stream_gather_kernel(const float* __restr
     float4 v = *reinterpret_cast<const float4*>(dx + ((size_t)b * L + off + l) * d + c);
     if (extra) {
       const float4 e = *reinterpret_cast<const float4*>(extra + (size_t)r * d + c);
-      v.x += e.x;
-      v.y += e.y;
-      v.z += e.z;
-      v.w += e.w;
+      v.x += e.x * extra_scale;
+      v.y += e.y * extra_scale;
+      v.z += e.z * extra_scale;
+      v.w += e.w * extra_scale;
     }
     *reinterpret_cast<uint2*>(out16 + (size_t)r * d + c) = make_uint2(cvt16x2(v.x, v.y, fmt), cvt16x2(v.z, v.w, fmt));
     s.x += v.x;
@@ -437,17 +437,17 @@ __global__ void __launch_bounds__(256) stream_gather_kernel(const float* __restr
     s.w += v.w;
   }
   if (colsum) {
-    atomicAdd(colsum + c, s.x);
-    atomicAdd(colsum + c + 1, s.y);
-    atomicAdd(colsum + c + 2, s.z);
-    atomicAdd(colsum + c + 3, s.w);
+    atomicAdd(colsum + c, s.x * cscale);
+    atomicAdd(colsum + c + 1, s.y * cscale);
+    atomicAdd(colsum + c + 2, s.z * cscale);
+    atomicAdd(colsum + c + 3, s.w * cscale);
   }
 }
 
-int launch_stream_gather(const float* dx_stream, int L, int off, const float* extra, uint16_t* out16, float* colsum, int B, int Ls,
-                         int d, int fmt, cudaStream_t stream) {
+int launch_stream_gather(const float* dx_stream, int L, int off, const float* extra, float extra_scale, uint16_t* out16,
+                         float* colsum, float colsum_scale, int B, int Ls, int d, int fmt, cudaStream_t stream) {
   dim3 grid((d / 4 + 255) / 256, (B * Ls + 31) / 32);
-  stream_gather_kernel<<<grid, 256, 0, stream>>>(dx_stream, L, off, extra, out16, colsum, B, Ls, d, fmt);
+  stream_gather_kernel<<<grid, 256, 0, stream>>>(dx_stream, L, off, extra, extra_scale, out16, colsum, colsum_scale, B, Ls, d, fmt);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("stream_gather launch failed: %s", cudaGetErrorString(e));
   return (int)e;

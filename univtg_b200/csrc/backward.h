@@ -27,12 +27,13 @@ struct LnBwdArgs {
   float* dgamma;           // [d] atomically accumulated, or null
   float* dbeta;            // [d]
   float* colsum;           // [d] atomically accumulated column sums of the values written to dbr16 (bias gradient), or null
+  float pgrad_scale;       // factor on dgamma / dbeta / colsum (1 / loss-scale: parameter gradients leave unscaled)
 };
 int launch_layernorm_bwd(const LnBwdArgs& a, cudaStream_t stream);
 
 // out16[r, c] = cvt(in32[r, c]) (+ column sums), rows x cols with leading dims
 int launch_cvt16_colsum(const float* in32, int ld_in, uint16_t* out16, int ld_out, int rows, int cols, int fmt, float* colsum,
-                        cudaStream_t stream);
+                        float colsum_scale, cudaStream_t stream);
 
 // delta[b, h, i] = sum_c dO[b, i, h, c] * O[b, i, h, c]
 int launch_attn_delta(const uint16_t* dO, int fmt_do, const uint16_t* O, int fmt_o, float* delta, int B, int L, int H, int dh,
@@ -74,6 +75,8 @@ struct HeadFinalBwdArgs {
   float* gb_span;            // [2]
   float* cs_cls;             // [d] column sums of dh_cls (bias gradient of conv layer 1) or null
   float* cs_span;
+  float in_scale;            // loss scale applied to the incoming output gradients (all downstream gradients are scaled)
+  float pgrad_scale;         // 1 / loss-scale for the parameter gradients written here
   int B, Lv, d, fmt_act, fmt_grad;
 };
 int launch_head_final_bwd(const HeadFinalBwdArgs& a, cudaStream_t stream);
@@ -85,14 +88,15 @@ struct PoolBwdArgs {
   const float* w;          // [d]
   const float* g_pooled;   // [B, d] dL/d txt_mem_proj
   float* dx_txt;           // [B, Lt, d] gradient w.r.t. the projected text tokens (written, not accumulated)
-  float* gw;               // [d] weightedpool.weight gradient (atomically accumulated)
+  float* gw;               // [d] weightedpool.weight gradient (atomically accumulated, unscaled)
+  float out_scale;         // loss scale applied to dx_txt
   int B, Lt, d;
 };
 int launch_pool_bwd(const PoolBwdArgs& a, cudaStream_t stream);
 
 // out16[b*Ls + l, :] = cvt(dx_stream[b*L + off + l, :] + extra[b*Ls + l, :]); colsum += column sums (bias + type-embedding grads)
-int launch_stream_gather(const float* dx_stream, int L, int off, const float* extra, uint16_t* out16, float* colsum, int B, int Ls,
-                         int d, int fmt, cudaStream_t stream);
+int launch_stream_gather(const float* dx_stream, int L, int off, const float* extra, float extra_scale, uint16_t* out16,
+                         float* colsum, float colsum_scale, int B, int Ls, int d, int fmt, cudaStream_t stream);
 
 // y[i] += x[i]
 int launch_axpy(float* y, const float* x, size_t n, cudaStream_t stream);

@@ -58,6 +58,14 @@ __device__ __forceinline__ bool decode_tile(const GemmGroup& g, int bn, int t, T
   return false;
 }
 
+__device__ __forceinline__ void stamp(unsigned long long* dbg, int slot) {
+  if (dbg != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    dbg[(size_t)blockIdx.x * 8 + slot] = t;
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmGroup g) {
   using Cfg = GemmCfg<BN>;
@@ -76,6 +84,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) stamp(g.dbg, 0);  // kernel entry
 
   if (warp == 0 && lane == 0) {
     for (int p = 0; p < g.num; ++p) {
@@ -99,6 +108,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  if (threadIdx.x == 0) stamp(g.dbg, 1);  // setup done (barriers, TMEM)
 
   if (warp == 0) {
     // ======================================= TMA producer =======================================
@@ -139,6 +149,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           }
         }
       }
+      stamp(g.dbg, 2);  // all TMA loads issued
     }
   } else if (warp == 1) {
     // ======================================== MMA issuer ========================================
@@ -156,6 +167,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          if (kb == ti.kb0 && t == (int)blockIdx.x) stamp(g.dbg, 3);  // first operand stage landed
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
@@ -176,6 +188,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           }
         }
         umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+        stamp(g.dbg, 4);              // last MMA of the tile issued
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
@@ -252,6 +265,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       __syncwarp();
 
       mbar_wait(&tmem_full[as], aphase);
+      if (ew == 0 && lane == 0) stamp(g.dbg, 5);  // accumulator ready
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + as * BN + half * (BN / 2);
 
@@ -386,7 +400,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float sj = warp_sum(v[j]);
-            if (lane == j && n0 + j < pN) atomicAdd(colsum + n0 + j, sj);
+            if (lane == j && n0 + j < pN) atomicAdd(colsum + n0 + j, sj * pr.colsum_scale);
           }
         }
       }
@@ -394,6 +408,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (ew == 7 && lane == 0) stamp(g.dbg, 6);  // epilogue of the tile done (last warp)
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -407,11 +422,14 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
+  if (threadIdx.x == 0) stamp(g.dbg, 7);  // exit
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static unsigned long long* g_timeline = nullptr;
+void set_gemm_timeline_buffer(unsigned long long* buf) { g_timeline = buf; }
 static thread_local char g_err[512] = "";
 const char* last_error() { return g_err; }
 void set_error(const char* fmt, ...) {
@@ -498,6 +516,7 @@ static int launch_bn(GemmGroup& g, int num_sms, cudaStream_t stream) {
   }
   if (total == 0) return 0;
   const int grid = total < num_sms ? total : num_sms;
+  g.dbg = g_timeline;
   gemm_tcgen05_kernel<BN><<<grid, 384, Cfg::kSmemBytes, stream>>>(g);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -66,6 +66,7 @@ struct GemmProblem {
   int ld_mask;
   float* pre32;            // fp32 (acc + bias) BEFORE the activation, indexed like out32 (saved for GELU backward)
   int ld_pre;
+  float colsum_scale;      // factor applied to the column sums (1/loss-scale for bias gradients)
   float* colsum;           // fp32 [N]: atomically accumulates the column sums of the stored values (bias gradients)
   int cs32;                // column stride of out32 (0/1: dense); 3 writes a Conv1d weight-gradient tap in [n, c, 3] layout
   int skip_sep;            // rows with (m % rps_in) == rps_in-1 are not stored at all
@@ -75,6 +76,7 @@ struct GemmProblem {
 struct GemmGroup {
   int num;
   int fmt;  // 0 fp16, 1 bf16
+  unsigned long long* dbg;  // optional [gridDim.x][8] %globaltimer stamps per CTA (profiling aid), normally null
   GemmProblem p[GEMM_MAX_GROUP];
 };
 
@@ -86,6 +88,7 @@ int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream);
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
                  uint32_t box_cols);
 
+void set_gemm_timeline_buffer(unsigned long long* buf);  // debugging: stamps for every following GEMM launch
 const char* last_error();
 void set_error(const char* fmt, ...);
 

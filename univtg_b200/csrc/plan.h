@@ -262,6 +262,7 @@ void init_problem(GemmProblem& p) {
   p.ksplit = 1;
   p.alpha = 1.f;
   p.a_fmt = p.b_fmt = p.out_fmt = -1;
+  p.colsum_scale = 1.f;
   // default coordinate rules: K-major A [M,K] and B [N,K]
   p.ca = OperandCoord{0, 0, 0, 1, 0, 1, 0, 0};
   p.cb = OperandCoord{0, 0, 0, 1, 0, 1, 0, 0};

@@ -137,7 +137,10 @@ TrainWs make_train_ws(const univtg_config& c, const univtg_shape& s, const Packe
   return w;
 }
 
-constexpr int FMT_BF16 = 1;  // gradients travel as bf16 (fp16 would underflow)
+// Gradient operands use the plan's 16-bit format (one tcgen05.mma takes A and B in ONE format).  With fp16 they would
+// underflow, so the whole backward runs on gradients multiplied by a power-of-two loss scale S: the upstream output
+// gradients are scaled on entry, every intermediate stays scaled, and each PARAMETER gradient is multiplied by 1/S where it
+// is written (GEMM alpha, column-sum / LayerNorm / head kernels).  bf16 plans simply use S = 1.
 
 }  // namespace
 
@@ -162,10 +165,6 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
   }
   cudaStream_t st = (cudaStream_t)stream;
   const univtg_config& c = P->cfg;
-  if (c.operand_format != FMT_BF16) {
-    set_error("training plans must use operand_format = 1 (bf16): gradients are bf16 and one tcgen05.mma takes A and B in one format");
-    return 1;
-  }
   const PackedLayout& Lw = P->lay;
   const uint8_t* pk = P->packed;
   auto F32 = [&](size_t off) { return reinterpret_cast<const float*>(pk + off); };
@@ -453,16 +452,12 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
 // drop_masks / droppath_scale: the same arrays that were passed to the forward.
 int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float* src_vid, const float* droppath_scale,
                     const float* const* drop_masks, const float* g_logits, const float* g_spans, const float* g_vid_mem_proj,
-                    const float* g_txt_mem_proj, float* const* grads, int32_t n_grads, void* stream) {
-  if (!P || !ws || !grads || !src_txt || !src_vid) {
+                    const float* g_txt_mem_proj, float grad_scale, float* const* grads, int32_t n_grads, void* stream) {
+  if (!P || !ws || !grads || !src_txt || !src_vid || !(grad_scale > 0.f)) {
     set_error("univtg_backward: null argument");
     return 1;
   }
   const univtg_config& c = P->cfg;
-  if (c.operand_format != FMT_BF16) {
-    set_error("training plans must use operand_format = 1 (bf16)");
-    return 1;
-  }
   if (n_grads != univtg_num_params(&c)) {
     set_error("univtg_backward: expected %d gradient tensors, got %d", univtg_num_params(&c), n_grads);
     return 1;
@@ -476,6 +471,9 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
   const int d = P->d, ff = P->ff, fmt = c.operand_format, M = P->M, Mv = P->Mv, Mt = P->Mt, Mh = P->Mh, L = P->L, Lv = P->Lv,
             Lt = P->Lt, B = P->B;
   const int sms = P->num_sms;
+  const int FMT_G = fmt;                 // gradient operand format == activation operand format
+  const float GS = grad_scale;           // loss scale carried by every intermediate gradient
+  const float INV = 1.0f / grad_scale;   // applied wherever a parameter gradient is written
   int rc = 0;
   GemmGroup g;
   // parameter-gradient index map (univtg_pack_weights order)
@@ -516,7 +514,9 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     a.Lv = Lv;
     a.d = d;
     a.fmt_act = fmt;
-    a.fmt_grad = FMT_BF16;
+    a.fmt_grad = FMT_G;
+    a.in_scale = GS;
+    a.pgrad_scale = INV;
     rc = launch_head_final_bwd(a, st);
     if (rc) return rc;
 
@@ -530,7 +530,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       p.taps = 3;
       p.kblk_per_tap = Kc / 64;
       p.b_mn = 1;
-      p.a_fmt = FMT_BF16;
+      p.a_fmt = FMT_G;
       p.b_fmt = fmt;
       p.ca = OperandCoord{0, 0, 0, 1, 0, 1, 1, 0};              // rows m0 + t', cols k
       p.cb = OperandCoord{2 * Cin, 1, -Cin, 0, 0, 0, 0, 1};     // cols n0 + (2 - t') * Cin, rows k (out channel)
@@ -547,7 +547,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       p.N = Cin;
       p.a_mn = 1;
       p.b_mn = 1;
-      p.a_fmt = FMT_BF16;
+      p.a_fmt = FMT_G;
       p.b_fmt = fmt;
       p.kblk_per_tap = (Mh + 63) / 64;
       p.ca = OperandCoord{0, 1, 0, 0, 1, 0, 0, 1};      // cols m0 (out channel), rows 1 + k
@@ -557,6 +557,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       p.out32 = gw + t;
       p.ld32 = 3 * Cin;
       p.cs32 = 3;
+      p.alpha = INV;
       return r;
     };
     const int bn = P->bn_main;
@@ -577,8 +578,9 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       p.ld_mask = 2 * d;
       p.out16 = T.dh1 + s * d;
       p.ld16 = 2 * d;
-      p.out_fmt = FMT_BF16;
+      p.out_fmt = FMT_G;
       p.colsum = s == 0 ? G_cls(1) : G_span(1);  // bias gradient of conv layer 0
+      p.colsum_scale = INV;
     }
     rc = launch_gemm_group(g, bn, sms, st);
     if (rc) return rc;
@@ -643,10 +645,11 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       a.dy32 = T.dy;
       a.dbr16 = T.dbr16;
       a.ld16 = d;
-      a.fmt16 = FMT_BF16;
+      a.fmt16 = FMT_G;
       a.dgamma = G_layer(l, 10);
       a.dbeta = G_layer(l, 11);
       a.colsum = G_layer(l, 7);  // linear2.bias
+      a.pgrad_scale = INV;
       rc = launch_layernorm_bwd(a, st);
       if (rc) return rc;
     }
@@ -656,15 +659,16 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.fmt = fmt;
     rc = setup_gemm(g.p[0], Mat16{T.dbr16, M, d, d}, 0, Mat16{W16(lp.w2), d, ff, ff}, 1, M, ff, d, pick_bn(ff));
     if (rc) return rc;
-    g.p[0].a_fmt = FMT_BF16;
+    g.p[0].a_fmt = FMT_G;
     g.p[0].b_fmt = fmt;
     g.p[0].aux32 = T.hpre[l];
     g.p[0].ld_aux = ff;
     g.p[0].aux_mode = 1;
     g.p[0].out16 = T.dhpre16;
     g.p[0].ld16 = ff;
-    g.p[0].out_fmt = FMT_BF16;
+    g.p[0].out_fmt = FMT_G;
     g.p[0].colsum = G_layer(l, 5);  // linear1.bias
+    g.p[0].colsum_scale = INV;
     rc = launch_gemm_group(g, pick_bn(ff), sms, st);
     if (rc) return rc;
     memset(&g, 0, sizeof(g));
@@ -675,12 +679,13 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       rc |= setup_gemm(g.p[0], Mat16{T.dbr16, M, d, d}, 1, Mat16{T.h16[l], M, ff, ff}, 1, d, ff, M, bnw);
       rc |= setup_gemm(g.p[1], Mat16{T.dhpre16, M, ff, ff}, 1, Mat16{T.x1_16[l], M, d, d}, 1, ff, d, M, bnw);
       if (rc) return rc;
-      g.p[0].a_fmt = g.p[1].a_fmt = FMT_BF16;
+      g.p[0].a_fmt = g.p[1].a_fmt = FMT_G;
       g.p[0].b_fmt = g.p[1].b_fmt = fmt;
       g.p[0].out32 = G_layer(l, 6);  // linear2.weight [d, ff]
       g.p[0].ld32 = ff;
       g.p[1].out32 = G_layer(l, 4);  // linear1.weight [ff, d]
       g.p[1].ld32 = d;
+      g.p[0].alpha = g.p[1].alpha = INV;
       g.p[0].ksplit = g.p[1].ksplit = pick_ksplit(d, ff, bnw, (M + 63) / 64, sms / 2);
       rc = launch_gemm_group(g, bnw, sms, st);
       if (rc) return rc;
@@ -691,7 +696,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.fmt = fmt;
     rc = setup_gemm(g.p[0], Mat16{T.dhpre16, M, ff, ff}, 0, Mat16{W16(lp.w1), ff, d, d}, 1, M, d, ff, bn);
     if (rc) return rc;
-    g.p[0].a_fmt = FMT_BF16;
+    g.p[0].a_fmt = FMT_G;
     g.p[0].b_fmt = fmt;
     g.p[0].resid = T.dy;
     g.p[0].ld_resid = d;
@@ -717,10 +722,11 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       a.dy32 = T.dy;
       a.dbr16 = T.dbr16;
       a.ld16 = d;
-      a.fmt16 = FMT_BF16;
+      a.fmt16 = FMT_G;
       a.dgamma = G_layer(l, 8);
       a.dbeta = G_layer(l, 9);
       a.colsum = G_layer(l, 3);  // out_proj.bias
+      a.pgrad_scale = INV;
       rc = launch_layernorm_bwd(a, st);
       if (rc) return rc;
     }
@@ -730,11 +736,11 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.fmt = fmt;
     rc = setup_gemm(g.p[0], Mat16{T.dbr16, M, d, d}, 0, Mat16{W16(lp.w_out), d, d, d}, 1, M, d, d, bn);
     if (rc) return rc;
-    g.p[0].a_fmt = FMT_BF16;
+    g.p[0].a_fmt = FMT_G;
     g.p[0].b_fmt = fmt;
     g.p[0].out16 = T.dO16;
     g.p[0].ld16 = d;
-    g.p[0].out_fmt = FMT_BF16;
+    g.p[0].out_fmt = FMT_G;
     rc = launch_gemm_group(g, bn, sms, st);
     if (rc) return rc;
     memset(&g, 0, sizeof(g));
@@ -742,15 +748,16 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.fmt = fmt;
     rc = setup_gemm(g.p[0], Mat16{T.dbr16, M, d, d}, 1, Mat16{T.attn16[l], M, d, d}, 1, d, d, M, bn);
     if (rc) return rc;
-    g.p[0].a_fmt = FMT_BF16;
+    g.p[0].a_fmt = FMT_G;
     g.p[0].b_fmt = fmt;
     g.p[0].out32 = G_layer(l, 2);
     g.p[0].ld32 = d;
+    g.p[0].alpha = INV;
     g.p[0].ksplit = pick_ksplit(d, d, bn, (M + 63) / 64, sms);
     rc = launch_gemm_group(g, bn, sms, st);
     if (rc) return rc;
     // ---- attention core backward -> dqkv32 -> dqkv16 (+ in_proj_bias gradient) ----
-    rc = launch_attn_delta(T.dO16, FMT_BF16, T.attn16[l], fmt, T.delta, B, L, P->H, P->dh, st);
+    rc = launch_attn_delta(T.dO16, FMT_G, T.attn16[l], fmt, T.delta, B, L, P->H, P->dh, st);
     if (rc) return rc;
     {
       AttnBwdArgs a;
@@ -768,7 +775,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       a.dh = P->dh;
       a.d = d;
       a.fmt_act = fmt;
-      a.fmt_grad = FMT_BF16;
+      a.fmt_grad = FMT_G;
       const bool tc = (P->dh == 64 || P->dh == 128);
       const int num_kv = (L + 127) / 128;
       a.dq_atomic = (!tc || num_kv > 1) ? 1 : 0;
@@ -782,7 +789,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       }
       if (rc) return rc;
     }
-    rc = launch_cvt16_colsum(T.dqkv32, 3 * d, T.dqkv16, 3 * d, M, 3 * d, FMT_BF16, G_layer(l, 1), st);
+    rc = launch_cvt16_colsum(T.dqkv32, 3 * d, T.dqkv16, 3 * d, M, 3 * d, FMT_G, G_layer(l, 1), INV, st);
     if (rc) return rc;
     // ---- in-projections: dgrad dx = dy + [dq|dk|dv] [Wq;Wk;Wv]; wgrad dWqk = [dq|dk]^T (x+pos), dWv = dv^T x ----
     memset(&g, 0, sizeof(g));
@@ -790,7 +797,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.fmt = fmt;
     rc = setup_gemm(g.p[0], Mat16{T.dqkv16, M, 3 * d, 3 * d}, 0, Mat16{W16(lp.w_in), 3 * d, d, d}, 1, M, d, 3 * d, bn);
     if (rc) return rc;
-    g.p[0].a_fmt = FMT_BF16;
+    g.p[0].a_fmt = FMT_G;
     g.p[0].b_fmt = fmt;
     g.p[0].resid = T.dy;
     g.p[0].ld_resid = d;
@@ -804,12 +811,13 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     rc |= setup_gemm(g.p[0], Mat16{T.dqkv16, M, 2 * d, 3 * d}, 1, Mat16{T.xpos16[l], M, d, d}, 1, 2 * d, d, M, bn);
     rc |= setup_gemm(g.p[1], Mat16{T.dqkv16 + 2 * d, M, d, 3 * d}, 1, Mat16{T.xin16[l], M, d, d}, 1, d, d, M, bn);
     if (rc) return rc;
-    g.p[0].a_fmt = g.p[1].a_fmt = FMT_BF16;
+    g.p[0].a_fmt = g.p[1].a_fmt = FMT_G;
     g.p[0].b_fmt = g.p[1].b_fmt = fmt;
     g.p[0].out32 = G_layer(l, 0);
     g.p[0].ld32 = d;
     g.p[1].out32 = G_layer(l, 0) + (size_t)2 * d * d;
     g.p[1].ld32 = d;
+    g.p[0].alpha = g.p[1].alpha = INV;
     g.p[0].ksplit = g.p[1].ksplit = pick_ksplit(3 * d, d, bn, (M + 63) / 64, sms);
     rc = launch_gemm_group(g, bn, sms, st);
     if (rc) return rc;
@@ -825,6 +833,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     a.g_pooled = g_txt_mem_proj;
     a.dx_txt = T.dxt_pool;
     a.gw = G_pool;
+    a.out_scale = GS;
     a.B = B;
     a.Lt = Lt;
     a.d = d;
@@ -832,9 +841,9 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     if (rc) return rc;
   }
   // column sums = bias gradient of the last projector layer AND the token-type embedding rows
-  rc = launch_stream_gather(T.dx, L, 0, g_vid_mem_proj, T.dxv16, G_type + d, B, Lv, d, FMT_BF16, st);
+  rc = launch_stream_gather(T.dx, L, 0, g_vid_mem_proj, GS, T.dxv16, G_type + d, INV, B, Lv, d, FMT_G, st);
   if (rc) return rc;
-  rc = launch_stream_gather(T.dx, L, Lv, g_txt_mem_proj ? T.dxt_pool : nullptr, T.dxt16, G_type, B, Lt, d, FMT_BF16, st);
+  rc = launch_stream_gather(T.dx, L, Lv, g_txt_mem_proj ? T.dxt_pool : nullptr, 1.0f, T.dxt16, G_type, INV, B, Lt, d, FMT_G, st);
   if (rc) return rc;
   cudaMemcpyAsync(G_vid(np - 1, 3), G_type + d, (size_t)d * 4, cudaMemcpyDeviceToDevice, st);
   cudaMemcpyAsync(G_txt(np - 1, 3), G_type, (size_t)d * 4, cudaMemcpyDeviceToDevice, st);
@@ -848,12 +857,13 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     rc |= setup_gemm(g.p[0], Mat16{T.dxv16, Mv, d, d}, 1, Mat16{T.a_vid[i], Mv, kpv, kpv}, 1, d, dinv, Mv, bn);
     rc |= setup_gemm(g.p[1], Mat16{T.dxt16, Mt, d, d}, 1, Mat16{T.a_txt[i], Mt, kpt, kpt}, 1, d, dint, Mt, bn);
     if (rc) return rc;
-    g.p[0].a_fmt = g.p[1].a_fmt = FMT_BF16;
+    g.p[0].a_fmt = g.p[1].a_fmt = FMT_G;
     g.p[0].b_fmt = g.p[1].b_fmt = fmt;
     g.p[0].out32 = G_vid(i, 2);
     g.p[0].ld32 = dinv;
     g.p[1].out32 = G_txt(i, 2);
     g.p[1].ld32 = dint;
+    g.p[0].alpha = g.p[1].alpha = INV;
     rc = launch_gemm_group(g, bn, sms, st);
     if (rc) return rc;
     // dgrad: dA_i = (dOut W_i) * dropout mask   (fp32, [rows, din_i])
@@ -863,7 +873,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     rc |= setup_gemm(g.p[0], Mat16{T.dxv16, Mv, d, d}, 0, Mat16{W16(Lw.vid[i].w16), d, kpv, kpv}, 1, Mv, dinv, d, bn);
     rc |= setup_gemm(g.p[1], Mat16{T.dxt16, Mt, d, d}, 0, Mat16{W16(Lw.txt[i].w16), d, kpt, kpt}, 1, Mt, dint, d, bn);
     if (rc) return rc;
-    g.p[0].a_fmt = g.p[1].a_fmt = FMT_BF16;
+    g.p[0].a_fmt = g.p[1].a_fmt = FMT_G;
     g.p[0].b_fmt = g.p[1].b_fmt = fmt;
     g.p[0].out32 = T.dA_v;
     g.p[0].ld32 = dinv;
@@ -895,11 +905,12 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       a.d = pp.din;
       a.dgamma = s == 0 ? G_vid(i, 0) : G_txt(i, 0);
       a.dbeta = s == 0 ? G_vid(i, 1) : G_txt(i, 1);
+      a.pgrad_scale = INV;
       if (i > 0) {
         a.relu_mask_y = 1;
         a.dbr16 = s == 0 ? T.dxv16 : T.dxt16;
         a.ld16 = d;
-        a.fmt16 = FMT_BF16;
+        a.fmt16 = FMT_G;
         a.colsum = s == 0 ? G_vid(i - 1, 3) : G_txt(i - 1, 3);
       }
       rc = launch_layernorm_bwd(a, st);
@@ -951,7 +962,7 @@ int univtg_op_attention_bwd(const void* qkv, const void* dO, const void* O, cons
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int d = H * dh, M = B * L;
-  int rc = launch_attn_delta(reinterpret_cast<const uint16_t*>(dO), FMT_BF16, reinterpret_cast<const uint16_t*>(O), fmt_act,
+  int rc = launch_attn_delta(reinterpret_cast<const uint16_t*>(dO), fmt_act, reinterpret_cast<const uint16_t*>(O), fmt_act,
                              delta_ws, B, L, H, dh, st);
   if (rc) return rc;
   AttnBwdArgs a;
@@ -969,12 +980,8 @@ int univtg_op_attention_bwd(const void* qkv, const void* dO, const void* O, cons
   a.dh = dh;
   a.d = d;
   a.fmt_act = fmt_act;
-  a.fmt_grad = FMT_BF16;
+  a.fmt_grad = fmt_act;
   const bool tc = impl == 0;
-  if (tc && fmt_act != FMT_BF16) {
-    set_error("univtg_op_attention_bwd: the tensor-core path needs bf16 activations (A and B of one MMA share a format)");
-    return 1;
-  }
   a.dq_atomic = (!tc || (L + 127) / 128 > 1) ? 1 : 0;
   if (a.dq_atomic) cudaMemsetAsync(dqkv32, 0, (size_t)M * 3 * d * 4, st);
   if (!tc) return launch_attention_bwd_simt(a, st);

@@ -111,6 +111,7 @@ class Model(nn.Module):
         self.use_txt_pos = bool(args.use_txt_pos)
         self.max_v_l = int(getattr(args, "max_v_l", 75))
         self.operand_format = {"fp16": 0, "bf16": 1}[getattr(args, "operand_format", "fp16")]
+        self.grad_scale = float(getattr(args, "grad_scale", 1024.0 if self.operand_format == 0 else 1.0))
         if bool(getattr(args, "pre_norm", False)):
             # the reference raises AttributeError here (forward_pre is not defined, transformer_encoder_droppath.py:128-134)
             raise NotImplementedError("pre_norm is not supported by the UniVTG encoder (reference has no forward_pre)")
@@ -134,8 +135,9 @@ class Model(nn.Module):
         self.weightedpool = _Params(weight=(d, 1))
         self.reset_parameters()
 
-        # eval: fp16 operands by default (11-bit significand keeps the north-star tolerance); training: bf16 operands for
-        # activations, weights AND gradients (fp16 gradients underflow, and one tcgen05.mma takes A and B in one format).
+        # One 16-bit operand format per model (a tcgen05.mma takes A and B in ONE format): fp16 by default - its 11-bit
+        # significand keeps the north-star tolerance - with gradients carried under a power-of-two loss scale in backward
+        # (fp16 would underflow otherwise); "bf16" needs no scaling but is 8x coarser.
         self._packed = {}
         self._packed_key = {}
         self._plans = {}
@@ -199,7 +201,7 @@ class Model(nn.Module):
         return self.weightedpool.weight.device
 
     def _fmt(self, training):
-        return 1 if training else self.operand_format
+        return self.operand_format  # one 16-bit format per model: fp16 (default) or bf16, in eval and in training
 
     def _ensure_packed(self, training=False):
         """(Re)pack the fp32 parameters into the 16-bit operand buffer of the mode's format when any parameter changed."""
@@ -250,7 +252,7 @@ class Model(nn.Module):
             if len(cache) >= 4:
                 cache.pop(next(iter(cache)))
             shp = _lib.Shape(B, Lv, Lt, 1)
-            nbytes = lib.univtg_train_workspace_bytes(ctypes.byref(self._cfgs[1]), ctypes.byref(shp))
+            nbytes = lib.univtg_train_workspace_bytes(ctypes.byref(self._cfg), ctypes.byref(shp))
             if nbytes == 0:
                 raise RuntimeError("univtg_b200: " + _lib.last_error())
             ws = torch.zeros(nbytes, dtype=torch.uint8, device=self._device())
