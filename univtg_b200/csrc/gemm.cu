@@ -269,35 +269,57 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + as * BN + half * (BN / 2);
 
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = n_base + c * 16;
-        if (n0 >= pN) break;  // warp-uniform
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(t_addr + c * 16, r);
-        float rv[16];
-        if (vec && valid && resid_row != nullptr) {  // issue the residual loads before waiting on TMEM
+      // number of 16-column steps this warp owns in this tile (warp-uniform)
+      int nsteps = (pN - n_base + 15) / 16;
+      nsteps = nsteps < 0 ? 0 : (nsteps > BN / 32 ? BN / 32 : nsteps);
+      const bool load_resid = vec && valid && (resid_row != nullptr);
+      uint32_t r[16];
+      float rv_next[16];
+      // software pipeline: the TMEM load and the residual loads of step c+1 are in flight while step c is processed
+      if (nsteps > 0) {
+        tmem_ld_32x32b_x16(t_addr, r);
+        if (load_resid) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 t4 = *reinterpret_cast<const float4*>(resid_row + n0 + 4 * q);
-            rv[4 * q] = t4.x; rv[4 * q + 1] = t4.y; rv[4 * q + 2] = t4.z; rv[4 * q + 3] = t4.w;
+            const float4 t4 = *reinterpret_cast<const float4*>(resid_row + n_base + 4 * q);
+            rv_next[4 * q] = t4.x; rv_next[4 * q + 1] = t4.y; rv_next[4 * q + 2] = t4.z; rv_next[4 * q + 3] = t4.w;
           }
         }
+      }
+      for (int c = 0; c < nsteps; ++c) {
+        const int n0 = n_base + c * 16;
         tmem_ld_wait();
-        float v[16];
+        float v[16], rv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          v[j] = __uint_as_float(r[j]) + bias_s[c * 16 + j];
+          rv[j] = rv_next[j];
+        }
+        if (c + 1 < nsteps) {
+          tmem_ld_32x32b_x16(t_addr + (c + 1) * 16, r);
+          if (load_resid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 t4 = *reinterpret_cast<const float4*>(resid_row + n0 + 16 + 4 * q);
+              rv_next[4 * q] = t4.x; rv_next[4 * q + 1] = t4.y; rv_next[4 * q + 2] = t4.z; rv_next[4 * q + 3] = t4.w;
+            }
+          }
+        }
         if (pre_row != nullptr && valid) {  // training: keep the pre-activation (needs N % 4 == 0, checked on the host)
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             if (n0 + 4 * q < pN)
-              *reinterpret_cast<float4*>(pre_row + n0 + 4 * q) = make_float4(
-                  __uint_as_float(r[4 * q]) + bias_s[c * 16 + 4 * q], __uint_as_float(r[4 * q + 1]) + bias_s[c * 16 + 4 * q + 1],
-                  __uint_as_float(r[4 * q + 2]) + bias_s[c * 16 + 4 * q + 2], __uint_as_float(r[4 * q + 3]) + bias_s[c * 16 + 4 * q + 3]);
+              *reinterpret_cast<float4*>(pre_row + n0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
+        if (act == ACT_GELU) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float x = __uint_as_float(r[j]) + bias_s[c * 16 + j];
-          if (act == ACT_RELU) x = fmaxf(x, 0.f);
-          else if (act == ACT_GELU) x = gelu_erf(x);
-          v[j] = x * rsc;
+          for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]) * rsc;
+        } else if (act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f) * rsc;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= rsc;
         }
         if (vec) {
           if (valid) {

@@ -202,7 +202,19 @@ UV_DEVINL float erf_fast(float x) {
   const float r = fmaf(-y, __expf(-ax * ax), 1.0f);
   return copysignf(r, x);
 }
-UV_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f)); }
+// gelu(x) = 0.5 x (1 + erf(x / sqrt 2)) = 0.5 (x + |x| erf(|x| / sqrt 2)), with the same A&S 7.1.26 erf, constants folded
+UV_DEVINL float gelu_erf(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f));
+  float y = fmaf(1.061405429f, t, -1.453152027f);
+  y = fmaf(y, t, 1.421413741f);
+  y = fmaf(y, t, -0.284496736f);
+  y = fmaf(y, t, 0.254829592f);
+  y = y * t;
+  const float e = exp2f(ax * ax * (-0.5f * 1.4426950408889634f));  // exp(-x^2 / 2)
+  const float r = fmaf(-y, e, 1.0f);                                // erf(|x| / sqrt 2)
+  return 0.5f * fmaf(ax, r, x);
+}
 // d/dx gelu_erf(x) = Phi(x) + x * phi(x)
 UV_DEVINL float gelu_erf_grad(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
