@@ -95,10 +95,11 @@ def multi_head_attention(xq, xv, key_valid, w_in, b_in, w_out, b_out, nheads, op
 def encoder_layer(x, pos, key_valid, sd, pre, nheads, s1, s2, opq):
     a = multi_head_attention(x + pos, x, key_valid, sd[pre + "self_attn.in_proj_weight"], sd[pre + "self_attn.in_proj_bias"],
                              sd[pre + "self_attn.out_proj.weight"], sd[pre + "self_attn.out_proj.bias"], nheads, opq)
-    x = layer_norm(x + s1[:, None, None] * a, sd[pre + "norm1.weight"], sd[pre + "norm1.bias"])
+    # the CUDA path stores the DropPath-scaled branch as a 16-bit operand before adding it to the fp32 residual stream
+    x = layer_norm(x + opq(s1[:, None, None] * a), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"])
     h = gelu_erf(mm(x, sd[pre + "linear1.weight"], opq, sd[pre + "linear1.bias"]))
     f = mm(h, sd[pre + "linear2.weight"], opq, sd[pre + "linear2.bias"])
-    x = layer_norm(x + s2[:, None, None] * f, sd[pre + "norm2.weight"], sd[pre + "norm2.bias"])
+    x = layer_norm(x + opq(s2[:, None, None] * f), sd[pre + "norm2.weight"], sd[pre + "norm2.bias"])
     return x
 
 

@@ -162,7 +162,7 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
   P->key_mask = reinterpret_cast<float*>(ws + w.key_mask);
   P->pool_logits = reinterpret_cast<float*>(ws + w.pool_logits);
   P->x32 = reinterpret_cast<float*>(ws + w.x32);
-  P->y32 = reinterpret_cast<float*>(ws + w.y32);
+  P->br16 = reinterpret_cast<uint16_t*>(ws + w.br16);
   P->x16 = reinterpret_cast<uint16_t*>(ws + w.x16);
   P->xpos16 = reinterpret_cast<uint16_t*>(ws + w.xpos16);
   P->qkv16 = reinterpret_cast<uint16_t*>(ws + w.qkv16);
@@ -267,10 +267,8 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
       g.p[0].bias = F32(lp.b_out);
       g.p[0].rps_in = P->L;
       g.p[0].rps_out = P->L;
-      g.p[0].resid = P->x32;
-      g.p[0].ld_resid = d;
-      g.p[0].out32 = P->y32;
-      g.p[0].ld32 = d;
+      g.p[0].out16 = P->br16;  // DropPath-scaled branch; the LayerNorm kernel adds it to the fp32 residual stream
+      g.p[0].ld16 = d;
     }
     {
       GemmGroup& g = P->g_ffn1[l];
@@ -292,10 +290,8 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
       g.p[0].bias = F32(lp.b2);
       g.p[0].rps_in = P->L;
       g.p[0].rps_out = P->L;
-      g.p[0].resid = P->x32;
-      g.p[0].ld_resid = d;
-      g.p[0].out32 = P->y32;
-      g.p[0].ld32 = d;
+      g.p[0].out16 = P->br16;
+      g.p[0].ld16 = d;
     }
   }
   // ---- conv heads (k=3, pad=1) as 3-tap GEMMs over the separated layout ----
@@ -443,8 +439,10 @@ int univtg_forward(univtg_plan* P, const float* src_txt, const float* src_txt_ma
     {
       LnArgs a;
       memset(&a, 0, sizeof(a));
-      a.in = P->y32;
+      a.in = P->x32;
       a.ld_in = d;
+      a.add16 = P->br16;
+      a.ld_add16 = d;
       a.rows = P->M;
       a.d = d;
       a.gamma = F32(lp.n1w);
@@ -471,8 +469,10 @@ int univtg_forward(univtg_plan* P, const float* src_txt, const float* src_txt_ma
     {
       LnArgs a;
       memset(&a, 0, sizeof(a));
-      a.in = P->y32;
+      a.in = P->x32;
       a.ld_in = d;
+      a.add16 = P->br16;
+      a.ld_add16 = d;
       a.rows = P->M;
       a.d = d;
       a.gamma = F32(lp.n2w);

@@ -11,7 +11,8 @@
 //   warp 0 lane 0 : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier expect_tx)
 //   warp 1 lane 0 : MMA issuer     (tcgen05.mma cta_group::1, M=128, N=BN, K=16 x4 per 64-wide k-block)
 //   warp 2        : TMEM allocator (2 accumulator stages of BN fp32 columns)
-//   warps 4..11   : epilogue       (tcgen05.ld 32x32b -> swizzled smem tile -> full-line 128-bit global loads/stores)
+//   warps 4..11   : epilogue       (tcgen05.ld 32x32b; thread = row owns whole 32 B sectors -> 128-bit global loads/stores;
+//                                   the TMEM load + residual loads of step c+1 are in flight while step c is processed)
 #include <stdarg.h>
 #include <stdio.h>
 
@@ -26,8 +27,8 @@ struct GemmCfg {
   static constexpr int kABytes = GEMM_BM * 128;          // 128 rows x 64 x 2 B
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;  // multiple of 1024
-  static constexpr int kEpiFloats = 8 * 1024 + 2 * 8 * 32;  // per-warp 32x32 fp32 staging tiles + per-row (out row, scale)
-  static constexpr int kSmemBytes = 512 /*align slack*/ + kStages * kStageBytes + kEpiFloats * 4 + 192;
+  static constexpr int kEpiFloats = 8 * (BN / 2);         // per-epilogue-warp bias slice
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kEpiFloats * 4 + 256;
   static constexpr uint32_t kTmemCols = 2 * BN;          // 256 or 512 (power of two)
 };
 
@@ -72,7 +73,6 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t align_off = (1024u - (raw_addr & 1023u)) & 1023u;  // 0 when the runtime honours the 1024 B alignment
-  if (align_off > 512u) __trap();                                  // the allocation carries only 512 B of slack
   uint8_t* smem = smem_raw + align_off;
 
   uint8_t* stage_base = smem;
@@ -200,18 +200,13 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
   } else if (warp >= 4) {
     // ========================================= epilogue =========================================
     // 8 warps: warp w may only touch TMEM lanes [32*(w%4), +32); the two warps of a lane quarter split the columns.
-    // Per 32x32 step: tcgen05.ld (thread = row) -> XOR-swizzled 4 KB smem tile -> "coalesced domain" where 8 lanes cover
-    // one 128 B row segment (4 rows per 128-bit instruction).  All math, residual/aux loads and stores happen in the
-    // coalesced domain, so every global access is a full 128 B line (the LSU wavefront count is what bounds this phase).
+    // thread = output row: every thread owns 16 consecutive columns per step = 32 B (16-bit) / 64 B (fp32) of one row,
+    // i.e. whole 32-byte sectors, so loads and stores go straight from/to registers with 128-bit accesses.
     const int wq = warp & 3;
     const int half = (warp - 4) >> 2;
     const int ew = warp - 4;
-    float* stg = epi_buf + ew * 1024;                 // [32 rows][32 cols] fp32, quad q of row r at physical quad q ^ (r & 7)
-    int* orow_s = reinterpret_cast<int*>(epi_buf + 8 * 1024) + ew * 32;   // output row per tile row (-1: skip)
-    float* rsc_s = epi_buf + 8 * 1024 + 8 * 32 + ew * 32;                 // alpha * row_scale per tile row
+    float* bias_s = epi_buf + ew * (BN / 2);
     const int fmt = g.fmt;
-    const int rsub = lane >> 3;  // row inside a group of 4
-    const int cq = lane & 7;     // 4-column quad inside the 32-column step
     int as = 0;
     uint32_t aphase = 0;
     TileInfo ti;
@@ -227,35 +222,47 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       float* __restrict__ out32_id = pr.out32_id;
       uint16_t* __restrict__ out16 = pr.out16;
       uint16_t* __restrict__ out16p = pr.out16p;
-      float* __restrict__ pre32 = pr.pre32;
-      const float* __restrict__ aux32 = pr.aux32;
-      const uint16_t* __restrict__ mask16 = pr.mask16;
-      float* __restrict__ colsum = pr.colsum;
-      const int ld_resid = pr.ld_resid, ld_addtab = pr.ld_addtab, ld32 = pr.ld32, ld32_id = pr.ld32_id, ld16 = pr.ld16;
-      const int ld_pre = pr.ld_pre, ld_aux = pr.ld_aux, ld_mask = pr.ld_mask, aux_mode = pr.aux_mode;
       const bool atomic = (pr.accumulate != 0) || (pr.ksplit > 1);
       const bool vec = pr.vec_ok != 0;
       const int ofmt = pr.out_fmt < 0 ? fmt : pr.out_fmt;
+      const float* __restrict__ aux32 = pr.aux32;
+      const int aux_mode = pr.aux_mode;
+      const uint16_t* __restrict__ mask16 = pr.mask16;
+      float* __restrict__ colsum = pr.colsum;
       const int cs32 = pr.cs32 > 1 ? pr.cs32 : 1;
+      float* __restrict__ pre32 = pr.pre32;
 
       const int m0 = ti.m_blk * GEMM_BM + wq * 32;
       const int n_base = ti.n_blk * BN + half * (BN / 2);
-      // ---- per-row bookkeeping (thread = row) ----
+      // ---- this thread's row ----
+      const int m = m0 + lane;
+      int b = 0, l = m;
+      if (rps_in > 0) {
+        b = m / rps_in;
+        l = m - b * rps_in;
+      }
+      const bool is_sep = (rps_in > 0) && (l == rps_in - 1);
+      const bool valid = (m < pM) && !(pr.skip_sep && is_sep);
+      float rsc = pr.alpha;
+      if (pr.row_scale != nullptr && m < pM) rsc *= pr.row_scale[b];
+      if (pr.zero_sep && is_sep) rsc = 0.f;
+      const size_t orow = (size_t)((rps_in > 0 ? b * pr.rps_out + l : m) + pr.row_off);
+      const float* resid_row = resid ? resid + orow * pr.ld_resid : nullptr;
+      const float* aux_row = aux32 ? aux32 + orow * pr.ld_aux : nullptr;
+      const uint16_t* mask_row = mask16 ? mask16 + orow * pr.ld_mask : nullptr;
+      const float* add_row = addtab ? addtab + (size_t)m * pr.ld_addtab : nullptr;
+      float* o32_row = out32 ? out32 + orow * pr.ld32 : nullptr;
+      float* o32i_row = out32_id ? out32_id + (size_t)m * pr.ld32_id : nullptr;
+      uint16_t* o16_row = out16 ? out16 + orow * pr.ld16 : nullptr;
+      uint16_t* o16p_row = out16p ? out16p + orow * pr.ld16 : nullptr;
+      float* pre_row = pre32 ? pre32 + orow * pr.ld_pre : nullptr;
+
+      // bias slice of this warp's columns -> smem (broadcast reads in the column loop)
       __syncwarp();
-      {
-        const int m = m0 + lane;
-        int b = 0, l = m;
-        if (rps_in > 0) {
-          b = m / rps_in;
-          l = m - b * rps_in;
-        }
-        const bool is_sep = (rps_in > 0) && (l == rps_in - 1);
-        const bool valid = (m < pM) && !(pr.skip_sep && is_sep);
-        float rsc = pr.alpha;
-        if (pr.row_scale != nullptr && m < pM) rsc *= pr.row_scale[b];
-        if (pr.zero_sep && is_sep) rsc = 0.f;
-        orow_s[lane] = valid ? ((rps_in > 0 ? b * pr.rps_out + l : m) + pr.row_off) : -1;
-        rsc_s[lane] = rsc;
+#pragma unroll
+      for (int j = lane; j < BN / 2; j += 32) {
+        const int n = n_base + j;
+        bias_s[j] = (bias != nullptr && n < pN) ? __ldg(bias + n) : 0.f;
       }
       __syncwarp();
 
@@ -263,139 +270,163 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       if (ew == 0 && lane == 0) stamp(g.dbg, 5);  // accumulator ready
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + as * BN + half * (BN / 2);
-      int nsteps = (pN - n_base + 31) / 32;  // 32-column steps this warp owns in this tile (warp-uniform)
-      nsteps = nsteps < 0 ? 0 : (nsteps > BN / 64 ? BN / 64 : nsteps);
 
-      uint32_t r[32];
-      if (nsteps > 0) tmem_ld_32x32b_x32(t_addr, r);
+      // number of 16-column steps this warp owns in this tile (warp-uniform)
+      int nsteps = (pN - n_base + 15) / 16;
+      nsteps = nsteps < 0 ? 0 : (nsteps > BN / 32 ? BN / 32 : nsteps);
+      const bool load_resid = vec && valid && (resid_row != nullptr);
+      uint32_t r[16];
+      float rv_next[16];
+      // software pipeline: the TMEM load and the residual loads of step c+1 are in flight while step c is processed
+      if (nsteps > 0) {
+        tmem_ld_32x32b_x16(t_addr, r);
+        if (load_resid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 t4 = *reinterpret_cast<const float4*>(resid_row + n_base + 4 * q);
+            rv_next[4 * q] = t4.x; rv_next[4 * q + 1] = t4.y; rv_next[4 * q + 2] = t4.z; rv_next[4 * q + 3] = t4.w;
+          }
+        }
+      }
       for (int c = 0; c < nsteps; ++c) {
-        const int n0 = n_base + c * 32;
-        const int n = n0 + 4 * cq;  // this lane's 4 columns
-        // residual rows of this step: issue the loads before waiting on TMEM
-        float4 rv[8];
-        if (vec && resid != nullptr && n < pN) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int orr = orow_s[rsub + 4 * i];
-            rv[i] = orr >= 0 ? *reinterpret_cast<const float4*>(resid + (size_t)orr * ld_resid + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias != nullptr && n < pN) {
-          if (vec) bv = __ldg(reinterpret_cast<const float4*>(bias + n));
-          else {
-            bv.x = __ldg(bias + n);
-            if (n + 1 < pN) bv.y = __ldg(bias + n + 1);
-            if (n + 2 < pN) bv.z = __ldg(bias + n + 2);
-            if (n + 3 < pN) bv.w = __ldg(bias + n + 3);
-          }
-        }
+        const int n0 = n_base + c * 16;
         tmem_ld_wait();
+        float v[16], rv[16];
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<uint4*>(stg + lane * 32 + 4 * (q ^ (lane & 7))) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
-        __syncwarp();
-        if (c + 1 < nsteps) tmem_ld_32x32b_x32(t_addr + (c + 1) * 32, r);  // in flight while this step is processed
-
-        float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (n < pN) {
+        for (int j = 0; j < 16; ++j) {
+          v[j] = __uint_as_float(r[j]) + bias_s[c * 16 + j];
+          rv[j] = rv_next[j];
+        }
+        if (c + 1 < nsteps) {
+          tmem_ld_32x32b_x16(t_addr + (c + 1) * 16, r);
+          if (load_resid) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = rsub + 4 * i;
-            const int orr = orow_s[rr];
-            if (orr < 0) continue;
-            float4 v = *reinterpret_cast<const float4*>(stg + rr * 32 + 4 * (cq ^ (rr & 7)));
-            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-            const int mrow = m0 + rr;
-            if (pre32 != nullptr) *reinterpret_cast<float4*>(pre32 + (size_t)orr * ld_pre + n) = v;  // pre-activation (training)
-            if (act == ACT_GELU) {
-              v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
-            } else if (act == ACT_RELU) {
-              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            for (int q = 0; q < 4; ++q) {
+              const float4 t4 = *reinterpret_cast<const float4*>(resid_row + n0 + 16 + 4 * q);
+              rv_next[4 * q] = t4.x; rv_next[4 * q + 1] = t4.y; rv_next[4 * q + 2] = t4.z; rv_next[4 * q + 3] = t4.w;
             }
-            const float rs = rsc_s[rr];
-            v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
-            if (vec) {
-              if (resid != nullptr) {
-                v.x += rv[i].x; v.y += rv[i].y; v.z += rv[i].z; v.w += rv[i].w;
-              }
-              if (aux32 != nullptr) {
-                const float4 av = *reinterpret_cast<const float4*>(aux32 + (size_t)orr * ld_aux + n);
+          }
+        }
+        if (pre_row != nullptr && valid) {  // training: keep the pre-activation (needs N % 4 == 0, checked on the host)
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (n0 + 4 * q < pN)
+              *reinterpret_cast<float4*>(pre_row + n0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        if (act == ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]) * rsc;
+        } else if (act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f) * rsc;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= rsc;
+        }
+        if (vec) {
+          if (valid) {
+            if (resid_row != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] += rv[j];
+            }
+            if (aux_row != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 a4 = *reinterpret_cast<const float4*>(aux_row + n0 + 4 * q);
                 if (aux_mode == 1) {
-                  v.x *= gelu_erf_grad(av.x); v.y *= gelu_erf_grad(av.y); v.z *= gelu_erf_grad(av.z); v.w *= gelu_erf_grad(av.w);
+                  v[4 * q] *= gelu_erf_grad(a4.x); v[4 * q + 1] *= gelu_erf_grad(a4.y);
+                  v[4 * q + 2] *= gelu_erf_grad(a4.z); v[4 * q + 3] *= gelu_erf_grad(a4.w);
                 } else {
-                  v.x *= av.x; v.y *= av.y; v.z *= av.z; v.w *= av.w;
+                  v[4 * q] *= a4.x; v[4 * q + 1] *= a4.y; v[4 * q + 2] *= a4.z; v[4 * q + 3] *= a4.w;
                 }
-              }
-              if (mask16 != nullptr) {
-                const uint2 mk = *reinterpret_cast<const uint2*>(mask16 + (size_t)orr * ld_mask + n);
-                if (!pos16((uint16_t)(mk.x & 0xffff))) v.x = 0.f;
-                if (!pos16((uint16_t)(mk.x >> 16))) v.y = 0.f;
-                if (!pos16((uint16_t)(mk.y & 0xffff))) v.z = 0.f;
-                if (!pos16((uint16_t)(mk.y >> 16))) v.w = 0.f;
-              }
-              csum.x += v.x; csum.y += v.y; csum.z += v.z; csum.w += v.w;
-              if (out32 != nullptr) {
-                float* dst = out32 + (size_t)orr * ld32 + n;
-                if (atomic) {
-                  atomicAdd(dst, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
-                } else {
-                  *reinterpret_cast<float4*>(dst) = v;
-                }
-              }
-              if (out32_id != nullptr) *reinterpret_cast<float4*>(out32_id + (size_t)mrow * ld32_id + n) = v;
-              if (out16 != nullptr)
-                *reinterpret_cast<uint2*>(out16 + (size_t)orr * ld16 + n) = make_uint2(cvt16x2(v.x, v.y, ofmt), cvt16x2(v.z, v.w, ofmt));
-              if (out16p != nullptr) {
-                float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (addtab != nullptr) pv = *reinterpret_cast<const float4*>(addtab + (size_t)mrow * ld_addtab + n);
-                *reinterpret_cast<uint2*>(out16p + (size_t)orr * ld16 + n) =
-                    make_uint2(cvt16x2(v.x + pv.x, v.y + pv.y, ofmt), cvt16x2(v.z + pv.z, v.w + pv.w, ofmt));
-              }
-            } else {
-              // unaligned leading dimensions / ragged N (e.g. the [d, 2818] projector weight gradient): scalar accesses
-              const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (n + e >= pN) break;
-                float x = vv[e];
-                if (resid != nullptr) x += resid[(size_t)orr * ld_resid + n + e];
-                if (aux32 != nullptr) {
-                  const float av = aux32[(size_t)orr * ld_aux + n + e];
-                  x *= (aux_mode == 1) ? gelu_erf_grad(av) : av;
-                }
-                if (mask16 != nullptr && !pos16(mask16[(size_t)orr * ld_mask + n + e])) x = 0.f;
-                (&csum.x)[e] += x;
-                if (out32 != nullptr) {
-                  float* dst = out32 + (size_t)orr * ld32 + (size_t)(n + e) * cs32;
-                  if (atomic) atomicAdd(dst, x);
-                  else *dst = x;
-                }
-                if (out32_id != nullptr) out32_id[(size_t)mrow * ld32_id + n + e] = x;
-                if (out16 != nullptr) out16[(size_t)orr * ld16 + n + e] = cvt16(x, ofmt);
-                if (out16p != nullptr)
-                  out16p[(size_t)orr * ld16 + n + e] = cvt16(x + (addtab ? addtab[(size_t)mrow * ld_addtab + n + e] : 0.f), ofmt);
               }
             }
-          }
-        }
-        if (colsum != nullptr) {  // warp-uniform; lanes cq, cq+8, cq+16, cq+24 hold partial sums of the same 4 columns
+            if (mask_row != nullptr) {
 #pragma unroll
-          for (int o = 8; o < 32; o <<= 1) {
-            csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o);
-            csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
-            csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o);
-            csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
+              for (int q = 0; q < 2; ++q) {
+                const uint4 mk = *reinterpret_cast<const uint4*>(mask_row + n0 + 8 * q);
+                const uint32_t w4[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (!pos16((uint16_t)(w4[e] & 0xffff))) v[8 * q + 2 * e] = 0.f;
+                  if (!pos16((uint16_t)(w4[e] >> 16))) v[8 * q + 2 * e + 1] = 0.f;
+                }
+              }
+            }
+            if (o32_row != nullptr) {
+              if (atomic) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) atomicAdd(o32_row + n0 + j, v[j]);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  *reinterpret_cast<float4*>(o32_row + n0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              }
+            }
+            if (o32i_row != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(o32i_row + n0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+            if (o16_row != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 2; ++q)
+                *reinterpret_cast<uint4*>(o16_row + n0 + 8 * q) =
+                    make_uint4(cvt16x2(v[8 * q], v[8 * q + 1], ofmt), cvt16x2(v[8 * q + 2], v[8 * q + 3], ofmt),
+                               cvt16x2(v[8 * q + 4], v[8 * q + 5], ofmt), cvt16x2(v[8 * q + 6], v[8 * q + 7], ofmt));
+            }
+            if (o16p_row != nullptr) {
+              float p[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) p[j] = v[j];
+              if (add_row != nullptr) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 a4 = *reinterpret_cast<const float4*>(add_row + n0 + 4 * q);
+                  p[4 * q] += a4.x; p[4 * q + 1] += a4.y; p[4 * q + 2] += a4.z; p[4 * q + 3] += a4.w;
+                }
+              }
+#pragma unroll
+              for (int q = 0; q < 2; ++q)
+                *reinterpret_cast<uint4*>(o16p_row + n0 + 8 * q) =
+                    make_uint4(cvt16x2(p[8 * q], p[8 * q + 1], ofmt), cvt16x2(p[8 * q + 2], p[8 * q + 3], ofmt),
+                               cvt16x2(p[8 * q + 4], p[8 * q + 5], ofmt), cvt16x2(p[8 * q + 6], p[8 * q + 7], ofmt));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.f;  // invalid rows contribute nothing to the column sums
           }
-          if (rsub == 0 && n < pN) {
-            const float cs = pr.colsum_scale;
-            atomicAdd(colsum + n, csum.x * cs);
-            if (n + 1 < pN) atomicAdd(colsum + n + 1, csum.y * cs);
-            if (n + 2 < pN) atomicAdd(colsum + n + 2, csum.z * cs);
-            if (n + 3 < pN) atomicAdd(colsum + n + 3, csum.w * cs);
+        } else {
+          // unaligned leading dimensions / ragged N (e.g. the [d, 2818] projector weight gradient): scalar accesses
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = n0 + j;
+            float x = v[j];
+            if (valid && n < pN) {
+              if (resid_row != nullptr) x += resid_row[n];
+              if (aux_row != nullptr) x *= (aux_mode == 1) ? gelu_erf_grad(aux_row[n]) : aux_row[n];
+              if (mask_row != nullptr && !pos16(mask_row[n])) x = 0.f;
+              if (o32_row != nullptr) {
+                float* dst = o32_row + (size_t)n * cs32;
+                if (atomic) atomicAdd(dst, x);
+                else *dst = x;
+              }
+              if (o32i_row != nullptr) o32i_row[n] = x;
+              if (o16_row != nullptr) o16_row[n] = cvt16(x, ofmt);
+              if (o16p_row != nullptr) o16p_row[n] = cvt16(x + (add_row ? add_row[n] : 0.f), ofmt);
+            } else {
+              x = 0.f;
+            }
+            v[j] = x;
           }
         }
-        __syncwarp();  // staging tile is free again
+        if (colsum != nullptr) {  // warp-uniform: column sums over this warp's 32 rows, one atomic per column
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float sj = warp_sum(v[j]);
+            if (lane == j && n0 + j < pN) atomicAdd(colsum + n0 + j, sj * pr.colsum_scale);
+          }
+        }
       }
       // release the accumulator stage
       tc_fence_before();
@@ -501,13 +532,12 @@ static int launch_bn(GemmGroup& g, int num_sms, cudaStream_t stream) {
     total += ((pr.M + GEMM_BM - 1) / GEMM_BM) * ((pr.N + BN - 1) / BN) * pr.ksplit;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     GemmProblem& w = g.p[p];
-    w.vec_ok = (pr.N % 4 == 0) && (pr.cs32 <= 1) && al16(pr.bias) && (!pr.aux32 || (al16(pr.aux32) && pr.ld_aux % 4 == 0)) &&
-               (!pr.pre32 || (al16(pr.pre32) && pr.ld_pre % 4 == 0)) &&
-               (!pr.mask16 || ((reinterpret_cast<uintptr_t>(pr.mask16) & 7) == 0 && pr.ld_mask % 4 == 0)) && (!pr.resid || (al16(pr.resid) && pr.ld_resid % 4 == 0)) &&
-               (!pr.addtab || (al16(pr.addtab) && pr.ld_addtab % 4 == 0)) && (!pr.out32 || (al16(pr.out32) && pr.ld32 % 4 == 0)) &&
-               (!pr.out32_id || (al16(pr.out32_id) && pr.ld32_id % 4 == 0)) &&
-               ((!pr.out16 && !pr.out16p) || (pr.ld16 % 4 == 0 && (reinterpret_cast<uintptr_t>(pr.out16) & 7) == 0 &&
-                                              (reinterpret_cast<uintptr_t>(pr.out16p) & 7) == 0));
+    // v3 epilogue (thread = row, 16 columns per step): 128-bit accesses need N % 16 == 0 and aligned leading dimensions
+    w.vec_ok = (pr.N % 16 == 0) && (pr.cs32 <= 1) && (!pr.aux32 || (al16(pr.aux32) && pr.ld_aux % 4 == 0)) &&
+               (!pr.pre32 || (al16(pr.pre32) && pr.ld_pre % 4 == 0)) && (!pr.mask16 || (al16(pr.mask16) && pr.ld_mask % 8 == 0)) &&
+               (!pr.resid || (al16(pr.resid) && pr.ld_resid % 4 == 0)) && (!pr.addtab || (al16(pr.addtab) && pr.ld_addtab % 4 == 0)) &&
+               (!pr.out32 || (al16(pr.out32) && pr.ld32 % 4 == 0)) && (!pr.out32_id || (al16(pr.out32_id) && pr.ld32_id % 4 == 0)) &&
+               ((!pr.out16 && !pr.out16p) || (pr.ld16 % 8 == 0 && al16(pr.out16) && al16(pr.out16p)));
   }
   if (total == 0) return 0;
   const int grid = total < num_sms ? total : num_sms;

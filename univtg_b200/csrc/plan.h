@@ -218,8 +218,8 @@ struct univtg_plan {
   float* pos;                     // [Mv, d]
   float* key_mask;                // [B, L]
   float* pool_logits;             // [B, Lt]
-  float *x32, *y32;               // residual stream / pre-LayerNorm sum
-  uint16_t *x16, *xpos16, *qkv16, *attn16, *h16;
+  float* x32;                     // fp32 residual stream (LayerNorm works in place on it)
+  uint16_t *x16, *xpos16, *qkv16, *attn16, *h16, *br16;  // br16: DropPath-scaled residual branch (out-proj / FFN2 output)
   uint16_t *hA, *h1, *hc2, *hs2;  // conv-head buffers (separated layout)
   // launch descriptors
   GemmGroup g_proj[3];
@@ -289,7 +289,7 @@ int setup_linear(GemmProblem& p, const uint16_t* A, int M, int K, int lda, const
 namespace {
 
 struct WsLayout {
-  size_t a_vid[3], a_txt[3], p_vid32, p_txt32, txtproj32, pos, key_mask, pool_logits, x32, y32, x16, xpos16, qkv16, attn16, h16, hA,
+  size_t a_vid[3], a_txt[3], p_vid32, p_txt32, txtproj32, pos, key_mask, pool_logits, x32, br16, x16, xpos16, qkv16, attn16, h16, hA,
       h1, hc2, hs2, total;
 };
 
@@ -311,7 +311,7 @@ WsLayout make_ws(const univtg_config& c, const univtg_shape& s, const PackedLayo
   w.key_mask = cur.take(B * Lc * 4);
   w.pool_logits = cur.take(B * Lt * 4);
   w.x32 = cur.take(M * d * 4);
-  w.y32 = cur.take(M * d * 4);
+  w.br16 = cur.take(M * d * 2);
   w.x16 = cur.take(M * d * 2);
   w.xpos16 = cur.take(M * d * 2);
   w.qkv16 = cur.take(M * 3 * d * 2);

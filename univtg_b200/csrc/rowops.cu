@@ -74,7 +74,16 @@ __global__ void __launch_bounds__(256) layernorm_rows_vec_kernel(const LnArgs a)
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    v[i] = *reinterpret_cast<const float4*>(x + (i * 32 + lane) * 4);
+    const int j = (i * 32 + lane) * 4;
+    v[i] = *reinterpret_cast<const float4*>(x + j);
+    if (a.add16) {
+      const uint2 h = *reinterpret_cast<const uint2*>(a.add16 + (size_t)warp * a.ld_add16 + j);
+      v[i].x += ld16((uint16_t)(h.x & 0xffff), a.fmt);
+      v[i].y += ld16((uint16_t)(h.x >> 16), a.fmt);
+      v[i].z += ld16((uint16_t)(h.y & 0xffff), a.fmt);
+      v[i].w += ld16((uint16_t)(h.y >> 16), a.fmt);
+      if (a.sum_out) *reinterpret_cast<float4*>(a.sum_out + (size_t)warp * a.d + j) = v[i];
+    }
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   const float mean = warp_sum(s) / (float)a.d;
@@ -146,6 +155,10 @@ __global__ void __launch_bounds__(128) layernorm_rows_block_kernel(const LnArgs 
   for (int i = 0; i < EPT; ++i) {
     const int j = tid + 128 * i;
     v[i] = j < a.d ? x[j] : 0.f;
+    if (a.add16 && j < a.d) {
+      v[i] += ld16(a.add16[(size_t)row * a.ld_add16 + j], a.fmt);
+      if (a.sum_out) a.sum_out[(size_t)row * a.d + j] = v[i];
+    }
     s += v[i];
   }
   s = warp_sum(s);
@@ -193,7 +206,13 @@ int launch_layernorm(const LnArgs& a, cudaStream_t stream) {
   else if (vec_ok && a.d == 256) layernorm_rows_vec_kernel<2><<<blocks, threads, 0, stream>>>(a);
   else if (a.d <= 128 * 8) layernorm_rows_block_kernel<8><<<a.rows, 128, 0, stream>>>(a);
   else if (a.d <= 128 * 24) layernorm_rows_block_kernel<24><<<a.rows, 128, 0, stream>>>(a);
-  else layernorm_rows_generic_kernel<<<blocks, threads, 0, stream>>>(a);
+  else {
+    if (a.add16) {
+      set_error("layernorm: fused branch add needs d <= 3072");
+      return (int)cudaErrorInvalidValue;
+    }
+    layernorm_rows_generic_kernel<<<blocks, threads, 0, stream>>>(a);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("layernorm launch failed: %s", cudaGetErrorString(e));
   return (int)e;

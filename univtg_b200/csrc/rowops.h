@@ -9,6 +9,9 @@ namespace uv {
 struct LnArgs {
   const float* in;  // [rows, ld_in] fp32
   int ld_in;
+  const uint16_t* add16;  // optional 16-bit [rows, ld_add16] branch added to `in` before normalising (x + DropPath(branch))
+  int ld_add16;
+  float* sum_out;         // optional fp32 [rows, d]: the pre-normalisation sum (saved for LayerNorm backward)
   int rows, d;
   const float* gamma;
   const float* beta;

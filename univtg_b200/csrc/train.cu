@@ -53,7 +53,7 @@ struct TrainWs {
   uint16_t *qkv16[16], *attn16[16], *x1_16[16], *h16[16];
   float *lse[16], *y1[16], *mean1[16], *rstd1[16], *hpre[16], *y2[16], *mean2[16], *rstd2[16];
   float *x32, *x1_32;
-  uint16_t *hA, *h1, *hc2, *hs2;
+  uint16_t *hA, *h1, *hc2, *hs2, *br16;
   float *pred_logits, *pred_spans, *vid_mem_proj, *txt_mem_proj;  // copies of the outputs the backward needs
   // ---- backward scratch ----
   float *dx, *dy, *dqkv32, *delta, *dz, *dxt_pool, *dA_v, *dA_t;
@@ -112,6 +112,7 @@ TrainWs make_train_ws(const univtg_config& c, const univtg_shape& s, const Packe
   w.h1 = take16((Mh + 2) * 2 * d);
   w.hc2 = take16((Mh + 2) * d);
   w.hs2 = take16((Mh + 2) * d);
+  w.br16 = take16(M * d);
   w.pred_logits = take32(Mv);
   w.pred_spans = take32(Mv * 2);
   w.vid_mem_proj = take32(Mv * d);
@@ -284,17 +285,18 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
     g.p[0].rps_in = L;
     g.p[0].rps_out = L;
     g.p[0].row_scale = droppath_scale ? droppath_scale + (size_t)(2 * l) * P->B : nullptr;
-    g.p[0].resid = T.x32;
-    g.p[0].ld_resid = d;
-    g.p[0].out32 = T.y1[l];
-    g.p[0].ld32 = d;
+    g.p[0].out16 = T.br16;
+    g.p[0].ld16 = d;
     rc = launch_gemm_group(g, bn, sms, st);
     if (rc) return rc;
     {
       LnArgs a;
       memset(&a, 0, sizeof(a));
-      a.in = T.y1[l];
+      a.in = T.x32;
       a.ld_in = d;
+      a.add16 = T.br16;
+      a.ld_add16 = d;
+      a.sum_out = T.y1[l];
       a.rows = M;
       a.d = d;
       a.gamma = F32(lp.n1w);
@@ -331,17 +333,18 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
     g.p[0].rps_in = L;
     g.p[0].rps_out = L;
     g.p[0].row_scale = droppath_scale ? droppath_scale + (size_t)(2 * l + 1) * P->B : nullptr;
-    g.p[0].resid = T.x1_32;
-    g.p[0].ld_resid = d;
-    g.p[0].out32 = T.y2[l];
-    g.p[0].ld32 = d;
+    g.p[0].out16 = T.br16;
+    g.p[0].ld16 = d;
     rc = launch_gemm_group(g, bn, sms, st);
     if (rc) return rc;
     {
       LnArgs a;
       memset(&a, 0, sizeof(a));
-      a.in = T.y2[l];
+      a.in = T.x1_32;
       a.ld_in = d;
+      a.add16 = T.br16;
+      a.ld_add16 = d;
+      a.sum_out = T.y2[l];
       a.rows = M;
       a.d = d;
       a.gamma = F32(lp.n2w);
