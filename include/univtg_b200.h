@@ -133,7 +133,8 @@ int univtg_plan_read_profile(univtg_plan* plan, float* ms, int32_t* kinds, int32
 
 /* C[M,N] = act(A*B^T + bias) * alpha.  a: [M,K] (a_mn=0) or [K,M] (a_mn=1); b: [N,K] (b_mn=0) or [K,N] (b_mn=1),
  * 16-bit operands in `fmt`; K and the leading dimensions must be multiples of 8 elements.  out32 [M,N] f32 and/or
- * out16 [M,N] 16-bit.  bn in {128,256}; ksplit>1 accumulates atomically into a pre-zeroed out32. */
+ * out16 [M,N] 16-bit.  bn: tile width, multiple of 16 in [32,256] (multiple of 64 when b_mn); ksplit>1 accumulates
+ * atomically into a pre-zeroed out32. */
 int univtg_op_gemm(const void* a, const void* b, int32_t M, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn, int32_t fmt,
                    int32_t bn, int32_t ksplit, const float* bias, int32_t act, float alpha, float* out32, void* out16,
                    void* stream);

@@ -196,6 +196,12 @@ CASES = {
     "gemm_k_big_fp16": (case_gemm, (3424, 1024, 1024, 0, 0, 0, 256, 1, 2, True)),
     "gemm_k_big_multi_wave": (case_gemm, (3424, 3072, 1024, 0, 0, 0, 256, 1, 0, True)),
     "gemm_k_ksplit": (case_gemm, (1024, 1024, 3424, 0, 0, 0, 256, 4, 0, False)),
+    "gemm_bn208": (case_gemm, (3424, 1024, 1024, 0, 0, 0, 208, 1, 2, True)),
+    "gemm_bn144_ragged": (case_gemm, (300, 400, 200, 0, 0, 0, 144, 1, 1, True)),
+    "gemm_bn192_bmn": (case_gemm, (256, 384, 192, 0, 1, 0, 192, 1, 0, True)),
+    "tl_ffn1_bn208": (case_gemm_timeline, (3424, 1024, 1024, 2, False, True, 208)),
+    "tl_plain16_bn208": (case_gemm_timeline, (3424, 1024, 1024, 0, False, True, 208)),
+    "tl_qkv_bn208": (case_gemm_timeline, (3424, 3072, 1024, 0, False, True, 208)),
     "gemm_amn": (case_gemm, (256, 256, 192, 1, 0, 0, 256, 1, 0, True)),
     "gemm_bmn": (case_gemm, (256, 256, 192, 0, 1, 0, 256, 1, 0, True)),
     "gemm_abmn_bn128": (case_gemm, (256, 384, 200, 1, 1, 0, 128, 1, 0, True)),

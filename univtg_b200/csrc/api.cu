@@ -181,6 +181,21 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
   int rc = 0;
   // tile width: 256 when the N extent has at least one full 256 tile, else 128
   P->bn_main = (d % 256 == 0) ? 256 : 128;
+  {
+    // per-launch tile widths: fill the SMs with as little wave quantisation as possible
+    const int sms = P->num_sms;
+    auto bn2 = [&](int M0, int N0, int M1, int N1) {
+      const int Ms[2] = {M0, M1}, Ns[2] = {N0, N1};
+      return choose_bn(Ms, Ns, nullptr, M1 > 0 ? 2 : 1, sms, 16);
+    };
+    for (int i = 0; i < cfg->n_input_proj; ++i) P->bn_proj[i] = bn2(P->Mv, d, P->Mt, d);
+    P->bn_qkv = bn2(P->M, 2 * d, P->M, d);
+    P->bn_out = bn2(P->M, d, 0, 0);
+    P->bn_ffn1 = bn2(P->M, ff, 0, 0);
+    P->bn_ffn2 = bn2(P->M, d, 0, 0);
+    P->bn_conv1 = bn2(P->Mh, 2 * d, 0, 0);
+    P->bn_conv2 = bn2(P->Mh, d, P->Mh, d);
+  }
 
   // ---- input projectors: one grouped launch per projector depth (video + text problems) ----
   for (int i = 0; i < cfg->n_input_proj && !rc; ++i) {
@@ -189,8 +204,7 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
     g.num = 2;
     g.fmt = fmt;
     const bool last = (i == cfg->n_input_proj - 1);
-    const int bn = P->bn_main;
-    P->bn_proj[i] = bn;
+    const int bn = P->bn_proj[i];
     GemmProblem& pv = g.p[0];
     GemmProblem& pt = g.p[1];
     rc |= setup_linear(pv, P->a_vid[i], P->Mv, Lw.vid[i].kpad, Lw.vid[i].kpad, W16(Lw.vid[i].w16), d, Lw.vid[i].kpad, bn);
@@ -233,8 +247,8 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
       g.num = 2;
       g.fmt = fmt;
       // q = k = x + pos -> columns [0, 2d) of qkv16; v = x -> columns [2d, 3d)   (in_proj rows: Wq, Wk, Wv)
-      rc |= setup_linear(g.p[0], P->xpos16, P->M, d, d, W16(lp.w_in), 2 * d, d, P->bn_main);
-      rc |= setup_linear(g.p[1], P->x16, P->M, d, d, W16(lp.w_in) + (size_t)2 * d * d, d, d, P->bn_main);
+      rc |= setup_linear(g.p[0], P->xpos16, P->M, d, d, W16(lp.w_in), 2 * d, d, P->bn_qkv);
+      rc |= setup_linear(g.p[1], P->x16, P->M, d, d, W16(lp.w_in) + (size_t)2 * d * d, d, d, P->bn_qkv);
       g.p[0].bias = F32(lp.b_in);
       g.p[0].out16 = P->qkv16;
       g.p[0].ld16 = 3 * d;
@@ -263,7 +277,7 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
       memset(&g, 0, sizeof(g));
       g.num = 1;
       g.fmt = fmt;
-      rc |= setup_linear(g.p[0], P->attn16, P->M, d, d, W16(lp.w_out), d, d, P->bn_main);
+      rc |= setup_linear(g.p[0], P->attn16, P->M, d, d, W16(lp.w_out), d, d, P->bn_out);
       g.p[0].bias = F32(lp.b_out);
       g.p[0].rps_in = P->L;
       g.p[0].rps_out = P->L;
@@ -275,7 +289,7 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
       memset(&g, 0, sizeof(g));
       g.num = 1;
       g.fmt = fmt;
-      rc |= setup_linear(g.p[0], P->x16, P->M, d, d, W16(lp.w1), ff, d, (ff % 256 == 0) ? 256 : 128);
+      rc |= setup_linear(g.p[0], P->x16, P->M, d, d, W16(lp.w1), ff, d, P->bn_ffn1);
       g.p[0].bias = F32(lp.b1);
       g.p[0].act = ACT_GELU;
       g.p[0].out16 = P->h16;
@@ -286,7 +300,7 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
       memset(&g, 0, sizeof(g));
       g.num = 1;
       g.fmt = fmt;
-      rc |= setup_linear(g.p[0], P->h16, P->M, ff, ff, W16(lp.w2), d, ff, P->bn_main);
+      rc |= setup_linear(g.p[0], P->h16, P->M, ff, ff, W16(lp.w2), d, ff, P->bn_ffn2);
       g.p[0].bias = F32(lp.b2);
       g.p[0].rps_in = P->L;
       g.p[0].rps_out = P->L;
@@ -296,9 +310,8 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
   }
   // ---- conv heads (k=3, pad=1) as 3-tap GEMMs over the separated layout ----
   if (!rc) {
-    const int bn = P->bn_main;
     auto conv_problem = [&](GemmProblem& p, const uint16_t* A, int lda, const uint16_t* W, int N, const float* bias,
-                            uint16_t* out, int ldo) -> int {
+                            uint16_t* out, int ldo, int bn) -> int {
       init_problem(p);
       p.M = P->Mh;
       p.N = N;
@@ -323,12 +336,12 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
     memset(&P->g_conv1, 0, sizeof(GemmGroup));
     P->g_conv1.num = 1;
     P->g_conv1.fmt = fmt;
-    rc |= conv_problem(P->g_conv1.p[0], P->hA, d, W16(Lw.conv1_w), 2 * d, F32(Lw.conv1_b), P->h1, 2 * d);
+    rc |= conv_problem(P->g_conv1.p[0], P->hA, d, W16(Lw.conv1_w), 2 * d, F32(Lw.conv1_b), P->h1, 2 * d, P->bn_conv1);
     memset(&P->g_conv2, 0, sizeof(GemmGroup));
     P->g_conv2.num = 2;
     P->g_conv2.fmt = fmt;
-    rc |= conv_problem(P->g_conv2.p[0], P->h1, 2 * d, W16(Lw.conv2c_w), d, F32(Lw.conv2c_b), P->hc2, d);
-    rc |= conv_problem(P->g_conv2.p[1], P->h1 + d, 2 * d, W16(Lw.conv2s_w), d, F32(Lw.conv2s_b), P->hs2, d);
+    rc |= conv_problem(P->g_conv2.p[0], P->h1, 2 * d, W16(Lw.conv2c_w), d, F32(Lw.conv2c_b), P->hc2, d, P->bn_conv2);
+    rc |= conv_problem(P->g_conv2.p[1], P->h1 + d, 2 * d, W16(Lw.conv2s_w), d, F32(Lw.conv2s_b), P->hs2, d, P->bn_conv2);
   }
   if (rc) {
     delete P;
@@ -422,7 +435,7 @@ int univtg_forward(univtg_plan* P, const float* src_txt, const float* src_txt_ma
   // ---- encoder layers (post-norm; TransformerEncoderLayer.forward_post) ----
   for (int l = 0; l < c.enc_layers; ++l) {
     const LayerPacked& lp = Lw.layer[l];
-    rc = launch_gemm_group(P->g_qkv[l], P->bn_main, P->num_sms, st);
+    rc = launch_gemm_group(P->g_qkv[l], P->bn_qkv, P->num_sms, st);
     if (rc) return rc;
     prof_mark(P, st, 1);
     if (P->dh == 64 || P->dh == 128) rc = launch_attention(P->attn[l], st);
@@ -432,7 +445,7 @@ int univtg_forward(univtg_plan* P, const float* src_txt, const float* src_txt_ma
     {
       GemmGroup g = P->g_out[l];
       g.p[0].row_scale = droppath_scale ? droppath_scale + (size_t)(2 * l) * P->B : nullptr;
-      rc = launch_gemm_group(g, P->bn_main, P->num_sms, st);
+      rc = launch_gemm_group(g, P->bn_out, P->num_sms, st);
       if (rc) return rc;
       prof_mark(P, st, 1);
     }
@@ -456,13 +469,13 @@ int univtg_forward(univtg_plan* P, const float* src_txt, const float* src_txt_ma
       if (rc) return rc;
       prof_mark(P, st, 0);
     }
-    rc = launch_gemm_group(P->g_ffn1[l], (P->ff % 256 == 0) ? 256 : 128, P->num_sms, st);
+    rc = launch_gemm_group(P->g_ffn1[l], P->bn_ffn1, P->num_sms, st);
     if (rc) return rc;
     prof_mark(P, st, 1);
     {
       GemmGroup g = P->g_ffn2[l];
       g.p[0].row_scale = droppath_scale ? droppath_scale + (size_t)(2 * l + 1) * P->B : nullptr;
-      rc = launch_gemm_group(g, P->bn_main, P->num_sms, st);
+      rc = launch_gemm_group(g, P->bn_ffn2, P->num_sms, st);
       if (rc) return rc;
       prof_mark(P, st, 1);
     }
@@ -494,10 +507,10 @@ int univtg_forward(univtg_plan* P, const float* src_txt, const float* src_txt_ma
   }
 
   // ---- heads ----
-  rc = launch_gemm_group(P->g_conv1, P->bn_main, P->num_sms, st);
+  rc = launch_gemm_group(P->g_conv1, P->bn_conv1, P->num_sms, st);
   if (rc) return rc;
   prof_mark(P, st, 1);
-  rc = launch_gemm_group(P->g_conv2, P->bn_main, P->num_sms, st);
+  rc = launch_gemm_group(P->g_conv2, P->bn_conv2, P->num_sms, st);
   if (rc) return rc;
   prof_mark(P, st, 1);
   {
@@ -546,7 +559,7 @@ int univtg_forward(univtg_plan* P, const float* src_txt, const float* src_txt_ma
 int univtg_op_gemm(const void* a, const void* b, int32_t M, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn, int32_t fmt,
                    int32_t bn, int32_t ksplit, const float* bias, int32_t act, float alpha, float* out32, void* out16,
                    void* stream) {
-  if (!a || !b || M < 1 || N < 1 || K < 1 || (bn != 128 && bn != 256)) {
+  if (!a || !b || M < 1 || N < 1 || K < 1 || bn < 32 || bn > 256 || bn % 16 != 0) {
     set_error("univtg_op_gemm: bad argument");
     return 1;
   }

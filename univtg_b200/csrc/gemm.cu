@@ -21,15 +21,18 @@
 
 namespace uv {
 
-template <int BN>
+// The tile width BN is a RUN-TIME value (multiple of 16, 32..256; multiple of 64 when B is MN-major): the host picks it per
+// launch so that the tile count fills the 148 SMs with as little wave quantisation as possible.  Stage and TMEM strides are
+// sized for the maximum (256).
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = 4;
   static constexpr int kABytes = GEMM_BM * 128;          // 128 rows x 64 x 2 B
-  static constexpr int kBBytes = BN * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;  // multiple of 1024
-  static constexpr int kEpiFloats = 8 * (BN / 2);         // per-epilogue-warp bias slice
+  static constexpr int kBBytesMax = 256 * 128;
+  static constexpr int kStageBytes = kABytes + kBBytesMax;  // multiple of 1024
+  static constexpr int kEpiFloats = 8 * 128;              // per-epilogue-warp bias slice (<= 128 columns per warp)
   static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kEpiFloats * 4 + 256;
-  static constexpr uint32_t kTmemCols = 2 * BN;          // 256 or 512 (power of two)
+  static constexpr uint32_t kTmemCols = 512;              // two accumulator stages of up to 256 fp32 columns
+  static constexpr int kAccStride = 256;
 };
 
 struct TileInfo {
@@ -67,9 +70,9 @@ __device__ __forceinline__ void stamp(unsigned long long* dbg, int slot) {
   }
 }
 
-template <int BN>
 __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmGroup g) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg;
+  const int BN = g.bn;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t align_off = (1024u - (raw_addr & 1023u)) & 1023u;  // 0 when the runtime honours the 1024 B alignment
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kABytes + BN * 128);
           const int a0 = pr.ca.base0 + m0 * pr.ca.mn0s + tap * pr.ca.tap0 + kk * pr.ca.k0s;
           const int a1 = pr.ca.base1 + m0 * pr.ca.mn1s + tap * pr.ca.tap1 + kk * pr.ca.k1s;
           if (!pr.a_mn) {
@@ -142,7 +145,6 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           if (!pr.b_mn) {
             tma_load_2d(sb, &pr.tm_b, &full_bar[stage], b0, b1);
           } else {
-#pragma unroll
             for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &pr.tm_b, &full_bar[stage], b0 + 64 * j, b1);
           }
           if (++stage == Cfg::kStages) {
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
         const uint32_t idesc = make_idesc_f16_ab(GEMM_BM, BN, pr.a_fmt < 0 ? g.fmt : pr.a_fmt, pr.b_fmt < 0 ? g.fmt : pr.b_fmt, pr.a_mn, pr.b_mn);
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
+        const uint32_t d_tmem = tmem_base + as * Cfg::kAccStride;
         for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           if (kb == ti.kb0 && t == (int)blockIdx.x) stamp(g.dbg, 3);  // first operand stage landed
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
     const int wq = warp & 3;
     const int half = (warp - 4) >> 2;
     const int ew = warp - 4;
-    float* bias_s = epi_buf + ew * (BN / 2);
+    float* bias_s = epi_buf + ew * 128;
     const int fmt = g.fmt;
     int as = 0;
     uint32_t aphase = 0;
@@ -233,7 +235,11 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       float* __restrict__ pre32 = pr.pre32;
 
       const int m0 = ti.m_blk * GEMM_BM + wq * 32;
-      const int n_base = ti.n_blk * BN + half * (BN / 2);
+      // the BN/16 column steps of the tile are split between the two warps of this lane quarter (first warp gets the extra one)
+      const int tot_steps = BN / 16;
+      const int my_first = half ? (tot_steps + 1) / 2 : 0;
+      const int my_steps = half ? tot_steps / 2 : (tot_steps + 1) / 2;
+      const int n_base = ti.n_blk * BN + my_first * 16;
       // ---- this thread's row ----
       const int m = m0 + lane;
       int b = 0, l = m;
@@ -259,8 +265,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
 
       // bias slice of this warp's columns -> smem (broadcast reads in the column loop)
       __syncwarp();
-#pragma unroll
-      for (int j = lane; j < BN / 2; j += 32) {
+      for (int j = lane; j < my_steps * 16; j += 32) {
         const int n = n_base + j;
         bias_s[j] = (bias != nullptr && n < pN) ? __ldg(bias + n) : 0.f;
       }
@@ -269,11 +274,11 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       mbar_wait(&tmem_full[as], aphase);
       if (ew == 0 && lane == 0) stamp(g.dbg, 5);  // accumulator ready
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + as * BN + half * (BN / 2);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + as * Cfg::kAccStride + my_first * 16;
 
       // number of 16-column steps this warp owns in this tile (warp-uniform)
       int nsteps = (pN - n_base + 15) / 16;
-      nsteps = nsteps < 0 ? 0 : (nsteps > BN / 32 ? BN / 32 : nsteps);
+      nsteps = nsteps < 0 ? 0 : (nsteps > my_steps ? my_steps : nsteps);
       const bool load_resid = vec && valid && (resid_row != nullptr);
       uint32_t r[16];
       float rv_next[16];
@@ -504,12 +509,19 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
   return 0;
 }
 
-template <int BN>
-static int launch_bn(GemmGroup& g, int num_sms, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
+  using Cfg = GemmCfg;
+  if (g.num < 1 || g.num > GEMM_MAX_GROUP) {
+    set_error("gemm group size %d out of range", g.num);
+    return (int)cudaErrorInvalidValue;
+  }
+  if (bn < 32 || bn > 256 || bn % 16 != 0) {
+    set_error("unsupported BN %d (multiple of 16 in [32, 256])", bn);
+    return (int)cudaErrorInvalidValue;
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm, smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
       return (int)e;
@@ -523,16 +535,20 @@ static int launch_bn(GemmGroup& g, int num_sms, cudaStream_t stream) {
       set_error("gemm problem %d: bad k configuration (taps %d kblk %d ksplit %d)", p, pr.taps, pr.kblk_per_tap, pr.ksplit);
       return (int)cudaErrorInvalidValue;
     }
+    if (pr.b_mn && bn % 64 != 0) {
+      set_error("gemm problem %d: MN-major B needs BN %% 64 == 0 (got %d)", p, bn);
+      return (int)cudaErrorInvalidValue;
+    }
     const int total_kb = pr.taps * pr.kblk_per_tap;
     const int per = (total_kb + pr.ksplit - 1) / pr.ksplit;
     if ((pr.ksplit - 1) * per >= total_kb) {
       set_error("gemm problem %d: ksplit %d leaves an empty split for %d k-blocks", p, pr.ksplit, total_kb);
       return (int)cudaErrorInvalidValue;
     }
-    total += ((pr.M + GEMM_BM - 1) / GEMM_BM) * ((pr.N + BN - 1) / BN) * pr.ksplit;
+    total += ((pr.M + GEMM_BM - 1) / GEMM_BM) * ((pr.N + bn - 1) / bn) * pr.ksplit;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     GemmProblem& w = g.p[p];
-    // v3 epilogue (thread = row, 16 columns per step): 128-bit accesses need N % 16 == 0 and aligned leading dimensions
+    // epilogue (thread = row, 16 columns per step): 128-bit accesses need N % 16 == 0 and aligned leading dimensions
     w.vec_ok = (pr.N % 16 == 0) && (pr.cs32 <= 1) && (!pr.aux32 || (al16(pr.aux32) && pr.ld_aux % 4 == 0)) &&
                (!pr.pre32 || (al16(pr.pre32) && pr.ld_pre % 4 == 0)) && (!pr.mask16 || (al16(pr.mask16) && pr.ld_mask % 8 == 0)) &&
                (!pr.resid || (al16(pr.resid) && pr.ld_resid % 4 == 0)) && (!pr.addtab || (al16(pr.addtab) && pr.ld_addtab % 4 == 0)) &&
@@ -541,8 +557,9 @@ static int launch_bn(GemmGroup& g, int num_sms, cudaStream_t stream) {
   }
   if (total == 0) return 0;
   const int grid = total < num_sms ? total : num_sms;
+  g.bn = bn;
   g.dbg = g_timeline;
-  gemm_tcgen05_kernel<BN><<<grid, 384, Cfg::kSmemBytes, stream>>>(g);
+  gemm_tcgen05_kernel<<<grid, 384, Cfg::kSmemBytes, stream>>>(g);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("gemm launch failed: %s", cudaGetErrorString(e));
@@ -551,15 +568,24 @@ static int launch_bn(GemmGroup& g, int num_sms, cudaStream_t stream) {
   return 0;
 }
 
-int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
-  if (g.num < 1 || g.num > GEMM_MAX_GROUP) {
-    set_error("gemm group size %d out of range", g.num);
-    return (int)cudaErrorInvalidValue;
+// Tile width that minimises (waves x per-tile time) for a set of problems sharing one launch.
+//   tiles(bn) = sum_p ceil(M_p/128) * ceil(N_p/bn) * ksplit_p ;  cost = ceil(tiles / sms) * (bn + fixed)
+// `step` = 16 for K-major B, 64 for MN-major B.
+int choose_bn(const int* Ms, const int* Ns, const int* ksplits, int num, int num_sms, int step) {
+  int best = 256;
+  long best_cost = -1;
+  for (int bn = 256; bn >= 64; bn -= step) {
+    long tiles = 0;
+    for (int p = 0; p < num; ++p)
+      tiles += (long)((Ms[p] + GEMM_BM - 1) / GEMM_BM) * ((Ns[p] + bn - 1) / bn) * (ksplits ? ksplits[p] : 1);
+    const long waves = (tiles + num_sms - 1) / num_sms;
+    const long cost = waves * (bn + 40);  // +40: per-tile fixed cost (pipeline fill, epilogue tail) in "column" units
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
   }
-  if (bn == 256) return launch_bn<256>(g, num_sms, stream);
-  if (bn == 128) return launch_bn<128>(g, num_sms, stream);
-  set_error("unsupported BN %d", bn);
-  return (int)cudaErrorInvalidValue;
+  return best;
 }
 
 }  // namespace uv

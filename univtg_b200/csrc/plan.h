@@ -226,7 +226,8 @@ struct univtg_plan {
   GemmGroup g_qkv[16], g_out[16], g_ffn1[16], g_ffn2[16];
   GemmGroup g_conv1, g_conv2;
   AttnArgs attn[16];
-  int bn_proj[3], bn_main;
+  int bn_proj[3], bn_main;  // tile widths chosen per launch (choose_bn)
+  int bn_qkv, bn_out, bn_ffn1, bn_ffn2, bn_conv1, bn_conv2;
   int launches;
   // optional per-launch CUDA-event timeline (bench / profiling only)
   int profiling;
