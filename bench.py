@@ -249,7 +249,9 @@ def main():
     if train:
         model.train()
         crit.train()
-        opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-4)
+        # the reference's optimizer (main/config.py:349-350) with torch's fused multi-tensor implementation
+        opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-4, fused=True)
+        model.direct_grad = True  # gradients reach param.grad as views of the flat buffer (no per-parameter copies)
         if dist is not None:
             ddp.broadcast_parameters(model)
             ddp.attach_flat_allreduce(model)  # ONE NCCL all-reduce of the flat gradient buffer per step

@@ -138,6 +138,11 @@ int univtg_plan_read_profile(univtg_plan* plan, float* ms, int32_t* kinds, int32
 int univtg_op_gemm(const void* a, const void* b, int32_t M, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn, int32_t fmt,
                    int32_t bn, int32_t ksplit, const float* bias, int32_t act, float alpha, float* out32, void* out16,
                    void* stream);
+/* Same GEMM launched as 2-CTA clusters: vertically adjacent tiles share their B tile through TMA multicast (half the
+ * L2 -> SM traffic of B).  bn multiple of 32 (of 128 when b_mn). */
+int univtg_op_gemm_cluster(const void* a, const void* b, int32_t M, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn,
+                           int32_t fmt, int32_t bn, int32_t ksplit, const float* bias, int32_t act, float alpha, float* out32,
+                           void* out16, void* stream);
 /* Profiling aid: when `buf` (device, >= 148*8 uint64) is non-NULL every following GEMM launch stamps %globaltimer per CTA:
  * [0] entry, [1] setup done, [2] all TMA issued, [3] first stage landed, [4] last MMA issued, [5] accumulator ready,
  * [6] epilogue done, [7] exit.  Pass NULL to switch it off. */

@@ -15,10 +15,11 @@ def _t16(x, fmt):
     return x.to(torch.bfloat16 if fmt else torch.float16)
 
 
-def case_gemm(M, N, K, a_mn, b_mn, fmt, bn, ksplit, act, use_bias):
+def case_gemm(M, N, K, a_mn, b_mn, fmt, bn, ksplit, act, use_bias, cluster=False):
     import torch
     from univtg_b200 import _lib
     lib = _lib.load_library()
+    gemm_fn = lib.univtg_op_gemm_cluster if cluster else lib.univtg_op_gemm
     g = torch.Generator(device="cpu").manual_seed(1234 + M + N + K)
     A = torch.randn(M, K, generator=g).cuda()
     Bm = torch.randn(N, K, generator=g).cuda()
@@ -36,8 +37,8 @@ def case_gemm(M, N, K, a_mn, b_mn, fmt, bn, ksplit, act, use_bias):
     b_in = B16.t().contiguous() if b_mn else B16.contiguous()
     out32 = torch.zeros(M, N, device="cuda")
     out16 = torch.zeros(M, N, device="cuda", dtype=A16.dtype) if ksplit == 1 else None
-    rc = lib.univtg_op_gemm(_lib.ptr(a_in), _lib.ptr(b_in), M, N, K, a_mn, b_mn, fmt, bn, ksplit, _lib.ptr(bias), act, 0.5,
-                            _lib.ptr(out32), _lib.ptr(out16), _lib.stream_ptr())
+    rc = gemm_fn(_lib.ptr(a_in), _lib.ptr(b_in), M, N, K, a_mn, b_mn, fmt, bn, ksplit, _lib.ptr(bias), act, 0.5,
+                 _lib.ptr(out32), _lib.ptr(out16), _lib.stream_ptr())
     _lib.check(rc, "op_gemm")
     torch.cuda.synchronize()
     err = (out32 - ref).abs().max().item()
@@ -54,7 +55,7 @@ def case_gemm(M, N, K, a_mn, b_mn, fmt, bn, ksplit, act, use_bias):
     return res
 
 
-def case_gemm_timeline(M, N, K, act, want32, want16, bn):
+def case_gemm_timeline(M, N, K, act, want32, want16, bn, cluster=False):
     """Per-CTA phase timeline (ns) of one GEMM launch: where does the time go?"""
     import torch
     from univtg_b200 import _lib
@@ -66,9 +67,11 @@ def case_gemm_timeline(M, N, K, act, want32, want16, bn):
     out16 = torch.zeros(M, N, device="cuda", dtype=torch.float16) if want16 else None
     buf = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
 
+    fn = lib.univtg_op_gemm_cluster if cluster else lib.univtg_op_gemm
+
     def run():
-        _lib.check(lib.univtg_op_gemm(_lib.ptr(A), _lib.ptr(Bm), M, N, K, 0, 0, 0, bn, 1, _lib.ptr(bias), act, 1.0, _lib.ptr(out32),
-                                      _lib.ptr(out16), _lib.stream_ptr()), "op_gemm")
+        _lib.check(fn(_lib.ptr(A), _lib.ptr(Bm), M, N, K, 0, 0, 0, bn, 1, _lib.ptr(bias), act, 1.0, _lib.ptr(out32),
+                      _lib.ptr(out16), _lib.stream_ptr()), "op_gemm")
     for _ in range(3):
         run()
     torch.cuda.synchronize()
@@ -202,6 +205,14 @@ CASES = {
     "tl_ffn1_bn208": (case_gemm_timeline, (3424, 1024, 1024, 2, False, True, 208)),
     "tl_plain16_bn208": (case_gemm_timeline, (3424, 1024, 1024, 0, False, True, 208)),
     "tl_qkv_bn208": (case_gemm_timeline, (3424, 3072, 1024, 0, False, True, 208)),
+    "gemmcl_small": (case_gemm, (256, 256, 128, 0, 0, 0, 256, 1, 0, True, True)),
+    "gemmcl_ragged": (case_gemm, (300, 384, 200, 0, 0, 0, 128, 1, 1, True, True)),
+    "gemmcl_big": (case_gemm, (3424, 1024, 1024, 0, 0, 0, 256, 1, 2, True, True)),
+    "gemmcl_big3": (case_gemm, (3424, 3072, 1024, 0, 0, 0, 256, 1, 0, True, True)),
+    "gemmcl_abmn": (case_gemm, (1024, 1024, 3424, 1, 1, 0, 256, 2, 0, False, True)),
+    "tlcl_plain16": (case_gemm_timeline, (3424, 1024, 1024, 0, False, True, 256, True)),
+    "tlcl_qkv": (case_gemm_timeline, (3424, 3072, 1024, 0, False, True, 256, True)),
+    "tl_plain16": (case_gemm_timeline, (3424, 1024, 1024, 0, False, True, 256)),
     "gemm_amn": (case_gemm, (256, 256, 192, 1, 0, 0, 256, 1, 0, True)),
     "gemm_bmn": (case_gemm, (256, 256, 192, 0, 1, 0, 256, 1, 0, True)),
     "gemm_abmn_bn128": (case_gemm, (256, 384, 200, 1, 1, 0, 128, 1, 0, True)),

@@ -101,6 +101,17 @@ class _UniVTGFunction(torch.autograd.Function):
             hook = getattr(model, "_flat_grad_hook", None)
             if hook is not None:
                 hook(flat)  # e.g. the single NCCL all-reduce of univtg_b200.ddp
+        if getattr(model, "direct_grad", False):
+            # Hand the flat buffer's views to param.grad directly: no per-parameter AccumulateGrad copies (77 memcpys / step).
+            # Used with univtg_b200.ddp (one flat all-reduce); torch DDP needs the autograd route below.
+            for v, p in zip(views, params):
+                if not p.requires_grad:
+                    continue
+                if p.grad is None:
+                    p.grad = v
+                elif p.grad.data_ptr() != v.data_ptr():
+                    p.grad.add_(v)
+            return (None,) * (5 + len(params))
         grads = tuple(v if p.requires_grad else None for v, p in zip(views, params))
         return (None, None, None, None, None) + grads
 

@@ -39,7 +39,11 @@ int univtg_pack_weights(const univtg_config* cfg, const float* const* params, in
     }
   const PackedLayout L = make_layout(*cfg);
   const int d = cfg->hidden_dim, ff = cfg->dim_feedforward;
-  Packer pk{reinterpret_cast<uint8_t*>(packed), cfg->operand_format, (cudaStream_t)stream};
+  Packer pk;
+  pk.base = reinterpret_cast<uint8_t*>(packed);
+  pk.fmt = cfg->operand_format;
+  pk.st = (cudaStream_t)stream;
+  pk.tab.n = 0;
   int idx = 0;
   const int type_idx = 8 * cfg->n_input_proj;  // token_type_embeddings.weight [2, d]
   const float* type_emb = params[type_idx];
@@ -90,6 +94,7 @@ int univtg_pack_weights(const univtg_config* cfg, const float* const* params, in
   pk.vec(sp[5], L.conv3s_b, 2);
   idx += 12;
   pk.vec(params[idx], L.pool_w, d);
+  pk.flush();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("univtg_pack_weights: %s", cudaGetErrorString(e));
@@ -556,9 +561,9 @@ int univtg_forward(univtg_plan* P, const float* src_txt, const float* src_txt_ma
 // ------------------------------------------------------------------------------------------------
 // single operators
 // ------------------------------------------------------------------------------------------------
-int univtg_op_gemm(const void* a, const void* b, int32_t M, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn, int32_t fmt,
-                   int32_t bn, int32_t ksplit, const float* bias, int32_t act, float alpha, float* out32, void* out16,
-                   void* stream) {
+static int op_gemm_impl(const void* a, const void* b, int32_t M, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn, int32_t fmt,
+                        int32_t bn, int32_t ksplit, const float* bias, int32_t act, float alpha, float* out32, void* out16,
+                        int32_t cluster, void* stream) {
   if (!a || !b || M < 1 || N < 1 || K < 1 || bn < 32 || bn > 256 || bn % 16 != 0) {
     set_error("univtg_op_gemm: bad argument");
     return 1;
@@ -567,6 +572,7 @@ int univtg_op_gemm(const void* a, const void* b, int32_t M, int32_t N, int32_t K
   memset(&g, 0, sizeof(g));
   g.num = 1;
   g.fmt = fmt;
+  g.cluster = cluster;
   GemmProblem& p = g.p[0];
   init_problem(p);
   p.M = M;
@@ -583,7 +589,7 @@ int univtg_op_gemm(const void* a, const void* b, int32_t M, int32_t N, int32_t K
     p.ca = OperandCoord{0, 1, 0, 0, 0, 0, 0, 1};  // c0 = m0, c1 = k
   }
   if (!b_mn) {
-    rc |= make_tmap_2d(&p.tm_b, b, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)bn, 64);
+    rc |= make_tmap_2d(&p.tm_b, b, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)(cluster == 2 ? bn / 2 : bn), 64);
   } else {
     rc |= make_tmap_2d(&p.tm_b, b, (uint64_t)K, (uint64_t)N, (uint64_t)N, 64, 64);
     p.cb = OperandCoord{0, 1, 0, 0, 0, 0, 0, 1};
@@ -600,6 +606,18 @@ int univtg_op_gemm(const void* a, const void* b, int32_t M, int32_t N, int32_t K
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   return launch_gemm_group(g, bn, sms, (cudaStream_t)stream);
+}
+
+int univtg_op_gemm(const void* a, const void* b, int32_t M, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn, int32_t fmt,
+                   int32_t bn, int32_t ksplit, const float* bias, int32_t act, float alpha, float* out32, void* out16,
+                   void* stream) {
+  return op_gemm_impl(a, b, M, N, K, a_mn, b_mn, fmt, bn, ksplit, bias, act, alpha, out32, out16, 1, stream);
+}
+
+int univtg_op_gemm_cluster(const void* a, const void* b, int32_t M, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn,
+                           int32_t fmt, int32_t bn, int32_t ksplit, const float* bias, int32_t act, float alpha, float* out32,
+                           void* out16, void* stream) {
+  return op_gemm_impl(a, b, M, N, K, a_mn, b_mn, fmt, bn, ksplit, bias, act, alpha, out32, out16, 2, stream);
 }
 
 int univtg_debug_gemm_timeline(void* buf) {

@@ -15,6 +15,7 @@
 //                                   the TMEM load + residual loads of step c+1 are in flight while step c is processed)
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "kernels.h"
 #include "ptx.cuh"
@@ -39,17 +40,21 @@ struct TileInfo {
   int p, m_blk, n_blk, kb0, kb1, split;
 };
 
-__device__ __forceinline__ bool decode_tile(const GemmGroup& g, int bn, int t, TileInfo& ti) {
+// CL = 1: `t` is this CTA's tile index.  CL = 2 (cluster pairs): `t` indexes a PAIR of vertically adjacent tiles
+// (m_blk = 2*pair + rank, same n_blk); the odd tail tile of a problem is a phantom whose rows are all out of range.
+template <int CL>
+__device__ __forceinline__ bool decode_tile(const GemmGroup& g, int bn, int t, int rank, TileInfo& ti) {
   for (int p = 0; p < g.num; ++p) {
     const GemmProblem& pr = g.p[p];
-    const int tm = (pr.M + GEMM_BM - 1) / GEMM_BM;
+    const int tm_real = (pr.M + GEMM_BM - 1) / GEMM_BM;
+    const int tm = (tm_real + CL - 1) / CL;
     const int tn = (pr.N + bn - 1) / bn;
     const int cnt = tm * tn * pr.ksplit;
     if (t < cnt) {
       ti.p = p;
       ti.n_blk = t % tn;
       const int rest = t / tn;
-      ti.m_blk = rest % tm;
+      ti.m_blk = (rest % tm) * CL + rank;
       ti.split = rest / tm;
       const int total_kb = pr.taps * pr.kblk_per_tap;
       const int per = (total_kb + pr.ksplit - 1) / pr.ksplit;
@@ -70,9 +75,13 @@ __device__ __forceinline__ void stamp(unsigned long long* dbg, int slot) {
   }
 }
 
+template <int CL>
 __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmGroup g) {
   using Cfg = GemmCfg;
   const int BN = g.bn;
+  const int crank = (CL > 1) ? (int)cluster_ctarank() : 0;          // rank inside the CTA pair
+  const int tile0 = (CL > 1) ? (int)(blockIdx.x / CL) : (int)blockIdx.x;
+  const int tstep = (int)(gridDim.x / CL);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t align_off = (1024u - (raw_addr & 1023u)) & 1023u;  // 0 when the runtime honours the 1024 B alignment
@@ -100,7 +109,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);  // with cluster multicast a stage is free once BOTH CTAs' MMAs retired it
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -111,6 +120,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_holder);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before any multicast can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
   if (threadIdx.x == 0) stamp(g.dbg, 1);  // setup done (barriers, TMEM)
@@ -121,7 +131,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       TileInfo ti;
-      for (int t = blockIdx.x; decode_tile(g, BN, t, ti); t += gridDim.x) {
+      for (int t = tile0; decode_tile<CL>(g, BN, t, crank, ti); t += tstep) {
         const GemmProblem& pr = g.p[ti.p];
         const int m0 = ti.m_blk * GEMM_BM;
         const int n0 = ti.n_blk * BN;
@@ -142,10 +152,24 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           }
           const int b0 = pr.cb.base0 + n0 * pr.cb.mn0s + tap * pr.cb.tap0 + kk * pr.cb.k0s;
           const int b1 = pr.cb.base1 + n0 * pr.cb.mn1s + tap * pr.cb.tap1 + kk * pr.cb.k1s;
-          if (!pr.b_mn) {
-            tma_load_2d(sb, &pr.tm_b, &full_bar[stage], b0, b1);
+          if (CL == 1) {
+            if (!pr.b_mn) {
+              tma_load_2d(sb, &pr.tm_b, &full_bar[stage], b0, b1);
+            } else {
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &pr.tm_b, &full_bar[stage], b0 + 64 * j, b1);
+            }
           } else {
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &pr.tm_b, &full_bar[stage], b0 + 64 * j, b1);
+            // each CTA of the pair fetches HALF of the shared B tile and multicasts it to both (halves the L2 -> SM traffic of B)
+            if (!pr.b_mn) {
+              const int hr = BN / 2;  // tensor-map box = BN/2 rows
+              tma_load_2d_mcast(sb + crank * hr * 128, &pr.tm_b, &full_bar[stage], b0, b1 + crank * hr, (uint16_t)0x3);
+            } else {
+              const int nb = BN / 128;  // 64-wide N blocks per CTA
+              for (int j = 0; j < nb; ++j) {
+                const int blk = crank * nb + j;
+                tma_load_2d_mcast(sb + blk * 8192, &pr.tm_b, &full_bar[stage], b0 + 64 * blk, b1, (uint16_t)0x3);
+              }
+            }
           }
           if (++stage == Cfg::kStages) {
             stage = 0;
@@ -163,7 +187,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       int as = 0;
       uint32_t aphase = 0;
       TileInfo ti;
-      for (int t = blockIdx.x; decode_tile(g, BN, t, ti); t += gridDim.x) {
+      for (int t = tile0; decode_tile<CL>(g, BN, t, crank, ti); t += tstep) {
         const GemmProblem& pr = g.p[ti.p];
         const uint32_t idesc = make_idesc_f16_ab(GEMM_BM, BN, pr.a_fmt < 0 ? g.fmt : pr.a_fmt, pr.b_fmt < 0 ? g.fmt : pr.b_fmt, pr.a_mn, pr.b_mn);
         mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -171,7 +195,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
         const uint32_t d_tmem = tmem_base + as * Cfg::kAccStride;
         for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
-          if (kb == ti.kb0 && t == (int)blockIdx.x) stamp(g.dbg, 3);  // first operand stage landed
+          if (kb == ti.kb0 && t == tile0) stamp(g.dbg, 3);  // first operand stage landed
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
@@ -185,7 +209,8 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
                                         : make_smem_desc_sw128(sb + k * 32, 16, 1024);
             umma_f16_ss(d_tmem, da, db, idesc, (kb > ti.kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (CL == 1) umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          else umma_commit_mcast(&empty_bar[stage], (uint16_t)0x3);  // ... in both CTAs of the pair
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -212,7 +237,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
     int as = 0;
     uint32_t aphase = 0;
     TileInfo ti;
-    for (int t = blockIdx.x; decode_tile(g, BN, t, ti); t += gridDim.x) {
+    for (int t = tile0; decode_tile<CL>(g, BN, t, crank, ti); t += tstep) {
       const GemmProblem& pr = g.p[ti.p];
       // hoist the problem description into registers (the struct lives in the constant bank)
       const int pM = pr.M, pN = pr.N, rps_in = pr.rps_in;
@@ -447,6 +472,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or signal its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
@@ -519,14 +545,21 @@ int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
     set_error("unsupported BN %d (multiple of 16 in [32, 256])", bn);
     return (int)cudaErrorInvalidValue;
   }
+  const int cl = g.cluster == 2 ? 2 : 1;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm, smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
       return (int)e;
     }
     attr_set = true;
+  }
+  if (cl == 2 && (bn % 32 != 0)) {
+    set_error("cluster GEMM needs BN %% 32 == 0 (got %d)", bn);
+    return (int)cudaErrorInvalidValue;
   }
   int total = 0;
   for (int p = 0; p < g.num; ++p) {
@@ -535,8 +568,8 @@ int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
       set_error("gemm problem %d: bad k configuration (taps %d kblk %d ksplit %d)", p, pr.taps, pr.kblk_per_tap, pr.ksplit);
       return (int)cudaErrorInvalidValue;
     }
-    if (pr.b_mn && bn % 64 != 0) {
-      set_error("gemm problem %d: MN-major B needs BN %% 64 == 0 (got %d)", p, bn);
+    if (pr.b_mn && bn % (64 * cl) != 0) {
+      set_error("gemm problem %d: MN-major B needs BN %% %d == 0 (got %d)", p, 64 * cl, bn);
       return (int)cudaErrorInvalidValue;
     }
     const int total_kb = pr.taps * pr.kblk_per_tap;
@@ -545,7 +578,7 @@ int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
       set_error("gemm problem %d: ksplit %d leaves an empty split for %d k-blocks", p, pr.ksplit, total_kb);
       return (int)cudaErrorInvalidValue;
     }
-    total += ((pr.M + GEMM_BM - 1) / GEMM_BM) * ((pr.N + bn - 1) / bn) * pr.ksplit;
+    total += ((((pr.M + GEMM_BM - 1) / GEMM_BM) + cl - 1) / cl) * ((pr.N + bn - 1) / bn) * pr.ksplit;  // tiles (CL=1) or tile pairs
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     GemmProblem& w = g.p[p];
     // epilogue (thread = row, 16 columns per step): 128-bit accesses need N % 16 == 0 and aligned leading dimensions
@@ -556,11 +589,31 @@ int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
                ((!pr.out16 && !pr.out16p) || (pr.ld16 % 8 == 0 && al16(pr.out16) && al16(pr.out16p)));
   }
   if (total == 0) return 0;
-  const int grid = total < num_sms ? total : num_sms;
   g.bn = bn;
   g.dbg = g_timeline;
-  gemm_tcgen05_kernel<<<grid, 384, Cfg::kSmemBytes, stream>>>(g);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+  if (cl == 1) {
+    const int grid = total < num_sms ? total : num_sms;
+    gemm_tcgen05_kernel<1><<<grid, 384, Cfg::kSmemBytes, stream>>>(g);
+    e = cudaGetLastError();
+  } else {
+    const int max_clusters = num_sms / 2;
+    const int clusters = total < max_clusters ? total : max_clusters;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(384);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2>, g);
+  }
   if (e != cudaSuccess) {
     set_error("gemm launch failed: %s", cudaGetErrorString(e));
     return (int)e;

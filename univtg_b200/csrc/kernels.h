@@ -77,6 +77,7 @@ struct GemmGroup {
   int num;
   int fmt;  // 0 fp16, 1 bf16
   int bn;   // tile width of this launch (set by launch_gemm_group)
+  int cluster;  // 2: CTA pairs share the B tile through TMA multicast (K-major B maps must then use box rows = bn/2)
   unsigned long long* dbg;  // optional [gridDim.x][8] %globaltimer stamps per CTA (profiling aid), normally null
   GemmProblem p[GEMM_MAX_GROUP];
 };

@@ -307,11 +307,11 @@ __global__ void __launch_bounds__(256) loss_bwd_vid_kernel(const LossBwdArgs a) 
 }
 
 // one block per sample b: d xt[b, :]
-__global__ void __launch_bounds__(256) loss_bwd_txt_kernel(const LossBwdArgs a) {
+__global__ void __launch_bounds__(128) loss_bwd_txt_kernel(const LossBwdArgs a) {
   const int b = blockIdx.x;
   const float w_inter = a.w[3], w_intra = a.w[4];
   const float tn = a.tnorm[b];
-  for (int j = threadIdx.x; j < a.d; j += blockDim.x) {
+  for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < a.d; j += gridDim.y * blockDim.x) {
     const float tj = a.xt[(size_t)b * a.d + j];
     float o = 0.f;
     for (int l = 0; l < a.Lv; ++l) {
@@ -334,7 +334,7 @@ int launch_loss_backward(const LossBwdArgs& a, cudaStream_t stream) {
   const int n = a.B * a.Lv;
   loss_bwd_small_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a);
   loss_bwd_vid_kernel<<<(n * 32 + 255) / 256, 256, 0, stream>>>(a);
-  loss_bwd_txt_kernel<<<a.B, 256, 0, stream>>>(a);
+  loss_bwd_txt_kernel<<<dim3(a.B, (a.d + 127) / 128), 128, 0, stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("loss backward launch failed: %s", cudaGetErrorString(e));
   return (int)e;

@@ -179,22 +179,69 @@ inline int grid_for(size_t total) {
   return (int)(g > 1184 ? 1184 : (g < 1 ? 1 : g));
 }
 
+// All (re)packing work of one univtg_pack_weights call is described by a task table and executed by a handful of launches
+// (the table travels as a kernel parameter, <= 4 KB per launch) instead of ~75 tiny kernels.
+struct PackTask {
+  const float* src;
+  const float* add;  // kind 3: optional second vector added element-wise
+  void* dst;
+  int kind;          // 0: rows -> 16-bit [rows, ld] zero-padded, 1: conv [N,C,3] -> 16-bit [N, 3C], 2: conv -> fp32 [N,3,C], 3: vector copy(+add)
+  int rows, cols, ld;
+};
+constexpr int kPackTasksPerLaunch = 64;
+struct PackTable {
+  int n, fmt;
+  PackTask t[kPackTasksPerLaunch];
+};
+
+__global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__ PackTable tab) {
+  const PackTask& k = tab.t[blockIdx.y];
+  const int fmt = tab.fmt;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (k.kind == 0) {
+    const size_t total = (size_t)k.rows * k.ld;
+    uint16_t* dst = reinterpret_cast<uint16_t*>(k.dst);
+    for (size_t i = i0; i < total; i += stride) {
+      const int r = (int)(i / k.ld), c = (int)(i % k.ld);
+      dst[i] = c < k.cols ? cvt16(k.src[(size_t)r * k.cols + c], fmt) : (uint16_t)0;
+    }
+  } else if (k.kind == 1 || k.kind == 2) {
+    const int N = k.rows, C = k.cols;
+    const size_t total = (size_t)N * 3 * C;
+    for (size_t i = i0; i < total; i += stride) {
+      const int n = (int)(i / (3 * C));
+      const int rem = (int)(i % (3 * C));
+      const int t = rem / C, c = rem % C;
+      const float v = k.src[((size_t)n * C + c) * 3 + t];
+      if (k.kind == 1) reinterpret_cast<uint16_t*>(k.dst)[i] = cvt16(v, fmt);
+      else reinterpret_cast<float*>(k.dst)[i] = v;
+    }
+  } else {
+    float* dst = reinterpret_cast<float*>(k.dst);
+    for (size_t i = i0; i < (size_t)k.rows; i += stride) dst[i] = k.src[i] + (k.add ? k.add[i] : 0.f);
+  }
+}
+
 struct Packer {
   uint8_t* base;
   int fmt;
   cudaStream_t st;
-  void rows(const float* src, size_t off, int rows_, int cols, int ld) {
-    pack_rows_kernel<<<grid_for((size_t)rows_ * ld), 256, 0, st>>>(src, reinterpret_cast<uint16_t*>(base + off), rows_, cols, ld, fmt);
+  PackTable tab;
+  void push(const PackTask& t) {
+    if (tab.n == kPackTasksPerLaunch) flush();
+    tab.t[tab.n++] = t;
   }
-  void conv(const float* src, size_t off, int N, int C) {
-    pack_conv_kernel<<<grid_for((size_t)N * 3 * C), 256, 0, st>>>(src, reinterpret_cast<uint16_t*>(base + off), N, C, fmt);
+  void flush() {
+    if (tab.n == 0) return;
+    tab.fmt = fmt;
+    pack_multi_kernel<<<dim3(48, tab.n), 256, 0, st>>>(tab);
+    tab.n = 0;
   }
-  void conv_f32(const float* src, size_t off, int N, int C) {
-    pack_conv_f32_kernel<<<grid_for((size_t)N * 3 * C), 256, 0, st>>>(src, reinterpret_cast<float*>(base + off), N, C);
-  }
-  void vec(const float* src, size_t off, int n, const float* add = nullptr) {
-    copy_add_kernel<<<grid_for(n), 256, 0, st>>>(src, add, reinterpret_cast<float*>(base + off), n);
-  }
+  void rows(const float* src, size_t off, int rows_, int cols, int ld) { push(PackTask{src, nullptr, base + off, 0, rows_, cols, ld}); }
+  void conv(const float* src, size_t off, int N, int C) { push(PackTask{src, nullptr, base + off, 1, N, C, 0}); }
+  void conv_f32(const float* src, size_t off, int N, int C) { push(PackTask{src, nullptr, base + off, 2, N, C, 0}); }
+  void vec(const float* src, size_t off, int n, const float* add = nullptr) { push(PackTask{src, add, base + off, 3, n, 0, 0}); }
 };
 
 }  // namespace

@@ -36,6 +36,24 @@ int setup_gemm(GemmProblem& p, Mat16 A, int a_mn, Mat16 B, int b_mn, int M, int 
 
 inline int pick_bn(int N) { return (N % 256 == 0) ? 256 : 128; }
 
+// tile width for a launch of up to 2 problems (step 64 when a B operand is MN-major)
+inline int bn_for(int sms, int step, int M0, int N0, int M1 = 0, int N1 = 0) {
+  const int Ms[2] = {M0, M1}, Ns[2] = {N0, N1};
+  return choose_bn(Ms, Ns, nullptr, M1 > 0 ? 2 : 1, sms, step);
+}
+
+inline int bn_for3(int sms, int step, int M, int N) {  // three equal problems in one launch (conv weight-gradient taps)
+  const int Ms[3] = {M, M, M}, Ns[3] = {N, N, N};
+  return choose_bn(Ms, Ns, nullptr, 3, sms, step);
+}
+
+inline int pick_ksplit2(int M0, int N0, int M1, int N1, int bn, int kblocks, int num_sms) {
+  const int tiles = ((M0 + GEMM_BM - 1) / GEMM_BM) * ((N0 + bn - 1) / bn) + ((M1 + GEMM_BM - 1) / GEMM_BM) * ((N1 + bn - 1) / bn);
+  int ks = 1;
+  while (tiles * ks * 2 <= num_sms && ks * 2 <= kblocks / 4 && ks < 16) ks *= 2;
+  return ks;
+}
+
 inline int pick_ksplit(int M, int N, int bn, int kblocks, int num_sms) {
   const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + bn - 1) / bn);
   int ks = 1;
@@ -205,8 +223,8 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
     g.num = 2;
     g.fmt = fmt;
     const bool last = (i == c.n_input_proj - 1);
-    rc |= setup_linear(g.p[0], T.a_vid[i], Mv, Lw.vid[i].kpad, Lw.vid[i].kpad, W16(Lw.vid[i].w16), d, Lw.vid[i].kpad, bn);
-    rc |= setup_linear(g.p[1], T.a_txt[i], Mt, Lw.txt[i].kpad, Lw.txt[i].kpad, W16(Lw.txt[i].w16), d, Lw.txt[i].kpad, bn);
+    rc |= setup_linear(g.p[0], T.a_vid[i], Mv, Lw.vid[i].kpad, Lw.vid[i].kpad, W16(Lw.vid[i].w16), d, Lw.vid[i].kpad, P->bn_proj[i]);
+    rc |= setup_linear(g.p[1], T.a_txt[i], Mt, Lw.txt[i].kpad, Lw.txt[i].kpad, W16(Lw.txt[i].w16), d, Lw.txt[i].kpad, P->bn_proj[i]);
     if (rc) return rc;
     g.p[0].bias = F32(Lw.vid[i].bias);
     g.p[1].bias = F32(Lw.txt[i].bias);
@@ -234,7 +252,7 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
       g.p[0].out32_id = vid_mem_proj;
       g.p[1].out32_id = T.txtproj32;
     }
-    rc = launch_gemm_group(g, bn, sms, st);
+    rc = launch_gemm_group(g, P->bn_proj[i], sms, st);
     if (rc) return rc;
   }
 
@@ -244,8 +262,8 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
     memset(&g, 0, sizeof(g));
     g.num = 2;
     g.fmt = fmt;
-    rc |= setup_linear(g.p[0], T.xpos16[l], M, d, d, W16(lp.w_in), 2 * d, d, bn);
-    rc |= setup_linear(g.p[1], T.xin16[l], M, d, d, W16(lp.w_in) + (size_t)2 * d * d, d, d, bn);
+    rc |= setup_linear(g.p[0], T.xpos16[l], M, d, d, W16(lp.w_in), 2 * d, d, P->bn_qkv);
+    rc |= setup_linear(g.p[1], T.xin16[l], M, d, d, W16(lp.w_in) + (size_t)2 * d * d, d, d, P->bn_qkv);
     if (rc) return rc;
     g.p[0].bias = F32(lp.b_in);
     g.p[0].out16 = T.qkv16[l];
@@ -253,7 +271,7 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
     g.p[1].bias = F32(lp.b_in) + 2 * d;
     g.p[1].out16 = T.qkv16[l] + 2 * d;
     g.p[1].ld16 = 3 * d;
-    rc = launch_gemm_group(g, bn, sms, st);
+    rc = launch_gemm_group(g, P->bn_qkv, sms, st);
     if (rc) return rc;
     {
       AttnArgs a;
@@ -279,7 +297,7 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
     memset(&g, 0, sizeof(g));
     g.num = 1;
     g.fmt = fmt;
-    rc = setup_linear(g.p[0], T.attn16[l], M, d, d, W16(lp.w_out), d, d, bn);
+    rc = setup_linear(g.p[0], T.attn16[l], M, d, d, W16(lp.w_out), d, d, P->bn_out);
     if (rc) return rc;
     g.p[0].bias = F32(lp.b_out);
     g.p[0].rps_in = L;
@@ -287,7 +305,7 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
     g.p[0].row_scale = droppath_scale ? droppath_scale + (size_t)(2 * l) * P->B : nullptr;
     g.p[0].out16 = T.br16;
     g.p[0].ld16 = d;
-    rc = launch_gemm_group(g, bn, sms, st);
+    rc = launch_gemm_group(g, P->bn_out, sms, st);
     if (rc) return rc;
     {
       LnArgs a;
@@ -314,7 +332,7 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
     memset(&g, 0, sizeof(g));
     g.num = 1;
     g.fmt = fmt;
-    rc = setup_linear(g.p[0], T.x1_16[l], M, d, d, W16(lp.w1), ff, d, pick_bn(ff));
+    rc = setup_linear(g.p[0], T.x1_16[l], M, d, d, W16(lp.w1), ff, d, P->bn_ffn1);
     if (rc) return rc;
     g.p[0].bias = F32(lp.b1);
     g.p[0].act = ACT_GELU;
@@ -322,12 +340,12 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
     g.p[0].ld16 = ff;
     g.p[0].pre32 = T.hpre[l];
     g.p[0].ld_pre = ff;
-    rc = launch_gemm_group(g, pick_bn(ff), sms, st);
+    rc = launch_gemm_group(g, P->bn_ffn1, sms, st);
     if (rc) return rc;
     memset(&g, 0, sizeof(g));
     g.num = 1;
     g.fmt = fmt;
-    rc = setup_linear(g.p[0], T.h16[l], M, ff, ff, W16(lp.w2), d, ff, bn);
+    rc = setup_linear(g.p[0], T.h16[l], M, ff, ff, W16(lp.w2), d, ff, P->bn_ffn2);
     if (rc) return rc;
     g.p[0].bias = F32(lp.b2);
     g.p[0].rps_in = L;
@@ -335,7 +353,7 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
     g.p[0].row_scale = droppath_scale ? droppath_scale + (size_t)(2 * l + 1) * P->B : nullptr;
     g.p[0].out16 = T.br16;
     g.p[0].ld16 = d;
-    rc = launch_gemm_group(g, bn, sms, st);
+    rc = launch_gemm_group(g, P->bn_ffn2, sms, st);
     if (rc) return rc;
     {
       LnArgs a;
@@ -393,7 +411,7 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
   g.fmt = fmt;
   rc = conv_problem(g.p[0], T.hA, d, W16(Lw.conv1_w), 2 * d, F32(Lw.conv1_b), T.h1, 2 * d);
   if (rc) return rc;
-  rc = launch_gemm_group(g, bn, sms, st);
+  rc = launch_gemm_group(g, P->bn_conv1, sms, st);
   if (rc) return rc;
   memset(&g, 0, sizeof(g));
   g.num = 2;
@@ -401,7 +419,7 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
   rc |= conv_problem(g.p[0], T.h1, 2 * d, W16(Lw.conv2c_w), d, F32(Lw.conv2c_b), T.hc2, d);
   rc |= conv_problem(g.p[1], T.h1 + d, 2 * d, W16(Lw.conv2s_w), d, F32(Lw.conv2s_b), T.hs2, d);
   if (rc) return rc;
-  rc = launch_gemm_group(g, bn, sms, st);
+  rc = launch_gemm_group(g, P->bn_conv2, sms, st);
   if (rc) return rc;
   {
     HeadFinalArgs a;
@@ -563,7 +581,8 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       p.alpha = INV;
       return r;
     };
-    const int bn = P->bn_main;
+    const int bn_c2d = bn_for(sms, 64, Mh, d, Mh, d), bn_c1d = bn_for(sms, 64, Mh, d), bn_cw = bn_for3(sms, 64, d, d);
+    const int bn = bn_c2d;
     // ---- conv layer 2 (two heads): dgrad -> dh1 [Mh+2, 2d] (class cols [0,d), span cols [d,2d)), ReLU mask of h1 ----
     memset(&g, 0, sizeof(g));
     g.num = 2;
@@ -585,7 +604,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       p.colsum = s == 0 ? G_cls(1) : G_span(1);  // bias gradient of conv layer 0
       p.colsum_scale = INV;
     }
-    rc = launch_gemm_group(g, bn, sms, st);
+    rc = launch_gemm_group(g, bn_c2d, sms, st);
     if (rc) return rc;
     // wgrad conv layer 2: 2 heads x 3 taps
     for (int s = 0; s < 2; ++s) {
@@ -595,7 +614,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       for (int t = 0; t < 3; ++t)
         rc |= conv_wgrad(g.p[t], s == 0 ? T.dhc2 : T.dhs2, d, d, T.h1 + s * d, 2 * d, d, t, s == 0 ? G_cls(2) : G_span(2));
       if (rc) return rc;
-      rc = launch_gemm_group(g, bn, sms, st);
+      rc = launch_gemm_group(g, bn_cw, sms, st);
       if (rc) return rc;
     }
     // ---- conv layer 1 (fused N = 2d): dgrad -> stream gradient of the video rows ----
@@ -610,7 +629,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.p[0].skip_sep = 1;
     g.p[0].out32 = T.dx;
     g.p[0].ld32 = d;
-    rc = launch_gemm_group(g, bn, sms, st);
+    rc = launch_gemm_group(g, bn_c1d, sms, st);
     if (rc) return rc;
     // wgrad conv layer 1: class rows [0,d) and span rows [d,2d) of the fused weight
     for (int s = 0; s < 2; ++s) {
@@ -619,7 +638,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       g.fmt = fmt;
       for (int t = 0; t < 3; ++t) rc |= conv_wgrad(g.p[t], T.dh1 + s * d, 2 * d, d, T.hA, d, d, t, s == 0 ? G_cls(0) : G_span(0));
       if (rc) return rc;
-      rc = launch_gemm_group(g, bn, sms, st);
+      rc = launch_gemm_group(g, bn_cw, sms, st);
       if (rc) return rc;
     }
   }
@@ -629,7 +648,8 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     const LayerPacked& lp = Lw.layer[l];
     const float* s1 = droppath_scale ? droppath_scale + (size_t)(2 * l) * B : nullptr;
     const float* s2 = droppath_scale ? droppath_scale + (size_t)(2 * l + 1) * B : nullptr;
-    const int bn = P->bn_main;
+    const int bn_dff = bn_for(sms, 64, M, ff), bn_dd = bn_for(sms, 64, M, d);
+    const int bn_wo = bn_for(sms, 64, d, d), bn_wq = bn_for(sms, 64, 2 * d, d, d, d);
     // ---- LN2 backward: dx (grad of the layer output) -> dy (grad of x1 + s2 * F), branch operand s2 * dy ----
     {
       LnBwdArgs a;
@@ -660,7 +680,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     memset(&g, 0, sizeof(g));
     g.num = 1;
     g.fmt = fmt;
-    rc = setup_gemm(g.p[0], Mat16{T.dbr16, M, d, d}, 0, Mat16{W16(lp.w2), d, ff, ff}, 1, M, ff, d, pick_bn(ff));
+    rc = setup_gemm(g.p[0], Mat16{T.dbr16, M, d, d}, 0, Mat16{W16(lp.w2), d, ff, ff}, 1, M, ff, d, bn_dff);
     if (rc) return rc;
     g.p[0].a_fmt = FMT_G;
     g.p[0].b_fmt = fmt;
@@ -672,13 +692,13 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.p[0].out_fmt = FMT_G;
     g.p[0].colsum = G_layer(l, 5);  // linear1.bias
     g.p[0].colsum_scale = INV;
-    rc = launch_gemm_group(g, pick_bn(ff), sms, st);
+    rc = launch_gemm_group(g, bn_dff, sms, st);
     if (rc) return rc;
     memset(&g, 0, sizeof(g));
     g.num = 2;
     g.fmt = fmt;
     {
-      const int bnw = pick_bn(ff);
+      const int bnw = bn_for(sms, 64, d, ff, ff, d);
       rc |= setup_gemm(g.p[0], Mat16{T.dbr16, M, d, d}, 1, Mat16{T.h16[l], M, ff, ff}, 1, d, ff, M, bnw);
       rc |= setup_gemm(g.p[1], Mat16{T.dhpre16, M, ff, ff}, 1, Mat16{T.x1_16[l], M, d, d}, 1, ff, d, M, bnw);
       if (rc) return rc;
@@ -689,7 +709,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       g.p[1].out32 = G_layer(l, 4);  // linear1.weight [ff, d]
       g.p[1].ld32 = d;
       g.p[0].alpha = g.p[1].alpha = INV;
-      g.p[0].ksplit = g.p[1].ksplit = pick_ksplit(d, ff, bnw, (M + 63) / 64, sms / 2);
+      g.p[0].ksplit = g.p[1].ksplit = pick_ksplit2(d, ff, ff, d, bnw, (M + 63) / 64, sms);
       rc = launch_gemm_group(g, bnw, sms, st);
       if (rc) return rc;
     }
@@ -697,7 +717,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     memset(&g, 0, sizeof(g));
     g.num = 1;
     g.fmt = fmt;
-    rc = setup_gemm(g.p[0], Mat16{T.dhpre16, M, ff, ff}, 0, Mat16{W16(lp.w1), ff, d, d}, 1, M, d, ff, bn);
+    rc = setup_gemm(g.p[0], Mat16{T.dhpre16, M, ff, ff}, 0, Mat16{W16(lp.w1), ff, d, d}, 1, M, d, ff, bn_dd);
     if (rc) return rc;
     g.p[0].a_fmt = FMT_G;
     g.p[0].b_fmt = fmt;
@@ -705,7 +725,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.p[0].ld_resid = d;
     g.p[0].out32 = T.dx;
     g.p[0].ld32 = d;
-    rc = launch_gemm_group(g, bn, sms, st);
+    rc = launch_gemm_group(g, bn_dd, sms, st);
     if (rc) return rc;
     // ---- LN1 backward ----
     {
@@ -737,27 +757,27 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     memset(&g, 0, sizeof(g));
     g.num = 1;
     g.fmt = fmt;
-    rc = setup_gemm(g.p[0], Mat16{T.dbr16, M, d, d}, 0, Mat16{W16(lp.w_out), d, d, d}, 1, M, d, d, bn);
+    rc = setup_gemm(g.p[0], Mat16{T.dbr16, M, d, d}, 0, Mat16{W16(lp.w_out), d, d, d}, 1, M, d, d, bn_dd);
     if (rc) return rc;
     g.p[0].a_fmt = FMT_G;
     g.p[0].b_fmt = fmt;
     g.p[0].out16 = T.dO16;
     g.p[0].ld16 = d;
     g.p[0].out_fmt = FMT_G;
-    rc = launch_gemm_group(g, bn, sms, st);
+    rc = launch_gemm_group(g, bn_dd, sms, st);
     if (rc) return rc;
     memset(&g, 0, sizeof(g));
     g.num = 1;
     g.fmt = fmt;
-    rc = setup_gemm(g.p[0], Mat16{T.dbr16, M, d, d}, 1, Mat16{T.attn16[l], M, d, d}, 1, d, d, M, bn);
+    rc = setup_gemm(g.p[0], Mat16{T.dbr16, M, d, d}, 1, Mat16{T.attn16[l], M, d, d}, 1, d, d, M, bn_wo);
     if (rc) return rc;
     g.p[0].a_fmt = FMT_G;
     g.p[0].b_fmt = fmt;
     g.p[0].out32 = G_layer(l, 2);
     g.p[0].ld32 = d;
     g.p[0].alpha = INV;
-    g.p[0].ksplit = pick_ksplit(d, d, bn, (M + 63) / 64, sms);
-    rc = launch_gemm_group(g, bn, sms, st);
+    g.p[0].ksplit = pick_ksplit(d, d, bn_wo, (M + 63) / 64, sms);
+    rc = launch_gemm_group(g, bn_wo, sms, st);
     if (rc) return rc;
     // ---- attention core backward -> dqkv32 -> dqkv16 (+ in_proj_bias gradient) ----
     rc = launch_attn_delta(T.dO16, FMT_G, T.attn16[l], fmt, T.delta, B, L, P->H, P->dh, st);
@@ -798,7 +818,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     memset(&g, 0, sizeof(g));
     g.num = 1;
     g.fmt = fmt;
-    rc = setup_gemm(g.p[0], Mat16{T.dqkv16, M, 3 * d, 3 * d}, 0, Mat16{W16(lp.w_in), 3 * d, d, d}, 1, M, d, 3 * d, bn);
+    rc = setup_gemm(g.p[0], Mat16{T.dqkv16, M, 3 * d, 3 * d}, 0, Mat16{W16(lp.w_in), 3 * d, d, d}, 1, M, d, 3 * d, bn_dd);
     if (rc) return rc;
     g.p[0].a_fmt = FMT_G;
     g.p[0].b_fmt = fmt;
@@ -806,13 +826,13 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.p[0].ld_resid = d;
     g.p[0].out32 = T.dx;
     g.p[0].ld32 = d;
-    rc = launch_gemm_group(g, bn, sms, st);
+    rc = launch_gemm_group(g, bn_dd, sms, st);
     if (rc) return rc;
     memset(&g, 0, sizeof(g));
     g.num = 2;
     g.fmt = fmt;
-    rc |= setup_gemm(g.p[0], Mat16{T.dqkv16, M, 2 * d, 3 * d}, 1, Mat16{T.xpos16[l], M, d, d}, 1, 2 * d, d, M, bn);
-    rc |= setup_gemm(g.p[1], Mat16{T.dqkv16 + 2 * d, M, d, 3 * d}, 1, Mat16{T.xin16[l], M, d, d}, 1, d, d, M, bn);
+    rc |= setup_gemm(g.p[0], Mat16{T.dqkv16, M, 2 * d, 3 * d}, 1, Mat16{T.xpos16[l], M, d, d}, 1, 2 * d, d, M, bn_wq);
+    rc |= setup_gemm(g.p[1], Mat16{T.dqkv16 + 2 * d, M, d, 3 * d}, 1, Mat16{T.xin16[l], M, d, d}, 1, d, d, M, bn_wq);
     if (rc) return rc;
     g.p[0].a_fmt = g.p[1].a_fmt = FMT_G;
     g.p[0].b_fmt = g.p[1].b_fmt = fmt;
@@ -821,8 +841,8 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.p[1].out32 = G_layer(l, 0) + (size_t)2 * d * d;
     g.p[1].ld32 = d;
     g.p[0].alpha = g.p[1].alpha = INV;
-    g.p[0].ksplit = g.p[1].ksplit = pick_ksplit(3 * d, d, bn, (M + 63) / 64, sms);
-    rc = launch_gemm_group(g, bn, sms, st);
+    g.p[0].ksplit = g.p[1].ksplit = pick_ksplit(3 * d, d, bn_wq, (M + 63) / 64, sms);
+    rc = launch_gemm_group(g, bn_wq, sms, st);
     if (rc) return rc;
   }
 
@@ -851,12 +871,13 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
   cudaMemcpyAsync(G_vid(np - 1, 3), G_type + d, (size_t)d * 4, cudaMemcpyDeviceToDevice, st);
   cudaMemcpyAsync(G_txt(np - 1, 3), G_type, (size_t)d * 4, cudaMemcpyDeviceToDevice, st);
   for (int i = np - 1; i >= 0; --i) {
-    const int bn = P->bn_main;
     // wgrad: dW_i = dOut^T a_i   (video + text in one launch)
     memset(&g, 0, sizeof(g));
     g.num = 2;
     g.fmt = fmt;
     const int kpv = Lw.vid[i].kpad, kpt = Lw.txt[i].kpad, dinv = Lw.vid[i].din, dint = Lw.txt[i].din;
+    const int bn = bn_for(sms, 64, d, dinv, d, dint);
+    const int bn_pd = bn_for(sms, 64, Mv, dinv, Mt, dint);
     rc |= setup_gemm(g.p[0], Mat16{T.dxv16, Mv, d, d}, 1, Mat16{T.a_vid[i], Mv, kpv, kpv}, 1, d, dinv, Mv, bn);
     rc |= setup_gemm(g.p[1], Mat16{T.dxt16, Mt, d, d}, 1, Mat16{T.a_txt[i], Mt, kpt, kpt}, 1, d, dint, Mt, bn);
     if (rc) return rc;
@@ -873,8 +894,8 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     memset(&g, 0, sizeof(g));
     g.num = 2;
     g.fmt = fmt;
-    rc |= setup_gemm(g.p[0], Mat16{T.dxv16, Mv, d, d}, 0, Mat16{W16(Lw.vid[i].w16), d, kpv, kpv}, 1, Mv, dinv, d, bn);
-    rc |= setup_gemm(g.p[1], Mat16{T.dxt16, Mt, d, d}, 0, Mat16{W16(Lw.txt[i].w16), d, kpt, kpt}, 1, Mt, dint, d, bn);
+    rc |= setup_gemm(g.p[0], Mat16{T.dxv16, Mv, d, d}, 0, Mat16{W16(Lw.vid[i].w16), d, kpv, kpv}, 1, Mv, dinv, d, bn_pd);
+    rc |= setup_gemm(g.p[1], Mat16{T.dxt16, Mt, d, d}, 0, Mat16{W16(Lw.txt[i].w16), d, kpt, kpt}, 1, Mt, dint, d, bn_pd);
     if (rc) return rc;
     g.p[0].a_fmt = g.p[1].a_fmt = FMT_G;
     g.p[0].b_fmt = g.p[1].b_fmt = fmt;
@@ -890,7 +911,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       g.p[1].ld_aux = dint;
       g.p[1].aux_mode = 2;
     }
-    rc = launch_gemm_group(g, bn, sms, st);
+    rc = launch_gemm_group(g, bn_pd, sms, st);
     if (rc) return rc;
     // LayerNorm_i backward: parameter gradients; for i > 0 also the gradient of the previous layer's ReLU output
     for (int s = 0; s < 2; ++s) {

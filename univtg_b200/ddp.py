@@ -42,9 +42,11 @@ def make_flat_allreduce_hook(group=None):
 def attach_flat_allreduce(model, group=None):
     """Install the single-collective gradient exchange on a univtg_b200 model (runs inside its fused backward)."""
     model._flat_grad_hook = make_flat_allreduce_hook(group)
+    model.direct_grad = True  # gradients are handed to param.grad as views of the flat buffer (no autograd accumulation copies)
     return model
 
 
 def detach_flat_allreduce(model):
     model._flat_grad_hook = None
+    model.direct_grad = False
     return model
