@@ -328,6 +328,7 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
       p.cb = OperandCoord{0, 0, d, 1, 0, 1, 0, 0};
       int r = make_tmap_2d(&p.tm_a, A, (uint64_t)P->Mh + 2, (uint64_t)d, (uint64_t)lda, GEMM_BM, 64);
       r |= make_tmap_2d(&p.tm_b, W, (uint64_t)N, (uint64_t)3 * d, (uint64_t)3 * d, (uint32_t)bn, 64);
+      p.b_box_rows = bn;
       p.bias = bias;
       p.act = ACT_RELU;
       p.rps_in = P->Lv + 1;
@@ -590,6 +591,7 @@ static int op_gemm_impl(const void* a, const void* b, int32_t M, int32_t N, int3
   }
   if (!b_mn) {
     rc |= make_tmap_2d(&p.tm_b, b, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)(cluster == 2 ? bn / 2 : bn), 64);
+    p.b_box_rows = cluster == 2 ? bn / 2 : bn;
   } else {
     rc |= make_tmap_2d(&p.tm_b, b, (uint64_t)K, (uint64_t)N, (uint64_t)N, 64, 64);
     p.cb = OperandCoord{0, 1, 0, 0, 0, 0, 0, 1};

@@ -568,6 +568,10 @@ int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
       set_error("gemm problem %d: bad k configuration (taps %d kblk %d ksplit %d)", p, pr.taps, pr.kblk_per_tap, pr.ksplit);
       return (int)cudaErrorInvalidValue;
     }
+    if (!pr.b_mn && pr.b_box_rows != bn / cl) {
+      set_error("gemm problem %d: B tensor-map box has %d rows but the launch uses bn %d (cluster %d)", p, pr.b_box_rows, bn, cl);
+      return (int)cudaErrorInvalidValue;
+    }
     if (pr.b_mn && bn % (64 * cl) != 0) {
       set_error("gemm problem %d: MN-major B needs BN %% %d == 0 (got %d)", p, 64 * cl, bn);
       return (int)cudaErrorInvalidValue;

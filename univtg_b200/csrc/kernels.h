@@ -31,6 +31,7 @@ struct GemmProblem {
   CUtensorMap tm_b;
   OperandCoord ca, cb;
   int a_mn, b_mn;    // 1: operand is MN-major in memory
+  int b_box_rows;    // rows of tm_b's TMA box (K-major B): must equal the launch's bn (bn/2 for cluster pairs); checked at launch
   int M, N;
   int taps;          // 1 = plain; 3 = k=3 conv expressed as 3 K segments
   int kblk_per_tap;  // 64-wide k-blocks per tap

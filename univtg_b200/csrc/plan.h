@@ -328,6 +328,7 @@ int setup_linear(GemmProblem& p, const uint16_t* A, int M, int K, int lda, const
   }
   if (make_tmap_2d(&p.tm_a, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM, 64)) return 1;
   if (make_tmap_2d(&p.tm_b, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn, 64)) return 1;
+  p.b_box_rows = bn;
   return 0;
 }
 

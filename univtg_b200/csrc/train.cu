@@ -27,6 +27,7 @@ int setup_gemm(GemmProblem& p, Mat16 A, int a_mn, Mat16 B, int b_mn, int M, int 
   }
   if (!b_mn) {
     rc |= make_tmap_2d(&p.tm_b, B.p, (uint64_t)B.rows, (uint64_t)B.cols, (uint64_t)B.ld, (uint32_t)bn, 64);
+    p.b_box_rows = bn;
   } else {
     rc |= make_tmap_2d(&p.tm_b, B.p, (uint64_t)B.rows, (uint64_t)B.cols, (uint64_t)B.ld, 64, 64);
     p.cb = OperandCoord{0, 1, 0, 0, 0, 0, 0, 1};
@@ -190,7 +191,7 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
   auto W16 = [&](size_t off) { return reinterpret_cast<const uint16_t*>(pk + off); };
   const TrainWs T = make_train_ws(c, P->shp, Lw, reinterpret_cast<uint8_t*>(ws));
   const int d = P->d, ff = P->ff, fmt = c.operand_format, M = P->M, Mv = P->Mv, Mt = P->Mt, Mh = P->Mh, L = P->L, Lv = P->Lv;
-  const int bn = P->bn_main, sms = P->num_sms;
+  const int sms = P->num_sms;
   int rc = 0;
   GemmGroup g;
 
@@ -386,7 +387,7 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
 
   // ---- heads ----
   auto conv_problem = [&](GemmProblem& p, const uint16_t* A, int lda, const uint16_t* W, int N, const float* bias, uint16_t* out,
-                          int ldo) -> int {
+                          int ldo, int bn) -> int {
     init_problem(p);
     p.M = Mh;
     p.N = N;
@@ -396,6 +397,7 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
     p.cb = OperandCoord{0, 0, d, 1, 0, 1, 0, 0};
     int r = make_tmap_2d(&p.tm_a, A, (uint64_t)Mh + 2, (uint64_t)d, (uint64_t)lda, GEMM_BM, 64);
     r |= make_tmap_2d(&p.tm_b, W, (uint64_t)N, (uint64_t)3 * d, (uint64_t)3 * d, (uint32_t)bn, 64);
+    p.b_box_rows = bn;
     p.bias = bias;
     p.act = ACT_RELU;
     p.rps_in = Lv + 1;
@@ -409,15 +411,15 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
   memset(&g, 0, sizeof(g));
   g.num = 1;
   g.fmt = fmt;
-  rc = conv_problem(g.p[0], T.hA, d, W16(Lw.conv1_w), 2 * d, F32(Lw.conv1_b), T.h1, 2 * d);
+  rc = conv_problem(g.p[0], T.hA, d, W16(Lw.conv1_w), 2 * d, F32(Lw.conv1_b), T.h1, 2 * d, P->bn_conv1);
   if (rc) return rc;
   rc = launch_gemm_group(g, P->bn_conv1, sms, st);
   if (rc) return rc;
   memset(&g, 0, sizeof(g));
   g.num = 2;
   g.fmt = fmt;
-  rc |= conv_problem(g.p[0], T.h1, 2 * d, W16(Lw.conv2c_w), d, F32(Lw.conv2c_b), T.hc2, d);
-  rc |= conv_problem(g.p[1], T.h1 + d, 2 * d, W16(Lw.conv2s_w), d, F32(Lw.conv2s_b), T.hs2, d);
+  rc |= conv_problem(g.p[0], T.h1, 2 * d, W16(Lw.conv2c_w), d, F32(Lw.conv2c_b), T.hc2, d, P->bn_conv2);
+  rc |= conv_problem(g.p[1], T.h1 + d, 2 * d, W16(Lw.conv2s_w), d, F32(Lw.conv2s_b), T.hs2, d, P->bn_conv2);
   if (rc) return rc;
   rc = launch_gemm_group(g, P->bn_conv2, sms, st);
   if (rc) return rc;
