@@ -4,8 +4,10 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
 
 A "step" is one pass of the hot path over one synthetic batch:
-  cfg2_fwd   BASELINE.json configs[1]: B=32, L_v=75, L_t=32, d=1024, 4 layers, forward (inference)       [default]
-  cfg5_fwd   configs[4]: B=8, L_v=1200, L_t=77, 6 layers, forward
+  cfg3_train BASELINE.json configs[2]: B=32, L_v=75, L_t=32, d=1024, 4 layers: forward + criterion + backward + grad-clip +
+             AdamW - the metric BASELINE.json quotes ("pairs/sec (fwd+bwd)")                               [default]
+  cfg2_fwd   configs[1]: same shapes, inference forward (also reported as "forward_only" inside the default line)
+  cfg4_train configs[3]: per-rank shard of the vlp_ddp batch (B=32/rank, L_v=150); cfg4_fwd / cfg5_fwd: forward only
 Metric: video-query pairs/sec (whole job, all ranks).  `value` is measured with inputs resident in HBM; `e2e` through the
 public plugin API (`model(**inputs)`) with pinned HOST inputs, H2D + D2H inside the timed region.
 N>1: one process per GPU (torchrun), each rank runs its own replica on its own batch (the path shards by sample; inference
@@ -37,7 +39,8 @@ WORKLOADS = {
     # configs[3]: per-rank shard (B=32, L_v=150) of the vlp_ddp pre-training batch; N ranks -> global batch 32 N
     "cfg4_train": dict(cfg="cfg4", mode="train"),
 }
-DEFAULT_WORKLOAD = "cfg2_fwd"
+# BASELINE.json's metric is "video-query pairs/sec (fwd+bwd) at L_v=75, d=1024": the full train step on cfg2 shapes.
+DEFAULT_WORKLOAD = "cfg3_train"
 SMI_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -151,7 +154,7 @@ def run_reference_arm(args, wl, cfg):
     dt = time.perf_counter() - t0
     val = B * args.steps / dt
     line = {
-        "impl": "reference", "metric": "video-query pairs/sec", "value": val, "unit": "pairs/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": "video-query pairs/sec" + (" (fwd+bwd)" if wl["mode"] == "train" else " (fwd)"), "value": val, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "mode": wl["mode"], "batch": B, "l_vid": cfg["l_vid"], "l_txt": cfg["l_txt"],
@@ -368,6 +371,25 @@ def main():
     ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ------------------- forward-only (inference) throughput on the same shapes, reported beside a train workload -----------
+    fwd_only = None
+    if train:
+        model.eval()
+        with torch.no_grad():
+            for i in range(3):
+                model(**dev_batches[i % n_rot])
+            sync_all()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for i in range(args.steps):
+                model(**dev_batches[i % n_rot])
+            g1.record()
+            sync_all()
+        ms_fwd = g0.elapsed_time(g1)
+        fwd_only = {"value": B * args.steps * n_gpus / (ms_fwd * 1e-3), "unit": "pairs/s", "ms_per_step": ms_fwd / args.steps,
+                    "note": "BASELINE configs[1]: inference forward on the same shapes (max over ranks not applied)"}
+        model.train()
+
     # ------------------- per-kernel-class durations of the forward (CUDA events between launches) ---------------------
     kind_ms = {0: [], 1: [], 2: []}
     n_kind = {0: 0, 1: 0, 2: 0}
@@ -439,6 +461,8 @@ def main():
                          "flops_per_launch": gflops / n_gemm,
                          "step_share": {"gemm_ms": gemm_ms, "attention_ms": attn_ms, "row_kernels_ms": row_ms}},
         }
+        if fwd_only is not None:
+            line["forward_only"] = fwd_only
         if n_gpus == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cfg, wl, args.workload)
         print(json.dumps(line), flush=True)
