@@ -252,9 +252,10 @@ def main():
     if train:
         model.train()
         crit.train()
-        # the reference's optimizer (main/config.py:349-350) with torch's fused multi-tensor implementation
-        opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-4, fused=True)
-        model.direct_grad = True  # gradients reach param.grad as views of the flat buffer (no per-parameter copies)
+        # the reference's update (main/config.py:349-350 AdamW; train_vlp_ddp.py:66-68 clip 0.1 + step) fused over the flat
+        # parameter / gradient buffers: univtg_adamw_step, two launches per step
+        from univtg_b200.optim import FlatAdamW
+        opt = FlatAdamW(model, lr=1e-4, weight_decay=1e-4, max_grad_norm=0.1)
         if dist is not None:
             ddp.broadcast_parameters(model)
             ddp.attach_flat_allreduce(model)  # ONE NCCL all-reduce of the flat gradient buffer per step
@@ -286,8 +287,7 @@ def main():
         total = sum(ld[k] * crit.weight_dict[k] for k in ld if k in crit.weight_dict)
         opt.zero_grad(set_to_none=True)
         total.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)  # reference --grad_clip 0.1
-        opt.step()
+        opt.step()  # clip_grad_norm_(0.1) (reference --grad_clip 0.1) + AdamW
         return total
 
     def device_step(i):

@@ -147,6 +147,18 @@ int univtg_op_gemm_cluster(const void* a, const void* b, int32_t M, int32_t N, i
  * [0] entry, [1] setup done, [2] all TMA issued, [3] first stage landed, [4] last MMA issued, [5] accumulator ready,
  * [6] epilogue done, [7] exit.  Pass NULL to switch it off. */
 int univtg_debug_gemm_timeline(void* buf);
+/* Parameter update of the reference's training loop (main/train_vlp_ddp.py:66-68 = main/train_mr.py:64-66; optimizer built at
+ * main/config.py:350 as torch.optim.AdamW(lr, weight_decay)) over ONE flat fp32 buffer of n floats (n % 4 == 0, 16-byte
+ * aligned; the plugin lays every parameter and its gradient out at the same offsets):
+ *   total_norm = ||grads||_2;  if max_grad_norm > 0: g *= min(1, max_grad_norm / (total_norm + 1e-6))   (clip_grad_norm_)
+ *   p *= 1 - lr*wd;  m = m + (1-beta1)(g - m);  v = beta2 v + (1-beta2) g^2;
+ *   p -= lr/(1-beta1^step) * m / (sqrt(v)/sqrt(1-beta2^step) + eps)                                      (AdamW, step >= 1)
+ * scratch2: device fp32 [2]; on return [1] holds total_norm (what clip_grad_norm_ returns).  write_clipped_grads != 0
+ * also stores the clipped gradients back (clip_grad_norm_ scales .grad in place). */
+int univtg_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, int32_t step, float max_grad_norm,
+                      int32_t write_clipped_grads, float* scratch2, void* stream);
+
 /* LayerNorm rows: in [rows,d] f32 -> out32 [rows,d] f32 and/or out16 [rows,ld16] 16-bit (zero padded). */
 int univtg_op_layernorm(const float* in, int32_t rows, int32_t d, const float* gamma, const float* beta, float eps,
                         int32_t fmt, float* out32, void* out16, int32_t ld16, void* stream);

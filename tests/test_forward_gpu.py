@@ -149,3 +149,20 @@ def test_missing_gpu_tensor_raises():
     with pytest.raises(RuntimeError):
         with torch.no_grad():
             model(**inp)  # CPU tensors: there is no CPU path
+
+
+def test_cuda_graph_replay_matches_eager_launches():
+    cfg = synth.CONFIGS["tiny"]
+    sd = synth.make_state_dict(cfg, seed=21)
+    model = _model(cfg, sd)
+    inp = synth.make_inputs(cfg, seed=22, ragged=True, batch=4)
+    ref = _run(model, inp)
+    model.use_cuda_graphs = True
+    a = _run(model, inp)
+    inp2 = synth.make_inputs(cfg, seed=23, ragged=True, batch=4)
+    b = _run(model, inp2)
+    model.use_cuda_graphs = False
+    ref2 = _run(model, inp2)
+    for k in ("pred_logits", "pred_spans", "saliency_scores", "vid_mem_proj", "txt_mem_proj"):
+        assert torch.equal(a[k], ref[k]), k
+        assert torch.equal(b[k], ref2[k]), k

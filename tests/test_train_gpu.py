@@ -159,3 +159,54 @@ def test_optimizer_step_decreases_loss():
         opt.step()
         vals.append(float(total))
     assert vals[-1] < vals[0], vals
+
+
+@pytest.mark.parametrize("gscale", [1e-4, 3.0])  # below / above the clip threshold of 0.1
+def test_flat_adamw_matches_torch_clip_plus_adamw(gscale):
+    """univtg_adamw_step == clip_grad_norm_ + torch.optim.AdamW (train_vlp_ddp.py:66-68) on the same gradients."""
+    from univtg_b200.optim import FlatAdamW
+
+    cfg = synth.CONFIGS["tiny"]
+    model, _ = _models(cfg, synth.make_state_dict(cfg, seed=3))
+    ref_params = [p.detach().clone().requires_grad_(True) for p in model._abi_params()]
+    opt_ref = torch.optim.AdamW(ref_params, lr=1e-3, weight_decay=1e-2)
+    opt = FlatAdamW(model, lr=1e-3, weight_decay=1e-2, max_grad_norm=0.1)
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    for _ in range(4):
+        flat, views = model._grad_buffer()
+        flat.zero_()
+        for v, rp in zip(views, ref_params):
+            g = torch.randn(v.shape, device="cuda", generator=gen) * gscale
+            v.copy_(g)
+            rp.grad = g.clone()
+        n_ref = torch.nn.utils.clip_grad_norm_(ref_params, 0.1)
+        opt_ref.step()
+        n = opt.step()
+        assert abs(float(n) - float(n_ref)) <= 1e-5 * float(n_ref)
+        for p, rp in zip(model._abi_params(), ref_params):
+            torch.testing.assert_close(p.detach(), rp.detach(), rtol=2e-5, atol=2e-7)
+
+
+def test_training_loop_with_flat_adamw_decreases_loss_and_repacks():
+    from univtg_b200.optim import FlatAdamW
+
+    cfg = synth.CONFIGS["tiny"]
+    model, crit = _models(cfg, synth.make_state_dict(cfg, seed=3))
+    model.train()
+    raw = synth.make_inputs(cfg, seed=4, ragged=True, batch=8)
+    inp = {k: v.cuda() for k, v in raw.items()}
+    tgt = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in synth.make_targets(raw, seed=5).items()}
+    opt = FlatAdamW(model, lr=1e-4, weight_decay=1e-4, max_grad_norm=0.1)
+    vals = []
+    for _ in range(12):
+        out = model(**inp)
+        ld = crit(out, tgt)
+        total = sum(ld[k] * crit.weight_dict[k] for k in ld)
+        opt.zero_grad()
+        total.backward()
+        opt.step()
+        vals.append(float(total))
+    assert vals[-1] < vals[0], vals
+    # the state_dict still exposes the (updated) parameters under the reference keys
+    sd = model.state_dict()
+    assert all(torch.isfinite(v).all() for v in sd.values())

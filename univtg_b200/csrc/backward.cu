@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const LnBwdArgs a) {
       xh[i] = 0.f;
       g[i] = 0.f;
       if (j < a.d) {
-        const float dj = dout[j];
+        float dj = dout[j];
+        if (a.dout_mul) dj *= a.dout_mul[(size_t)row * a.d + j];
         xh[i] = (y[j] - mean) * rstd;
         g[i] = dj * a.gamma[j];
         acc_g[i] += dj * xh[i];
@@ -81,10 +82,147 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const LnBwdArgs a) {
   }
 }
 
+// 128-bit variant for row lengths that are multiples of 4 (d <= 512 * NV): the next row's operands are fetched before the
+// current row's block reduction so the DRAM latency of consecutive rows overlaps.
+template <int NV>
+__global__ void __launch_bounds__(128) layernorm_bwd_vec_kernel(const LnBwdArgs a) {
+  __shared__ float s_red[2][4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float4 acc_g[NV], acc_b[NV], acc_c[NV], gam[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    acc_g[i] = acc_b[i] = acc_c[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int j = (tid + 128 * i) * 4;
+    gam[i] = j < a.d ? *reinterpret_cast<const float4*>(a.gamma + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float inv_d = 1.0f / (float)a.d;
+  float4 nd[NV], ny[NV];
+  auto fetch = [&](int row) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int j = (tid + 128 * i) * 4;
+      nd[i] = ny[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < a.rows && j < a.d) {
+        nd[i] = __ldg(reinterpret_cast<const float4*>(a.dout + (size_t)row * a.ld_dout + j));
+        ny[i] = __ldg(reinterpret_cast<const float4*>(a.y + (size_t)row * a.ld_y + j));
+        if (a.dout_mul) {
+          const float4 m = __ldg(reinterpret_cast<const float4*>(a.dout_mul + (size_t)row * a.d + j));
+          nd[i].x *= m.x, nd[i].y *= m.y, nd[i].z *= m.z, nd[i].w *= m.w;
+        }
+      }
+    }
+  };
+  fetch(blockIdx.x);
+  for (int row = blockIdx.x; row < a.rows; row += gridDim.x) {
+    const float mean = a.mean[row], rstd = a.rstd[row];
+    float4 dj[NV], yv[NV], xh[NV], g[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      dj[i] = nd[i];
+      yv[i] = ny[i];
+    }
+    fetch(row + gridDim.x);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int j = (tid + 128 * i) * 4;
+      const bool in = j < a.d;
+#define UV_LNB(c)                                          \
+  xh[i].c = in ? (yv[i].c - mean) * rstd : 0.f;            \
+  g[i].c = dj[i].c * gam[i].c;                             \
+  acc_g[i].c += dj[i].c * xh[i].c;                         \
+  acc_b[i].c += dj[i].c;                                   \
+  s1 += g[i].c;                                            \
+  s2 += g[i].c * xh[i].c;
+      UV_LNB(x) UV_LNB(y) UV_LNB(z) UV_LNB(w)
+#undef UV_LNB
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    __syncthreads();
+    if (lane == 0) {
+      s_red[0][warp] = s1;
+      s_red[1][warp] = s2;
+    }
+    __syncthreads();
+    const float c1 = (s_red[0][0] + s_red[0][1] + s_red[0][2] + s_red[0][3]) * inv_d;
+    const float c2 = (s_red[1][0] + s_red[1][1] + s_red[1][2] + s_red[1][3]) * inv_d;
+    float rs = 1.f;
+    if (a.row_scale != nullptr) rs = a.row_scale[a.L > 0 ? row / a.L : 0];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int j = (tid + 128 * i) * 4;
+      if (j < a.d) {
+        float4 dy;
+        dy.x = rstd * (g[i].x - c1 - xh[i].x * c2);
+        dy.y = rstd * (g[i].y - c1 - xh[i].y * c2);
+        dy.z = rstd * (g[i].z - c1 - xh[i].z * c2);
+        dy.w = rstd * (g[i].w - c1 - xh[i].w * c2);
+        if (a.relu_mask_y) {
+          if (!(yv[i].x > 0.f)) dy.x = 0.f;
+          if (!(yv[i].y > 0.f)) dy.y = 0.f;
+          if (!(yv[i].z > 0.f)) dy.z = 0.f;
+          if (!(yv[i].w > 0.f)) dy.w = 0.f;
+        }
+        if (a.dy32) *reinterpret_cast<float4*>(a.dy32 + (size_t)row * a.d + j) = dy;
+        const float4 br = make_float4(dy.x * rs, dy.y * rs, dy.z * rs, dy.w * rs);
+        acc_c[i].x += br.x, acc_c[i].y += br.y, acc_c[i].z += br.z, acc_c[i].w += br.w;
+        if (a.dbr16)
+          *reinterpret_cast<uint2*>(a.dbr16 + (size_t)row * a.ld16 + j) =
+              make_uint2(cvt16x2(br.x, br.y, a.fmt16), cvt16x2(br.z, br.w, a.fmt16));
+      }
+    }
+    if (a.dbr16)
+      for (int j = a.d + tid; j < a.ld16; j += 128) a.dbr16[(size_t)row * a.ld16 + j] = 0;
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = (tid + 128 * i) * 4;
+    if (j < a.d) {
+      const float ps = a.pgrad_scale;
+      if (a.dgamma) red_add_f32x4(a.dgamma + j, make_float4(acc_g[i].x * ps, acc_g[i].y * ps, acc_g[i].z * ps, acc_g[i].w * ps));
+      if (a.dbeta) red_add_f32x4(a.dbeta + j, make_float4(acc_b[i].x * ps, acc_b[i].y * ps, acc_b[i].z * ps, acc_b[i].w * ps));
+      if (a.colsum) red_add_f32x4(a.colsum + j, make_float4(acc_c[i].x * ps, acc_c[i].y * ps, acc_c[i].z * ps, acc_c[i].w * ps));
+    }
+  }
+}
+
+// Parameter gradients only (no dy requested): a pure column reduction, no per-row statistics of the gradient are needed.
+// Thread = one column, block = 256 columns x kRowsPerBlock rows.
+constexpr int kLnParamRows = 32;
+__global__ void __launch_bounds__(256) layernorm_bwd_params_kernel(const LnBwdArgs a) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= a.d) return;
+  const int r0 = blockIdx.y * kLnParamRows;
+  const int r1 = min(a.rows, r0 + kLnParamRows);
+  float ag = 0.f, ab = 0.f;
+#pragma unroll 8
+  for (int r = r0; r < r1; ++r) {
+    float dj = __ldg(a.dout + (size_t)r * a.ld_dout + j);
+    if (a.dout_mul) dj *= __ldg(a.dout_mul + (size_t)r * a.d + j);
+    const float xh = (__ldg(a.y + (size_t)r * a.ld_y + j) - __ldg(a.mean + r)) * __ldg(a.rstd + r);
+    ag += dj * xh;
+    ab += dj;
+  }
+  if (a.dgamma) atomicAdd(a.dgamma + j, ag * a.pgrad_scale);
+  if (a.dbeta) atomicAdd(a.dbeta + j, ab * a.pgrad_scale);
+}
+
 int launch_layernorm_bwd(const LnBwdArgs& a, cudaStream_t stream) {
   if (a.rows <= 0) return 0;
+  if (a.dy32 == nullptr && a.dbr16 == nullptr) {
+    layernorm_bwd_params_kernel<<<dim3((a.d + 255) / 256, (a.rows + kLnParamRows - 1) / kLnParamRows), 256, 0, stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) set_error("layernorm_bwd launch failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
   const int grid = a.rows < 592 ? a.rows : 592;  // 4 blocks per SM; each block keeps register partials over its rows
-  if (a.d <= 128 * 8) layernorm_bwd_kernel<8><<<grid, 128, 0, stream>>>(a);
+  const bool vec = a.d % 4 == 0 && a.ld_dout % 4 == 0 && a.ld_y % 4 == 0 && (!a.dbr16 || a.ld16 % 4 == 0) &&
+                   (((uintptr_t)a.dout | (uintptr_t)a.y | (uintptr_t)a.gamma | (uintptr_t)a.dy32 | (uintptr_t)a.dout_mul) & 15) == 0 &&
+                   (((uintptr_t)a.dgamma | (uintptr_t)a.dbeta | (uintptr_t)a.colsum) & 15) == 0 && ((uintptr_t)a.dbr16 & 7) == 0;
+  if (vec && a.d <= 512) layernorm_bwd_vec_kernel<1><<<grid, 128, 0, stream>>>(a);
+  else if (vec && a.d <= 1024) layernorm_bwd_vec_kernel<2><<<grid, 128, 0, stream>>>(a);
+  else if (a.d <= 128 * 8) layernorm_bwd_kernel<8><<<grid, 128, 0, stream>>>(a);
   else if (a.d <= 128 * 24) layernorm_bwd_kernel<24><<<grid, 128, 0, stream>>>(a);
   else {
     set_error("layernorm_bwd: d %d > 3072 not supported", a.d);

@@ -28,6 +28,7 @@ struct LnBwdArgs {
   float* dbeta;            // [d]
   float* colsum;           // [d] atomically accumulated column sums of the values written to dbr16 (bias gradient), or null
   float pgrad_scale;       // factor on dgamma / dbeta / colsum (1 / loss-scale: parameter gradients leave unscaled)
+  const float* dout_mul;   // optional [rows, d] multiplier applied to dout on load (input-dropout mask incl. 1/(1-p))
 };
 int launch_layernorm_bwd(const LnBwdArgs& a, cudaStream_t stream);
 

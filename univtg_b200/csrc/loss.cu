@@ -59,28 +59,29 @@ __global__ void __launch_bounds__(256) loss_cos_kernel(const LossArgs a) {
   }
 }
 
-// block-wide sum of one float per thread (256 threads)
+// block-wide sum of one float per thread (up to 1024 threads; s_red holds 32 floats)
 __device__ __forceinline__ float block_sum(float v, float* s_red) {
   v = warp_sum(v);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
   __syncthreads();
   float t = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) t += s_red[i];
+  const int nw = blockDim.x >> 5;
+  for (int i = 0; i < nw; ++i) t += s_red[i];
   return t;
 }
 
 // ------------------------------------------------------------------------------------------------
 // kernel 2 (single block): all five losses + gradients w.r.t. pred_spans / pred_logits / cos_in / sim.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) loss_finish_kernel(const LossArgs a) {
+__global__ void __launch_bounds__(1024) loss_finish_kernel(const LossArgs a) {
   extern __shared__ float sm[];
   float* s_rowlse = sm;                // [B]   logsumexp over l of z[b, :]
   float* s_collse = s_rowlse + a.B;    // [B]   logsumexp over b' of z[b', pos_b]  (column pos_b)
   float* s_irow = s_collse + a.B;      // [B]   inter: logsumexp over b' of sim[b, b'] / tau
   float* s_icol = s_irow + a.B;        // [B]   inter: logsumexp over b of sim[b, b'] / tau
-  __shared__ float s_red[8];
+  int* s_pos = reinterpret_cast<int*>(s_icol + a.B);  // [B] positive clip index per sample
+  __shared__ float s_red[32];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int B = a.B, Lv = a.Lv, n = B * Lv;
   const float inv_tau = 1.0f / a.temperature;
@@ -175,15 +176,19 @@ __global__ void __launch_bounds__(256) loss_finish_kernel(const LossArgs a) {
     }
     return;
   }
-  // inter-video: sim [B, B]
-  for (int r = tid; r < 2 * B; r += nt) {
+  for (int b = tid; b < B; b += nt) s_pos[b] = (int)a.pos_idx[b];
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+  // inter-video: sim [B, B]; one warp per row / column
+  for (int r = warp; r < 2 * B; r += nwarps) {
     const int b = r % B;
     const bool col = r >= B;
     float mx = -INFINITY;
-    for (int k = 0; k < B; ++k) mx = fmaxf(mx, (col ? a.sim[k * B + b] : a.sim[b * B + k]) * inv_tau);
+    for (int k = lane; k < B; k += 32) mx = fmaxf(mx, (col ? a.sim[k * B + b] : a.sim[b * B + k]) * inv_tau);
+    mx = warp_max(mx);
     float s = 0.f;
-    for (int k = 0; k < B; ++k) s += expf((col ? a.sim[k * B + b] : a.sim[b * B + k]) * inv_tau - mx);
-    (col ? s_icol : s_irow)[b] = mx + logf(s);
+    for (int k = lane; k < B; k += 32) s += expf((col ? a.sim[k * B + b] : a.sim[b * B + k]) * inv_tau - mx);
+    s = warp_sum(s);
+    if (lane == 0) (col ? s_icol : s_irow)[b] = mx + logf(s);
   }
   __syncthreads();
   float l_inter = 0.f;
@@ -198,31 +203,27 @@ __global__ void __launch_bounds__(256) loss_finish_kernel(const LossArgs a) {
   // intra-video: z[b,l] = (cos_in[b,l] + log(keep + 1e-45)) / tau
   //   keep[b,l] = ((sal[b,l] < sal[b,pos_b]) or l == pos_b) and tmask[b,l]
   auto zval = [&](int b, int l) -> float {
-    const int p = (int)a.pos_idx[b];
+    const int p = s_pos[b];
     const bool keep = ((a.sal[b * Lv + l] < a.sal[b * Lv + p]) || (l == p)) && (a.tmask[b * Lv + l] != 0.f);
     return (a.cos_in[b * Lv + l] + logf((keep ? 1.f : 0.f) + 1e-45f)) * inv_tau;
   };
-  for (int r = tid; r < 2 * B; r += nt) {
+  for (int r = warp; r < 2 * B; r += nwarps) {
     const int b = r % B;
-    if (r < B) {  // row b: over l
-      float mx = -INFINITY;
-      for (int l = 0; l < Lv; ++l) mx = fmaxf(mx, zval(b, l));
-      float s = 0.f;
-      for (int l = 0; l < Lv; ++l) s += expf(zval(b, l) - mx);
-      s_rowlse[b] = mx + logf(s);
-    } else {  // column pos_b: over samples b'
-      const int p = (int)a.pos_idx[b];
-      float mx = -INFINITY;
-      for (int k = 0; k < B; ++k) mx = fmaxf(mx, zval(k, p));
-      float s = 0.f;
-      for (int k = 0; k < B; ++k) s += expf(zval(k, p) - mx);
-      s_collse[b] = mx + logf(s);
-    }
+    const bool col = r >= B;  // row b: over clips l; column pos_b: over samples b'
+    const int p = s_pos[b];
+    const int cnt = col ? B : Lv;
+    float mx = -INFINITY;
+    for (int k = lane; k < cnt; k += 32) mx = fmaxf(mx, col ? zval(k, p) : zval(b, k));
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int k = lane; k < cnt; k += 32) s += expf((col ? zval(k, p) : zval(b, k)) - mx);
+    s = warp_sum(s);
+    if (lane == 0) (col ? s_collse : s_rowlse)[b] = mx + logf(s);
   }
   __syncthreads();
   float l_intra = 0.f;
   for (int b = tid; b < B; b += nt) {
-    const float zp = zval(b, (int)a.pos_idx[b]);
+    const float zp = zval(b, s_pos[b]);
     l_intra += 2.f * zp - s_rowlse[b] - s_collse[b];
   }
   l_intra = block_sum(l_intra, s_red);
@@ -231,9 +232,9 @@ __global__ void __launch_bounds__(256) loss_finish_kernel(const LossArgs a) {
     const float z = zval(b, l);
     // d/dz[b,l] of -(1/B) sum_b'' [ z[b'',p''] - rowlse[b''] + z[b'',p''] - collse(p'')[b''] ]
     float g = -expf(z - s_rowlse[b]);
-    if (l == (int)a.pos_idx[b]) g += 2.f;
+    if (l == s_pos[b]) g += 2.f;
     for (int k = 0; k < B; ++k)
-      if ((int)a.pos_idx[k] == l) g -= expf(z - s_collse[k]);
+      if (s_pos[k] == l) g -= expf(z - s_collse[k]);
     a.g_cos_in[i] = -g * inv_tau / (float)B;
   }
   if (tid == 0) {
@@ -247,7 +248,7 @@ int launch_loss_forward(const LossArgs& a, cudaStream_t stream) {
     const int warps = a.B * a.Lv + a.B * a.B;
     loss_cos_kernel<<<(warps * 32 + 255) / 256, 256, 0, stream>>>(a);
   }
-  loss_finish_kernel<<<1, 256, (size_t)4 * a.B * sizeof(float), stream>>>(a);
+  loss_finish_kernel<<<1, 1024, (size_t)5 * a.B * sizeof(float), stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("loss forward launch failed: %s", cudaGetErrorString(e));
   return (int)e;
@@ -280,22 +281,33 @@ __global__ void __launch_bounds__(256) loss_bwd_vid_kernel(const LossBwdArgs a) 
   const bool is_pos = a.pos_idx != nullptr && (int)a.pos_idx[b] == l;
   const float* u = a.xv + (size_t)gw * a.d;
   float* out = a.d_xv + (size_t)gw * a.d;
+  extern __shared__ float s_c1[];  // [8 warps][B] coefficients of xt[k] for the positive row of a sample
+  float* c1w = s_c1 + (size_t)(threadIdx.x >> 5) * a.B;
+  const float s1 = gi / (un * a.tnorm[b]);
+  float s2 = gi * ci / (un * un);
+  if (is_pos) {
+    float s2p = 0.f;
+    for (int k = lane; k < a.B; k += 32) {
+      const float gx = w_inter * a.g_sim[b * a.B + k];
+      c1w[k] = gx / (un * a.tnorm[k]);
+      s2p += gx * a.sim[b * a.B + k] / (un * un);
+    }
+    s2 += warp_sum(s2p);
+    __syncwarp();
+  }
   for (int j = lane * 4; j < a.d; j += 128) {
     const float4 x = *reinterpret_cast<const float4*>(u + j);
     const float4 t = *reinterpret_cast<const float4*>(a.xt + (size_t)b * a.d + j);
-    const float s1 = gi / (un * a.tnorm[b]);
-    float s2 = gi * ci / (un * un);
     float4 o = make_float4(s1 * t.x, s1 * t.y, s1 * t.z, s1 * t.w);
     if (is_pos) {
+#pragma unroll 4
       for (int k = 0; k < a.B; ++k) {
-        const float gx = w_inter * a.g_sim[b * a.B + k];
         const float4 tk = *reinterpret_cast<const float4*>(a.xt + (size_t)k * a.d + j);
-        const float c1 = gx / (un * a.tnorm[k]);
+        const float c1 = c1w[k];
         o.x += c1 * tk.x;
         o.y += c1 * tk.y;
         o.z += c1 * tk.z;
         o.w += c1 * tk.w;
-        s2 += gx * a.sim[b * a.B + k] / (un * un);
       }
     }
     o.x -= s2 * x.x;
@@ -314,12 +326,14 @@ __global__ void __launch_bounds__(128) loss_bwd_txt_kernel(const LossBwdArgs a) 
   for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < a.d; j += gridDim.y * blockDim.x) {
     const float tj = a.xt[(size_t)b * a.d + j];
     float o = 0.f;
-    for (int l = 0; l < a.Lv; ++l) {
+#pragma unroll 5
+    for (int l = 0; l < a.Lv; ++l) {  // vnorm and tnorm are clamped >= 1e-8 by the forward, so no term is inf * 0
       const int i = b * a.Lv + l;
       const float g = w_intra * a.g_cos_in[i];
-      if (g != 0.f) o += g * (a.xv[(size_t)i * a.d + j] / (a.vnorm[i] * tn) - a.cos_in[i] * tj / (tn * tn));
+      o += g * (a.xv[(size_t)i * a.d + j] / (a.vnorm[i] * tn) - a.cos_in[i] * tj / (tn * tn));
     }
     if (a.pos_idx != nullptr) {
+#pragma unroll 4
       for (int k = 0; k < a.B; ++k) {
         const float g = w_inter * a.g_sim[k * a.B + b];
         const int i = k * a.Lv + (int)a.pos_idx[k];
@@ -333,7 +347,7 @@ __global__ void __launch_bounds__(128) loss_bwd_txt_kernel(const LossBwdArgs a) 
 int launch_loss_backward(const LossBwdArgs& a, cudaStream_t stream) {
   const int n = a.B * a.Lv;
   loss_bwd_small_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a);
-  loss_bwd_vid_kernel<<<(n * 32 + 255) / 256, 256, 0, stream>>>(a);
+  loss_bwd_vid_kernel<<<(n * 32 + 255) / 256, 256, (size_t)8 * a.B * sizeof(float), stream>>>(a);
   loss_bwd_txt_kernel<<<dim3(a.B, (a.d + 127) / 128), 128, 0, stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("loss backward launch failed: %s", cudaGetErrorString(e));

@@ -1,0 +1,113 @@
+// Parameter update of the reference's training loop over ONE flat fp32 buffer (main/train_vlp_ddp.py:66-68, main/train_mr.py:64-66,
+// optimizer built at main/config.py:350): total-norm gradient clipping (torch.nn.utils.clip_grad_norm_, L2) followed by
+// torch.optim.AdamW (decoupled weight decay, bias-corrected, no amsgrad).  Two launches: sum of squares, then the update with
+// the clip coefficient computed on the device - no host round trip.  HBM-bound: 16 B read + 12 B written per parameter.
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/univtg_b200.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace uv {
+namespace {
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n4, float* __restrict__ out) {
+  __shared__ float s_red[8];
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float s = 0.f;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
+    const float4 v = __ldg(g4 + i);
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += s_red[i];
+    atomicAdd(out, t);
+  }
+}
+
+struct AdamArgs {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  size_t n4;
+  float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, max_norm;
+  float* scratch;  // [0] = sum of squares of g (in), [1] = total norm (out)
+  float* g_out;    // clipped gradients written back (clip_grad_norm_ scales .grad in place) or null
+};
+
+__global__ void __launch_bounds__(256) adamw_kernel(const AdamArgs a) {
+  const float norm = sqrtf(a.scratch[0]);
+  float clip = 1.f;
+  if (a.max_norm > 0.f) clip = fminf(a.max_norm / (norm + 1e-6f), 1.f);
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.scratch[1] = norm;
+  float4* p4 = reinterpret_cast<float4*>(a.p);
+  const float4* g4 = reinterpret_cast<const float4*>(a.g);
+  float4* m4 = reinterpret_cast<float4*>(a.m);
+  float4* v4 = reinterpret_cast<float4*>(a.v);
+  const float decay = 1.f - a.lr * a.wd, step = a.lr / a.bc1, ob1 = 1.f - a.beta1, ob2 = 1.f - a.beta2;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < a.n4; i += (size_t)gridDim.x * 256) {
+    float4 p = p4[i], g = __ldg(g4 + i), m = m4[i], v = v4[i];
+#define UV_ADAM(c)                                         \
+  g.c *= clip;                                             \
+  p.c *= decay;                                            \
+  m.c = fmaf(g.c - m.c, ob1, m.c);                         \
+  v.c = fmaf(a.beta2, v.c, ob2 * g.c * g.c);               \
+  p.c -= step * m.c / (sqrtf(v.c) / a.bc2_sqrt + a.eps);
+    UV_ADAM(x) UV_ADAM(y) UV_ADAM(z) UV_ADAM(w)
+#undef UV_ADAM
+    p4[i] = p;
+    m4[i] = m;
+    v4[i] = v;
+    if (a.g_out) reinterpret_cast<float4*>(a.g_out)[i] = g;
+  }
+}
+
+}  // namespace
+}  // namespace uv
+
+extern "C" int univtg_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                                 float beta2, float eps, float weight_decay, int32_t step, float max_grad_norm,
+                                 int32_t write_clipped_grads, float* scratch2, void* stream) {
+  using namespace uv;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (n == 0) return 0;
+  if (n % 4 != 0 || step < 1 || ((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq)) & 15) != 0 ||
+      scratch2 == nullptr) {
+    set_error("univtg_adamw_step: buffers must be 16-byte aligned with n %% 4 == 0, step >= 1, scratch non-null");
+    return (int)cudaErrorInvalidValue;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t n4 = n / 4;
+  size_t blocks = (n4 + 255) / 256;
+  if (blocks > (size_t)sms * 8) blocks = (size_t)sms * 8;
+  cudaMemsetAsync(scratch2, 0, 2 * sizeof(float), st);
+  sumsq_kernel<<<(unsigned)blocks, 256, 0, st>>>(grads, n4, scratch2);
+  AdamArgs a;
+  a.p = params;
+  a.g = grads;
+  a.m = exp_avg;
+  a.v = exp_avg_sq;
+  a.n4 = n4;
+  a.lr = lr;
+  a.beta1 = beta1;
+  a.beta2 = beta2;
+  a.eps = eps;
+  a.wd = weight_decay;
+  a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  a.max_norm = max_grad_norm;
+  a.scratch = scratch2;
+  a.g_out = write_clipped_grads ? grads : nullptr;
+  adamw_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) set_error("univtg_adamw_step launch failed: %s", cudaGetErrorString(e));
+  return (int)e;
+}

@@ -187,39 +187,79 @@ struct PackTask {
   void* dst;
   int kind;          // 0: rows -> 16-bit [rows, ld] zero-padded, 1: conv [N,C,3] -> 16-bit [N, 3C], 2: conv -> fp32 [N,3,C], 3: vector copy(+add)
   int rows, cols, ld;
+  int blk0;          // first block of this task in the launch (blocks are dealt out in proportion to the task's size)
 };
 constexpr int kPackTasksPerLaunch = 64;
+constexpr int kPackItemsPerBlock = 256 * 8;  // work items per block (an item = 4 output elements, or one conv (n, c) pair)
 struct PackTable {
   int n, fmt;
   PackTask t[kPackTasksPerLaunch];
 };
 
+inline size_t pack_task_items(const PackTask& k) {
+  if (k.kind == 0) return ((size_t)k.rows * k.ld + 3) / 4;  // ld % 4 == 0 for every packed matrix (K padded to 64)
+  if (k.kind == 1 || k.kind == 2) return (size_t)k.rows * k.cols;
+  return ((size_t)k.rows + 3) / 4;
+}
+
 __global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__ PackTable tab) {
-  const PackTask& k = tab.t[blockIdx.y];
+  int ti = 0;
+  while (ti + 1 < tab.n && (int)blockIdx.x >= tab.t[ti + 1].blk0) ++ti;
+  const PackTask& k = tab.t[ti];
   const int fmt = tab.fmt;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t first = (size_t)(blockIdx.x - k.blk0) * kPackItemsPerBlock;
   if (k.kind == 0) {
-    const size_t total = (size_t)k.rows * k.ld;
-    uint16_t* dst = reinterpret_cast<uint16_t*>(k.dst);
-    for (size_t i = i0; i < total; i += stride) {
-      const int r = (int)(i / k.ld), c = (int)(i % k.ld);
-      dst[i] = c < k.cols ? cvt16(k.src[(size_t)r * k.cols + c], fmt) : (uint16_t)0;
+    const size_t items = ((size_t)k.rows * k.ld) / 4;
+    const bool dense = k.ld == k.cols && (k.cols & 3) == 0 && (((uintptr_t)k.src) & 15) == 0;
+    uint2* dst2 = reinterpret_cast<uint2*>(k.dst);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const size_t it = first + u * 256 + threadIdx.x;
+      if (it >= items) break;
+      float4 v;
+      if (dense) {
+        v = __ldg(reinterpret_cast<const float4*>(k.src) + it);
+      } else {
+        const int r = (int)((it * 4) / k.ld), c = (int)((it * 4) % k.ld);  // 4 consecutive columns of one row (ld % 4 == 0)
+        const float* row = k.src + (size_t)r * k.cols;
+        v.x = c + 0 < k.cols ? __ldg(row + c + 0) : 0.f;
+        v.y = c + 1 < k.cols ? __ldg(row + c + 1) : 0.f;
+        v.z = c + 2 < k.cols ? __ldg(row + c + 2) : 0.f;
+        v.w = c + 3 < k.cols ? __ldg(row + c + 3) : 0.f;
+      }
+      dst2[it] = make_uint2(cvt16x2(v.x, v.y, fmt), cvt16x2(v.z, v.w, fmt));
     }
   } else if (k.kind == 1 || k.kind == 2) {
-    const int N = k.rows, C = k.cols;
-    const size_t total = (size_t)N * 3 * C;
-    for (size_t i = i0; i < total; i += stride) {
-      const int n = (int)(i / (3 * C));
-      const int rem = (int)(i % (3 * C));
-      const int t = rem / C, c = rem % C;
-      const float v = k.src[((size_t)n * C + c) * 3 + t];
-      if (k.kind == 1) reinterpret_cast<uint16_t*>(k.dst)[i] = cvt16(v, fmt);
-      else reinterpret_cast<float*>(k.dst)[i] = v;
+    // item = one (n, c) pair: three consecutive source floats (taps), scattered to the three tap planes of row n
+    const int C = k.cols;
+    const size_t items = (size_t)k.rows * C;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const size_t it = first + u * 256 + threadIdx.x;
+      if (it >= items) break;
+      const int n = (int)(it / C), c = (int)(it % C);
+      const float* sp = k.src + it * 3;
+      const float v0 = __ldg(sp), v1 = __ldg(sp + 1), v2 = __ldg(sp + 2);
+      const size_t o = (size_t)n * 3 * C + c;
+      if (k.kind == 1) {
+        uint16_t* d16 = reinterpret_cast<uint16_t*>(k.dst);
+        d16[o] = cvt16(v0, fmt);
+        d16[o + C] = cvt16(v1, fmt);
+        d16[o + 2 * C] = cvt16(v2, fmt);
+      } else {
+        float* d32 = reinterpret_cast<float*>(k.dst);
+        d32[o] = v0;
+        d32[o + C] = v1;
+        d32[o + 2 * C] = v2;
+      }
     }
   } else {
     float* dst = reinterpret_cast<float*>(k.dst);
-    for (size_t i = i0; i < (size_t)k.rows; i += stride) dst[i] = k.src[i] + (k.add ? k.add[i] : 0.f);
+    for (int u = 0; u < 8 * 4; ++u) {
+      const size_t i = first * 4 + (size_t)u * 256 + threadIdx.x;
+      if (i >= (size_t)k.rows) break;
+      dst[i] = k.src[i] + (k.add ? k.add[i] : 0.f);
+    }
   }
 }
 
@@ -235,13 +275,18 @@ struct Packer {
   void flush() {
     if (tab.n == 0) return;
     tab.fmt = fmt;
-    pack_multi_kernel<<<dim3(48, tab.n), 256, 0, st>>>(tab);
+    int blocks = 0;
+    for (int i = 0; i < tab.n; ++i) {
+      tab.t[i].blk0 = blocks;
+      blocks += (int)((pack_task_items(tab.t[i]) + kPackItemsPerBlock - 1) / kPackItemsPerBlock);
+    }
+    if (blocks > 0) pack_multi_kernel<<<blocks, 256, 0, st>>>(tab);
     tab.n = 0;
   }
-  void rows(const float* src, size_t off, int rows_, int cols, int ld) { push(PackTask{src, nullptr, base + off, 0, rows_, cols, ld}); }
-  void conv(const float* src, size_t off, int N, int C) { push(PackTask{src, nullptr, base + off, 1, N, C, 0}); }
-  void conv_f32(const float* src, size_t off, int N, int C) { push(PackTask{src, nullptr, base + off, 2, N, C, 0}); }
-  void vec(const float* src, size_t off, int n, const float* add = nullptr) { push(PackTask{src, add, base + off, 3, n, 0, 0}); }
+  void rows(const float* src, size_t off, int rows_, int cols, int ld) { push(PackTask{src, nullptr, base + off, 0, rows_, cols, ld, 0}); }
+  void conv(const float* src, size_t off, int N, int C) { push(PackTask{src, nullptr, base + off, 1, N, C, 0, 0}); }
+  void conv_f32(const float* src, size_t off, int N, int C) { push(PackTask{src, nullptr, base + off, 2, N, C, 0, 0}); }
+  void vec(const float* src, size_t off, int n, const float* add = nullptr) { push(PackTask{src, add, base + off, 3, n, 0, 0, 0}); }
 };
 
 }  // namespace

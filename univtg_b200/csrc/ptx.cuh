@@ -211,6 +211,10 @@ UV_DEVINL float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// one 128-bit reduction (four fp32 adds, relaxed, gpu scope) - addr must be 16-byte aligned
+UV_DEVINL void red_add_f32x4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 UV_DEVINL float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -241,9 +245,18 @@ UV_DEVINL float gelu_erf(float x) {
   const float r = fmaf(-y, e, 1.0f);                                // erf(|x| / sqrt 2)
   return 0.5f * fmaf(ax, r, x);
 }
-// d/dx gelu_erf(x) = Phi(x) + x * phi(x)
+// d/dx gelu(x) = Phi(x) + x phi(x), Phi(x) = 0.5 (1 + erf(x / sqrt 2)), phi(x) = exp(-x^2/2) / sqrt(2 pi); same erf as above
 UV_DEVINL float gelu_erf_grad(float x) {
-  return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f));
+  float y = fmaf(1.061405429f, t, -1.453152027f);
+  y = fmaf(y, t, 1.421413741f);
+  y = fmaf(y, t, -0.284496736f);
+  y = fmaf(y, t, 0.254829592f);
+  y = y * t;
+  const float e = exp2f(ax * ax * (-0.5f * 1.4426950408889634f));
+  const float r = fmaf(-y, e, 1.0f);  // erf(|x| / sqrt 2)
+  return fmaf(0.5f, copysignf(r, x), 0.5f) + x * 0.3989422804014327f * e;
 }
 UV_DEVINL bool pos16(uint16_t h) { return (h & 0x8000u) == 0 && (h & 0x7fffu) != 0; }  // 16-bit float > 0 (fp16 or bf16)
 

@@ -879,7 +879,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.fmt = fmt;
     const int kpv = Lw.vid[i].kpad, kpt = Lw.txt[i].kpad, dinv = Lw.vid[i].din, dint = Lw.txt[i].din;
     const int bn = bn_for(sms, 64, d, dinv, d, dint);
-    const int bn_pd = bn_for(sms, 64, Mv, dinv, Mt, dint);
+    const int bn_pd = bn_for(sms, 64, Mv, kpv, Mt, kpt);
     rc |= setup_gemm(g.p[0], Mat16{T.dxv16, Mv, d, d}, 1, Mat16{T.a_vid[i], Mv, kpv, kpv}, 1, d, dinv, Mv, bn);
     rc |= setup_gemm(g.p[1], Mat16{T.dxt16, Mt, d, d}, 1, Mat16{T.a_txt[i], Mt, kpt, kpt}, 1, d, dint, Mt, bn);
     if (rc) return rc;
@@ -892,27 +892,21 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.p[0].alpha = g.p[1].alpha = INV;
     rc = launch_gemm_group(g, bn, sms, st);
     if (rc) return rc;
-    // dgrad: dA_i = (dOut W_i) * dropout mask   (fp32, [rows, din_i])
+    // dgrad: dA_i = dOut W_i  (fp32, [rows, kpad_i]: N is padded to the packed weight's K so the epilogue stays on its
+    // 128-bit path even for the 2818-wide video features; the padded columns are zeros).  The input-dropout mask is applied
+    // by the LayerNorm backward when it loads dA.
     memset(&g, 0, sizeof(g));
     g.num = 2;
     g.fmt = fmt;
-    rc |= setup_gemm(g.p[0], Mat16{T.dxv16, Mv, d, d}, 0, Mat16{W16(Lw.vid[i].w16), d, kpv, kpv}, 1, Mv, dinv, d, bn_pd);
-    rc |= setup_gemm(g.p[1], Mat16{T.dxt16, Mt, d, d}, 0, Mat16{W16(Lw.txt[i].w16), d, kpt, kpt}, 1, Mt, dint, d, bn_pd);
+    rc |= setup_gemm(g.p[0], Mat16{T.dxv16, Mv, d, d}, 0, Mat16{W16(Lw.vid[i].w16), d, kpv, kpv}, 1, Mv, kpv, d, bn_pd);
+    rc |= setup_gemm(g.p[1], Mat16{T.dxt16, Mt, d, d}, 0, Mat16{W16(Lw.txt[i].w16), d, kpt, kpt}, 1, Mt, kpt, d, bn_pd);
     if (rc) return rc;
     g.p[0].a_fmt = g.p[1].a_fmt = FMT_G;
     g.p[0].b_fmt = g.p[1].b_fmt = fmt;
     g.p[0].out32 = T.dA_v;
-    g.p[0].ld32 = dinv;
+    g.p[0].ld32 = kpv;
     g.p[1].out32 = T.dA_t;
-    g.p[1].ld32 = dint;
-    if (drop_masks) {
-      g.p[0].aux32 = drop_masks[i];
-      g.p[0].ld_aux = dinv;
-      g.p[0].aux_mode = 2;
-      g.p[1].aux32 = drop_masks[np + i];
-      g.p[1].ld_aux = dint;
-      g.p[1].aux_mode = 2;
-    }
+    g.p[1].ld32 = kpt;
     rc = launch_gemm_group(g, bn_pd, sms, st);
     if (rc) return rc;
     // LayerNorm_i backward: parameter gradients; for i > 0 also the gradient of the previous layer's ReLU output
@@ -921,7 +915,8 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       memset(&a, 0, sizeof(a));
       const ProjPacked& pp = s == 0 ? Lw.vid[i] : Lw.txt[i];
       a.dout = s == 0 ? T.dA_v : T.dA_t;
-      a.ld_dout = pp.din;
+      a.ld_dout = pp.kpad;
+      a.dout_mul = drop_masks ? drop_masks[s * np + i] : nullptr;
       a.y = i == 0 ? (s == 0 ? src_vid : src_txt) : (s == 0 ? T.p_vid32[i - 1] : T.p_txt32[i - 1]);
       a.ld_y = pp.din;
       a.mean = s == 0 ? T.pmean_v[i] : T.pmean_t[i];

@@ -232,6 +232,7 @@ class Model(nn.Module):
 
     def _drop_plans(self):
         lib = _lib.load_library()
+        self.__dict__["_graphs"] = {}  # captured graphs reference the plans' workspaces and tensor maps
         for e in self._plans.values():
             lib.univtg_plan_destroy(e.handle)
         self._plans = {}
@@ -263,13 +264,15 @@ class Model(nn.Module):
         """One flat fp32 gradient buffer with a view per parameter (C-ABI order); also the all-reduce payload."""
         params = self._abi_params()
         buf = self.__dict__.get("_flat_grad")
-        total = sum(p.numel() for p in params)
+        # every view starts on a 16-byte boundary (128-bit reductions / stores in the backward kernels); the padding
+        # floats stay zero, so the buffer is still a valid all-reduce / clip-norm payload
+        total = sum((p.numel() + 3) // 4 * 4 for p in params)
         if buf is None or buf[0].device != self._device() or buf[0].numel() != total:
             flat = torch.zeros(total, dtype=torch.float32, device=self._device())
             views, off = [], 0
             for p in params:
                 views.append(flat[off:off + p.numel()].view_as(p))
-                off += p.numel()
+                off += (p.numel() + 3) // 4 * 4
             buf = (flat, views)
             self.__dict__["_flat_grad"] = buf
         return buf
@@ -336,7 +339,50 @@ class Model(nn.Module):
             from .autograd import forward_train  # backward kernels live in the same library
 
             return forward_train(self, src_txt, src_txt_mask, src_vid, src_vid_mask)
+        if getattr(self, "use_cuda_graphs", False):
+            return self._forward_graphed(src_txt, src_txt_mask, src_vid, src_vid_mask)
         return self._forward_inference(src_txt, src_txt_mask, src_vid, src_vid_mask)
+
+    def _forward_graphed(self, src_txt, src_txt_mask, src_vid, src_vid_mask):
+        """Inference forward replayed from a CUDA graph (one per input shape): the ~41 kernel launches of a forward are
+        captured once on static input buffers; each call copies the inputs in, replays, and returns fresh output tensors."""
+        dev = self._device()
+        B, Lv, _ = src_vid.shape
+        Lt = src_txt.shape[1]
+        key = (B, Lv, Lt)
+        cache = self.__dict__.setdefault("_graphs", {})
+        with torch.cuda.device(dev):
+            self._ensure_packed()
+            cache = self.__dict__.setdefault("_graphs", {})  # _ensure_packed may have dropped plans + graphs
+            ent = cache.get(key)
+            if ent is None:
+                if len(cache) >= 4:
+                    cache.pop(next(iter(cache)))
+                static = {"src_txt": torch.zeros(B, Lt, self.txt_dim, device=dev), "src_txt_mask": torch.zeros(B, Lt, device=dev),
+                          "src_vid": torch.zeros(B, Lv, self.vid_dim, device=dev), "src_vid_mask": torch.zeros(B, Lv, device=dev)}
+                for k, v in (("src_txt", src_txt), ("src_txt_mask", src_txt_mask), ("src_vid", src_vid), ("src_vid_mask", src_vid_mask)):
+                    static[k].copy_(v)
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(2):  # warm-up outside capture (plans, function attributes, allocator)
+                        self._forward_inference(**static)
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    outs = self._forward_inference(**static)
+                ent = {"graph": graph, "static": static, "outs": outs}
+                cache[key] = ent
+            st = ent["static"]
+            st["src_txt"].copy_(src_txt, non_blocking=True)
+            st["src_txt_mask"].copy_(src_txt_mask, non_blocking=True)
+            st["src_vid"].copy_(src_vid, non_blocking=True)
+            st["src_vid_mask"].copy_(src_vid_mask, non_blocking=True)
+            ent["graph"].replay()
+            o = ent["outs"]
+            return {"pred_logits": o["pred_logits"].clone(), "pred_spans": o["pred_spans"].clone(), "src_vid_mask": src_vid_mask,
+                    "vid_mem_proj": o["vid_mem_proj"].clone(), "txt_mem_proj": o["txt_mem_proj"].clone(),
+                    "saliency_scores": o["saliency_scores"].clone()}
 
     def _forward_inference(self, src_txt, src_txt_mask, src_vid, src_vid_mask, droppath_scale=None):
         lib = _lib.load_library()
