@@ -147,6 +147,9 @@ int univtg_op_gemm_cluster(const void* a, const void* b, int32_t M, int32_t N, i
  * [0] entry, [1] setup done, [2] all TMA issued, [3] first stage landed, [4] last MMA issued, [5] accumulator ready,
  * [6] epilogue done, [7] exit.  Pass NULL to switch it off. */
 int univtg_debug_gemm_timeline(void* buf);
+/* tcgen05.mma issue-rate probe (M=128, N=n, K=16 from resident smem): out_ns[block] = ns per MMA.  Profiling aid only. */
+int univtg_debug_mma_rate(int32_t n, int32_t iters, int32_t per_commit, int32_t kstep_bytes, int32_t blocks, float* out_ns,
+                          void* stream);
 /* Parameter update of the reference's training loop (main/train_vlp_ddp.py:66-68 = main/train_mr.py:64-66; optimizer built at
  * main/config.py:350 as torch.optim.AdamW(lr, weight_decay)) over ONE flat fp32 buffer of n floats (n % 4 == 0, 16-byte
  * aligned; the plugin lays every parameter and its gradient out at the same offsets):

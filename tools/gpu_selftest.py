@@ -90,7 +90,25 @@ def case_gemm_timeline(M, N, K, act, want32, want16, bn, cluster=False):
     names = ["entry", "setup", "tma_issued", "first_stage", "last_mma", "acc_ready", "epi_done", "exit"]
     res = {"event_us": e0.elapsed_time(e1) * 1e3, "ctas": int(used.sum()), "ok": True}
     for i, n in enumerate(names):
-        res[n] = [round(float(rel[:, i].min()), 2), round(float(rel[:, i].median()), 2), round(float(rel[:, i].max()), 2)]
+        col = rel[:, i][t[:, i] > 0]  # CTA-pair mode: only the leader CTA stamps the MMA-side events
+        res[n] = [round(float(col.min()), 2), round(float(col.median()), 2), round(float(col.max()), 2)] if col.numel() else None
+    return res
+
+
+def case_mma_rate():
+    """ns per tcgen05.mma (M=128, K=16) vs N, operands resident in smem: the tensor-pipe rate without any operand feed."""
+    import torch
+    from univtg_b200 import _lib
+    lib = _lib.load_library()
+    res = {"ok": True}
+    for blocks in (1, 148):
+        for n in (64, 128, 256):
+            for per_commit, kstep in ((4, 32), (4, 0), (1, 32)):
+                out = torch.zeros(blocks, device="cuda")
+                for _ in range(2):
+                    _lib.check(lib.univtg_debug_mma_rate(n, 512, per_commit, kstep, blocks, _lib.ptr(out), _lib.stream_ptr()), "mma_rate")
+                torch.cuda.synchronize()
+                res[f"b{blocks}_n{n}_pc{per_commit}_ks{kstep}"] = round(float(out.median()), 1)
     return res
 
 
@@ -213,6 +231,13 @@ CASES = {
     "tlcl_plain16": (case_gemm_timeline, (3424, 1024, 1024, 0, False, True, 256, True)),
     "tlcl_qkv": (case_gemm_timeline, (3424, 3072, 1024, 0, False, True, 256, True)),
     "tl_plain16": (case_gemm_timeline, (3424, 1024, 1024, 0, False, True, 256)),
+    # steady-state mainloop probes: 148 (bn 256) / 296 (bn 128) tiles of 64 k-blocks
+    "tl_k4096_bn256": (case_gemm_timeline, (9472, 512, 4096, 0, False, True, 256)),
+    "tlcl_k4096_bn256": (case_gemm_timeline, (9472, 512, 4096, 0, False, True, 256, True)),
+    "tl_k4096_bn128": (case_gemm_timeline, (9472, 512, 4096, 0, False, True, 128)),
+    "tlcl_k4096_bn128": (case_gemm_timeline, (9472, 512, 4096, 0, False, True, 128, True)),
+    "tl_k4096_bn64": (case_gemm_timeline, (9472, 512, 4096, 0, False, True, 64)),
+    "tlcl_k4096_bn64": (case_gemm_timeline, (9472, 512, 4096, 0, False, True, 64, True)),
     "gemm_amn": (case_gemm, (256, 256, 192, 1, 0, 0, 256, 1, 0, True)),
     "gemm_bmn": (case_gemm, (256, 256, 192, 0, 1, 0, 256, 1, 0, True)),
     "gemm_abmn_bn128": (case_gemm, (256, 384, 200, 1, 1, 0, 128, 1, 0, True)),
@@ -221,6 +246,7 @@ CASES = {
     "tl_outproj": (case_gemm_timeline, (3424, 1024, 1024, 0, True, False, 256)),
     "tl_qkv_bn256": (case_gemm_timeline, (3424, 3072, 1024, 0, False, True, 256)),
     "tl_ffn1_bn128": (case_gemm_timeline, (3424, 1024, 1024, 2, False, True, 128)),
+    "mma_rate": (case_mma_rate, ()),
     "ln_1024": (case_layernorm, (3424, 1024, 1024, 0)),
     "ln_256_bf16": (case_layernorm, (77, 256, 256, 1)),
     "ln_2818": (case_layernorm, (300, 2818, 2880, 0)),
@@ -251,7 +277,7 @@ def main():
     for name in names:
         try:
             p = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", name], capture_output=True, text=True,
-                               timeout=150)
+                               timeout=60)
             line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
             if line:
                 results[name] = json.loads(line[-1][7:])

@@ -17,12 +17,13 @@ inp = {k: v.cuda() for k, v in synth.make_inputs(cfg, seed=1).items()}
 tgt = {k: v.cuda() for k, v in synth.make_targets(synth.make_inputs(cfg, seed=1), seed=2).items()}
 if mode == "train":
     model.train()
-    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4)
+    from univtg_b200.optim import FlatAdamW
+    opt = FlatAdamW(model, lr=1e-4, weight_decay=1e-4, max_grad_norm=0.1)
     def step():
         out = model(**inp); ld = crit(out, tgt)
         total = sum(ld[k] * crit.weight_dict[k] for k in ld)
         opt.zero_grad(set_to_none=True); total.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1); opt.step()
+        opt.step()
 else:
     model.eval()
     def step():

@@ -622,6 +622,11 @@ int univtg_op_gemm_cluster(const void* a, const void* b, int32_t M, int32_t N, i
   return op_gemm_impl(a, b, M, N, K, a_mn, b_mn, fmt, bn, ksplit, bias, act, alpha, out32, out16, 2, stream);
 }
 
+int univtg_debug_mma_rate(int32_t n, int32_t iters, int32_t per_commit, int32_t kstep_bytes, int32_t blocks, float* out_ns,
+                          void* stream) {
+  return uv::debug_mma_rate(n, iters, per_commit, kstep_bytes, blocks, out_ns, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int univtg_debug_gemm_timeline(void* buf) {
   uv::set_gemm_timeline_buffer(reinterpret_cast<unsigned long long*>(buf));
   return 0;

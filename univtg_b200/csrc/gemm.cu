@@ -25,23 +25,32 @@ namespace uv {
 // The tile width BN is a RUN-TIME value (multiple of 16, 32..256; multiple of 64 when B is MN-major): the host picks it per
 // launch so that the tile count fills the 148 SMs with as little wave quantisation as possible.  Stage and TMEM strides are
 // sized for the maximum (256).
+// Operand ring: kRingBytes of shared memory cut into as many stages as the run-time tile width allows (a stage = the 16 KB A tile
+// + BN x 128 B of B, or half of that B in CTA-pair mode where each CTA stages only its half), at most kMaxStages.  The TMA round
+// trip under load is ~1.5 us, so the mainloop needs that many k-blocks in flight to keep the tensor pipe fed.
+template <int CL>
 struct GemmCfg {
-  static constexpr int kStages = 4;
+  static constexpr int kMaxStages = 8;
   static constexpr int kABytes = GEMM_BM * 128;          // 128 rows x 64 x 2 B
-  static constexpr int kBBytesMax = 256 * 128;
-  static constexpr int kStageBytes = kABytes + kBBytesMax;  // multiple of 1024
+  static constexpr int kRingBytes = 4 * (kABytes + 256 * 128);  // 192 KB
   static constexpr int kEpiFloats = 8 * 128;              // per-epilogue-warp bias slice (<= 128 columns per warp)
-  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kEpiFloats * 4 + 256;
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kRingBytes + kEpiFloats * 4 + 256;
   static constexpr uint32_t kTmemCols = 512;              // two accumulator stages of up to 256 fp32 columns
   static constexpr int kAccStride = 256;
+  __host__ __device__ static constexpr int stage_bytes(int bn) { return kABytes + (bn / CL) * 128; }  // multiple of 1024 (bn % 16 == 0, % 32 for pairs)
+  __host__ __device__ static constexpr int num_stages(int bn) {
+    return kRingBytes / stage_bytes(bn) < kMaxStages ? kRingBytes / stage_bytes(bn) : kMaxStages;
+  }
 };
 
 struct TileInfo {
   int p, m_blk, n_blk, kb0, kb1, split;
 };
 
-// CL = 1: `t` is this CTA's tile index.  CL = 2 (cluster pairs): `t` indexes a PAIR of vertically adjacent tiles
-// (m_blk = 2*pair + rank, same n_blk); the odd tail tile of a problem is a phantom whose rows are all out of range.
+// CL = 1: `t` is this CTA's tile index.  CL = 2 (CTA pairs, tcgen05 cta_group::2): `t` indexes a 256-row PAIR tile made of two
+// vertically adjacent 128-row tiles (m_blk = 2*pair + rank, same n_blk); the leader CTA (rank 0) issues one M=256 MMA for both,
+// each CTA stages its own A rows and HALF of the B rows (32 KB instead of 48 KB per k-block through the SM's 64 B/clk L2 port -
+// the limiter of the single-CTA mainloop).  The odd tail tile of a problem is a phantom whose rows are all out of range.
 template <int CL>
 __device__ __forceinline__ bool decode_tile(const GemmGroup& g, int bn, int t, int rank, TileInfo& ti) {
   for (int p = 0; p < g.num; ++p) {
@@ -77,8 +86,10 @@ __device__ __forceinline__ void stamp(unsigned long long* dbg, int slot) {
 
 template <int CL>
 __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmGroup g) {
-  using Cfg = GemmCfg;
+  using Cfg = GemmCfg<CL>;
   const int BN = g.bn;
+  const int kStageBytes = Cfg::stage_bytes(BN);
+  const int kStages = Cfg::num_stages(BN);
   const int crank = (CL > 1) ? (int)cluster_ctarank() : 0;          // rank inside the CTA pair
   const int tile0 = (CL > 1) ? (int)(blockIdx.x / CL) : (int)blockIdx.x;
   const int tstep = (int)(gridDim.x / CL);
@@ -88,11 +99,11 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
   uint8_t* smem = smem_raw + align_off;
 
   uint8_t* stage_base = smem;
-  float* epi_buf = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  float* epi_buf = reinterpret_cast<float*>(smem + Cfg::kRingBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + Cfg::kEpiFloats);
-  uint64_t* full_bar = bars;                        // [kStages]
-  uint64_t* empty_bar = bars + Cfg::kStages;        // [kStages]
-  uint64_t* tmem_full = bars + 2 * Cfg::kStages;    // [2]
+  uint64_t* full_bar = bars;                           // [kMaxStages]
+  uint64_t* empty_bar = bars + Cfg::kMaxStages;        // [kMaxStages]
+  uint64_t* tmem_full = bars + 2 * Cfg::kMaxStages;    // [2]
   uint64_t* tmem_empty = tmem_full + 2;             // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -107,17 +118,20 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CL);  // with cluster multicast a stage is free once BOTH CTAs' MMAs retired it
+      mbar_init(&empty_bar[s], 1);  // CL = 2: the leader's multicast commit arrives here in both CTAs
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 8);
+      mbar_init(&tmem_empty[s], 8 * CL);  // CL = 2: the leader's barrier collects the epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_holder);
+  if (warp == 2) {
+    if (CL == 1) tmem_alloc<Cfg::kTmemCols>(tmem_holder);
+    else tmem_alloc_2sm<Cfg::kTmemCols>(tmem_holder);
+  }
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before any multicast can reach them
@@ -139,39 +153,44 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           const int tap = kb / pr.kblk_per_tap;
           const int kk = (kb - tap * pr.kblk_per_tap) * GEMM_BK;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
+          uint8_t* sa = stage_base + stage * kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kABytes + BN * 128);
           const int a0 = pr.ca.base0 + m0 * pr.ca.mn0s + tap * pr.ca.tap0 + kk * pr.ca.k0s;
           const int a1 = pr.ca.base1 + m0 * pr.ca.mn1s + tap * pr.ca.tap1 + kk * pr.ca.k1s;
-          if (!pr.a_mn) {
-            tma_load_2d(sa, &pr.tm_a, &full_bar[stage], a0, a1);
-          } else {
-#pragma unroll
-            for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_2d(sa + j * 8192, &pr.tm_a, &full_bar[stage], a0 + 64 * j, a1);
-          }
           const int b0 = pr.cb.base0 + n0 * pr.cb.mn0s + tap * pr.cb.tap0 + kk * pr.cb.k0s;
           const int b1 = pr.cb.base1 + n0 * pr.cb.mn1s + tap * pr.cb.tap1 + kk * pr.cb.k1s;
           if (CL == 1) {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kABytes + BN * 128);
+            if (!pr.a_mn) {
+              tma_load_2d(sa, &pr.tm_a, &full_bar[stage], a0, a1);
+            } else {
+#pragma unroll
+              for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_2d(sa + j * 8192, &pr.tm_a, &full_bar[stage], a0 + 64 * j, a1);
+            }
             if (!pr.b_mn) {
               tma_load_2d(sb, &pr.tm_b, &full_bar[stage], b0, b1);
             } else {
               for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &pr.tm_b, &full_bar[stage], b0 + 64 * j, b1);
             }
           } else {
-            // each CTA of the pair fetches HALF of the shared B tile and multicasts it to both (halves the L2 -> SM traffic of B)
+            // both CTAs credit the LEADER's barrier: it expects the A tile + half B tile of each CTA
+            const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kABytes + BN * 128);
+            if (!pr.a_mn) {
+              tma_load_2d_2sm(sa, &pr.tm_a, lead_bar, a0, a1);
+            } else {
+#pragma unroll
+              for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_2d_2sm(sa + j * 8192, &pr.tm_a, lead_bar, a0 + 64 * j, a1);
+            }
             if (!pr.b_mn) {
-              const int hr = BN / 2;  // tensor-map box = BN/2 rows
-              tma_load_2d_mcast(sb + crank * hr * 128, &pr.tm_b, &full_bar[stage], b0, b1 + crank * hr, (uint16_t)0x3);
+              const int hr = BN / 2;  // tensor-map box = BN/2 rows: this CTA's half of the B tile, at the same smem offset in both CTAs
+              tma_load_2d_2sm(sb, &pr.tm_b, lead_bar, b0, b1 + crank * hr);
             } else {
               const int nb = BN / 128;  // 64-wide N blocks per CTA
-              for (int j = 0; j < nb; ++j) {
-                const int blk = crank * nb + j;
-                tma_load_2d_mcast(sb + blk * 8192, &pr.tm_b, &full_bar[stage], b0 + 64 * blk, b1, (uint16_t)0x3);
-              }
+              for (int j = 0; j < nb; ++j) tma_load_2d_2sm(sb + j * 8192, &pr.tm_b, lead_bar, b0 + 64 * (crank * nb + j), b1);
             }
           }
-          if (++stage == Cfg::kStages) {
+          if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
@@ -181,7 +200,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ======================================== MMA issuer ========================================
-    if (lane == 0) {
+    if (lane == 0 && (CL == 1 || crank == 0)) {  // CTA pair: the leader issues for both
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -189,7 +208,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       TileInfo ti;
       for (int t = tile0; decode_tile<CL>(g, BN, t, crank, ti); t += tstep) {
         const GemmProblem& pr = g.p[ti.p];
-        const uint32_t idesc = make_idesc_f16_ab(GEMM_BM, BN, pr.a_fmt < 0 ? g.fmt : pr.a_fmt, pr.b_fmt < 0 ? g.fmt : pr.b_fmt, pr.a_mn, pr.b_mn);
+        const uint32_t idesc = make_idesc_f16_ab(GEMM_BM * CL, BN, pr.a_fmt < 0 ? g.fmt : pr.a_fmt, pr.b_fmt < 0 ? g.fmt : pr.b_fmt, pr.a_mn, pr.b_mn);
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * Cfg::kAccStride;
@@ -197,7 +216,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           mbar_wait(&full_bar[stage], phase);
           if (kb == ti.kb0 && t == tile0) stamp(g.dbg, 3);  // first operand stage landed
           tc_fence_after();
-          const uint32_t sa = smem_u32(stage_base + stage * Cfg::kStageBytes);
+          const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
@@ -207,16 +226,18 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
                                         : make_smem_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t db = pr.b_mn ? make_smem_desc_sw128(sb + k * 2048, 8192, 1024)
                                         : make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            umma_f16_ss(d_tmem, da, db, idesc, (kb > ti.kb0 || k > 0) ? 1u : 0u);
+            if (CL == 1) umma_f16_ss(d_tmem, da, db, idesc, (kb > ti.kb0 || k > 0) ? 1u : 0u);
+            else umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb > ti.kb0 || k > 0) ? 1u : 0u);
           }
           if (CL == 1) umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          else umma_commit_mcast(&empty_bar[stage], (uint16_t)0x3);  // ... in both CTAs of the pair
-          if (++stage == Cfg::kStages) {
+          else umma_commit_2sm(&empty_bar[stage], (uint16_t)0x3);  // ... in both CTAs of the pair
+          if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+        if (CL == 1) umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+        else umma_commit_2sm(&tmem_full[as], (uint16_t)0x3);
         stamp(g.dbg, 4);              // last MMA of the tile issued
         if (++as == 2) {
           as = 0;
@@ -461,7 +482,10 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       // release the accumulator stage
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (lane == 0) {
+        if (CL == 1 || crank == 0) mbar_arrive(&tmem_empty[as]);
+        else mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+      }
       if (ew == 7 && lane == 0) stamp(g.dbg, 6);  // epilogue of the tile done (last warp)
       if (++as == 2) {
         as = 0;
@@ -475,9 +499,71 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
   if (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or signal its barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (CL == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
   }
   if (threadIdx.x == 0) stamp(g.dbg, 7);  // exit
+}
+
+// ------------------------------------------------------------------------------------------------
+// Microbenchmark: issue rate of tcgen05.mma (M=128, N=n, K=16, SW128 K-major operands resident in shared memory, no TMA in the
+// loop).  One CTA per SM; thread 0 issues `iters` groups of `per_commit` MMAs, each group followed by a commit, and waits for
+// the last commit.  out[blockIdx.x] = nanoseconds per MMA.  Used to separate the tensor-pipe rate from the operand feed.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, int per_commit, int kstep_bytes, float* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t holder;
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // fp16 1.0
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 8);
+    fence_barrier_init();
+  }
+  fence_proxy_async_smem();
+  if (threadIdx.x < 32) tmem_alloc<512>(&holder);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = holder;
+  if (threadIdx.x == 0) {
+    const uint32_t sa = smem_u32(smem), sb = sa + 16384;
+    const uint32_t idesc = make_idesc_f16_ab(128, n, 0, 0, 0, 0);
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    uint32_t phase = 0;
+    for (int it = 0; it < iters; ++it) {
+      for (int k = 0; k < per_commit; ++k) {
+        const uint32_t off = (uint32_t)((k & 3) * kstep_bytes);
+        umma_f16_ss(tmem, make_smem_desc_sw128(sa + off, 16, 1024), make_smem_desc_sw128(sb + off, 16, 1024), idesc, 1u);
+      }
+      umma_commit(&bar);
+      if ((it & 7) == 7) {  // eight commits complete one barrier phase (iters is a multiple of 8)
+        mbar_wait(&bar, phase);
+        phase ^= 1;
+      }
+    }
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    out[blockIdx.x] = (float)(t1 - t0) / (float)((long long)iters * per_commit);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+int debug_mma_rate(int n, int iters, int per_commit, int kstep_bytes, int blocks, float* out, cudaStream_t stream) {
+  iters = (iters + 7) / 8 * 8;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 50 * 1024);
+    attr = true;
+  }
+  mma_rate_kernel<<<blocks, 128, 50 * 1024, stream>>>(n, iters, per_commit, kstep_bytes, out);
+  return (int)cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -536,7 +622,8 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 }
 
 int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
-  using Cfg = GemmCfg;
+  using Cfg = GemmCfg<1>;
+  static_assert(GemmCfg<1>::kSmemBytes == GemmCfg<2>::kSmemBytes, "both variants use the same dynamic shared memory size");
   if (g.num < 1 || g.num > GEMM_MAX_GROUP) {
     set_error("gemm group size %d out of range", g.num);
     return (int)cudaErrorInvalidValue;

@@ -96,5 +96,6 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 void set_gemm_timeline_buffer(unsigned long long* buf);  // debugging: stamps for every following GEMM launch
 const char* last_error();
 void set_error(const char* fmt, ...);
+int debug_mma_rate(int n, int iters, int per_commit, int kstep_bytes, int blocks, float* out, cudaStream_t stream);
 
 }  // namespace uv
