@@ -216,6 +216,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--operand-format", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: one all-reduce after the backward instead of stage slices")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     wl = WORKLOADS[args.workload]
@@ -258,7 +259,8 @@ def main():
         opt = FlatAdamW(model, lr=1e-4, weight_decay=1e-4, max_grad_norm=0.1)
         if dist is not None:
             ddp.broadcast_parameters(model)
-            ddp.attach_flat_allreduce(model)  # ONE NCCL all-reduce of the flat gradient buffer per step
+            # NCCL all-reduce of the flat gradient buffer, issued in backward-stage slices on a side stream (overlaps backward)
+            ddp.attach_flat_allreduce(model, overlap=not args.no_overlap)
     else:
         model.eval()
 
@@ -322,10 +324,10 @@ def main():
     ready = [torch.cuda.Event() for _ in range(n_slot)]   # staging slot filled
     freed = [torch.cuda.Event() for _ in range(n_slot)]   # staging slot consumed by compute
     if train:
-        out_host = {"loss": torch.empty(()).pin_memory()}
+        out_host = [{"loss": torch.empty(()).pin_memory()} for _ in range(2)]
     else:
-        out_host = {"pred_logits": torch.empty(B, Lv, 1).pin_memory(), "pred_spans": torch.empty(B, Lv, 2).pin_memory(),
-                    "saliency_scores": torch.empty(B, Lv).pin_memory()}
+        out_host = [{"pred_logits": torch.empty(B, Lv, 1).pin_memory(), "pred_spans": torch.empty(B, Lv, 2).pin_memory(),
+                     "saliency_scores": torch.empty(B, Lv).pin_memory()} for _ in range(2)]
 
     def issue_copy(i):
         slot = i % n_slot
@@ -341,25 +343,40 @@ def main():
             ready[slot].record(copy_stream)
 
     def e2e_run(n):
+        """Host loop with one step of look-ahead: step i+1 is enqueued before the host blocks on step i's result, so the GPU
+        never waits for Python.  Every step still copies ITS inputs from pinned host memory and ITS result is read on the host
+        (result buffers are double-buffered; `seen` receives each step's value)."""
         main = torch.cuda.current_stream()
         for s_ in range(n_slot):
             freed[s_].record(main)
         issue_copy(0)
+        done = [torch.cuda.Event() for _ in range(2)]
+        seen = []
         for i in range(n):
             slot = i % n_slot
             if i + 1 < n:
                 issue_copy(i + 1)
             main.wait_event(ready[slot])
+            hb = out_host[i % 2]
             if train:
                 total = train_step(stage[slot], stage_t[slot])
-                out_host["loss"].copy_(total.detach(), non_blocking=True)  # the reference logs float(losses) every step
+                hb["loss"].copy_(total.detach(), non_blocking=True)  # the reference logs float(losses) every step
             else:
                 with torch.no_grad():
                     out = model(**stage[slot])
-                for k, hbuf in out_host.items():
+                for k, hbuf in hb.items():
                     hbuf.copy_(out[k], non_blocking=True)
             freed[slot].record(main)
-            main.synchronize()  # the caller consumes the step's result on the host
+            done[i % 2].record(main)
+            if i >= 1:  # consume step i-1's result on the host while step i runs
+                done[(i - 1) % 2].synchronize()
+                prev = out_host[(i - 1) % 2]
+                seen.append(float(prev["loss"]) if train else float(prev["saliency_scores"][0, 0]))
+        if n >= 1:
+            done[(n - 1) % 2].synchronize()
+            last = out_host[(n - 1) % 2]
+            seen.append(float(last["loss"]) if train else float(last["saliency_scores"][0, 0]))
+        return seen
 
     e2e_run(3)
     sync_all()
@@ -430,7 +447,7 @@ def main():
         h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
         if train:
             h2d += sum(v.numel() * v.element_size() for v in host_targets[0].values())
-        d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+        d2h = sum(v.numel() * v.element_size() for v in out_host[0].values())
         step_ms = ms_total / args.steps
         line = {
             "metric": "video-query pairs/sec" + (" (fwd+bwd)" if train else " (fwd)"), "value": value, "unit": "pairs/s",
@@ -440,9 +457,9 @@ def main():
             "config": {"workload": args.workload, "mode": wl["mode"], "batch_per_gpu": B, "global_batch": B * n_gpus, "l_vid": Lv,
                        "l_txt": Lt, "hidden_dim": d, "nheads": cfg["nheads"], "dim_feedforward": cfg["dim_feedforward"],
                        "enc_layers": cfg["enc_layers"], "v_feat_dim": cfg["v_feat_dim"], "t_feat_dim": cfg["t_feat_dim"],
-                       "operands": "fp16 activations/weights, bf16 gradients, f32 accumulate + statistics",
+                       "operands": "fp16 activations/weights/gradients (gradients under a 2^10 loss scale), f32 accumulate + statistics + master weights",
                        "step": ("forward + criterion + backward + clip_grad_norm(0.1) + AdamW" if train else "forward"),
-                       "parallelism": (f"dp{n_gpus}: shard by sample, one flat-gradient NCCL all-reduce per step" if train
+                       "parallelism": (f"dp{n_gpus}: shard by sample; flat fp32 gradient buffer NCCL all-reduced (AVG) in backward-stage slices on a side stream" if train
                                        else f"replicas x{n_gpus} (shard by sample, no collective)"),
                        "l2_policy": f"{n_rot} rotating input batches ({n_rot * per_batch / 1e6:.0f} MB > 126 MB L2)",
                        "clips_per_s": value * Lv},

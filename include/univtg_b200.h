@@ -107,6 +107,17 @@ int univtg_backward(univtg_plan* plan, void* train_ws, const float* src_txt, con
                     const float* const* drop_masks, const float* g_logits, const float* g_spans, const float* g_vid_mem_proj,
                     const float* g_txt_mem_proj, float grad_scale, float* const* grads, int32_t n_grads, void* stream);
 
+/* Gradient-exchange overlap (the reference relies on DistributedDataParallel's bucketed all-reduce overlapping backward,
+ * main/train_vlp_ddp.py:272-275).  univtg_backward finalises parameter gradients in n = enc_layers + 2 stages:
+ *   stage 0: conv heads; stage 1 + k: encoder layer enc_layers-1-k; stage n-1: projectors, token-type embedding, pooling weight.
+ * univtg_backward_stages writes, per stage, two half-open parameter-index ranges {first0, last0, first1, last1}
+ * (univtg_pack_weights order; an empty second range is 0,0) and returns n (ranges == NULL: just returns n).
+ * univtg_plan_set_grad_events installs n cudaEvent_t handles; univtg_backward records event k on its stream as soon as stage
+ * k's gradients are final, so a communication stream can wait on it and reduce that slice while the backward continues.
+ * n = 0 removes them.  (enc_layers <= 16, so n <= 18.) */
+int univtg_backward_stages(const univtg_config* cfg, int32_t* ranges, int32_t max_stages);
+int univtg_plan_set_grad_events(univtg_plan* plan, void* const* events, int32_t n);
+
 /* SetCriterion for model_id=univtg (reference model/univtg.py:195-282): losses5 = {loss_b, loss_g, loss_f, loss_s_inter,
  * loss_s_intra}.  targets as main/dataset.py:1078-1098 builds them (all f32 except saliency_pos_idx = saliency_pos_labels[:,0],
  * int64, NULL when absent).  `scratch` (univtg_loss_scratch_bytes) carries per-loss gradients to univtg_loss_backward. */

@@ -210,3 +210,41 @@ def test_training_loop_with_flat_adamw_decreases_loss_and_repacks():
     # the state_dict still exposes the (updated) parameters under the reference keys
     sd = model.state_dict()
     assert all(torch.isfinite(v).all() for v in sd.values())
+
+
+def test_stage_events_fire_only_after_their_gradients_are_final():
+    """Overlap path of univtg_b200.ddp: at stage event k the stage's slice of the flat gradient buffer is snapshotted on a
+    side stream while the rest of the backward is still running; every snapshot must equal the final buffer bit for bit."""
+    from univtg_b200 import ddp
+
+    cfg = synth.CONFIGS["cfg2"]
+    model, crit = _models(cfg, synth.make_state_dict(cfg, seed=3))
+    model.train()
+    raw = synth.make_inputs(cfg, seed=4, ragged=True, batch=16)
+    inp = {k: v.cuda() for k, v in raw.items()}
+    tgt = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in synth.make_targets(raw, seed=5).items()}
+
+    class Snapshot(ddp.OverlappedGradExchange):
+        def __init__(self, model):  # no process group: pretend world 2 and record instead of reducing
+            self.group, self.world, self.backend = None, 2, "snapshot"
+            self.stages = ddp.grad_stage_slices(model)
+            self.events, self.comm_stream, self._armed, self.snaps = None, None, set(), []
+
+        def _reduce(self, t):
+            self.snaps.append((t, t.clone()))
+
+    model.direct_grad = True
+    model._grad_sync = Snapshot(model)
+    for _ in range(2):
+        model._grad_sync.snaps = []
+        out = model(**inp)
+        ld = crit(out, tgt)
+        sum(ld[k] * crit.weight_dict[k] for k in ld).backward()
+    torch.cuda.synchronize()
+    snaps = model._grad_sync.snaps
+    assert len(snaps) == cfg["enc_layers"] + 3  # the last stage has two slices
+    flat, _ = model._grad_buffer()
+    assert sum(s.numel() for s, _ in snaps) == flat.numel()
+    for i, (live, snap) in enumerate(snaps):
+        assert torch.equal(live, snap), f"stage slice {i} changed after its event fired"
+        assert float(snap.abs().sum()) > 0.0

@@ -95,11 +95,16 @@ class _UniVTGFunction(torch.autograd.Function):
                 g_logits = g_logits if g_logits is not None else torch.zeros(B, Lv, 1, device=dev)
                 g_spans = g_spans if g_spans is not None else torch.zeros(B, Lv, 2, device=dev)
             arr = (ctypes.c_void_p * len(views))(*[v.data_ptr() for v in views])
+            sync = getattr(model, "_grad_sync", None)  # univtg_b200.ddp.OverlappedGradExchange
+            if sync is not None:
+                sync.before_backward(ctx.plan)
             _lib.check(lib.univtg_backward(ctx.plan.handle, _lib.ptr(ctx.ws), _lib.ptr(txt), _lib.ptr(vid), _lib.ptr(scales),
                                            mask_arr, _lib.ptr(g_logits), _lib.ptr(g_spans), _lib.ptr(g_vmp), _lib.ptr(g_tmp),
                                            float(model.grad_scale), arr, len(views), _lib.stream_ptr()), "univtg_backward")
             hook = getattr(model, "_flat_grad_hook", None)
-            if hook is not None:
+            if sync is not None:
+                sync.after_backward(flat)  # stage-wise all-reduce on a side stream, chained behind the stage events
+            elif hook is not None:
                 hook(flat)  # e.g. the single NCCL all-reduce of univtg_b200.ddp
         if getattr(model, "direct_grad", False):
             # Hand the flat buffer's views to param.grad directly: no per-parameter AccumulateGrad copies (77 memcpys / step).

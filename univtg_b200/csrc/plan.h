@@ -321,6 +321,9 @@ struct univtg_plan {
   int bn_proj[3], bn_main;  // tile widths chosen per launch (choose_bn)
   int bn_qkv, bn_out, bn_ffn1, bn_ffn2, bn_conv1, bn_conv2;
   int launches;
+  // optional "gradients of stage k are final" events recorded by univtg_backward (gradient-exchange overlap)
+  int n_grad_events;
+  cudaEvent_t grad_events[24];
   // optional per-launch CUDA-event timeline (bench / profiling only)
   int profiling;
   int n_marks;

@@ -645,6 +645,12 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     }
   }
 
+  // stage events: gradients of a parameter group are final once the stream reaches this point (univtg_backward_stages)
+  auto stage_done = [&](int k) {
+    if (P->n_grad_events > 0 && k < P->n_grad_events) cudaEventRecord(P->grad_events[k], st);
+  };
+  stage_done(0);  // conv heads
+
   // ================================================ encoder ================================================
   for (int l = c.enc_layers - 1; l >= 0; --l) {
     const LayerPacked& lp = Lw.layer[l];
@@ -846,6 +852,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.p[0].ksplit = g.p[1].ksplit = pick_ksplit(3 * d, d, bn_wq, (M + 63) / 64, sms);
     rc = launch_gemm_group(g, bn_wq, sms, st);
     if (rc) return rc;
+    stage_done(1 + (c.enc_layers - 1 - l));  // encoder layer l
   }
 
   // ================================================ projectors ================================================
@@ -938,11 +945,52 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       if (rc) return rc;
     }
   }
+  stage_done(c.enc_layers + 1);  // projectors, token-type embedding, pooling weight
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("univtg_backward: %s", cudaGetErrorString(e));
     return (int)e;
   }
+  return 0;
+}
+
+int univtg_backward_stages(const univtg_config* cfg, int32_t* ranges, int32_t max_stages) {
+  const int n_params = univtg_num_params(cfg);
+  if (n_params < 0) return -1;
+  const int np = cfg->n_input_proj, nl = cfg->enc_layers;
+  const int n = nl + 2;
+  if (ranges == nullptr) return n;
+  if (max_stages < n) {
+    set_error("univtg_backward_stages: need room for %d stages", n);
+    return -1;
+  }
+  const int hb = 8 * np + 1 + 12 * nl;
+  auto put = [&](int k, int a0, int a1, int b0, int b1) {
+    ranges[4 * k + 0] = a0;
+    ranges[4 * k + 1] = a1;
+    ranges[4 * k + 2] = b0;
+    ranges[4 * k + 3] = b1;
+  };
+  put(0, hb, hb + 12, 0, 0);  // span_embed + class_embed
+  for (int k = 0; k < nl; ++k) {
+    const int l = nl - 1 - k;
+    put(1 + k, 8 * np + 1 + 12 * l, 8 * np + 1 + 12 * (l + 1), 0, 0);
+  }
+  put(nl + 1, 0, 8 * np + 1, hb + 12, hb + 13);  // both projectors + token_type_embeddings, weightedpool.weight
+  return n;
+}
+
+int univtg_plan_set_grad_events(univtg_plan* plan, void* const* events, int32_t n) {
+  if (!plan || n < 0 || n > 24 || (n > 0 && !events)) {
+    set_error("univtg_plan_set_grad_events: bad argument");
+    return 1;
+  }
+  if (n > 0 && n != plan->cfg.enc_layers + 2) {
+    set_error("univtg_plan_set_grad_events: expected %d events (univtg_backward_stages), got %d", plan->cfg.enc_layers + 2, n);
+    return 1;
+  }
+  plan->n_grad_events = n;
+  for (int i = 0; i < n; ++i) plan->grad_events[i] = reinterpret_cast<cudaEvent_t>(events[i]);
   return 0;
 }
 

@@ -277,6 +277,15 @@ class Model(nn.Module):
             self.__dict__["_flat_grad"] = buf
         return buf
 
+    def _grad_offsets(self):
+        """Float offsets of the per-parameter views inside the flat gradient buffer, plus the total ([n_params + 1])."""
+        offs, off = [], 0
+        for p in self._abi_params():
+            offs.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        offs.append(off)
+        return offs
+
     def _get_dim_t(self, dev):
         if self._dim_t is None or self._dim_t.device != dev:
             # PositionEmbeddingSine (model/position_encoding.py:72-75), evaluated with the same fp32 torch expression
