@@ -216,6 +216,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--operand-format", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="inference workloads: launch the forward eagerly")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one all-reduce after the backward instead of stage slices")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -263,6 +264,7 @@ def main():
             ddp.attach_flat_allreduce(model, overlap=not args.no_overlap)
     else:
         model.eval()
+        model.use_cuda_graphs = not args.no_graphs  # the 41 launches of a forward replayed from one CUDA graph per shape
 
     # Rotating set of distinct input batches whose total size exceeds the 126 MB L2 (no L2-resident inputs between steps).
     per_batch = B * (Lv * cfg["v_feat_dim"] + Lt * cfg["t_feat_dim"] + Lv + Lt) * 4
@@ -392,6 +394,7 @@ def main():
     fwd_only = None
     if train:
         model.eval()
+        model.use_cuda_graphs = not args.no_graphs
         with torch.no_grad():
             for i in range(3):
                 model(**dev_batches[i % n_rot])
@@ -405,6 +408,7 @@ def main():
         ms_fwd = g0.elapsed_time(g1)
         fwd_only = {"value": B * args.steps * n_gpus / (ms_fwd * 1e-3), "unit": "pairs/s", "ms_per_step": ms_fwd / args.steps,
                     "note": "BASELINE configs[1]: inference forward on the same shapes (max over ranks not applied)"}
+        model.use_cuda_graphs = False
         model.train()
 
     # ------------------- per-kernel-class durations of the forward (CUDA events between launches) ---------------------
@@ -458,7 +462,8 @@ def main():
                        "l_txt": Lt, "hidden_dim": d, "nheads": cfg["nheads"], "dim_feedforward": cfg["dim_feedforward"],
                        "enc_layers": cfg["enc_layers"], "v_feat_dim": cfg["v_feat_dim"], "t_feat_dim": cfg["t_feat_dim"],
                        "operands": "fp16 activations/weights/gradients (gradients under a 2^10 loss scale), f32 accumulate + statistics + master weights",
-                       "step": ("forward + criterion + backward + clip_grad_norm(0.1) + AdamW" if train else "forward"),
+                       "step": ("forward + criterion + backward + clip_grad_norm(0.1) + AdamW" if train
+                                else ("forward (eager launches)" if args.no_graphs else "forward (CUDA-graph replay of the 41 launches)")),
                        "parallelism": (f"dp{n_gpus}: shard by sample; flat fp32 gradient buffer NCCL all-reduced (AVG) in backward-stage slices on a side stream" if train
                                        else f"replicas x{n_gpus} (shard by sample, no collective)"),
                        "l2_policy": f"{n_rot} rotating input batches ({n_rot * per_batch / 1e6:.0f} MB > 126 MB L2)",
