@@ -66,6 +66,10 @@ __global__ void __launch_bounds__(160, 2) attention_tcgen05_kernel(const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // Only now (this CTA owns its TMEM columns) may the next grid be scheduled: a dependent CTA that grabbed TMEM first and
+  // then blocked in griddepcontrol.wait could starve a CTA of this grid sharing its SM.
+  pdl_launch_dependents();
+  pdl_wait();  // barriers + TMEM are set up; from here on the kernel reads what the previous kernels wrote
   const uint32_t tmem_base = *tmem_holder;
   const uint32_t tmem_s = tmem_base;
   const uint32_t tmem_o = tmem_base + 128;
@@ -227,6 +231,7 @@ struct AttnSimtArgs {
 };
 
 __global__ void __launch_bounds__(128) attention_simt_kernel(const AttnSimtArgs a) {
+  pdl_prologue();
   extern __shared__ float s_sc[];  // [4 warps][L]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * 4 + warp;
@@ -282,7 +287,7 @@ static int launch_tc(const AttnArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((a.L + 127) / 128, a.H, a.B);
-  attention_tcgen05_kernel<DH><<<grid, 160, Cfg::kSmemBytes, stream>>>(a);
+  launch_k(attention_tcgen05_kernel<DH>, dim3(grid), dim3(160), Cfg::kSmemBytes, stream, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("attention launch failed: %s", cudaGetErrorString(e));
   return (int)e;
@@ -299,7 +304,7 @@ int launch_attention_simt(const AttnArgs& a, const uint16_t* qkv, cudaStream_t s
       return (int)e;
     }
   }
-  attention_simt_kernel<<<(warps + 3) / 4, 128, smem, stream>>>(s);
+  launch_k(attention_simt_kernel, dim3((warps + 3) / 4), dim3(128), smem, stream, s);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("attention_simt launch failed: %s", cudaGetErrorString(e));
   return (int)e;

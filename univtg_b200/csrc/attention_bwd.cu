@@ -72,6 +72,10 @@ __global__ void __launch_bounds__(160, 1) attention_bwd_tcgen05_kernel(const __g
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // Only now (this CTA owns its TMEM columns) may the next grid be scheduled: a dependent CTA that grabbed TMEM first and
+  // then blocked in griddepcontrol.wait could starve a CTA of this grid sharing its SM.
+  pdl_launch_dependents();
+  pdl_wait();  // setup done; everything below reads the previous kernels' outputs
   const uint32_t tmem_base = *tmem_holder;
   const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dv = tmem_base + 256, tm_dk = tmem_base + 384;
 
@@ -267,7 +271,7 @@ static int launch_bwd_tc(const AttnBwdArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((a.L + 127) / 128, a.H, a.B);
-  attention_bwd_tcgen05_kernel<DH><<<grid, 160, Cfg::kSmemBytes, stream>>>(a);
+  launch_k(attention_bwd_tcgen05_kernel<DH>, dim3(grid), dim3(160), Cfg::kSmemBytes, stream, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("attention_bwd launch failed: %s", cudaGetErrorString(e));
   return (int)e;

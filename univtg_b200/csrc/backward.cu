@@ -15,6 +15,7 @@ namespace uv {
 // ------------------------------------------------------------------------------------------------
 template <int EPT>
 __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const LnBwdArgs a) {
+  pdl_prologue();
   __shared__ float s_red[2][4];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float acc_g[EPT], acc_b[EPT], acc_c[EPT];
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const LnBwdArgs a) {
 // current row's block reduction so the DRAM latency of consecutive rows overlaps.
 template <int NV>
 __global__ void __launch_bounds__(128) layernorm_bwd_vec_kernel(const LnBwdArgs a) {
+  pdl_prologue();
   __shared__ float s_red[2][4];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float4 acc_g[NV], acc_b[NV], acc_c[NV], gam[NV];
@@ -191,6 +193,7 @@ __global__ void __launch_bounds__(128) layernorm_bwd_vec_kernel(const LnBwdArgs 
 // Thread = one column, block = 256 columns x kRowsPerBlock rows.
 constexpr int kLnParamRows = 32;
 __global__ void __launch_bounds__(256) layernorm_bwd_params_kernel(const LnBwdArgs a) {
+  pdl_prologue();
   const int j = blockIdx.x * 256 + threadIdx.x;
   if (j >= a.d) return;
   const int r0 = blockIdx.y * kLnParamRows;
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_params_kernel(const LnBwdAr
 int launch_layernorm_bwd(const LnBwdArgs& a, cudaStream_t stream) {
   if (a.rows <= 0) return 0;
   if (a.dy32 == nullptr && a.dbr16 == nullptr) {
-    layernorm_bwd_params_kernel<<<dim3((a.d + 255) / 256, (a.rows + kLnParamRows - 1) / kLnParamRows), 256, 0, stream>>>(a);
+    launch_k(layernorm_bwd_params_kernel, dim3(dim3((a.d + 255) / 256, (a.rows + kLnParamRows - 1) / kLnParamRows)), dim3(256), 0, stream, a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) set_error("layernorm_bwd launch failed: %s", cudaGetErrorString(e));
     return (int)e;
@@ -220,10 +223,10 @@ int launch_layernorm_bwd(const LnBwdArgs& a, cudaStream_t stream) {
   const bool vec = a.d % 4 == 0 && a.ld_dout % 4 == 0 && a.ld_y % 4 == 0 && (!a.dbr16 || a.ld16 % 4 == 0) &&
                    (((uintptr_t)a.dout | (uintptr_t)a.y | (uintptr_t)a.gamma | (uintptr_t)a.dy32 | (uintptr_t)a.dout_mul) & 15) == 0 &&
                    (((uintptr_t)a.dgamma | (uintptr_t)a.dbeta | (uintptr_t)a.colsum) & 15) == 0 && ((uintptr_t)a.dbr16 & 7) == 0;
-  if (vec && a.d <= 512) layernorm_bwd_vec_kernel<1><<<grid, 128, 0, stream>>>(a);
-  else if (vec && a.d <= 1024) layernorm_bwd_vec_kernel<2><<<grid, 128, 0, stream>>>(a);
-  else if (a.d <= 128 * 8) layernorm_bwd_kernel<8><<<grid, 128, 0, stream>>>(a);
-  else if (a.d <= 128 * 24) layernorm_bwd_kernel<24><<<grid, 128, 0, stream>>>(a);
+  if (vec && a.d <= 512) launch_k(layernorm_bwd_vec_kernel<1>, dim3(grid), dim3(128), 0, stream, a);
+  else if (vec && a.d <= 1024) launch_k(layernorm_bwd_vec_kernel<2>, dim3(grid), dim3(128), 0, stream, a);
+  else if (a.d <= 128 * 8) launch_k(layernorm_bwd_kernel<8>, dim3(grid), dim3(128), 0, stream, a);
+  else if (a.d <= 128 * 24) launch_k(layernorm_bwd_kernel<24>, dim3(grid), dim3(128), 0, stream, a);
   else {
     set_error("layernorm_bwd: d %d > 3072 not supported", a.d);
     return (int)cudaErrorInvalidValue;
@@ -238,6 +241,7 @@ int launch_layernorm_bwd(const LnBwdArgs& a, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) cvt16_colsum_kernel(const float* __restrict__ in32, int ld_in, uint16_t* __restrict__ out16,
                                                           int ld_out, int rows, int cols, int fmt, float* __restrict__ colsum, float cscale) {
+  pdl_prologue();
   const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
   if (c >= cols) return;
   const int r0 = blockIdx.y * 32;
@@ -265,7 +269,7 @@ int launch_cvt16_colsum(const float* in32, int ld_in, uint16_t* out16, int ld_ou
     return (int)cudaErrorInvalidValue;
   }
   dim3 grid((cols / 4 + 255) / 256, (rows + 31) / 32);
-  cvt16_colsum_kernel<<<grid, 256, 0, stream>>>(in32, ld_in, out16, ld_out, rows, cols, fmt, colsum, colsum_scale);
+  launch_k(cvt16_colsum_kernel, dim3(grid), dim3(256), 0, stream, in32, ld_in, out16, ld_out, rows, cols, fmt, colsum, colsum_scale);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("cvt16_colsum launch failed: %s", cudaGetErrorString(e));
   return (int)e;
@@ -276,6 +280,7 @@ int launch_cvt16_colsum(const float* in32, int ld_in, uint16_t* out16, int ld_ou
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) attn_delta_kernel(const uint16_t* __restrict__ dO, int fmt_do, const uint16_t* __restrict__ O,
                                                         int fmt_o, float* __restrict__ delta, int B, int L, int H, int dh) {
+  pdl_prologue();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= B * L) return;
@@ -295,7 +300,7 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const uint16_t* __restr
 int launch_attn_delta(const uint16_t* dO, int fmt_do, const uint16_t* O, int fmt_o, float* delta, int B, int L, int H, int dh,
                       cudaStream_t stream) {
   const int rows = B * L;
-  attn_delta_kernel<<<(rows * 32 + 255) / 256, 256, 0, stream>>>(dO, fmt_do, O, fmt_o, delta, B, L, H, dh);
+  launch_k(attn_delta_kernel, dim3((rows * 32 + 255) / 256), dim3(256), 0, stream, dO, fmt_do, O, fmt_o, delta, B, L, H, dh);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("attn_delta launch failed: %s", cudaGetErrorString(e));
   return (int)e;
@@ -305,6 +310,7 @@ int launch_attn_delta(const uint16_t* dO, int fmt_do, const uint16_t* O, int fmt
 // SIMT attention backward (any head size).  One warp per (b, h, query i); dK / dV / dQ accumulate atomically in fp32.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) attention_bwd_simt_kernel(const AttnBwdArgs a) {
+  pdl_prologue();
   extern __shared__ float s_buf[];  // [4 warps][2][L]: p and ds
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * 4 + warp;
@@ -362,7 +368,7 @@ int launch_attention_bwd_simt(const AttnBwdArgs& a, cudaStream_t stream) {
       return (int)e;
     }
   }
-  attention_bwd_simt_kernel<<<(warps + 3) / 4, 128, smem, stream>>>(a);
+  launch_k(attention_bwd_simt_kernel, dim3((warps + 3) / 4), dim3(128), smem, stream, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("attention_bwd_simt launch failed: %s", cudaGetErrorString(e));
   return (int)e;
@@ -376,6 +382,7 @@ int launch_attention_bwd_simt(const AttnBwdArgs& a, cudaStream_t stream) {
 // kernel 3: dW[o, c, t] = sum_m dz_o[m] h[m + t - 1, c],  db[o] = sum_m dz_o[m]
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) head_dz_kernel(const HeadFinalBwdArgs a) {
+  pdl_prologue();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int rows = a.B * (a.Lv + 1) + 2;
   if (idx >= rows) return;
@@ -397,6 +404,7 @@ __global__ void __launch_bounds__(256) head_dz_kernel(const HeadFinalBwdArgs a) 
 }
 
 __global__ void __launch_bounds__(256) head_dh_kernel(const HeadFinalBwdArgs a) {
+  pdl_prologue();
   // one warp per buffer row (1 .. B*(Lv+1)); lanes over channels
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -438,6 +446,7 @@ __global__ void __launch_bounds__(256) head_dh_kernel(const HeadFinalBwdArgs a) 
 }
 
 __global__ void __launch_bounds__(256) head_dw_kernel(const HeadFinalBwdArgs a) {
+  pdl_prologue();
   // thread = channel c (blockIdx.x * 256 + tid); blockIdx.y = slab of 64 logical rows
   const int c = blockIdx.x * 256 + threadIdx.x;
   const int Mh = a.B * (a.Lv + 1);
@@ -488,9 +497,9 @@ __global__ void __launch_bounds__(256) head_dw_kernel(const HeadFinalBwdArgs a) 
 
 int launch_head_final_bwd(const HeadFinalBwdArgs& a, cudaStream_t stream) {
   const int Mh = a.B * (a.Lv + 1);
-  head_dz_kernel<<<(Mh + 2 + 255) / 256, 256, 0, stream>>>(a);
-  head_dh_kernel<<<(Mh * 32 + 255) / 256, 256, 0, stream>>>(a);
-  head_dw_kernel<<<dim3((a.d + 255) / 256, (Mh + 63) / 64), 256, 0, stream>>>(a);
+  launch_k(head_dz_kernel, dim3((Mh + 2 + 255) / 256), dim3(256), 0, stream, a);
+  launch_k(head_dh_kernel, dim3((Mh * 32 + 255) / 256), dim3(256), 0, stream, a);
+  launch_k(head_dw_kernel, dim3(dim3((a.d + 255) / 256, (Mh + 63) / 64)), dim3(256), 0, stream, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("head_final_bwd launch failed: %s", cudaGetErrorString(e));
   return (int)e;
@@ -502,6 +511,7 @@ int launch_head_final_bwd(const HeadFinalBwdArgs& a, cudaStream_t stream) {
 //   dx_l = alpha_l g + dlogit_l w;  dw += sum_l dlogit_l x_l
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pool_bwd_kernel(const PoolBwdArgs a) {
+  pdl_prologue();
   extern __shared__ float sm[];
   float* s_da = sm;              // [Lt] dalpha, then dlogit
   __shared__ float s_dot;
@@ -540,7 +550,7 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const PoolBwdArgs a) {
 }
 
 int launch_pool_bwd(const PoolBwdArgs& a, cudaStream_t stream) {
-  pool_bwd_kernel<<<a.B, 256, (size_t)a.Lt * sizeof(float), stream>>>(a);
+  launch_k(pool_bwd_kernel, dim3(a.B), dim3(256), (size_t)a.Lt * sizeof(float), stream, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("pool_bwd launch failed: %s", cudaGetErrorString(e));
   return (int)e;
@@ -553,6 +563,7 @@ int launch_pool_bwd(const PoolBwdArgs& a, cudaStream_t stream) {
 __global__ void __launch_bounds__(256) stream_gather_kernel(const float* __restrict__ dx, int L, int off, const float* __restrict__ extra,
                                                            float extra_scale, uint16_t* __restrict__ out16,
                                                            float* __restrict__ colsum, float cscale, int B, int Ls, int d, int fmt) {
+  pdl_prologue();
   const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
   if (c >= d) return;
   const int r0 = blockIdx.y * 32;
@@ -585,18 +596,19 @@ __global__ void __launch_bounds__(256) stream_gather_kernel(const float* __restr
 int launch_stream_gather(const float* dx_stream, int L, int off, const float* extra, float extra_scale, uint16_t* out16,
                          float* colsum, float colsum_scale, int B, int Ls, int d, int fmt, cudaStream_t stream) {
   dim3 grid((d / 4 + 255) / 256, (B * Ls + 31) / 32);
-  stream_gather_kernel<<<grid, 256, 0, stream>>>(dx_stream, L, off, extra, extra_scale, out16, colsum, colsum_scale, B, Ls, d, fmt);
+  launch_k(stream_gather_kernel, dim3(grid), dim3(256), 0, stream, dx_stream, L, off, extra, extra_scale, out16, colsum, colsum_scale, B, Ls, d, fmt);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("stream_gather launch failed: %s", cudaGetErrorString(e));
   return (int)e;
 }
 
 __global__ void __launch_bounds__(256) axpy_kernel(float* __restrict__ y, const float* __restrict__ x, size_t n) {
+  pdl_prologue();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] += x[i];
 }
 int launch_axpy(float* y, const float* x, size_t n, cudaStream_t stream) {
   size_t g = (n + 255) / 256;
-  axpy_kernel<<<(int)(g > 1184 ? 1184 : g), 256, 0, stream>>>(y, x, n);
+  launch_k(axpy_kernel, dim3((int)(g > 1184 ? 1184 : g)), dim3(256), 0, stream, y, x, n);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("axpy launch failed: %s", cudaGetErrorString(e));
   return (int)e;

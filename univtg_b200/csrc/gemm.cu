@@ -15,6 +15,7 @@
 //                                   the TMEM load + residual loads of step c+1 are in flight while step c is processed)
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "kernels.h"
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) stamp(g.dbg, 0);  // kernel entry
+  if (threadIdx.x == 0) stamp(g.dbg, 0);  // kernel entry (profiling buffer only; never an output of a preceding kernel)
 
   if (warp == 0 && lane == 0) {
     for (int p = 0; p < g.num; ++p) {
@@ -137,6 +138,10 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
   if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before any multicast can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  // Only now (this CTA owns its TMEM columns) may the next grid be scheduled: a dependent CTA that grabbed TMEM first and
+  // then blocked in griddepcontrol.wait could starve a CTA of this grid sharing its SM.
+  pdl_launch_dependents();
+  pdl_wait();  // barriers, TMEM and tensor-map prefetch happened under the previous kernel's tail; its results are visible from here
   if (threadIdx.x == 0) stamp(g.dbg, 1);  // setup done (barriers, TMEM)
 
   if (warp == 0) {
@@ -571,6 +576,14 @@ int debug_mma_rate(int n, int iters, int per_commit, int kstep_bytes, int blocks
 // ------------------------------------------------------------------------------------------------
 static unsigned long long* g_timeline = nullptr;
 void set_gemm_timeline_buffer(unsigned long long* buf) { g_timeline = buf; }
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("UNIVTG_PDL");
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
 static thread_local char g_err[512] = "";
 const char* last_error() { return g_err; }
 void set_error(const char* fmt, ...) {
@@ -685,7 +698,7 @@ int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
   cudaError_t e;
   if (cl == 1) {
     const int grid = total < num_sms ? total : num_sms;
-    gemm_tcgen05_kernel<1><<<grid, 384, Cfg::kSmemBytes, stream>>>(g);
+    launch_k(gemm_tcgen05_kernel<1>, dim3(grid), dim3(384), Cfg::kSmemBytes, stream, g);
     e = cudaGetLastError();
   } else {
     const int max_clusters = num_sms / 2;
@@ -696,13 +709,15 @@ int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
     cfg.blockDim = dim3(384);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2>, g);
   }
   if (e != cudaSuccess) {

@@ -1,5 +1,6 @@
 // Internal (C++) interface between the C-ABI layer (api.cu) and the kernel translation units.
 #pragma once
+#include <string.h>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -96,6 +97,28 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 void set_gemm_timeline_buffer(unsigned long long* buf);  // debugging: stamps for every following GEMM launch
 const char* last_error();
 void set_error(const char* fmt, ...);
+// ---- kernel launches with programmatic dependent launch (PDL) ----
+// Every kernel of this library starts with pdl_prologue() (griddepcontrol.launch_dependents + griddepcontrol.wait, ptx.cuh):
+// the next kernel in the stream may be scheduled while this one is still running and blocks at its own
+// griddepcontrol.wait until this grid has completed and flushed - the launch latency and the next kernel's prologue
+// (barrier init, TMEM allocation, tensor-map prefetch) disappear under the current kernel's tail.  UNIVTG_PDL=0 disables it.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 int debug_mma_rate(int n, int iters, int per_commit, int kstep_bytes, int blocks, float* out, cudaStream_t stream);
 
 }  // namespace uv

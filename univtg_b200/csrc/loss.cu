@@ -18,6 +18,7 @@ namespace uv {
 //           warps [B*Lv, B*Lv + B*B): sim[b,b'] = cos(xv[b,pos_b], xt[b'])
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) loss_cos_kernel(const LossArgs a) {
+  pdl_prologue();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int n_in = a.B * a.Lv;
@@ -75,6 +76,7 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {
 // kernel 2 (single block): all five losses + gradients w.r.t. pred_spans / pred_logits / cos_in / sim.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) loss_finish_kernel(const LossArgs a) {
+  pdl_prologue();
   extern __shared__ float sm[];
   float* s_rowlse = sm;                // [B]   logsumexp over l of z[b, :]
   float* s_collse = s_rowlse + a.B;    // [B]   logsumexp over b' of z[b', pos_b]  (column pos_b)
@@ -246,9 +248,9 @@ __global__ void __launch_bounds__(1024) loss_finish_kernel(const LossArgs a) {
 int launch_loss_forward(const LossArgs& a, cudaStream_t stream) {
   if (a.pos_idx != nullptr) {
     const int warps = a.B * a.Lv + a.B * a.B;
-    loss_cos_kernel<<<(warps * 32 + 255) / 256, 256, 0, stream>>>(a);
+    launch_k(loss_cos_kernel, dim3((warps * 32 + 255) / 256), dim3(256), 0, stream, a);
   }
-  loss_finish_kernel<<<1, 1024, (size_t)5 * a.B * sizeof(float), stream>>>(a);
+  launch_k(loss_finish_kernel, dim3(1), dim3(1024), (size_t)5 * a.B * sizeof(float), stream, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("loss forward launch failed: %s", cudaGetErrorString(e));
   return (int)e;
@@ -259,6 +261,7 @@ int launch_loss_forward(const LossArgs& a, cudaStream_t stream) {
 //   d cos(u, v)/du = v / (|u||v|) - cos * u / |u|^2
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) loss_bwd_small_kernel(const LossBwdArgs a) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = a.B * a.Lv;
   if (i >= n) return;
@@ -270,6 +273,7 @@ __global__ void __launch_bounds__(256) loss_bwd_small_kernel(const LossBwdArgs a
 
 // one warp per (b, l): d xv[b, l, :]
 __global__ void __launch_bounds__(256) loss_bwd_vid_kernel(const LossBwdArgs a) {
+  pdl_prologue();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (gw >= a.B * a.Lv) return;
@@ -320,6 +324,7 @@ __global__ void __launch_bounds__(256) loss_bwd_vid_kernel(const LossBwdArgs a) 
 
 // one block per sample b: d xt[b, :]
 __global__ void __launch_bounds__(128) loss_bwd_txt_kernel(const LossBwdArgs a) {
+  pdl_prologue();
   const int b = blockIdx.x;
   const float w_inter = a.w[3], w_intra = a.w[4];
   const float tn = a.tnorm[b];
@@ -346,9 +351,9 @@ __global__ void __launch_bounds__(128) loss_bwd_txt_kernel(const LossBwdArgs a) 
 
 int launch_loss_backward(const LossBwdArgs& a, cudaStream_t stream) {
   const int n = a.B * a.Lv;
-  loss_bwd_small_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a);
-  loss_bwd_vid_kernel<<<(n * 32 + 255) / 256, 256, (size_t)8 * a.B * sizeof(float), stream>>>(a);
-  loss_bwd_txt_kernel<<<dim3(a.B, (a.d + 127) / 128), 128, 0, stream>>>(a);
+  launch_k(loss_bwd_small_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, a);
+  launch_k(loss_bwd_vid_kernel, dim3((n * 32 + 255) / 256), dim3(256), (size_t)8 * a.B * sizeof(float), stream, a);
+  launch_k(loss_bwd_txt_kernel, dim3(dim3(a.B, (a.d + 127) / 128)), dim3(128), 0, stream, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("loss backward launch failed: %s", cudaGetErrorString(e));
   return (int)e;

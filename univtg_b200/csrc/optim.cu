@@ -13,6 +13,7 @@ namespace uv {
 namespace {
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n4, float* __restrict__ out) {
+  pdl_prologue();
   __shared__ float s_red[8];
   const float4* g4 = reinterpret_cast<const float4*>(g);
   float s = 0.f;
@@ -42,6 +43,7 @@ struct AdamArgs {
 };
 
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamArgs a) {
+  pdl_prologue();
   const float norm = sqrtf(a.scratch[0]);
   float clip = 1.f;
   if (a.max_norm > 0.f) clip = fminf(a.max_norm / (norm + 1e-6f), 1.f);
@@ -89,7 +91,7 @@ extern "C" int univtg_adamw_step(float* params, float* grads, float* exp_avg, fl
   size_t blocks = (n4 + 255) / 256;
   if (blocks > (size_t)sms * 8) blocks = (size_t)sms * 8;
   cudaMemsetAsync(scratch2, 0, 2 * sizeof(float), st);
-  sumsq_kernel<<<(unsigned)blocks, 256, 0, st>>>(grads, n4, scratch2);
+  launch_k(sumsq_kernel, dim3((unsigned)blocks), dim3(256), 0, st, grads, n4, scratch2);
   AdamArgs a;
   a.p = params;
   a.g = grads;
@@ -106,7 +108,7 @@ extern "C" int univtg_adamw_step(float* params, float* grads, float* exp_avg, fl
   a.max_norm = max_grad_norm;
   a.scratch = scratch2;
   a.g_out = write_clipped_grads ? grads : nullptr;
-  adamw_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  launch_k(adamw_kernel, dim3((unsigned)blocks), dim3(256), 0, st, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("univtg_adamw_step launch failed: %s", cudaGetErrorString(e));
   return (int)e;

@@ -144,6 +144,7 @@ PackedLayout make_layout(const univtg_config& c) {
 // pack kernels
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_rows_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int rows, int cols, int ld, int fmt) {
+  pdl_prologue();
   const size_t total = (size_t)rows * ld;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / ld), c = (int)(i % ld);
@@ -152,6 +153,7 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, uint16_t* __rest
 }
 // Conv1d weight [N, C, 3] -> 16-bit [N, 3*C] with dst[n, t*C + c] = src[n, c, t]
 __global__ void pack_conv_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int N, int C, int fmt) {
+  pdl_prologue();
   const size_t total = (size_t)N * 3 * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int n = (int)(i / (3 * C));
@@ -162,6 +164,7 @@ __global__ void pack_conv_kernel(const float* __restrict__ src, uint16_t* __rest
 }
 // Conv1d weight [N, C, 3] -> fp32 [N, 3, C]
 __global__ void pack_conv_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int C) {
+  pdl_prologue();
   const size_t total = (size_t)N * 3 * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int n = (int)(i / (3 * C));
@@ -171,6 +174,7 @@ __global__ void pack_conv_f32_kernel(const float* __restrict__ src, float* __res
   }
 }
 __global__ void copy_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ dst, int n) {
+  pdl_prologue();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = a[i] + (b ? b[i] : 0.f);
 }
 
@@ -203,6 +207,7 @@ inline size_t pack_task_items(const PackTask& k) {
 }
 
 __global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__ PackTable tab) {
+  pdl_prologue();
   int ti = 0;
   while (ti + 1 < tab.n && (int)blockIdx.x >= tab.t[ti + 1].blk0) ++ti;
   const PackTask& k = tab.t[ti];
@@ -280,7 +285,7 @@ struct Packer {
       tab.t[i].blk0 = blocks;
       blocks += (int)((pack_task_items(tab.t[i]) + kPackItemsPerBlock - 1) / kPackItemsPerBlock);
     }
-    if (blocks > 0) pack_multi_kernel<<<blocks, 256, 0, st>>>(tab);
+    if (blocks > 0) launch_k(pack_multi_kernel, dim3(blocks), dim3(256), 0, st, tab);
     tab.n = 0;
   }
   void rows(const float* src, size_t off, int rows_, int cols, int ld) { push(PackTask{src, nullptr, base + off, 0, rows_, cols, ld, 0}); }

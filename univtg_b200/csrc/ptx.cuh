@@ -29,6 +29,17 @@ UV_DEVINL bool elect_one() {
 }
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch (see launch_k, kernels.h).  No-ops when the kernel was launched without the attribute.
+// ----------------------------------------------------------------------------------------------
+UV_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+UV_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// first statement of every kernel: let the next grid get scheduled, then wait until everything before this grid is visible
+UV_DEVINL void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 UV_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {

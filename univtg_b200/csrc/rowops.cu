@@ -66,6 +66,7 @@ struct LnStore {
 // d == NV * 128: the row lives in registers (NV float4 per lane), one global read.
 template <int NV>
 __global__ void __launch_bounds__(256) layernorm_rows_vec_kernel(const LnArgs a) {
+  pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= a.rows) return;
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(256) layernorm_rows_vec_kernel(const LnArgs a)
 
 // arbitrary d (e.g. 2818 = SlowFast+CLIP+TEF): three passes over the row, later passes hit L1/L2.
 __global__ void __launch_bounds__(256) layernorm_rows_generic_kernel(const LnArgs a) {
+  pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= a.rows) return;
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(256) layernorm_rows_generic_kernel(const LnArg
 // arbitrary d <= 128*EPT: one 128-thread block per row, the row lives in registers (single HBM read).
 template <int EPT>
 __global__ void __launch_bounds__(128) layernorm_rows_block_kernel(const LnArgs a) {
+  pdl_prologue();
   __shared__ float s_red[4];
   __shared__ float s_stat[2];
   const int row = blockIdx.x;
@@ -200,6 +203,7 @@ __global__ void __launch_bounds__(128) layernorm_rows_block_kernel(const LnArgs 
 // (the 2818-wide video features: 27 MB read once, 14 MB written).
 template <int EPT2>
 __global__ void __launch_bounds__(128) layernorm_rows_block2_kernel(const LnArgs a) {
+  pdl_prologue();
   __shared__ float s_red[4];
   __shared__ float s_stat[2];
   const int row = blockIdx.x;
@@ -264,22 +268,22 @@ int launch_layernorm(const LnArgs& a, cudaStream_t stream) {
   const int threads = 256;
   const int blocks = (a.rows * 32 + threads - 1) / threads;
   const bool vec_ok = (a.ld_in % 4 == 0) && (a.ld16 == a.d) && ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0);
-  if (vec_ok && a.d == 1024) layernorm_rows_vec_kernel<8><<<blocks, threads, 0, stream>>>(a);
-  else if (vec_ok && a.d == 512) layernorm_rows_vec_kernel<4><<<blocks, threads, 0, stream>>>(a);
-  else if (vec_ok && a.d == 256) layernorm_rows_vec_kernel<2><<<blocks, threads, 0, stream>>>(a);
+  if (vec_ok && a.d == 1024) launch_k(layernorm_rows_vec_kernel<8>, dim3(blocks), dim3(threads), 0, stream, a);
+  else if (vec_ok && a.d == 512) launch_k(layernorm_rows_vec_kernel<4>, dim3(blocks), dim3(threads), 0, stream, a);
+  else if (vec_ok && a.d == 256) launch_k(layernorm_rows_vec_kernel<2>, dim3(blocks), dim3(threads), 0, stream, a);
   else if (a.d > 1024 && a.d <= 256 * 12 && a.d % 2 == 0 && a.ld_in % 2 == 0 && a.ld16 % 2 == 0 && a.out16 && !a.out32 &&
            !a.out16p && !a.outc && !a.add16 && (reinterpret_cast<uintptr_t>(a.in) & 7) == 0 &&
            (reinterpret_cast<uintptr_t>(a.gamma) & 7) == 0 && (reinterpret_cast<uintptr_t>(a.beta) & 7) == 0 &&
            (!a.mul32 || (reinterpret_cast<uintptr_t>(a.mul32) & 7) == 0))
-    layernorm_rows_block2_kernel<12><<<a.rows, 128, 0, stream>>>(a);
-  else if (a.d <= 128 * 8) layernorm_rows_block_kernel<8><<<a.rows, 128, 0, stream>>>(a);
-  else if (a.d <= 128 * 24) layernorm_rows_block_kernel<24><<<a.rows, 128, 0, stream>>>(a);
+    launch_k(layernorm_rows_block2_kernel<12>, dim3(a.rows), dim3(128), 0, stream, a);
+  else if (a.d <= 128 * 8) launch_k(layernorm_rows_block_kernel<8>, dim3(a.rows), dim3(128), 0, stream, a);
+  else if (a.d <= 128 * 24) launch_k(layernorm_rows_block_kernel<24>, dim3(a.rows), dim3(128), 0, stream, a);
   else {
     if (a.add16) {
       set_error("layernorm: fused branch add needs d <= 3072");
       return (int)cudaErrorInvalidValue;
     }
-    layernorm_rows_generic_kernel<<<blocks, threads, 0, stream>>>(a);
+    launch_k(layernorm_rows_generic_kernel, dim3(blocks), dim3(threads), 0, stream, a);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("layernorm launch failed: %s", cudaGetErrorString(e));
@@ -294,6 +298,7 @@ int launch_layernorm(const LnArgs& a, cudaStream_t stream) {
 __global__ void __launch_bounds__(256) sine_pos_table_kernel(const float* __restrict__ mask, const float* __restrict__ txt_mask,
                                                             const float* __restrict__ dim_t, float* __restrict__ pos,
                                                             float* __restrict__ key_mask, int Lv, int Lt, int d) {
+  pdl_prologue();
   extern __shared__ float s_e[];  // [Lv] cumulative position, then the normalised angle
   __shared__ float s_part[256];
   const int b = blockIdx.x;
@@ -349,7 +354,7 @@ int launch_sine_pos(const float* mask, const float* txt_mask, const float* dim_t
   int chunks = (Lv * d + 4095) / 4096;
   if (chunks < 1) chunks = 1;
   if (chunks > 128) chunks = 128;
-  sine_pos_table_kernel<<<dim3(B, chunks), 256, Lv * sizeof(float), stream>>>(mask, txt_mask, dim_t, pos, key_mask, Lv, Lt, d);
+  launch_k(sine_pos_table_kernel, dim3(dim3(B, chunks)), dim3(256), Lv * sizeof(float), stream, mask, txt_mask, dim_t, pos, key_mask, Lv, Lt, d);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("sine_pos launch failed: %s", cudaGetErrorString(e));
   return (int)e;
@@ -362,6 +367,7 @@ int launch_sine_pos(const float* mask, const float* txt_mask, const float* dim_t
 // ------------------------------------------------------------------------------------------------
 // logits[b, l] = x_t[b, l] . w + (1 - mask) * -1e30: one warp per text token
 __global__ void __launch_bounds__(256) pool_logits_kernel(const PoolSalArgs a, float* __restrict__ logits) {
+  pdl_prologue();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (gw >= a.B * a.Lt) return;
@@ -378,6 +384,7 @@ __global__ void __launch_bounds__(256) pool_logits_kernel(const PoolSalArgs a, f
 
 // softmax over the tokens (recomputed per block, Lt is small) and pooled[b, j] for a 128-column slab
 __global__ void __launch_bounds__(128) weighted_pool_kernel(const PoolSalArgs a, const float* __restrict__ logits) {
+  pdl_prologue();
   extern __shared__ float s_alpha[];  // [Lt]
   __shared__ float s_stat[2];
   const int b = blockIdx.x;
@@ -414,6 +421,7 @@ __global__ void __launch_bounds__(128) weighted_pool_kernel(const PoolSalArgs a,
 
 // one warp per (b, l): cos(x_v[b,l], pooled[b]) + log(mask + 1e-45)
 __global__ void __launch_bounds__(256) cosine_saliency_kernel(const PoolSalArgs a) {
+  pdl_prologue();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (gw >= a.B * a.Lv) return;
@@ -439,10 +447,10 @@ __global__ void __launch_bounds__(256) cosine_saliency_kernel(const PoolSalArgs 
 }
 
 int launch_pool_saliency(const PoolSalArgs& a, cudaStream_t stream) {
-  pool_logits_kernel<<<(a.B * a.Lt * 32 + 255) / 256, 256, 0, stream>>>(a, a.logits_ws);
-  weighted_pool_kernel<<<dim3(a.B, (a.d + 127) / 128), 128, (size_t)a.Lt * sizeof(float), stream>>>(a, a.logits_ws);
+  launch_k(pool_logits_kernel, dim3((a.B * a.Lt * 32 + 255) / 256), dim3(256), 0, stream, a, a.logits_ws);
+  launch_k(weighted_pool_kernel, dim3(dim3(a.B, (a.d + 127) / 128)), dim3(128), (size_t)a.Lt * sizeof(float), stream, a, a.logits_ws);
   const int rows = a.B * a.Lv;
-  cosine_saliency_kernel<<<(rows * 32 + 255) / 256, 256, 0, stream>>>(a);
+  launch_k(cosine_saliency_kernel, dim3((rows * 32 + 255) / 256), dim3(256), 0, stream, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("pool_saliency launch failed: %s", cudaGetErrorString(e));
   return (int)e;
@@ -453,6 +461,7 @@ int launch_pool_saliency(const PoolSalArgs& a, cudaStream_t stream) {
 // Hidden activations are 16-bit in the separated conv layout: row 1 + b*(Lv+1) + l, zero separator rows.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv_head_final_kernel(const HeadFinalArgs a) {
+  pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= a.B * a.Lv) return;
@@ -492,7 +501,7 @@ int launch_conv_head_final(const HeadFinalArgs& a, cudaStream_t stream) {
   const int rows = a.B * a.Lv;
   const int threads = 256;
   const int blocks = (rows * 32 + threads - 1) / threads;
-  conv_head_final_kernel<<<blocks, threads, 0, stream>>>(a);
+  launch_k(conv_head_final_kernel, dim3(blocks), dim3(threads), 0, stream, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("conv_head_final launch failed: %s", cudaGetErrorString(e));
   return (int)e;
