@@ -276,7 +276,7 @@ def main():
             ddp.attach_flat_allreduce(model, overlap=not args.no_overlap)
     else:
         model.eval()
-        model.use_cuda_graphs = not (not args.graphs)  # the 41 launches of a forward replayed from one CUDA graph per shape
+        model.use_cuda_graphs = bool(args.graphs)  # the 41 launches of a forward replayed from one CUDA graph per shape
 
     # Rotating set of distinct input batches whose total size exceeds the 126 MB L2 (no L2-resident inputs between steps).
     per_batch = B * (Lv * cfg["v_feat_dim"] + Lt * cfg["t_feat_dim"] + Lv + Lt) * 4
@@ -300,7 +300,7 @@ def main():
     def train_step(inputs, targets):
         out = model(**inputs)
         ld = crit(out, targets)
-        total = sum(ld[k] * crit.weight_dict[k] for k in ld if k in crit.weight_dict)
+        total = crit.weighted_total(ld)  # = sum(ld[k] * weight_dict[k]) of the reference loop, as one dot product
         opt.zero_grad(set_to_none=True)
         total.backward()
         opt.step()  # clip_grad_norm_(0.1) (reference --grad_clip 0.1) + AdamW
@@ -406,7 +406,7 @@ def main():
     fwd_only = None
     if train:
         model.eval()
-        model.use_cuda_graphs = not (not args.graphs)
+        model.use_cuda_graphs = bool(args.graphs)
         with torch.no_grad():
             for i in range(3):
                 model(**dev_batches[i % n_rot])

@@ -21,7 +21,7 @@ if mode == "train":
     opt = FlatAdamW(model, lr=1e-4, weight_decay=1e-4, max_grad_norm=0.1)
     def step():
         out = model(**inp); ld = crit(out, tgt)
-        total = sum(ld[k] * crit.weight_dict[k] for k in ld)
+        total = crit.weighted_total(ld)
         opt.zero_grad(set_to_none=True); total.backward()
         opt.step()
 else:

@@ -28,6 +28,26 @@ struct AttnBwdCfg {
   static constexpr uint32_t kTmemCols = 512;
 };
 
+// 32 fp32 accumulator columns of this thread's row -> 16-bit at dqkv16[elem_off ..], and their column sums over the warp's
+// 32 rows -> colsum[col0 + lane] (one atomic per lane).  Warp-collective; rows with valid == false contribute zeros.
+__device__ __forceinline__ void store16_colsum(const AttnBwdArgs& a, const uint32_t (&r)[32], bool valid, size_t elem_off, int col0,
+                                               int lane) {
+  float v[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) v[e] = valid ? __uint_as_float(r[e]) : 0.f;
+  if (valid) {
+    uint16_t* dst = a.dqkv16 + elem_off;
+#pragma unroll
+    for (int e = 0; e < 32; e += 8)
+      *reinterpret_cast<uint4*>(dst + e) = make_uint4(cvt16x2(v[e], v[e + 1], a.fmt_grad), cvt16x2(v[e + 2], v[e + 3], a.fmt_grad),
+                                                      cvt16x2(v[e + 4], v[e + 5], a.fmt_grad), cvt16x2(v[e + 6], v[e + 7], a.fmt_grad));
+  }
+  if (a.colsum != nullptr) {
+    const float cs = warp_colsum32(v, lane);
+    atomicAdd(a.colsum + col0 + lane, cs * a.colsum_scale);
+  }
+}
+
 template <int DH>
 __global__ void __launch_bounds__(160, 1) attention_bwd_tcgen05_kernel(const __grid_constant__ AttnBwdArgs a) {
   using Cfg = AttnBwdCfg<DH>;
@@ -206,7 +226,9 @@ __global__ void __launch_bounds__(160, 1) attention_bwd_tcgen05_kernel(const __g
         uint32_t r[32];
         tmem_ld_32x32b_x32(tm_s + lane_addr + c * 32, r);
         tmem_ld_wait();
-        if (qvalid) {
+        if (a.dqkv16 != nullptr) {  // single key tile: final values, straight to the 16-bit GEMM operand (+ bias-gradient sums)
+          store16_colsum(a, r, qvalid, ((size_t)b * L + qi) * ld3 + h * DH + c * 32, h * DH + c * 32, lane);
+        } else if (qvalid) {
           float* dst = a.dqkv32 + ((size_t)b * L + qi) * ld3 + h * DH + c * 32;
           if (a.dq_atomic) {
 #pragma unroll
@@ -233,7 +255,9 @@ __global__ void __launch_bounds__(160, 1) attention_bwd_tcgen05_kernel(const __g
       uint32_t r[32];
       tmem_ld_32x32b_x32(tm_dv + lane_addr + c * 32, r);
       tmem_ld_wait();
-      if (kvalid) {
+      if (a.dqkv16 != nullptr) {
+        store16_colsum(a, r, kvalid, ((size_t)b * L + (kvalid ? kv : 0)) * ld3 + 2 * a.d + h * DH + c * 32, 2 * a.d + h * DH + c * 32, lane);
+      } else if (kvalid) {
 #pragma unroll
         for (int e = 0; e < 32; e += 4)
           *reinterpret_cast<float4*>(dv_dst + c * 32 + e) =
@@ -241,7 +265,9 @@ __global__ void __launch_bounds__(160, 1) attention_bwd_tcgen05_kernel(const __g
       }
       tmem_ld_32x32b_x32(tm_dk + lane_addr + c * 32, r);
       tmem_ld_wait();
-      if (kvalid) {
+      if (a.dqkv16 != nullptr) {
+        store16_colsum(a, r, kvalid, ((size_t)b * L + (kvalid ? kv : 0)) * ld3 + a.d + h * DH + c * 32, a.d + h * DH + c * 32, lane);
+      } else if (kvalid) {
 #pragma unroll
         for (int e = 0; e < 32; e += 4)
           *reinterpret_cast<float4*>(dk_dst + c * 32 + e) =

@@ -445,45 +445,92 @@ __global__ void __launch_bounds__(256) head_dh_kernel(const HeadFinalBwdArgs a) 
   }
 }
 
-__global__ void __launch_bounds__(256) head_dw_kernel(const HeadFinalBwdArgs a) {
+// Weight / bias gradients of the heads' last conv layer and the column sums of dh (bias gradient of the layer before).
+// thread = 8 consecutive channels (128-bit loads), block = 1024 channels x a slab of kHeadDwRows logical rows; the three tap
+// rows (m-1, m, m+1) slide through registers so every activation row is read once.
+constexpr int kHeadDwRows = 32;
+__device__ __forceinline__ void ld8(const uint16_t* p, int fmt, float (&v)[8]) {
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = ld16((uint16_t)(w[i] & 0xffff), fmt);
+    v[2 * i + 1] = ld16((uint16_t)(w[i] >> 16), fmt);
+  }
+}
+__global__ void __launch_bounds__(128) head_dw_kernel(const HeadFinalBwdArgs a) {
   pdl_prologue();
-  // thread = channel c (blockIdx.x * 256 + tid); blockIdx.y = slab of 64 logical rows
-  const int c = blockIdx.x * 256 + threadIdx.x;
+  const int c = (blockIdx.x * 128 + threadIdx.x) * 8;
   const int Mh = a.B * (a.Lv + 1);
-  const int m0 = blockIdx.y * 64;
-  if (c >= a.d) return;
-  float wc[3] = {0.f, 0.f, 0.f}, w0[3] = {0.f, 0.f, 0.f}, w1[3] = {0.f, 0.f, 0.f};
-  float cs_c = 0.f, cs_s = 0.f;
-  for (int m = m0; m < min(Mh, m0 + 64); ++m) {
-    const size_t row = (size_t)m + 1;
-    const float4 dz = *reinterpret_cast<const float4*>(a.dz + row * 4);
-    if (a.cs_cls) {
-      cs_c += ld16(a.dh_cls[row * a.d + c], a.fmt_grad);
-      cs_s += ld16(a.dh_span[row * a.d + c], a.fmt_grad);
-    }
-    if (dz.x == 0.f && dz.y == 0.f && dz.z == 0.f) continue;
+  const int m0 = blockIdx.y * kHeadDwRows;
+  const int m1 = min(Mh, m0 + kHeadDwRows);
+  if (c < a.d) {
+    float wc[3][8], w0[3][8], w1[3][8], cs_c[8], cs_s[8];
 #pragma unroll
-    for (int t = 0; t < 3; ++t) {
-      const float hc = ld16(a.h_cls[(row + t - 1) * a.d + c], a.fmt_act);
-      const float hs = ld16(a.h_span[(row + t - 1) * a.d + c], a.fmt_act);
-      wc[t] += dz.x * hc;
-      w0[t] += dz.y * hs;
-      w1[t] += dz.z * hs;
+    for (int j = 0; j < 8; ++j) {
+      cs_c[j] = cs_s[j] = 0.f;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) wc[t][j] = w0[t][j] = w1[t][j] = 0.f;
+    }
+    float pc[8], cc[8], nc[8], ps[8], cu[8], ns[8];  // previous / current / next activation row of both heads
+    ld8(a.h_cls + (size_t)m0 * a.d + c, a.fmt_act, pc);
+    ld8(a.h_span + (size_t)m0 * a.d + c, a.fmt_act, ps);
+    ld8(a.h_cls + (size_t)(m0 + 1) * a.d + c, a.fmt_act, cc);
+    ld8(a.h_span + (size_t)(m0 + 1) * a.d + c, a.fmt_act, cu);
+    for (int m = m0; m < m1; ++m) {
+      const size_t row = (size_t)m + 1;
+      ld8(a.h_cls + (row + 1) * a.d + c, a.fmt_act, nc);
+      ld8(a.h_span + (row + 1) * a.d + c, a.fmt_act, ns);
+      const float4 dz = *reinterpret_cast<const float4*>(a.dz + row * 4);
+      if (a.cs_cls) {
+        float gc[8], gs[8];
+        ld8(a.dh_cls + row * a.d + c, a.fmt_grad, gc);
+        ld8(a.dh_span + row * a.d + c, a.fmt_grad, gs);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          cs_c[j] += gc[j];
+          cs_s[j] += gs[j];
+        }
+      }
+      if (dz.x != 0.f || dz.y != 0.f || dz.z != 0.f) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          wc[0][j] += dz.x * pc[j];
+          wc[1][j] += dz.x * cc[j];
+          wc[2][j] += dz.x * nc[j];
+          w0[0][j] += dz.y * ps[j];
+          w0[1][j] += dz.y * cu[j];
+          w0[2][j] += dz.y * ns[j];
+          w1[0][j] += dz.z * ps[j];
+          w1[1][j] += dz.z * cu[j];
+          w1[2][j] += dz.z * ns[j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        pc[j] = cc[j];
+        cc[j] = nc[j];
+        ps[j] = cu[j];
+        cu[j] = ns[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        atomicAdd(a.gw_cls + (size_t)(c + j) * 3 + t, wc[t][j] * a.pgrad_scale);
+        atomicAdd(a.gw_span + (size_t)(c + j) * 3 + t, w0[t][j] * a.pgrad_scale);
+        atomicAdd(a.gw_span + ((size_t)a.d + c + j) * 3 + t, w1[t][j] * a.pgrad_scale);
+      }
+      if (a.cs_cls) {
+        atomicAdd(a.cs_cls + c + j, cs_c[j] * a.pgrad_scale);
+        atomicAdd(a.cs_span + c + j, cs_s[j] * a.pgrad_scale);
+      }
     }
   }
-#pragma unroll
-  for (int t = 0; t < 3; ++t) {
-    atomicAdd(a.gw_cls + (size_t)c * 3 + t, wc[t] * a.pgrad_scale);
-    atomicAdd(a.gw_span + (size_t)c * 3 + t, w0[t] * a.pgrad_scale);
-    atomicAdd(a.gw_span + ((size_t)a.d + c) * 3 + t, w1[t] * a.pgrad_scale);
-  }
-  if (a.cs_cls) {
-    atomicAdd(a.cs_cls + c, cs_c * a.pgrad_scale);
-    atomicAdd(a.cs_span + c, cs_s * a.pgrad_scale);
-  }
-  if (c == 0) {  // bias gradients: sum of dz over this slab
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // bias gradients: sum of dz over this slab
     float bc = 0.f, b0 = 0.f, b1 = 0.f;
-    for (int m = m0; m < min(Mh, m0 + 64); ++m) {
+    for (int m = m0; m < m1; ++m) {
       const float4 dz = *reinterpret_cast<const float4*>(a.dz + ((size_t)m + 1) * 4);
       bc += dz.x;
       b0 += dz.y;
@@ -499,7 +546,7 @@ int launch_head_final_bwd(const HeadFinalBwdArgs& a, cudaStream_t stream) {
   const int Mh = a.B * (a.Lv + 1);
   launch_k(head_dz_kernel, dim3((Mh + 2 + 255) / 256), dim3(256), 0, stream, a);
   launch_k(head_dh_kernel, dim3((Mh * 32 + 255) / 256), dim3(256), 0, stream, a);
-  launch_k(head_dw_kernel, dim3(dim3((a.d + 255) / 256, (Mh + 63) / 64)), dim3(256), 0, stream, a);
+  launch_k(head_dw_kernel, dim3((a.d + 1023) / 1024, (Mh + kHeadDwRows - 1) / kHeadDwRows), dim3(128), 0, stream, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("head_final_bwd launch failed: %s", cudaGetErrorString(e));
   return (int)e;

@@ -322,29 +322,42 @@ __global__ void __launch_bounds__(256) loss_bwd_vid_kernel(const LossBwdArgs a) 
   }
 }
 
-// one block per sample b: d xt[b, :]
+// one block per (sample b, 128-column chunk): d xt[b, :].  The per-row scalar factors are staged in shared memory first so
+// the column loop is one coalesced load + FMA per contributing clip row.
 __global__ void __launch_bounds__(128) loss_bwd_txt_kernel(const LossBwdArgs a) {
   pdl_prologue();
-  const int b = blockIdx.x;
+  extern __shared__ float s_coef[];                          // [Lv + B] factor of xv[row] in d xt[b]
+  int* s_row = reinterpret_cast<int*>(s_coef + a.Lv + a.B);  // [B] clip row of the positive of sample k
+  __shared__ float s_red[4];
+  const int b = blockIdx.x, tid = threadIdx.x;
   const float w_inter = a.w[3], w_intra = a.w[4];
   const float tn = a.tnorm[b];
-  for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < a.d; j += gridDim.y * blockDim.x) {
-    const float tj = a.xt[(size_t)b * a.d + j];
-    float o = 0.f;
-#pragma unroll 5
-    for (int l = 0; l < a.Lv; ++l) {  // vnorm and tnorm are clamped >= 1e-8 by the forward, so no term is inf * 0
-      const int i = b * a.Lv + l;
-      const float g = w_intra * a.g_cos_in[i];
-      o += g * (a.xv[(size_t)i * a.d + j] / (a.vnorm[i] * tn) - a.cos_in[i] * tj / (tn * tn));
-    }
-    if (a.pos_idx != nullptr) {
+  float part = 0.f;  // sum of g * cos: factor of -xt[b] / |xt[b]|^2
+  for (int l = tid; l < a.Lv; l += 128) {  // vnorm and tnorm are clamped >= 1e-8 by the forward
+    const int i = b * a.Lv + l;
+    const float g = w_intra * a.g_cos_in[i];
+    s_coef[l] = g / (a.vnorm[i] * tn);
+    part += g * a.cos_in[i];
+  }
+  const int nk = a.pos_idx != nullptr ? a.B : 0;
+  for (int k = tid; k < nk; k += 128) {
+    const float g = w_inter * a.g_sim[k * a.B + b];
+    const int i = k * a.Lv + (int)a.pos_idx[k];
+    s_coef[a.Lv + k] = g / (a.vnorm[i] * tn);
+    s_row[k] = i;
+    part += g * a.sim[k * a.B + b];
+  }
+  part = warp_sum(part);
+  if ((tid & 31) == 0) s_red[tid >> 5] = part;
+  __syncthreads();
+  const float c2 = (s_red[0] + s_red[1] + s_red[2] + s_red[3]) / (tn * tn);
+  for (int j = blockIdx.y * 128 + tid; j < a.d; j += gridDim.y * 128) {
+    float o = -c2 * a.xt[(size_t)b * a.d + j];
+    const float* xv = a.xv + (size_t)b * a.Lv * a.d + j;
+#pragma unroll 8
+    for (int l = 0; l < a.Lv; ++l) o += s_coef[l] * xv[(size_t)l * a.d];
 #pragma unroll 4
-      for (int k = 0; k < a.B; ++k) {
-        const float g = w_inter * a.g_sim[k * a.B + b];
-        const int i = k * a.Lv + (int)a.pos_idx[k];
-        o += g * (a.xv[(size_t)i * a.d + j] / (a.vnorm[i] * tn) - a.sim[k * a.B + b] * tj / (tn * tn));
-      }
-    }
+    for (int k = 0; k < nk; ++k) o += s_coef[a.Lv + k] * a.xv[(size_t)s_row[k] * a.d + j];
     a.d_xt[(size_t)b * a.d + j] = o;
   }
 }
@@ -353,7 +366,7 @@ int launch_loss_backward(const LossBwdArgs& a, cudaStream_t stream) {
   const int n = a.B * a.Lv;
   launch_k(loss_bwd_small_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, a);
   launch_k(loss_bwd_vid_kernel, dim3((n * 32 + 255) / 256), dim3(256), (size_t)8 * a.B * sizeof(float), stream, a);
-  launch_k(loss_bwd_txt_kernel, dim3(dim3(a.B, (a.d + 127) / 128)), dim3(128), 0, stream, a);
+  launch_k(loss_bwd_txt_kernel, dim3(a.B, (a.d + 127) / 128), dim3(128), (size_t)(a.Lv + 2 * a.B) * sizeof(float), stream, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("loss backward launch failed: %s", cudaGetErrorString(e));
   return (int)e;

@@ -275,6 +275,21 @@ UV_DEVINL float warp_sum(float v) {
 UV_DEVINL void red_add_f32x4(float* addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// Transposing reduction: every lane holds 32 values v[0..31] (its row of a 32 x 32 block); on return v[0] of lane i is the
+// sum over all lanes of their v[i] (the column sum of column i).  31 shuffles instead of 32 x 5.
+UV_DEVINL float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      const float send = hi ? v[k] : v[k + off];
+      const float keep = hi ? v[k + off] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
 UV_DEVINL float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

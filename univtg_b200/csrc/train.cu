@@ -790,6 +790,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     // ---- attention core backward -> dqkv32 -> dqkv16 (+ in_proj_bias gradient) ----
     rc = launch_attn_delta(T.dO16, FMT_G, T.attn16[l], fmt, T.delta, B, L, P->H, P->dh, st);
     if (rc) return rc;
+    bool fused16 = false;
     {
       AttnBwdArgs a;
       memset(&a, 0, sizeof(a));
@@ -810,6 +811,12 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       const bool tc = (P->dh == 64 || P->dh == 128);
       const int num_kv = (L + 127) / 128;
       a.dq_atomic = (!tc || num_kv > 1) ? 1 : 0;
+      fused16 = !a.dq_atomic;  // one key tile: the kernel emits the 16-bit operands and the in_proj_bias gradient itself
+      if (fused16) {
+        a.dqkv16 = T.dqkv16;
+        a.colsum = G_layer(l, 1);
+        a.colsum_scale = INV;
+      }
       if (a.dq_atomic) cudaMemsetAsync(T.dqkv32, 0, (size_t)M * 3 * d * 4, st);
       if (tc) {
         if (make_tmap_2d(&a.tm_qkv, T.qkv16[l], (uint64_t)M, (uint64_t)3 * d, (uint64_t)3 * d, 128, 64)) return 1;
@@ -820,8 +827,10 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       }
       if (rc) return rc;
     }
-    rc = launch_cvt16_colsum(T.dqkv32, 3 * d, T.dqkv16, 3 * d, M, 3 * d, FMT_G, G_layer(l, 1), INV, st);
-    if (rc) return rc;
+    if (!fused16) {
+      rc = launch_cvt16_colsum(T.dqkv32, 3 * d, T.dqkv16, 3 * d, M, 3 * d, FMT_G, G_layer(l, 1), INV, st);
+      if (rc) return rc;
+    }
     // ---- in-projections: dgrad dx = dy + [dq|dk|dv] [Wq;Wk;Wv]; wgrad dWqk = [dq|dk]^T (x+pos), dWv = dv^T x ----
     memset(&g, 0, sizeof(g));
     g.num = 1;

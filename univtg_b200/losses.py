@@ -6,6 +6,12 @@ from . import _lib
 LOSS_NAMES = ("loss_b", "loss_g", "loss_f", "loss_s_inter", "loss_s_intra")
 
 
+class LossDict(dict):
+    """The reference's loss dict; additionally carries the five losses as one tensor in `.vector`."""
+
+    vector = None
+
+
 class _LossFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred_logits, pred_spans, vid_mem_proj, txt_mem_proj, crit, tg):
@@ -67,7 +73,8 @@ def criterion_forward(crit, outputs, targets):
         tg["pos"] = None
     losses = _LossFunction.apply(outputs["pred_logits"], outputs["pred_spans"], outputs["vid_mem_proj"], outputs["txt_mem_proj"],
                                  crit, tg)
-    out = {}
+    out = LossDict()
+    out.vector = losses  # [loss_b, loss_g, loss_f, loss_s_inter, loss_s_intra] as ONE tensor (SetCriterion.weighted_total)
     if "spans" in crit.losses:
         out["loss_b"] = losses[0]
         out["loss_g"] = losses[1]
