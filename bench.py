@@ -252,6 +252,8 @@ def main():
         import torch.distributed as dist_mod
 
         dist = dist_mod
+        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed when NCCL_DEBUG is set) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
