@@ -158,6 +158,8 @@ int univtg_op_gemm_cluster(const void* a, const void* b, int32_t M, int32_t N, i
  * [0] entry, [1] setup done, [2] all TMA issued, [3] first stage landed, [4] last MMA issued, [5] accumulator ready,
  * [6] epilogue done, [7] exit.  Pass NULL to switch it off. */
 int univtg_debug_gemm_timeline(void* buf);
+/* tcgen05.ld rate probe with the GEMM epilogue's access pattern: out_ns[block] = ns per 16-column step.  Profiling aid only. */
+int univtg_debug_tmem_ld_rate(int32_t iters, int32_t mode, int32_t blocks, float* out_ns, float* sink, void* stream);
 /* tcgen05.mma issue-rate probe (M=128, N=n, K=16 from resident smem): out_ns[block] = ns per MMA.  Profiling aid only. */
 int univtg_debug_mma_rate(int32_t n, int32_t iters, int32_t per_commit, int32_t kstep_bytes, int32_t blocks, float* out_ns,
                           void* stream);

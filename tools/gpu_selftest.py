@@ -112,6 +112,23 @@ def case_mma_rate():
     return res
 
 
+def case_tmem_ld_rate():
+    """ns per 16-column tcgen05.ld step with the GEMM epilogue's access pattern (8 warps per CTA)."""
+    import torch
+    from univtg_b200 import _lib
+    lib = _lib.load_library()
+    res = {"ok": True}
+    sink = torch.zeros(256, device="cuda")
+    for blocks in (1, 148):
+        for mode in (0, 1, 2):
+            out = torch.zeros(blocks, device="cuda")
+            for _ in range(2):
+                _lib.check(lib.univtg_debug_tmem_ld_rate(2000, mode, blocks, _lib.ptr(out), _lib.ptr(sink), _lib.stream_ptr()), "tmem_ld_rate")
+            torch.cuda.synchronize()
+            res[f"b{blocks}_mode{mode}"] = round(float(out.median()), 1)
+    return res
+
+
 def case_layernorm(rows, d, ld16, fmt):
     import torch
     from univtg_b200 import _lib
@@ -231,6 +248,8 @@ CASES = {
     "tlcl_plain16": (case_gemm_timeline, (3424, 1024, 1024, 0, False, True, 256, True)),
     "tlcl_qkv": (case_gemm_timeline, (3424, 3072, 1024, 0, False, True, 256, True)),
     "tl_plain16": (case_gemm_timeline, (3424, 1024, 1024, 0, False, True, 256)),
+    "tl_nostore": (case_gemm_timeline, (3424, 1024, 1024, 0, False, False, 256)),
+    "tl_plain16_m1664": (case_gemm_timeline, (1664, 1024, 1024, 0, False, True, 256)),
     # steady-state mainloop probes: 148 (bn 256) / 296 (bn 128) tiles of 64 k-blocks
     "tl_k4096_bn256": (case_gemm_timeline, (9472, 512, 4096, 0, False, True, 256)),
     "tlcl_k4096_bn256": (case_gemm_timeline, (9472, 512, 4096, 0, False, True, 256, True)),
@@ -247,6 +266,7 @@ CASES = {
     "tl_qkv_bn256": (case_gemm_timeline, (3424, 3072, 1024, 0, False, True, 256)),
     "tl_ffn1_bn128": (case_gemm_timeline, (3424, 1024, 1024, 2, False, True, 128)),
     "mma_rate": (case_mma_rate, ()),
+    "tmem_ld_rate": (case_tmem_ld_rate, ()),
     "ln_1024": (case_layernorm, (3424, 1024, 1024, 0)),
     "ln_256_bf16": (case_layernorm, (77, 256, 256, 1)),
     "ln_2818": (case_layernorm, (300, 2818, 2880, 0)),

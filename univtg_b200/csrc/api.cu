@@ -627,6 +627,10 @@ int univtg_debug_mma_rate(int32_t n, int32_t iters, int32_t per_commit, int32_t 
   return uv::debug_mma_rate(n, iters, per_commit, kstep_bytes, blocks, out_ns, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int univtg_debug_tmem_ld_rate(int32_t iters, int32_t mode, int32_t blocks, float* out_ns, float* sink, void* stream) {
+  return uv::debug_tmem_ld_rate(iters, mode, blocks, out_ns, sink, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int univtg_debug_gemm_timeline(void* buf) {
   uv::set_gemm_timeline_buffer(reinterpret_cast<unsigned long long*>(buf));
   return 0;

@@ -262,6 +262,62 @@ __global__ void __launch_bounds__(256) cvt16_colsum_kernel(const float* __restri
   }
 }
 
+// dst[n][c][t] = src[t][n][c] for the 3 taps of a k=3 conv weight gradient: the wgrad GEMMs write tap-major planes with
+// 256-bit stores, this pass interleaves them into the reference's [out, in, 3] parameter layout (12 contiguous bytes per thread).
+__global__ void __launch_bounds__(256) tap_interleave_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t nc) {
+  pdl_prologue();
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nc; i += (size_t)gridDim.x * 256) {
+    const float a = __ldg(src + i), b = __ldg(src + nc + i), c = __ldg(src + 2 * nc + i);
+    float* o = dst + 3 * i;
+    o[0] = a;
+    o[1] = b;
+    o[2] = c;
+  }
+}
+int launch_tap_interleave(const float* src, float* dst, int N, int C, cudaStream_t stream) {
+  const size_t nc = (size_t)N * C;
+  size_t blocks = (nc + 255) / 256;
+  if (blocks > 2368) blocks = 2368;
+  launch_k(tap_interleave_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, src, dst, nc);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) set_error("tap_interleave launch failed: %s", cudaGetErrorString(e));
+  return (int)e;
+}
+
+// colsum[c] += scale * sum_r in16[r, c]: column sums of a 16-bit matrix (bias gradient of a GEMM whose output gradient was
+// written directly in 16-bit).  thread = 8 columns (128-bit loads), block = 1024 columns x 64 rows.
+__global__ void __launch_bounds__(128) colsum16_kernel(const uint16_t* __restrict__ in16, int ld, int rows, int cols, int fmt,
+                                                      float* __restrict__ colsum, float scale) {
+  pdl_prologue();
+  const int c = (blockIdx.x * 128 + threadIdx.x) * 8;
+  if (c >= cols) return;
+  const int r0 = blockIdx.y * 64, r1 = min(rows, r0 + 64);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int r = r0; r < r1; ++r) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(in16 + (size_t)r * ld + c));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      s[2 * i] += ld16((uint16_t)(w[i] & 0xffff), fmt);
+      s[2 * i + 1] += ld16((uint16_t)(w[i] >> 16), fmt);
+    }
+  }
+  red_add_f32x4(colsum + c, make_float4(s[0] * scale, s[1] * scale, s[2] * scale, s[3] * scale));
+  red_add_f32x4(colsum + c + 4, make_float4(s[4] * scale, s[5] * scale, s[6] * scale, s[7] * scale));
+}
+
+int launch_colsum16(const uint16_t* in16, int ld, int rows, int cols, int fmt, float* colsum, float scale, cudaStream_t stream) {
+  if (cols % 8 != 0 || ld % 8 != 0 || (reinterpret_cast<uintptr_t>(in16) & 15) != 0 || (reinterpret_cast<uintptr_t>(colsum) & 15) != 0) {
+    set_error("colsum16: columns / leading dimension must be multiples of 8 and the pointers 16-byte aligned");
+    return (int)cudaErrorInvalidValue;
+  }
+  launch_k(colsum16_kernel, dim3((cols / 8 + 127) / 128, (rows + 63) / 64), dim3(128), 0, stream, in16, ld, rows, cols, fmt, colsum, scale);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) set_error("colsum16 launch failed: %s", cudaGetErrorString(e));
+  return (int)e;
+}
+
 int launch_cvt16_colsum(const float* in32, int ld_in, uint16_t* out16, int ld_out, int rows, int cols, int fmt, float* colsum,
                         float colsum_scale, cudaStream_t stream) {
   if (cols % 4 != 0 || ld_in % 4 != 0 || ld_out % 4 != 0) {

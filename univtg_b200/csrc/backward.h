@@ -36,6 +36,12 @@ int launch_layernorm_bwd(const LnBwdArgs& a, cudaStream_t stream);
 int launch_cvt16_colsum(const float* in32, int ld_in, uint16_t* out16, int ld_out, int rows, int cols, int fmt, float* colsum,
                         float colsum_scale, cudaStream_t stream);
 
+// dst[n][c][t] = src[t][n][c], t < 3 (conv weight gradient planes -> reference [out, in, 3] layout)
+int launch_tap_interleave(const float* src, float* dst, int N, int C, cudaStream_t stream);
+
+// colsum[c] += scale * sum_r in16[r, c]
+int launch_colsum16(const uint16_t* in16, int ld, int rows, int cols, int fmt, float* colsum, float scale, cudaStream_t stream);
+
 // delta[b, h, i] = sum_c dO[b, i, h, c] * O[b, i, h, c]
 int launch_attn_delta(const uint16_t* dO, int fmt_do, const uint16_t* O, int fmt_o, float* delta, int B, int L, int H, int dh,
                       cudaStream_t stream);

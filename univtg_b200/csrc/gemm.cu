@@ -18,6 +18,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -85,7 +87,10 @@ __device__ __forceinline__ void stamp(unsigned long long* dbg, int slot) {
   }
 }
 
-template <int CL>
+// FULL = false drops the training-only epilogue options at compile time (pre-activation save, aux / mask multiplies, atomic and
+// strided fp32 stores, second fp32 output, column sums, scalar fallback): the forward's step loop then fits the instruction
+// cache (the all-options loop measured ~2x slower per step for the same work).  The host picks the variant per launch.
+template <int CL, bool FULL>
 __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmGroup g) {
   using Cfg = GemmCfg<CL>;
   const int BN = g.bn;
@@ -277,6 +282,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       uint16_t* __restrict__ out16p = pr.out16p;
       const bool atomic = (pr.accumulate != 0) || (pr.ksplit > 1);
       const bool vec = pr.vec_ok != 0;
+      const bool v256 = FULL ? (pr.vec_ok == 2) : true;  // the lean variant is only launched when every access can be 256-bit
       const int ofmt = pr.out_fmt < 0 ? fmt : pr.out_fmt;
       const float* __restrict__ aux32 = pr.aux32;
       const int aux_mode = pr.aux_mode;
@@ -337,13 +343,22 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       if (nsteps > 0) {
         tmem_ld_32x32b_x16(t_addr, r);
         if (load_resid) {
+          if (v256) {
+            ld_global_256f(resid_row + n_base, rv_next);
+            ld_global_256f(resid_row + n_base + 8, rv_next + 8);
+          } else {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 t4 = *reinterpret_cast<const float4*>(resid_row + n_base + 4 * q);
-            rv_next[4 * q] = t4.x; rv_next[4 * q + 1] = t4.y; rv_next[4 * q + 2] = t4.z; rv_next[4 * q + 3] = t4.w;
+            for (int q = 0; q < 4; ++q) {
+              const float4 t4 = *reinterpret_cast<const float4*>(resid_row + n_base + 4 * q);
+              rv_next[4 * q] = t4.x; rv_next[4 * q + 1] = t4.y; rv_next[4 * q + 2] = t4.z; rv_next[4 * q + 3] = t4.w;
+            }
           }
         }
       }
+      // The step loop is instantiated twice (vector / scalar accesses) so that each instance's body stays small: the epilogue is
+      // instruction-fetch sensitive (8 warps walking a multi-KB unrolled body).
+      auto step_loop = [&](auto vec_tag) {
+      constexpr bool VEC = decltype(vec_tag)::value;
       for (int c = 0; c < nsteps; ++c) {
         const int n0 = n_base + c * 16;
         tmem_ld_wait();
@@ -356,18 +371,28 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
         if (c + 1 < nsteps) {
           tmem_ld_32x32b_x16(t_addr + (c + 1) * 16, r);
           if (load_resid) {
+            if (v256) {
+              ld_global_256f(resid_row + n0 + 16, rv_next);
+              ld_global_256f(resid_row + n0 + 24, rv_next + 8);
+            } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 t4 = *reinterpret_cast<const float4*>(resid_row + n0 + 16 + 4 * q);
-              rv_next[4 * q] = t4.x; rv_next[4 * q + 1] = t4.y; rv_next[4 * q + 2] = t4.z; rv_next[4 * q + 3] = t4.w;
+              for (int q = 0; q < 4; ++q) {
+                const float4 t4 = *reinterpret_cast<const float4*>(resid_row + n0 + 16 + 4 * q);
+                rv_next[4 * q] = t4.x; rv_next[4 * q + 1] = t4.y; rv_next[4 * q + 2] = t4.z; rv_next[4 * q + 3] = t4.w;
+              }
             }
           }
         }
-        if (pre_row != nullptr && valid) {  // training: keep the pre-activation (needs N % 4 == 0, checked on the host)
+        if (FULL && pre_row != nullptr && valid) {  // training: keep the pre-activation (needs N % 4 == 0, checked on the host)
+          if (v256) {  // vec_ok implies N % 16 == 0: the whole step is in range
+            st_global_256f(pre_row + n0, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+            st_global_256f(pre_row + n0 + 8, v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
+          } else {
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (n0 + 4 * q < pN)
-              *reinterpret_cast<float4*>(pre_row + n0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            for (int q = 0; q < 4; ++q)
+              if (n0 + 4 * q < pN)
+                *reinterpret_cast<float4*>(pre_row + n0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
         }
         if (act == ACT_GELU) {
 #pragma unroll
@@ -379,13 +404,13 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] *= rsc;
         }
-        if (vec) {
+        if constexpr (VEC) {
           if (valid) {
             if (resid_row != nullptr) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] += rv[j];
             }
-            if (aux_row != nullptr) {
+            if (FULL && aux_row != nullptr) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const float4 a4 = *reinterpret_cast<const float4*>(aux_row + n0 + 4 * q);
@@ -397,7 +422,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
                 }
               }
             }
-            if (mask_row != nullptr) {
+            if (FULL && mask_row != nullptr) {
 #pragma unroll
               for (int q = 0; q < 2; ++q) {
                 const uint4 mk = *reinterpret_cast<const uint4*>(mask_row + n0 + 8 * q);
@@ -410,26 +435,41 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
               }
             }
             if (o32_row != nullptr) {
-              if (atomic) {
+              if (FULL && atomic) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) atomicAdd(o32_row + n0 + j, v[j]);
+              } else if (v256) {
+                st_global_256f(o32_row + n0, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+                st_global_256f(o32_row + n0 + 8, v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
               } else {
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                   *reinterpret_cast<float4*>(o32_row + n0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
               }
             }
-            if (o32i_row != nullptr) {
+            if (FULL && o32i_row != nullptr) {
+              if (v256) {
+                st_global_256f(o32i_row + n0, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+                st_global_256f(o32i_row + n0 + 8, v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
+              } else {
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<float4*>(o32i_row + n0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                for (int q = 0; q < 4; ++q)
+                  *reinterpret_cast<float4*>(o32i_row + n0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              }
             }
             if (o16_row != nullptr) {
+              if (v256) {
+                uint32_t w8[8];
 #pragma unroll
-              for (int q = 0; q < 2; ++q)
-                *reinterpret_cast<uint4*>(o16_row + n0 + 8 * q) =
-                    make_uint4(cvt16x2(v[8 * q], v[8 * q + 1], ofmt), cvt16x2(v[8 * q + 2], v[8 * q + 3], ofmt),
-                               cvt16x2(v[8 * q + 4], v[8 * q + 5], ofmt), cvt16x2(v[8 * q + 6], v[8 * q + 7], ofmt));
+                for (int q = 0; q < 8; ++q) w8[q] = cvt16x2(v[2 * q], v[2 * q + 1], ofmt);
+                st_global_256(o16_row + n0, w8);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                  *reinterpret_cast<uint4*>(o16_row + n0 + 8 * q) =
+                      make_uint4(cvt16x2(v[8 * q], v[8 * q + 1], ofmt), cvt16x2(v[8 * q + 2], v[8 * q + 3], ofmt),
+                                 cvt16x2(v[8 * q + 4], v[8 * q + 5], ofmt), cvt16x2(v[8 * q + 6], v[8 * q + 7], ofmt));
+              }
             }
             if (o16p_row != nullptr) {
               float p[16];
@@ -442,18 +482,25 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
                   p[4 * q] += a4.x; p[4 * q + 1] += a4.y; p[4 * q + 2] += a4.z; p[4 * q + 3] += a4.w;
                 }
               }
+              if (v256) {
+                uint32_t w8[8];
 #pragma unroll
-              for (int q = 0; q < 2; ++q)
-                *reinterpret_cast<uint4*>(o16p_row + n0 + 8 * q) =
-                    make_uint4(cvt16x2(p[8 * q], p[8 * q + 1], ofmt), cvt16x2(p[8 * q + 2], p[8 * q + 3], ofmt),
-                               cvt16x2(p[8 * q + 4], p[8 * q + 5], ofmt), cvt16x2(p[8 * q + 6], p[8 * q + 7], ofmt));
+                for (int q = 0; q < 8; ++q) w8[q] = cvt16x2(p[2 * q], p[2 * q + 1], ofmt);
+                st_global_256(o16p_row + n0, w8);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                  *reinterpret_cast<uint4*>(o16p_row + n0 + 8 * q) =
+                      make_uint4(cvt16x2(p[8 * q], p[8 * q + 1], ofmt), cvt16x2(p[8 * q + 2], p[8 * q + 3], ofmt),
+                                 cvt16x2(p[8 * q + 4], p[8 * q + 5], ofmt), cvt16x2(p[8 * q + 6], p[8 * q + 7], ofmt));
+              }
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = 0.f;  // invalid rows contribute nothing to the column sums
           }
         } else {
-          // unaligned leading dimensions / ragged N (e.g. the [d, 2818] projector weight gradient): scalar accesses
+          // unaligned leading dimensions / ragged N (e.g. the [d, 2818] projector weight gradient, strided conv wgrad): scalar accesses
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int n = n0 + j;
@@ -476,7 +523,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
             v[j] = x;
           }
         }
-        if (colsum != nullptr) {  // warp-uniform: column sums over this warp's 32 rows, one atomic per column
+        if (FULL && colsum != nullptr) {  // warp-uniform: column sums over this warp's 32 rows, one atomic per column
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float sj = warp_sum(v[j]);
@@ -484,6 +531,9 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           }
         }
       }
+      };
+      if (!FULL || vec) step_loop(std::true_type{});
+      else if constexpr (FULL) step_loop(std::false_type{});
       // release the accumulator stage
       tc_fence_before();
       __syncwarp();
@@ -558,6 +608,68 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, int 
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
+}
+
+// Microbenchmark: tcgen05.ld 32x32b.x16 rate with the epilogue's access pattern (8 warps, warp w reads lane quarter w % 4,
+// the two warps of a quarter read different column halves).  mode 0: load + wait per step; mode 1: next load in flight while the
+// current step's 16 values are consumed (the epilogue's software pipeline); mode 2: x32 loads.  out[block] = ns per 16-column step.
+__global__ void __launch_bounds__(256, 1) tmem_ld_rate_kernel(int iters, int mode, float* out, float* sink) {
+  __shared__ uint32_t holder;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) tmem_alloc<512>(&holder);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = holder + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 128;
+  float acc = 0.f;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (int it = 0; it < iters; ++it) {
+    if (mode == 0) {
+      for (int c = 0; c < 8; ++c) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(base + c * 16, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc += __uint_as_float(r[j]);
+      }
+    } else if (mode == 1) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(base, r);
+      for (int c = 0; c < 8; ++c) {
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        if (c + 1 < 8) tmem_ld_32x32b_x16(base + (c + 1) * 16, r);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc += v[j];
+      }
+    } else {
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(base + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc += __uint_as_float(r[j]);
+      }
+    }
+  }
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  if (threadIdx.x == 0) out[blockIdx.x] = (float)(t1 - t0) / (float)((long long)iters * 8);
+  if (acc == 123.456f) sink[threadIdx.x] = acc;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(holder);
+  }
+  (void)lane;
+}
+
+int debug_tmem_ld_rate(int iters, int mode, int blocks, float* out, float* sink, cudaStream_t stream) {
+  tmem_ld_rate_kernel<<<blocks, 256, 0, stream>>>(iters, mode, out, sink);
+  return (int)cudaGetLastError();
 }
 
 int debug_mma_rate(int n, int iters, int per_commit, int kstep_bytes, int blocks, float* out, cudaStream_t stream) {
@@ -648,9 +760,13 @@ int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
   const int cl = g.cluster == 2 ? 2 : 1;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+      e = cudaFuncSetAttribute(gemm_tcgen05_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tcgen05_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tcgen05_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm, smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
       return (int)e;
@@ -691,14 +807,26 @@ int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
                (!pr.resid || (al16(pr.resid) && pr.ld_resid % 4 == 0)) && (!pr.addtab || (al16(pr.addtab) && pr.ld_addtab % 4 == 0)) &&
                (!pr.out32 || (al16(pr.out32) && pr.ld32 % 4 == 0)) && (!pr.out32_id || (al16(pr.out32_id) && pr.ld32_id % 4 == 0)) &&
                ((!pr.out16 && !pr.out16p) || (pr.ld16 % 8 == 0 && al16(pr.out16) && al16(pr.out16p)));
+    auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
+    // 256-bit accesses (one whole 32-byte sector per thread and instruction) when every leading dimension keeps rows 32-byte aligned
+    if (w.vec_ok && (!pr.pre32 || (al32(pr.pre32) && pr.ld_pre % 8 == 0)) && (!pr.resid || (al32(pr.resid) && pr.ld_resid % 8 == 0)) &&
+        (!pr.out32 || (al32(pr.out32) && pr.ld32 % 8 == 0)) && (!pr.out32_id || (al32(pr.out32_id) && pr.ld32_id % 8 == 0)) &&
+        ((!pr.out16 && !pr.out16p) || (pr.ld16 % 16 == 0 && al32(pr.out16) && al32(pr.out16p))))
+      w.vec_ok = 2;
   }
   if (total == 0) return 0;
+  bool full = false;  // does any problem of the group need an epilogue option only the FULL variant compiles in?
+  for (int p = 0; p < g.num; ++p) {
+    const GemmProblem& pr = g.p[p];
+    full = full || pr.vec_ok != 2 || pr.pre32 || pr.aux32 || pr.mask16 || pr.accumulate || pr.ksplit > 1 || pr.out32_id || pr.colsum || pr.cs32 > 1;
+  }
   g.bn = bn;
   g.dbg = g_timeline;
   cudaError_t e;
   if (cl == 1) {
     const int grid = total < num_sms ? total : num_sms;
-    launch_k(gemm_tcgen05_kernel<1>, dim3(grid), dim3(384), Cfg::kSmemBytes, stream, g);
+    if (full) launch_k(gemm_tcgen05_kernel<1, true>, dim3(grid), dim3(384), Cfg::kSmemBytes, stream, g);
+    else launch_k(gemm_tcgen05_kernel<1, false>, dim3(grid), dim3(384), Cfg::kSmemBytes, stream, g);
     e = cudaGetLastError();
   } else {
     const int max_clusters = num_sms / 2;
@@ -718,7 +846,7 @@ int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2>, g);
+    e = full ? cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, true>, g) : cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, false>, g);
   }
   if (e != cudaSuccess) {
     set_error("gemm launch failed: %s", cudaGetErrorString(e));

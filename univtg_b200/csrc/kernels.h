@@ -72,7 +72,7 @@ struct GemmProblem {
   float* colsum;           // fp32 [N]: atomically accumulates the column sums of the stored values (bias gradients)
   int cs32;                // column stride of out32 (0/1: dense); 3 writes a Conv1d weight-gradient tap in [n, c, 3] layout
   int skip_sep;            // rows with (m % rps_in) == rps_in-1 are not stored at all
-  int vec_ok;              // set by launch_gemm_group: every pointer / leading dimension allows 128-bit accesses
+  int vec_ok;              // set by launch_gemm_group: 1 = every pointer / leading dimension allows 128-bit accesses, 2 = 256-bit
 };
 
 struct GemmGroup {
@@ -119,6 +119,7 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+int debug_tmem_ld_rate(int iters, int mode, int blocks, float* out, float* sink, cudaStream_t stream);
 int debug_mma_rate(int n, int iters, int per_commit, int kstep_bytes, int blocks, float* out, cudaStream_t stream);
 
 }  // namespace uv

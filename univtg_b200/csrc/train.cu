@@ -75,7 +75,7 @@ struct TrainWs {
   uint16_t *hA, *h1, *hc2, *hs2, *br16;
   float *pred_logits, *pred_spans, *vid_mem_proj, *txt_mem_proj;  // copies of the outputs the backward needs
   // ---- backward scratch ----
-  float *dx, *dy, *dqkv32, *delta, *dz, *dxt_pool, *dA_v, *dA_t;
+  float *dx, *dy, *dqkv32, *delta, *dz, *dxt_pool, *dA_v, *dA_t, *wtap;
   uint16_t *dbr16, *dhpre16, *dO16, *dqkv16, *dhc2, *dhs2, *dh1, *dxv16, *dxt16;
   size_t total;
 };
@@ -144,6 +144,12 @@ TrainWs make_train_ws(const univtg_config& c, const univtg_shape& s, const Packe
   w.dxt_pool = take32(Mt * d);
   w.dA_v = take32(Mv * max_din_v);
   w.dA_t = take32(Mt * max_din_t);
+  {  // tap-major planes of one conv weight gradient; also the K-padded copy of a projector weight gradient whose width is not a multiple of 8
+    size_t n = (size_t)3 * d * d;
+    if ((size_t)d * max_din_v > n) n = (size_t)d * max_din_v;
+    if ((size_t)d * max_din_t > n) n = (size_t)d * max_din_t;
+    w.wtap = take32(n);
+  }
   w.dbr16 = take16(M * d);
   w.dhpre16 = take16(M * ff);
   w.dO16 = take16(M * d);
@@ -577,9 +583,9 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       p.cb = OperandCoord{0, 1, 0, 0, t, 0, 0, 1};      // cols n0 (in channel), rows t + k
       int r = make_tmap_2d(&p.tm_a, dY, (uint64_t)Mh + 2, (uint64_t)Nc, (uint64_t)ldy, 64, 64);
       r |= make_tmap_2d(&p.tm_b, X, (uint64_t)Mh + 2, (uint64_t)Cin, (uint64_t)ldx, 64, 64);
-      p.out32 = gw + t;
-      p.ld32 = 3 * Cin;
-      p.cs32 = 3;
+      (void)gw;  // written by launch_tap_interleave from the tap-major planes (256-bit stores here instead of stride-3 scalars)
+      p.out32 = T.wtap + (size_t)t * Nc * Cin;
+      p.ld32 = Cin;
       p.alpha = INV;
       return r;
     };
@@ -618,6 +624,8 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       if (rc) return rc;
       rc = launch_gemm_group(g, bn_cw, sms, st);
       if (rc) return rc;
+      rc = launch_tap_interleave(T.wtap, s == 0 ? G_cls(2) : G_span(2), d, d, st);
+      if (rc) return rc;
     }
     // ---- conv layer 1 (fused N = 2d): dgrad -> stream gradient of the video rows ----
     memset(&g, 0, sizeof(g));
@@ -641,6 +649,8 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       for (int t = 0; t < 3; ++t) rc |= conv_wgrad(g.p[t], T.dh1 + s * d, 2 * d, d, T.hA, d, d, t, s == 0 ? G_cls(0) : G_span(0));
       if (rc) return rc;
       rc = launch_gemm_group(g, bn_cw, sms, st);
+      if (rc) return rc;
+      rc = launch_tap_interleave(T.wtap, s == 0 ? G_cls(0) : G_span(0), d, d, st);
       if (rc) return rc;
     }
   }
@@ -812,11 +822,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       const int num_kv = (L + 127) / 128;
       a.dq_atomic = (!tc || num_kv > 1) ? 1 : 0;
       fused16 = !a.dq_atomic;  // one key tile: the kernel emits the 16-bit operands and the in_proj_bias gradient itself
-      if (fused16) {
-        a.dqkv16 = T.dqkv16;
-        a.colsum = G_layer(l, 1);
-        a.colsum_scale = INV;
-      }
+      if (fused16) a.dqkv16 = T.dqkv16;  // (the kernel could also accumulate the column sums; a separate pass measured faster)
       if (a.dq_atomic) cudaMemsetAsync(T.dqkv32, 0, (size_t)M * 3 * d * 4, st);
       if (tc) {
         if (make_tmap_2d(&a.tm_qkv, T.qkv16[l], (uint64_t)M, (uint64_t)3 * d, (uint64_t)3 * d, 128, 64)) return 1;
@@ -827,10 +833,9 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       }
       if (rc) return rc;
     }
-    if (!fused16) {
-      rc = launch_cvt16_colsum(T.dqkv32, 3 * d, T.dqkv16, 3 * d, M, 3 * d, FMT_G, G_layer(l, 1), INV, st);
-      if (rc) return rc;
-    }
+    if (!fused16) rc = launch_cvt16_colsum(T.dqkv32, 3 * d, T.dqkv16, 3 * d, M, 3 * d, FMT_G, G_layer(l, 1), INV, st);
+    else rc = launch_colsum16(T.dqkv16, 3 * d, M, 3 * d, FMT_G, G_layer(l, 1), INV, st);  // in_proj_bias gradient
+    if (rc) return rc;
     // ---- in-projections: dgrad dx = dy + [dq|dk|dv] [Wq;Wk;Wv]; wgrad dWqk = [dq|dk]^T (x+pos), dWv = dv^T x ----
     memset(&g, 0, sizeof(g));
     g.num = 1;
@@ -894,20 +899,25 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.num = 2;
     g.fmt = fmt;
     const int kpv = Lw.vid[i].kpad, kpt = Lw.txt[i].kpad, dinv = Lw.vid[i].din, dint = Lw.txt[i].din;
-    const int bn = bn_for(sms, 64, d, dinv, d, dint);
+    // a width like 2818 would force scalar epilogue stores: write rows padded to kpad with 256-bit stores, then a pitched copy
+    const bool pad_v = (dinv % 8) != 0;
+    const int nv = pad_v ? kpv : dinv;  // the operand a_vid[i] is zero beyond dinv
+    const int bn = bn_for(sms, 64, d, nv, d, dint);
     const int bn_pd = bn_for(sms, 64, Mv, kpv, Mt, kpt);
-    rc |= setup_gemm(g.p[0], Mat16{T.dxv16, Mv, d, d}, 1, Mat16{T.a_vid[i], Mv, kpv, kpv}, 1, d, dinv, Mv, bn);
+    rc |= setup_gemm(g.p[0], Mat16{T.dxv16, Mv, d, d}, 1, Mat16{T.a_vid[i], Mv, kpv, kpv}, 1, d, nv, Mv, bn);
     rc |= setup_gemm(g.p[1], Mat16{T.dxt16, Mt, d, d}, 1, Mat16{T.a_txt[i], Mt, kpt, kpt}, 1, d, dint, Mt, bn);
     if (rc) return rc;
     g.p[0].a_fmt = g.p[1].a_fmt = FMT_G;
     g.p[0].b_fmt = g.p[1].b_fmt = fmt;
-    g.p[0].out32 = G_vid(i, 2);
-    g.p[0].ld32 = dinv;
+    g.p[0].out32 = pad_v ? T.wtap : G_vid(i, 2);
+    g.p[0].ld32 = nv;
     g.p[1].out32 = G_txt(i, 2);
     g.p[1].ld32 = dint;
     g.p[0].alpha = g.p[1].alpha = INV;
     rc = launch_gemm_group(g, bn, sms, st);
     if (rc) return rc;
+    if (pad_v)
+      cudaMemcpy2DAsync(G_vid(i, 2), (size_t)dinv * 4, T.wtap, (size_t)kpv * 4, (size_t)dinv * 4, (size_t)d, cudaMemcpyDeviceToDevice, st);
     // dgrad: dA_i = dOut W_i  (fp32, [rows, kpad_i]: N is padded to the packed weight's K so the epilogue stays on its
     // 128-bit path even for the 2818-wide video features; the padded columns are zeros).  The input-dropout mask is applied
     // by the LayerNorm backward when it loads dA.
