@@ -175,6 +175,21 @@ int univtg_adamw_step(float* params, float* grads, float* exp_avg, float* exp_av
                       float beta2, float eps, float weight_decay, int32_t step, float max_grad_norm,
                       int32_t write_clipped_grads, float* scratch2, void* stream);
 
+/* Post-forward decode of the reference's MR evaluation loop, on the device.
+ * univtg_decode_mr = main/inference_mr.py:112-120,146-157 (and main_gradio.py:100-106 with duration == NULL):
+ *   score = pred_logits[b,l] (0 where timestamp_mask[b,l] == 0); (st, ed) = (timestamp + pred_spans)[b,l] * duration[b], clamped to
+ *   [0, duration[b]] (no scaling / clamping when duration == NULL); rows [st, ed, score] sorted by score, descending, ties in clip
+ *   order (Python's stable sort) when sort != 0.  windows [B,Lv,3] f32 receives the rows, windows_r4 [B,Lv,3] f64 (optional) the
+ *   same numbers rounded like float(f"{e:.4f}") (exact), order [B,Lv] (optional) the source clip index of every row.  Lv <= 4096.
+ * univtg_temporal_nms = utils/temporal_nms.py:25-74 as called by main/inference_mr.py:31-40: per sample, the first
+ *   min(n, max_before_nms) rows of windows [B,n,3] f64 (sorted by score) go through greedy NMS with the reference's
+ *   intersection / convex-hull "IoU" > nms_thd test in IEEE double; out [B,max_after_nms,3] f64, counts [B] rows kept. */
+int univtg_decode_mr(const float* pred_logits, const float* pred_spans, const float* timestamp, const float* timestamp_mask,
+                     const float* duration, int32_t B, int32_t Lv, int32_t sort, float* windows, double* windows_r4, int32_t* order,
+                     void* stream);
+int univtg_temporal_nms(const double* windows, int32_t B, int32_t n, int32_t max_before_nms, double nms_thd, int32_t max_after_nms,
+                        double* out, int32_t* counts, void* stream);
+
 /* LayerNorm rows: in [rows,d] f32 -> out32 [rows,d] f32 and/or out16 [rows,ld16] 16-bit (zero padded). */
 int univtg_op_layernorm(const float* in, int32_t rows, int32_t d, const float* gamma, const float* beta, float eps,
                         int32_t fmt, float* out32, void* out16, int32_t ld16, void* stream);

@@ -60,6 +60,9 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_void_p]),
     "univtg_backward_stages": (c_int, [ctypes.POINTER(Config), c_void_p, c_int]),
     "univtg_plan_set_grad_events": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_int]),
+    "univtg_decode_mr": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                 c_void_p]),
+    "univtg_temporal_nms": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "univtg_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_size_t, c_float, c_float, c_float, c_float,
                                   c_float, c_int, c_float, c_int, c_void_p, c_void_p]),
     "univtg_plan_set_profiling": (c_int, [c_void_p, c_int]),
