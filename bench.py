@@ -425,6 +425,38 @@ def main():
         model.use_cuda_graphs = False
         model.train()
 
+    # ------------------- decode + temporal NMS of the evaluation loop, inference workloads ----------
+    postproc_line = None
+    if not train and rank == 0:
+        from univtg_b200 import postproc as pp
+        durs = [150.0] * B
+        ts = ((torch.arange(Lv, dtype=torch.float32, device=dev) + 0.5) / Lv)[None, :, None].expand(B, Lv, 2).contiguous()
+        with torch.no_grad():
+            out = model(**dev_batches[0])
+        tgt = {"timestamp": ts, "timestamp_mask": dev_batches[0]["src_vid_mask"]}
+
+        def post():
+            dec = pp.decode_mr(out, tgt, durs)
+            return dec, pp.temporal_nms(dec["windows_r4"], 0.7, 10, 10)
+        for _ in range(3):
+            post()
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(20):
+            dec, _ = post()
+        p1.record()
+        torch.cuda.synchronize()
+        gpu_us = p0.elapsed_time(p1) / 20 * 1e3
+        from oracle import postproc_oracle as PO  # CPU leg: the reference's Python decode + NMS on the same outputs
+        cpu_out = {k: out[k].cpu() for k in ("pred_logits", "pred_spans")}
+        t0 = time.perf_counter()
+        rows = PO.decode_mr(cpu_out["pred_logits"], cpu_out["pred_spans"], ts.cpu(), tgt["timestamp_mask"].cpu(), durs)
+        PO.post_processing_mr_nms(rows, 0.7, 10, 10)
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        postproc_line = {"what": "decode_mr + temporal_nms(0.7, 10, 10) on one batch", "gpu_us_per_batch": gpu_us,
+                         "cpu_port_ms_per_batch": cpu_ms, "bit_exact_vs_port": bool(dec["windows_r4"].cpu().tolist() == rows)}
+
     # ------------------- per-kernel-class durations of the forward (CUDA events between launches) ---------------------
     kind_ms = {0: [], 1: [], 2: []}
     n_kind = {0: 0, 1: 0, 2: 0}
@@ -500,6 +532,8 @@ def main():
         }
         if fwd_only is not None:
             line["forward_only"] = fwd_only
+        if postproc_line is not None:
+            line["postproc"] = postproc_line
         if n_gpus == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cfg, wl, args.workload)
         print(json.dumps(line), flush=True)
