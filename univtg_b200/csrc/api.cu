@@ -189,17 +189,17 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
   {
     // per-launch tile widths: fill the SMs with as little wave quantisation as possible
     const int sms = P->num_sms;
-    auto bn2 = [&](int M0, int N0, int M1, int N1) {
-      const int Ms[2] = {M0, M1}, Ns[2] = {N0, N1};
-      return choose_bn(Ms, Ns, nullptr, M1 > 0 ? 2 : 1, sms, 16);
+    auto bn2 = [&](int M0, int N0, int K0, int M1, int N1, int K1) {  // K in elements
+      const int Ms[2] = {M0, M1}, Ns[2] = {N0, N1}, kb[2] = {(K0 + 63) / 64, (K1 + 63) / 64};
+      return choose_bn(Ms, Ns, kb, M1 > 0 ? 2 : 1, sms, 16);
     };
-    for (int i = 0; i < cfg->n_input_proj; ++i) P->bn_proj[i] = bn2(P->Mv, d, P->Mt, d);
-    P->bn_qkv = bn2(P->M, 2 * d, P->M, d);
-    P->bn_out = bn2(P->M, d, 0, 0);
-    P->bn_ffn1 = bn2(P->M, ff, 0, 0);
-    P->bn_ffn2 = bn2(P->M, d, 0, 0);
-    P->bn_conv1 = bn2(P->Mh, 2 * d, 0, 0);
-    P->bn_conv2 = bn2(P->Mh, d, P->Mh, d);
+    for (int i = 0; i < cfg->n_input_proj; ++i) P->bn_proj[i] = bn2(P->Mv, d, Lw.vid[i].kpad, P->Mt, d, Lw.txt[i].kpad);
+    P->bn_qkv = bn2(P->M, 2 * d, d, P->M, d, d);
+    P->bn_out = bn2(P->M, d, d, 0, 0, 0);
+    P->bn_ffn1 = bn2(P->M, ff, d, 0, 0, 0);
+    P->bn_ffn2 = bn2(P->M, d, ff, 0, 0, 0);
+    P->bn_conv1 = bn2(P->Mh, 2 * d, 3 * d, 0, 0, 0);
+    P->bn_conv2 = bn2(P->Mh, d, 3 * d, P->Mh, d, 3 * d);
   }
 
   // ---- input projectors: one grouped launch per projector depth (video + text problems) ----

@@ -28,23 +28,22 @@ struct AttnBwdCfg {
   static constexpr uint32_t kTmemCols = 512;
 };
 
-// 32 fp32 accumulator columns of this thread's row -> 16-bit at dqkv16[elem_off ..], and their column sums over the warp's
-// 32 rows -> colsum[col0 + lane] (one atomic per lane).  Warp-collective; rows with valid == false contribute zeros.
+// 32 fp32 accumulator columns of this thread's row -> 16-bit at dqkv16[elem_off ..] (single-key-tile fast path: the values are
+// final, so they go straight to the operand buffer of the in-projection dgrad / wgrad GEMMs; the in_proj_bias gradient is a
+// separate column-sum pass over that buffer - accumulating it here with a transposing warp reduction measured slower).
 __device__ __forceinline__ void store16_colsum(const AttnBwdArgs& a, const uint32_t (&r)[32], bool valid, size_t elem_off, int col0,
                                                int lane) {
-  float v[32];
-#pragma unroll
-  for (int e = 0; e < 32; ++e) v[e] = valid ? __uint_as_float(r[e]) : 0.f;
+  (void)col0;
+  (void)lane;
   if (valid) {
     uint16_t* dst = a.dqkv16 + elem_off;
 #pragma unroll
     for (int e = 0; e < 32; e += 8)
-      *reinterpret_cast<uint4*>(dst + e) = make_uint4(cvt16x2(v[e], v[e + 1], a.fmt_grad), cvt16x2(v[e + 2], v[e + 3], a.fmt_grad),
-                                                      cvt16x2(v[e + 4], v[e + 5], a.fmt_grad), cvt16x2(v[e + 6], v[e + 7], a.fmt_grad));
-  }
-  if (a.colsum != nullptr) {
-    const float cs = warp_colsum32(v, lane);
-    atomicAdd(a.colsum + col0 + lane, cs * a.colsum_scale);
+      *reinterpret_cast<uint4*>(dst + e) =
+          make_uint4(cvt16x2(__uint_as_float(r[e]), __uint_as_float(r[e + 1]), a.fmt_grad),
+                     cvt16x2(__uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]), a.fmt_grad),
+                     cvt16x2(__uint_as_float(r[e + 4]), __uint_as_float(r[e + 5]), a.fmt_grad),
+                     cvt16x2(__uint_as_float(r[e + 6]), __uint_as_float(r[e + 7]), a.fmt_grad));
   }
 }
 

@@ -570,18 +570,25 @@ __global__ void __launch_bounds__(128) head_dw_kernel(const HeadFinalBwdArgs a) 
         cu[j] = ns[j];
       }
     }
+    // this thread's 8 channels x 3 taps are 24 consecutive floats of each [.., d, 3] weight gradient: six 128-bit reductions
+    const float gsc = a.pgrad_scale;
+    float* dsts[3] = {a.gw_cls + (size_t)c * 3, a.gw_span + (size_t)c * 3, a.gw_span + ((size_t)a.d + c) * 3};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int w = 0; w < 3; ++w) {
+      float flat[24];
 #pragma unroll
-      for (int t = 0; t < 3; ++t) {
-        atomicAdd(a.gw_cls + (size_t)(c + j) * 3 + t, wc[t][j] * a.pgrad_scale);
-        atomicAdd(a.gw_span + (size_t)(c + j) * 3 + t, w0[t][j] * a.pgrad_scale);
-        atomicAdd(a.gw_span + ((size_t)a.d + c + j) * 3 + t, w1[t][j] * a.pgrad_scale);
-      }
-      if (a.cs_cls) {
-        atomicAdd(a.cs_cls + c + j, cs_c[j] * a.pgrad_scale);
-        atomicAdd(a.cs_span + c + j, cs_s[j] * a.pgrad_scale);
-      }
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int t = 0; t < 3; ++t) flat[j * 3 + t] = (w == 0 ? wc[t][j] : (w == 1 ? w0[t][j] : w1[t][j])) * gsc;
+#pragma unroll
+      for (int q = 0; q < 6; ++q)
+        red_add_f32x4(dsts[w] + 4 * q, make_float4(flat[4 * q], flat[4 * q + 1], flat[4 * q + 2], flat[4 * q + 3]));
+    }
+    if (a.cs_cls) {
+      red_add_f32x4(a.cs_cls + c, make_float4(cs_c[0] * gsc, cs_c[1] * gsc, cs_c[2] * gsc, cs_c[3] * gsc));
+      red_add_f32x4(a.cs_cls + c + 4, make_float4(cs_c[4] * gsc, cs_c[5] * gsc, cs_c[6] * gsc, cs_c[7] * gsc));
+      red_add_f32x4(a.cs_span + c, make_float4(cs_s[0] * gsc, cs_s[1] * gsc, cs_s[2] * gsc, cs_s[3] * gsc));
+      red_add_f32x4(a.cs_span + c + 4, make_float4(cs_s[4] * gsc, cs_s[5] * gsc, cs_s[6] * gsc, cs_s[7] * gsc));
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // bias gradients: sum of dz over this slab

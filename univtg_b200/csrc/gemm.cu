@@ -336,7 +336,10 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       // number of 16-column steps this warp owns in this tile (warp-uniform)
       int nsteps = (pN - n_base + 15) / 16;
       nsteps = nsteps < 0 ? 0 : (nsteps > my_steps ? my_steps : nsteps);
-      const bool load_resid = vec && valid && (resid_row != nullptr);
+      // the fp32 side input of a step (residual, or the aux multiplier when there is no residual) is fetched one step ahead
+      const float* side_row = resid_row != nullptr ? resid_row : ((FULL && aux_row != nullptr) ? aux_row : nullptr);
+      const bool aux_prefetched = FULL && resid_row == nullptr && side_row != nullptr;
+      const bool load_resid = vec && valid && (side_row != nullptr);
       uint32_t r[16];
       float rv_next[16];
       // software pipeline: the TMEM load and the residual loads of step c+1 are in flight while step c is processed
@@ -344,12 +347,12 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
         tmem_ld_32x32b_x16(t_addr, r);
         if (load_resid) {
           if (v256) {
-            ld_global_256f(resid_row + n_base, rv_next);
-            ld_global_256f(resid_row + n_base + 8, rv_next + 8);
+            ld_global_256f(side_row + n_base, rv_next);
+            ld_global_256f(side_row + n_base + 8, rv_next + 8);
           } else {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float4 t4 = *reinterpret_cast<const float4*>(resid_row + n_base + 4 * q);
+              const float4 t4 = *reinterpret_cast<const float4*>(side_row + n_base + 4 * q);
               rv_next[4 * q] = t4.x; rv_next[4 * q + 1] = t4.y; rv_next[4 * q + 2] = t4.z; rv_next[4 * q + 3] = t4.w;
             }
           }
@@ -372,12 +375,12 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           tmem_ld_32x32b_x16(t_addr + (c + 1) * 16, r);
           if (load_resid) {
             if (v256) {
-              ld_global_256f(resid_row + n0 + 16, rv_next);
-              ld_global_256f(resid_row + n0 + 24, rv_next + 8);
+              ld_global_256f(side_row + n0 + 16, rv_next);
+              ld_global_256f(side_row + n0 + 24, rv_next + 8);
             } else {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const float4 t4 = *reinterpret_cast<const float4*>(resid_row + n0 + 16 + 4 * q);
+                const float4 t4 = *reinterpret_cast<const float4*>(side_row + n0 + 16 + 4 * q);
                 rv_next[4 * q] = t4.x; rv_next[4 * q + 1] = t4.y; rv_next[4 * q + 2] = t4.z; rv_next[4 * q + 3] = t4.w;
               }
             }
@@ -411,15 +414,23 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
               for (int j = 0; j < 16; ++j) v[j] += rv[j];
             }
             if (FULL && aux_row != nullptr) {
+              float av[16];
+              if (aux_prefetched) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 a4 = *reinterpret_cast<const float4*>(aux_row + n0 + 4 * q);
-                if (aux_mode == 1) {
-                  v[4 * q] *= gelu_erf_grad(a4.x); v[4 * q + 1] *= gelu_erf_grad(a4.y);
-                  v[4 * q + 2] *= gelu_erf_grad(a4.z); v[4 * q + 3] *= gelu_erf_grad(a4.w);
-                } else {
-                  v[4 * q] *= a4.x; v[4 * q + 1] *= a4.y; v[4 * q + 2] *= a4.z; v[4 * q + 3] *= a4.w;
+                for (int j = 0; j < 16; ++j) av[j] = rv[j];
+              } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 a4 = *reinterpret_cast<const float4*>(aux_row + n0 + 4 * q);
+                  av[4 * q] = a4.x; av[4 * q + 1] = a4.y; av[4 * q + 2] = a4.z; av[4 * q + 3] = a4.w;
                 }
+              }
+              if (aux_mode == 1) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] *= gelu_erf_grad(av[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] *= av[j];
               }
             }
             if (FULL && mask_row != nullptr) {
@@ -435,9 +446,10 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
               }
             }
             if (o32_row != nullptr) {
-              if (FULL && atomic) {
+              if (FULL && atomic) {  // split-K / accumulate: 128-bit reductions (4x fewer L2 atomic operations than scalar REDs)
 #pragma unroll
-                for (int j = 0; j < 16; ++j) atomicAdd(o32_row + n0 + j, v[j]);
+                for (int q = 0; q < 4; ++q)
+                  red_add_f32x4(o32_row + n0 + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
               } else if (v256) {
                 st_global_256f(o32_row + n0, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
                 st_global_256f(o32_row + n0 + 8, v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
@@ -524,11 +536,8 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           }
         }
         if (FULL && colsum != nullptr) {  // warp-uniform: column sums over this warp's 32 rows, one atomic per column
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float sj = warp_sum(v[j]);
-            if (lane == j && n0 + j < pN) atomicAdd(colsum + n0 + j, sj * pr.colsum_scale);
-          }
+          const float sj = warp_colsum16(v, lane);  // 16 shuffles; lane l holds column l & 15
+          if (lane < 16 && n0 + lane < pN) atomicAdd(colsum + n0 + lane, sj * pr.colsum_scale);
         }
       }
       };
@@ -809,7 +818,7 @@ int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
                ((!pr.out16 && !pr.out16p) || (pr.ld16 % 8 == 0 && al16(pr.out16) && al16(pr.out16p)));
     auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
     // 256-bit accesses (one whole 32-byte sector per thread and instruction) when every leading dimension keeps rows 32-byte aligned
-    if (w.vec_ok && (!pr.pre32 || (al32(pr.pre32) && pr.ld_pre % 8 == 0)) && (!pr.resid || (al32(pr.resid) && pr.ld_resid % 8 == 0)) &&
+    if (w.vec_ok && (!pr.pre32 || (al32(pr.pre32) && pr.ld_pre % 8 == 0)) && (!pr.aux32 || (al32(pr.aux32) && pr.ld_aux % 8 == 0)) && (!pr.resid || (al32(pr.resid) && pr.ld_resid % 8 == 0)) &&
         (!pr.out32 || (al32(pr.out32) && pr.ld32 % 8 == 0)) && (!pr.out32_id || (al32(pr.out32_id) && pr.ld32_id % 8 == 0)) &&
         ((!pr.out16 && !pr.out16p) || (pr.ld16 % 16 == 0 && al32(pr.out16) && al32(pr.out16p))))
       w.vec_ok = 2;
@@ -855,24 +864,48 @@ int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
   return 0;
 }
 
-// Tile width that minimises (waves x per-tile time) for a set of problems sharing one launch.
-//   tiles(bn) = sum_p ceil(M_p/128) * ceil(N_p/bn) * ksplit_p ;  cost = ceil(tiles / sms) * (bn + fixed)
-// `step` = 16 for K-major B, 64 for MN-major B.
-int choose_bn(const int* Ms, const int* Ns, const int* ksplits, int num, int num_sms, int step) {
-  int best = 256;
-  long best_cost = -1;
-  for (int bn = 256; bn >= 64; bn -= step) {
-    long tiles = 0;
-    for (int p = 0; p < num; ++p)
-      tiles += (long)((Ms[p] + GEMM_BM - 1) / GEMM_BM) * ((Ns[p] + bn - 1) / bn) * (ksplits ? ksplits[p] : 1);
-    const long waves = (tiles + num_sms - 1) / num_sms;
-    const long cost = waves * (bn + 40);  // +40: per-tile fixed cost (pipeline fill, epilogue tail) in "column" units
-    if (best_cost < 0 || cost < best_cost) {
-      best_cost = cost;
-      best = bn;
+// Tile width (and split-K factor) that minimise the modelled time of one grouped launch.  Constants are measurements on B200
+// (profiles/README.md): a 64-wide k-block costs ~0.41 us per CTA WHATEVER the tile width (tcgen05.mma M128 x N x K16 retires
+// every ~95 ns for any N <= 256), ~2 us from kernel entry to the first MMA, an epilogue of ~0.5 us + 2.5 us x bn/256 (4 us x
+// bn/256 with split-K reductions), of which only a fraction is exposed when a CTA has further tiles to run.
+//   kblocks[p] = 64-wide k-blocks of problem p (taps included); max_split = 1 disables split-K.
+TileChoice choose_tile(const int* Ms, const int* Ns, const int* kblocks, int num, int num_sms, int step, int max_split) {
+  TileChoice best{256, 1};
+  double best_t = -1.0;
+  for (int ks = 1; ks <= max_split; ks *= 2) {
+    bool ok = true;
+    for (int p = 0; p < num; ++p) ok = ok && (ks == 1 || ks * 4 <= kblocks[p]);
+    if (!ok) break;
+    for (int bn = 256; bn >= 64; bn -= step) {
+      // persistent CTAs take whole tiles round-robin (tile t -> CTA t % sms, problems in order): k-blocks of the busiest CTA
+      long tiles = 0;
+      long load[256];
+      const int ncta = num_sms < 256 ? num_sms : 256;
+      for (int i = 0; i < ncta; ++i) load[i] = 0;
+      for (int p = 0; p < num; ++p) {
+        const long t = (long)((Ms[p] + GEMM_BM - 1) / GEMM_BM) * ((Ns[p] + bn - 1) / bn) * ks;
+        const int kb = (kblocks[p] + ks - 1) / ks;
+        for (long i = 0; i < t; ++i) load[(tiles + i) % ncta] += kb;
+        tiles += t;
+      }
+      long kb_cta = 0;
+      for (int i = 0; i < ncta; ++i) kb_cta = load[i] > kb_cta ? load[i] : kb_cta;
+      const long rounds = (tiles + ncta - 1) / ncta;
+      const double epi = 0.5 + bn * (ks > 1 ? 4.0 : 2.5) / 256.0;
+      const double t = 2.0 + 0.41 * (double)kb_cta + epi * (1.0 + 0.3 * (double)(rounds - 1));
+      if (best_t < 0 || t < best_t - 1e-9) {
+        best_t = t;
+        best = TileChoice{bn, ks};
+      }
     }
   }
   return best;
+}
+
+// Tile width only (no split-K), K = 1024 assumed when the caller has no k extents at hand.
+int choose_bn(const int* Ms, const int* Ns, const int* kblocks, int num, int num_sms, int step) {
+  int kb16[GEMM_MAX_GROUP] = {16, 16, 16, 16};
+  return choose_tile(Ms, Ns, kblocks ? kblocks : kb16, num, num_sms, step, 1).bn;
 }
 
 }  // namespace uv

@@ -87,7 +87,11 @@ struct GemmGroup {
 // bn: tile width, multiple of 16 in [32, 256] (multiple of 64 when a problem has an MN-major B).  Returns cudaError_t as int.
 int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream);
 // Tile width minimising waves x tile-time for problems that share a launch (step 16: K-major B, 64: MN-major B).
-int choose_bn(const int* Ms, const int* Ns, const int* ksplits, int num, int num_sms, int step);
+struct TileChoice {
+  int bn, ksplit;
+};
+TileChoice choose_tile(const int* Ms, const int* Ns, const int* kblocks, int num, int num_sms, int step, int max_split);
+int choose_bn(const int* Ms, const int* Ns, const int* kblocks, int num, int num_sms, int step);
 
 // Encode a 2-D tensor map over a row-major 16-bit matrix [rows, cols] with row pitch `ld` elements,
 // box {box_cols, box_rows}, 128-byte swizzle, zero fill out of bounds.  Returns 0 on success.

@@ -308,6 +308,20 @@ UV_DEVINL float warp_colsum32(float (&v)[32], int lane) {
   }
   return v[0];
 }
+// Same for 16 values per lane: on return every lane l holds the sum over all 32 lanes of their v[l & 15] (v is clobbered).
+UV_DEVINL float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      const float send = hi ? v[k] : v[k + off];
+      const float keep = hi ? v[k + off] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
 UV_DEVINL float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

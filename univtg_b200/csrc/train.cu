@@ -37,30 +37,18 @@ int setup_gemm(GemmProblem& p, Mat16 A, int a_mn, Mat16 B, int b_mn, int M, int 
 
 inline int pick_bn(int N) { return (N % 256 == 0) ? 256 : 128; }
 
-// tile width for a launch of up to 2 problems (step 64 when a B operand is MN-major)
-inline int bn_for(int sms, int step, int M0, int N0, int M1 = 0, int N1 = 0) {
-  const int Ms[2] = {M0, M1}, Ns[2] = {N0, N1};
-  return choose_bn(Ms, Ns, nullptr, M1 > 0 ? 2 : 1, sms, step);
+// Tile width + split-K factor for one grouped launch (cost model: choose_tile, gemm.cu).  K in elements; step 64 when a B operand
+// is MN-major; max_split = 1 for launches whose epilogue cannot accumulate.
+struct MNK {
+  int M, N, K;
+};
+inline TileChoice tile_for(int sms, int step, int max_split, MNK a, MNK b = MNK{0, 0, 0}, MNK c3 = MNK{0, 0, 0}) {
+  const int Ms[3] = {a.M, b.M, c3.M}, Ns[3] = {a.N, b.N, c3.N}, kb[3] = {(a.K + 63) / 64, (b.K + 63) / 64, (c3.K + 63) / 64};
+  const int num = c3.M > 0 ? 3 : (b.M > 0 ? 2 : 1);
+  return choose_tile(Ms, Ns, kb, num, sms, step, max_split);
 }
+inline int bn_for(int sms, int step, MNK a, MNK b = MNK{0, 0, 0}) { return tile_for(sms, step, 1, a, b).bn; }
 
-inline int bn_for3(int sms, int step, int M, int N) {  // three equal problems in one launch (conv weight-gradient taps)
-  const int Ms[3] = {M, M, M}, Ns[3] = {N, N, N};
-  return choose_bn(Ms, Ns, nullptr, 3, sms, step);
-}
-
-inline int pick_ksplit2(int M0, int N0, int M1, int N1, int bn, int kblocks, int num_sms) {
-  const int tiles = ((M0 + GEMM_BM - 1) / GEMM_BM) * ((N0 + bn - 1) / bn) + ((M1 + GEMM_BM - 1) / GEMM_BM) * ((N1 + bn - 1) / bn);
-  int ks = 1;
-  while (tiles * ks * 2 <= num_sms && ks * 2 <= kblocks / 4 && ks < 16) ks *= 2;
-  return ks;
-}
-
-inline int pick_ksplit(int M, int N, int bn, int kblocks, int num_sms) {
-  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + bn - 1) / bn);
-  int ks = 1;
-  while (tiles * ks * 2 <= num_sms && ks * 2 <= kblocks / 4 && ks < 16) ks *= 2;
-  return ks;
-}
 
 struct TrainWs {
   // ---- saved by the forward ----
@@ -569,6 +557,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       return r;
     };
     // wgrad of one tap: dW[n, c, t] = sum_m dY[m, n] X[m + t - 1, c]  -> written with column stride 3 into [N, C, 3]
+    const TileChoice t_cw = tile_for(sms, 64, 8, MNK{d, d, Mh}, MNK{d, d, Mh}, MNK{d, d, Mh});
     auto conv_wgrad = [&](GemmProblem& p, const uint16_t* dY, int ldy, int Nc, const uint16_t* X, int ldx, int Cin, int t,
                           float* gw) -> int {
       init_problem(p);
@@ -587,9 +576,11 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       p.out32 = T.wtap + (size_t)t * Nc * Cin;
       p.ld32 = Cin;
       p.alpha = INV;
+      p.ksplit = t_cw.ksplit;
       return r;
     };
-    const int bn_c2d = bn_for(sms, 64, Mh, d, Mh, d), bn_c1d = bn_for(sms, 64, Mh, d), bn_cw = bn_for3(sms, 64, d, d);
+    const int bn_c2d = bn_for(sms, 64, MNK{Mh, d, 3 * d}, MNK{Mh, d, 3 * d}), bn_c1d = bn_for(sms, 64, MNK{Mh, d, 6 * d});
+    const int bn_cw = t_cw.bn;
     const int bn = bn_c2d;
     // ---- conv layer 2 (two heads): dgrad -> dh1 [Mh+2, 2d] (class cols [0,d), span cols [d,2d)), ReLU mask of h1 ----
     memset(&g, 0, sizeof(g));
@@ -622,6 +613,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       for (int t = 0; t < 3; ++t)
         rc |= conv_wgrad(g.p[t], s == 0 ? T.dhc2 : T.dhs2, d, d, T.h1 + s * d, 2 * d, d, t, s == 0 ? G_cls(2) : G_span(2));
       if (rc) return rc;
+      if (t_cw.ksplit > 1) cudaMemsetAsync(T.wtap, 0, (size_t)3 * d * d * 4, st);  // split-K accumulates into the planes
       rc = launch_gemm_group(g, bn_cw, sms, st);
       if (rc) return rc;
       rc = launch_tap_interleave(T.wtap, s == 0 ? G_cls(2) : G_span(2), d, d, st);
@@ -648,6 +640,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       g.fmt = fmt;
       for (int t = 0; t < 3; ++t) rc |= conv_wgrad(g.p[t], T.dh1 + s * d, 2 * d, d, T.hA, d, d, t, s == 0 ? G_cls(0) : G_span(0));
       if (rc) return rc;
+      if (t_cw.ksplit > 1) cudaMemsetAsync(T.wtap, 0, (size_t)3 * d * d * 4, st);
       rc = launch_gemm_group(g, bn_cw, sms, st);
       if (rc) return rc;
       rc = launch_tap_interleave(T.wtap, s == 0 ? G_cls(0) : G_span(0), d, d, st);
@@ -666,8 +659,11 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     const LayerPacked& lp = Lw.layer[l];
     const float* s1 = droppath_scale ? droppath_scale + (size_t)(2 * l) * B : nullptr;
     const float* s2 = droppath_scale ? droppath_scale + (size_t)(2 * l + 1) * B : nullptr;
-    const int bn_dff = bn_for(sms, 64, M, ff), bn_dd = bn_for(sms, 64, M, d);
-    const int bn_wo = bn_for(sms, 64, d, d), bn_wq = bn_for(sms, 64, 2 * d, d, d, d);
+    const int bn_dff = bn_for(sms, 64, MNK{M, ff, d}), bn_dd1 = bn_for(sms, 64, MNK{M, d, ff}), bn_ddo = bn_for(sms, 64, MNK{M, d, d}),
+              bn_ddq = bn_for(sms, 64, MNK{M, d, 3 * d});
+    const TileChoice t_wo = tile_for(sms, 64, 16, MNK{d, d, M}), t_wq = tile_for(sms, 64, 16, MNK{2 * d, d, M}, MNK{d, d, M}),
+                     t_wf = tile_for(sms, 64, 16, MNK{d, ff, M}, MNK{ff, d, M});
+    const int bn_wo = t_wo.bn, bn_wq = t_wq.bn;
     // ---- LN2 backward: dx (grad of the layer output) -> dy (grad of x1 + s2 * F), branch operand s2 * dy ----
     {
       LnBwdArgs a;
@@ -716,7 +712,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.num = 2;
     g.fmt = fmt;
     {
-      const int bnw = bn_for(sms, 64, d, ff, ff, d);
+      const int bnw = t_wf.bn;
       rc |= setup_gemm(g.p[0], Mat16{T.dbr16, M, d, d}, 1, Mat16{T.h16[l], M, ff, ff}, 1, d, ff, M, bnw);
       rc |= setup_gemm(g.p[1], Mat16{T.dhpre16, M, ff, ff}, 1, Mat16{T.x1_16[l], M, d, d}, 1, ff, d, M, bnw);
       if (rc) return rc;
@@ -727,7 +723,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       g.p[1].out32 = G_layer(l, 4);  // linear1.weight [ff, d]
       g.p[1].ld32 = d;
       g.p[0].alpha = g.p[1].alpha = INV;
-      g.p[0].ksplit = g.p[1].ksplit = pick_ksplit2(d, ff, ff, d, bnw, (M + 63) / 64, sms);
+      g.p[0].ksplit = g.p[1].ksplit = t_wf.ksplit;
       rc = launch_gemm_group(g, bnw, sms, st);
       if (rc) return rc;
     }
@@ -735,7 +731,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     memset(&g, 0, sizeof(g));
     g.num = 1;
     g.fmt = fmt;
-    rc = setup_gemm(g.p[0], Mat16{T.dhpre16, M, ff, ff}, 0, Mat16{W16(lp.w1), ff, d, d}, 1, M, d, ff, bn_dd);
+    rc = setup_gemm(g.p[0], Mat16{T.dhpre16, M, ff, ff}, 0, Mat16{W16(lp.w1), ff, d, d}, 1, M, d, ff, bn_dd1);
     if (rc) return rc;
     g.p[0].a_fmt = FMT_G;
     g.p[0].b_fmt = fmt;
@@ -743,7 +739,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.p[0].ld_resid = d;
     g.p[0].out32 = T.dx;
     g.p[0].ld32 = d;
-    rc = launch_gemm_group(g, bn_dd, sms, st);
+    rc = launch_gemm_group(g, bn_dd1, sms, st);
     if (rc) return rc;
     // ---- LN1 backward ----
     {
@@ -775,14 +771,14 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     memset(&g, 0, sizeof(g));
     g.num = 1;
     g.fmt = fmt;
-    rc = setup_gemm(g.p[0], Mat16{T.dbr16, M, d, d}, 0, Mat16{W16(lp.w_out), d, d, d}, 1, M, d, d, bn_dd);
+    rc = setup_gemm(g.p[0], Mat16{T.dbr16, M, d, d}, 0, Mat16{W16(lp.w_out), d, d, d}, 1, M, d, d, bn_ddo);
     if (rc) return rc;
     g.p[0].a_fmt = FMT_G;
     g.p[0].b_fmt = fmt;
     g.p[0].out16 = T.dO16;
     g.p[0].ld16 = d;
     g.p[0].out_fmt = FMT_G;
-    rc = launch_gemm_group(g, bn_dd, sms, st);
+    rc = launch_gemm_group(g, bn_ddo, sms, st);
     if (rc) return rc;
     memset(&g, 0, sizeof(g));
     g.num = 1;
@@ -794,7 +790,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.p[0].out32 = G_layer(l, 2);
     g.p[0].ld32 = d;
     g.p[0].alpha = INV;
-    g.p[0].ksplit = pick_ksplit(d, d, bn_wo, (M + 63) / 64, sms);
+    g.p[0].ksplit = t_wo.ksplit;
     rc = launch_gemm_group(g, bn_wo, sms, st);
     if (rc) return rc;
     // ---- attention core backward -> dqkv32 -> dqkv16 (+ in_proj_bias gradient) ----
@@ -840,7 +836,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     memset(&g, 0, sizeof(g));
     g.num = 1;
     g.fmt = fmt;
-    rc = setup_gemm(g.p[0], Mat16{T.dqkv16, M, 3 * d, 3 * d}, 0, Mat16{W16(lp.w_in), 3 * d, d, d}, 1, M, d, 3 * d, bn_dd);
+    rc = setup_gemm(g.p[0], Mat16{T.dqkv16, M, 3 * d, 3 * d}, 0, Mat16{W16(lp.w_in), 3 * d, d, d}, 1, M, d, 3 * d, bn_ddq);
     if (rc) return rc;
     g.p[0].a_fmt = FMT_G;
     g.p[0].b_fmt = fmt;
@@ -848,7 +844,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.p[0].ld_resid = d;
     g.p[0].out32 = T.dx;
     g.p[0].ld32 = d;
-    rc = launch_gemm_group(g, bn_dd, sms, st);
+    rc = launch_gemm_group(g, bn_ddq, sms, st);
     if (rc) return rc;
     memset(&g, 0, sizeof(g));
     g.num = 2;
@@ -863,7 +859,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.p[1].out32 = G_layer(l, 0) + (size_t)2 * d * d;
     g.p[1].ld32 = d;
     g.p[0].alpha = g.p[1].alpha = INV;
-    g.p[0].ksplit = g.p[1].ksplit = pick_ksplit(3 * d, d, bn_wq, (M + 63) / 64, sms);
+    g.p[0].ksplit = g.p[1].ksplit = t_wq.ksplit;
     rc = launch_gemm_group(g, bn_wq, sms, st);
     if (rc) return rc;
     stage_done(1 + (c.enc_layers - 1 - l));  // encoder layer l
@@ -902,8 +898,9 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     // a width like 2818 would force scalar epilogue stores: write rows padded to kpad with 256-bit stores, then a pitched copy
     const bool pad_v = (dinv % 8) != 0;
     const int nv = pad_v ? kpv : dinv;  // the operand a_vid[i] is zero beyond dinv
-    const int bn = bn_for(sms, 64, d, nv, d, dint);
-    const int bn_pd = bn_for(sms, 64, Mv, kpv, Mt, kpt);
+    const TileChoice t_pw = tile_for(sms, 64, 16, MNK{d, nv, Mv}, MNK{d, dint, Mt});
+    const int bn = t_pw.bn;
+    const int bn_pd = bn_for(sms, 64, MNK{Mv, kpv, d}, MNK{Mt, kpt, d});
     rc |= setup_gemm(g.p[0], Mat16{T.dxv16, Mv, d, d}, 1, Mat16{T.a_vid[i], Mv, kpv, kpv}, 1, d, nv, Mv, bn);
     rc |= setup_gemm(g.p[1], Mat16{T.dxt16, Mt, d, d}, 1, Mat16{T.a_txt[i], Mt, kpt, kpt}, 1, d, dint, Mt, bn);
     if (rc) return rc;
@@ -914,6 +911,8 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.p[1].out32 = G_txt(i, 2);
     g.p[1].ld32 = dint;
     g.p[0].alpha = g.p[1].alpha = INV;
+    g.p[0].ksplit = g.p[1].ksplit = t_pw.ksplit;
+    if (pad_v && t_pw.ksplit > 1) cudaMemsetAsync(T.wtap, 0, (size_t)d * kpv * 4, st);  // split-K accumulates into the padded copy
     rc = launch_gemm_group(g, bn, sms, st);
     if (rc) return rc;
     if (pad_v)
