@@ -55,13 +55,13 @@ def case_gemm(M, N, K, a_mn, b_mn, fmt, bn, ksplit, act, use_bias, cluster=False
     return res
 
 
-def case_gemm_timeline(M, N, K, act, want32, want16, bn, cluster=False):
+def case_gemm_timeline(M, N, K, act, want32, want16, bn, cluster=False, a_mn=0, b_mn=0):
     """Per-CTA phase timeline (ns) of one GEMM launch: where does the time go?"""
     import torch
     from univtg_b200 import _lib
     lib = _lib.load_library()
-    A = torch.randn(M, K, device="cuda").half()
-    Bm = torch.randn(N, K, device="cuda").half()
+    A = torch.randn(K, M, device="cuda").half() if a_mn else torch.randn(M, K, device="cuda").half()
+    Bm = torch.randn(K, N, device="cuda").half() if b_mn else torch.randn(N, K, device="cuda").half()
     bias = torch.randn(N, device="cuda")
     out32 = torch.zeros(M, N, device="cuda") if want32 else None
     out16 = torch.zeros(M, N, device="cuda", dtype=torch.float16) if want16 else None
@@ -70,7 +70,7 @@ def case_gemm_timeline(M, N, K, act, want32, want16, bn, cluster=False):
     fn = lib.univtg_op_gemm_cluster if cluster else lib.univtg_op_gemm
 
     def run():
-        _lib.check(fn(_lib.ptr(A), _lib.ptr(Bm), M, N, K, 0, 0, 0, bn, 1, _lib.ptr(bias), act, 1.0, _lib.ptr(out32),
+        _lib.check(fn(_lib.ptr(A), _lib.ptr(Bm), M, N, K, a_mn, b_mn, 0, bn, 1, _lib.ptr(bias), act, 1.0, _lib.ptr(out32),
                       _lib.ptr(out16), _lib.stream_ptr()), "op_gemm")
     for _ in range(3):
         run()
@@ -109,6 +109,22 @@ def case_mma_rate():
                     _lib.check(lib.univtg_debug_mma_rate(n, 512, per_commit, kstep, blocks, _lib.ptr(out), _lib.stream_ptr()), "mma_rate")
                 torch.cuda.synchronize()
                 res[f"b{blocks}_n{n}_pc{per_commit}_ks{kstep}"] = round(float(out.median()), 1)
+    return res
+
+
+def case_mma_rate_major():
+    """ns per tcgen05.mma (M=128, N=256, K=16) for K-major / MN-major operand layouts (operands resident in smem)."""
+    import torch
+    from univtg_b200 import _lib
+    lib = _lib.load_library()
+    res = {"ok": True}
+    for name, flag in (("kk", 0), ("a_mn", 1 << 30), ("b_mn", 1 << 29), ("ab_mn", (1 << 30) | (1 << 29))):
+        for n in (64, 128, 256):
+            out = torch.zeros(148, device="cuda")
+            for _ in range(2):
+                _lib.check(lib.univtg_debug_mma_rate(n, 512, 4, 32 | flag, 148, _lib.ptr(out), _lib.stream_ptr()), "mma_rate")
+            torch.cuda.synchronize()
+            res[f"{name}_n{n}"] = round(float(out.median()), 1)
     return res
 
 
@@ -248,6 +264,10 @@ CASES = {
     "tlcl_plain16": (case_gemm_timeline, (3424, 1024, 1024, 0, False, True, 256, True)),
     "tlcl_qkv": (case_gemm_timeline, (3424, 3072, 1024, 0, False, True, 256, True)),
     "tl_plain16": (case_gemm_timeline, (3424, 1024, 1024, 0, False, True, 256)),
+    "tl_k3072_kmajor": (case_gemm_timeline, (3424, 1024, 3072, 0, True, False, 256, False, 0, 0)),
+    "tl_k3072_bmn": (case_gemm_timeline, (3424, 1024, 3072, 0, True, False, 256, False, 0, 1)),
+    "tl_k3072_abmn": (case_gemm_timeline, (3424, 1024, 3072, 0, True, False, 256, False, 1, 1)),
+    "tl_k3072_amn": (case_gemm_timeline, (3424, 1024, 3072, 0, True, False, 256, False, 1, 0)),
     "tl_nostore": (case_gemm_timeline, (3424, 1024, 1024, 0, False, False, 256)),
     "tl_plain16_m1664": (case_gemm_timeline, (1664, 1024, 1024, 0, False, True, 256)),
     # steady-state mainloop probes: 148 (bn 256) / 296 (bn 128) tiles of 64 k-blocks
@@ -267,6 +287,7 @@ CASES = {
     "tl_ffn1_bn128": (case_gemm_timeline, (3424, 1024, 1024, 2, False, True, 128)),
     "mma_rate": (case_mma_rate, ()),
     "tmem_ld_rate": (case_tmem_ld_rate, ()),
+    "mma_rate_major": (case_mma_rate_major, ()),
     "ln_1024": (case_layernorm, (3424, 1024, 1024, 0)),
     "ln_256_bf16": (case_layernorm, (77, 256, 256, 1)),
     "ln_2818": (case_layernorm, (300, 2818, 2880, 0)),

@@ -593,7 +593,7 @@ static int op_gemm_impl(const void* a, const void* b, int32_t M, int32_t N, int3
     rc |= make_tmap_2d(&p.tm_b, b, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)(cluster == 2 ? bn / 2 : bn), 64);
     p.b_box_rows = cluster == 2 ? bn / 2 : bn;
   } else {
-    rc |= make_tmap_2d(&p.tm_b, b, (uint64_t)K, (uint64_t)N, (uint64_t)N, 64, 64);
+    rc |= make_tmap_b_mn(p, b, (uint64_t)K, (uint64_t)N, (uint64_t)N, bn, cluster != 2);
     p.cb = OperandCoord{0, 1, 0, 0, 0, 0, 0, 1};
   }
   if (rc) return rc;
@@ -624,7 +624,9 @@ int univtg_op_gemm_cluster(const void* a, const void* b, int32_t M, int32_t N, i
 
 int univtg_debug_mma_rate(int32_t n, int32_t iters, int32_t per_commit, int32_t kstep_bytes, int32_t blocks, float* out_ns,
                           void* stream) {
-  return uv::debug_mma_rate(n, iters, per_commit, kstep_bytes, blocks, out_ns, reinterpret_cast<cudaStream_t>(stream));
+  // kstep_bytes: bit 30 selects an MN-major A operand, bit 29 an MN-major B operand (probe-only encoding)
+  return uv::debug_mma_rate(n, iters, per_commit, kstep_bytes & 0xffff, blocks, out_ns, reinterpret_cast<cudaStream_t>(stream),
+                            (kstep_bytes >> 30) & 1, (kstep_bytes >> 29) & 1);
 }
 
 int univtg_debug_tmem_ld_rate(int32_t iters, int32_t mode, int32_t blocks, float* out_ns, float* sink, void* stream) {

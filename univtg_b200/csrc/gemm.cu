@@ -179,6 +179,8 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
             }
             if (!pr.b_mn) {
               tma_load_2d(sb, &pr.tm_b, &full_bar[stage], b0, b1);
+            } else if (pr.b_3d) {
+              tma_load_3d(sb, &pr.tm_b, &full_bar[stage], 0, b1, b0 >> 6);  // all BN/64 blocks of the k-block in one TMA operation
             } else {
               for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &pr.tm_b, &full_bar[stage], b0 + 64 * j, b1);
             }
@@ -342,9 +344,15 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       const bool load_resid = vec && valid && (side_row != nullptr);
       uint32_t r[16];
       float rv_next[16];
+      uint4 mk_next[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+      const bool load_mask = FULL && vec && valid && (mask_row != nullptr);
       // software pipeline: the TMEM load and the residual loads of step c+1 are in flight while step c is processed
       if (nsteps > 0) {
         tmem_ld_32x32b_x16(t_addr, r);
+        if (load_mask) {
+          mk_next[0] = *reinterpret_cast<const uint4*>(mask_row + n_base);
+          mk_next[1] = *reinterpret_cast<const uint4*>(mask_row + n_base + 8);
+        }
         if (load_resid) {
           if (v256) {
             ld_global_256f(side_row + n_base, rv_next);
@@ -371,8 +379,13 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           v[j] = __uint_as_float(r[j]) + bias_s[c * 16 + j];
           rv[j] = rv_next[j];
         }
+        const uint4 mk_cur[2] = {mk_next[0], mk_next[1]};
         if (c + 1 < nsteps) {
           tmem_ld_32x32b_x16(t_addr + (c + 1) * 16, r);
+          if (load_mask) {
+            mk_next[0] = *reinterpret_cast<const uint4*>(mask_row + n0 + 16);
+            mk_next[1] = *reinterpret_cast<const uint4*>(mask_row + n0 + 24);
+          }
           if (load_resid) {
             if (v256) {
               ld_global_256f(side_row + n0 + 16, rv_next);
@@ -436,7 +449,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
             if (FULL && mask_row != nullptr) {
 #pragma unroll
               for (int q = 0; q < 2; ++q) {
-                const uint4 mk = *reinterpret_cast<const uint4*>(mask_row + n0 + 8 * q);
+                const uint4 mk = mk_cur[q];
                 const uint32_t w4[4] = {mk.x, mk.y, mk.z, mk.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -574,7 +587,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
 // loop).  One CTA per SM; thread 0 issues `iters` groups of `per_commit` MMAs, each group followed by a commit, and waits for
 // the last commit.  out[blockIdx.x] = nanoseconds per MMA.  Used to separate the tensor-pipe rate from the operand feed.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, int per_commit, int kstep_bytes, float* out) {
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, int per_commit, int kstep_bytes, float* out, int a_mn, int b_mn) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -593,14 +606,17 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, int 
   const uint32_t tmem = holder;
   if (threadIdx.x == 0) {
     const uint32_t sa = smem_u32(smem), sb = sa + 16384;
-    const uint32_t idesc = make_idesc_f16_ab(128, n, 0, 0, 0, 0);
+    const uint32_t idesc = make_idesc_f16_ab(128, n, 0, 0, a_mn, b_mn);
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     uint32_t phase = 0;
     for (int it = 0; it < iters; ++it) {
       for (int k = 0; k < per_commit; ++k) {
         const uint32_t off = (uint32_t)((k & 3) * kstep_bytes);
-        umma_f16_ss(tmem, make_smem_desc_sw128(sa + off, 16, 1024), make_smem_desc_sw128(sb + off, 16, 1024), idesc, 1u);
+        const uint32_t offm = (uint32_t)((k & 3) * 2048);  // MN-major: 16 k-rows = two 1024 B swizzle atoms
+        const uint64_t da = a_mn ? make_smem_desc_sw128(sa + offm, 8192, 1024) : make_smem_desc_sw128(sa + off, 16, 1024);
+        const uint64_t db = b_mn ? make_smem_desc_sw128(sb + offm, 8192, 1024) : make_smem_desc_sw128(sb + off, 16, 1024);
+        umma_f16_ss(tmem, da, db, idesc, 1u);
       }
       umma_commit(&bar);
       if ((it & 7) == 7) {  // eight commits complete one barrier phase (iters is a multiple of 8)
@@ -681,14 +697,14 @@ int debug_tmem_ld_rate(int iters, int mode, int blocks, float* out, float* sink,
   return (int)cudaGetLastError();
 }
 
-int debug_mma_rate(int n, int iters, int per_commit, int kstep_bytes, int blocks, float* out, cudaStream_t stream) {
+int debug_mma_rate(int n, int iters, int per_commit, int kstep_bytes, int blocks, float* out, cudaStream_t stream, int a_mn, int b_mn) {
   iters = (iters + 7) / 8 * 8;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 50 * 1024);
     attr = true;
   }
-  mma_rate_kernel<<<blocks, 128, 50 * 1024, stream>>>(n, iters, per_commit, kstep_bytes, out);
+  mma_rate_kernel<<<blocks, 128, 50 * 1024, stream>>>(n, iters, per_commit, kstep_bytes, out, a_mn, b_mn);
   return (int)cudaGetLastError();
 }
 
@@ -755,6 +771,31 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
   return 0;
 }
 
+int make_tmap_b_mn(GemmProblem& p, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, int bn, bool allow_3d) {
+  p.b_3d = 0;
+  if (!allow_3d || cols % 64 != 0 || bn % 64 != 0 || bn < 64) return make_tmap_2d(&p.tm_b, base, rows, cols, ld_elems, 64, 64);
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return 1;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld_elems * 2) % 16 != 0) {
+    set_error("tensor map: base %p / pitch %llu B not 16-byte aligned", base, (unsigned long long)(ld_elems * 2));
+    return 2;
+  }
+  cuuint64_t dims[3] = {64, rows, cols / 64};
+  cuuint64_t strides[2] = {ld_elems * 2, 128};
+  cuuint32_t box[3] = {64, 64, (cuuint32_t)(bn / 64)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(&p.tm_b, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3-D MN-major B) failed: CUresult %d (rows %llu cols %llu ld %llu bn %d)", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, bn);
+    return 3;
+  }
+  p.b_3d = bn / 64;
+  return 0;
+}
+
 int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<1>;
   static_assert(GemmCfg<1>::kSmemBytes == GemmCfg<2>::kSmemBytes, "both variants use the same dynamic shared memory size");
@@ -795,6 +836,10 @@ int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
     }
     if (!pr.b_mn && pr.b_box_rows != bn / cl) {
       set_error("gemm problem %d: B tensor-map box has %d rows but the launch uses bn %d (cluster %d)", p, pr.b_box_rows, bn, cl);
+      return (int)cudaErrorInvalidValue;
+    }
+    if (pr.b_mn && pr.b_3d != 0 && (cl != 1 || pr.b_3d != bn / 64)) {
+      set_error("gemm problem %d: 3-D B tensor map was built for bn %d, single-CTA launches (got bn %d, cluster %d)", p, 64 * pr.b_3d, bn, cl);
       return (int)cudaErrorInvalidValue;
     }
     if (pr.b_mn && bn % (64 * cl) != 0) {

@@ -72,6 +72,7 @@ struct GemmProblem {
   float* colsum;           // fp32 [N]: atomically accumulates the column sums of the stored values (bias gradients)
   int cs32;                // column stride of out32 (0/1: dense); 3 writes a Conv1d weight-gradient tap in [n, c, 3] layout
   int skip_sep;            // rows with (m % rps_in) == rps_in-1 are not stored at all
+  int b_3d;                // MN-major B through ONE 3-D TMA box per k-block: number of 64-wide N blocks in the box (0: one 2-D box per block)
   int vec_ok;              // set by launch_gemm_group: 1 = every pointer / leading dimension allows 128-bit accesses, 2 = 256-bit
 };
 
@@ -91,6 +92,9 @@ struct TileChoice {
   int bn, ksplit;
 };
 TileChoice choose_tile(const int* Ms, const int* Ns, const int* kblocks, int num, int num_sms, int step, int max_split);
+// MN-major B operand [rows = K, cols = N] (N contiguous): a 3-D view {64, K, N/64} lets one TMA instruction fetch the whole
+// 64 x bn tile of a k-block (five TMA operations per k-block instead of two measured 48 % slower); needs cols % 64 == 0.
+int make_tmap_b_mn(GemmProblem& p, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, int bn, bool allow_3d = true);
 int choose_bn(const int* Ms, const int* Ns, const int* kblocks, int num, int num_sms, int step);
 
 // Encode a 2-D tensor map over a row-major 16-bit matrix [rows, cols] with row pitch `ld` elements,
@@ -124,6 +128,6 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
 }
 
 int debug_tmem_ld_rate(int iters, int mode, int blocks, float* out, float* sink, cudaStream_t stream);
-int debug_mma_rate(int n, int iters, int per_commit, int kstep_bytes, int blocks, float* out, cudaStream_t stream);
+int debug_mma_rate(int n, int iters, int per_commit, int kstep_bytes, int blocks, float* out, cudaStream_t stream, int a_mn = 0, int b_mn = 0);
 
 }  // namespace uv

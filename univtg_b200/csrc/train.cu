@@ -29,7 +29,7 @@ int setup_gemm(GemmProblem& p, Mat16 A, int a_mn, Mat16 B, int b_mn, int M, int 
     rc |= make_tmap_2d(&p.tm_b, B.p, (uint64_t)B.rows, (uint64_t)B.cols, (uint64_t)B.ld, (uint32_t)bn, 64);
     p.b_box_rows = bn;
   } else {
-    rc |= make_tmap_2d(&p.tm_b, B.p, (uint64_t)B.rows, (uint64_t)B.cols, (uint64_t)B.ld, 64, 64);
+    rc |= make_tmap_b_mn(p, B.p, (uint64_t)B.rows, (uint64_t)B.cols, (uint64_t)B.ld, bn);
     p.cb = OperandCoord{0, 1, 0, 0, 0, 0, 0, 1};
   }
   return rc;
@@ -552,8 +552,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       p.ca = OperandCoord{0, 0, 0, 1, 0, 1, 1, 0};              // rows m0 + t', cols k
       p.cb = OperandCoord{2 * Cin, 1, -Cin, 0, 0, 0, 0, 1};     // cols n0 + (2 - t') * Cin, rows k (out channel)
       int r = make_tmap_2d(&p.tm_a, dY, (uint64_t)Mh + 2, (uint64_t)Kc, (uint64_t)ldy, GEMM_BM, 64);
-      r |= make_tmap_2d(&p.tm_b, Wp, (uint64_t)Kc, (uint64_t)3 * Cin, (uint64_t)3 * Cin, 64, 64);
-      (void)bnn;
+      r |= make_tmap_b_mn(p, Wp, (uint64_t)Kc, (uint64_t)3 * Cin, (uint64_t)3 * Cin, bnn);
       return r;
     };
     // wgrad of one tap: dW[n, c, t] = sum_m dY[m, n] X[m + t - 1, c]  -> written with column stride 3 into [N, C, 3]
@@ -571,7 +570,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       p.ca = OperandCoord{0, 1, 0, 0, 1, 0, 0, 1};      // cols m0 (out channel), rows 1 + k
       p.cb = OperandCoord{0, 1, 0, 0, t, 0, 0, 1};      // cols n0 (in channel), rows t + k
       int r = make_tmap_2d(&p.tm_a, dY, (uint64_t)Mh + 2, (uint64_t)Nc, (uint64_t)ldy, 64, 64);
-      r |= make_tmap_2d(&p.tm_b, X, (uint64_t)Mh + 2, (uint64_t)Cin, (uint64_t)ldx, 64, 64);
+      r |= make_tmap_b_mn(p, X, (uint64_t)Mh + 2, (uint64_t)Cin, (uint64_t)ldx, t_cw.bn);
       (void)gw;  // written by launch_tap_interleave from the tap-major planes (256-bit stores here instead of stride-3 scalars)
       p.out32 = T.wtap + (size_t)t * Nc * Cin;
       p.ld32 = Cin;
@@ -623,7 +622,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     memset(&g, 0, sizeof(g));
     g.num = 1;
     g.fmt = fmt;
-    rc = conv_dgrad(g.p[0], T.dh1, 2 * d, 2 * d, W16(Lw.conv1_w), d, bn);
+    rc = conv_dgrad(g.p[0], T.dh1, 2 * d, 2 * d, W16(Lw.conv1_w), d, bn_c1d);
     if (rc) return rc;
     g.p[0].rps_in = Lv + 1;
     g.p[0].rps_out = L;
