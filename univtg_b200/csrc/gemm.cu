@@ -339,8 +339,9 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       int nsteps = (pN - n_base + 15) / 16;
       nsteps = nsteps < 0 ? 0 : (nsteps > my_steps ? my_steps : nsteps);
       // the fp32 side input of a step (residual, or the aux multiplier when there is no residual) is fetched one step ahead
-      const float* side_row = resid_row != nullptr ? resid_row : ((FULL && aux_row != nullptr) ? aux_row : nullptr);
-      const bool aux_prefetched = FULL && resid_row == nullptr && side_row != nullptr;
+      const float* side_row = resid_row != nullptr ? resid_row : ((FULL && aux_row != nullptr) ? aux_row : add_row);
+      const bool aux_prefetched = FULL && resid_row == nullptr && aux_row != nullptr;
+      const bool add_prefetched = resid_row == nullptr && !(FULL && aux_row != nullptr) && add_row != nullptr;
       const bool load_resid = vec && valid && (side_row != nullptr);
       uint32_t r[16];
       float rv_next[16];
@@ -500,7 +501,10 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
               float p[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) p[j] = v[j];
-              if (add_row != nullptr) {
+              if (add_prefetched) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) p[j] += rv[j];
+              } else if (add_row != nullptr) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                   const float4 a4 = *reinterpret_cast<const float4*>(add_row + n0 + 4 * q);
@@ -863,7 +867,7 @@ int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
                ((!pr.out16 && !pr.out16p) || (pr.ld16 % 8 == 0 && al16(pr.out16) && al16(pr.out16p)));
     auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
     // 256-bit accesses (one whole 32-byte sector per thread and instruction) when every leading dimension keeps rows 32-byte aligned
-    if (w.vec_ok && (!pr.pre32 || (al32(pr.pre32) && pr.ld_pre % 8 == 0)) && (!pr.aux32 || (al32(pr.aux32) && pr.ld_aux % 8 == 0)) && (!pr.resid || (al32(pr.resid) && pr.ld_resid % 8 == 0)) &&
+    if (w.vec_ok && (!pr.pre32 || (al32(pr.pre32) && pr.ld_pre % 8 == 0)) && (!pr.aux32 || (al32(pr.aux32) && pr.ld_aux % 8 == 0)) && (!pr.addtab || (al32(pr.addtab) && pr.ld_addtab % 8 == 0)) && (!pr.resid || (al32(pr.resid) && pr.ld_resid % 8 == 0)) &&
         (!pr.out32 || (al32(pr.out32) && pr.ld32 % 8 == 0)) && (!pr.out32_id || (al32(pr.out32_id) && pr.ld32_id % 8 == 0)) &&
         ((!pr.out16 && !pr.out16p) || (pr.ld16 % 16 == 0 && al32(pr.out16) && al32(pr.out16p))))
       w.vec_ok = 2;
