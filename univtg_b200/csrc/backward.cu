@@ -712,16 +712,5 @@ int launch_stream_gather(const float* dx_stream, int L, int off, const float* ex
   return (int)e;
 }
 
-__global__ void __launch_bounds__(256) axpy_kernel(float* __restrict__ y, const float* __restrict__ x, size_t n) {
-  pdl_prologue();
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] += x[i];
-}
-int launch_axpy(float* y, const float* x, size_t n, cudaStream_t stream) {
-  size_t g = (n + 255) / 256;
-  launch_k(axpy_kernel, dim3((int)(g > 1184 ? 1184 : g)), dim3(256), 0, stream, y, x, n);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) set_error("axpy launch failed: %s", cudaGetErrorString(e));
-  return (int)e;
-}
 
 }  // namespace uv

@@ -108,7 +108,5 @@ int launch_pool_bwd(const PoolBwdArgs& a, cudaStream_t stream);
 int launch_stream_gather(const float* dx_stream, int L, int off, const float* extra, float extra_scale, uint16_t* out16,
                          float* colsum, float colsum_scale, int B, int Ls, int d, int fmt, cudaStream_t stream);
 
-// y[i] += x[i]
-int launch_axpy(float* y, const float* x, size_t n, cudaStream_t stream);
 
 }  // namespace uv

@@ -143,46 +143,6 @@ PackedLayout make_layout(const univtg_config& c) {
 // ------------------------------------------------------------------------------------------------
 // pack kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_rows_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int rows, int cols, int ld, int fmt) {
-  pdl_prologue();
-  const size_t total = (size_t)rows * ld;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / ld), c = (int)(i % ld);
-    dst[i] = c < cols ? cvt16(src[(size_t)r * cols + c], fmt) : (uint16_t)0;
-  }
-}
-// Conv1d weight [N, C, 3] -> 16-bit [N, 3*C] with dst[n, t*C + c] = src[n, c, t]
-__global__ void pack_conv_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int N, int C, int fmt) {
-  pdl_prologue();
-  const size_t total = (size_t)N * 3 * C;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int n = (int)(i / (3 * C));
-    const int rem = (int)(i % (3 * C));
-    const int t = rem / C, c = rem % C;
-    dst[i] = cvt16(src[((size_t)n * C + c) * 3 + t], fmt);
-  }
-}
-// Conv1d weight [N, C, 3] -> fp32 [N, 3, C]
-__global__ void pack_conv_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int C) {
-  pdl_prologue();
-  const size_t total = (size_t)N * 3 * C;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int n = (int)(i / (3 * C));
-    const int rem = (int)(i % (3 * C));
-    const int t = rem / C, c = rem % C;
-    dst[i] = src[((size_t)n * C + c) * 3 + t];
-  }
-}
-__global__ void copy_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ dst, int n) {
-  pdl_prologue();
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = a[i] + (b ? b[i] : 0.f);
-}
-
-inline int grid_for(size_t total) {
-  size_t g = (total + 255) / 256;
-  return (int)(g > 1184 ? 1184 : (g < 1 ? 1 : g));
-}
-
 // All (re)packing work of one univtg_pack_weights call is described by a task table and executed by a handful of launches
 // (the table travels as a kernel parameter, <= 4 KB per launch) instead of ~75 tiny kernels.
 struct PackTask {

@@ -86,15 +86,6 @@ UV_DEVINL void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, 
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-// Multicast variant: the tile lands at the same smem offset of every CTA in `cta_mask` and signals the mbarrier at the same
-// offset in each of them.
-UV_DEVINL void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-      :
-      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
-      : "memory");
-}
 UV_DEVINL uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -194,14 +185,6 @@ UV_DEVINL void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Same, arriving on the mbarrier at this offset in every CTA of `cta_mask` (cluster multicast).
-UV_DEVINL void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(cta_mask)
-               : "memory");
-}
-
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp reads TMEM lane (32*(warp%4) + i).
 UV_DEVINL void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -293,22 +276,8 @@ UV_DEVINL void ld_global_256f(const float* p, float* v) {
 UV_DEVINL void red_add_f32x4(float* addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-// Transposing reduction: every lane holds 32 values v[0..31] (its row of a 32 x 32 block); on return v[0] of lane i is the
-// sum over all lanes of their v[i] (the column sum of column i).  31 shuffles instead of 32 x 5.
-UV_DEVINL float warp_colsum32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool hi = (lane & off) != 0;
-#pragma unroll
-    for (int k = 0; k < off; ++k) {
-      const float send = hi ? v[k] : v[k + off];
-      const float keep = hi ? v[k + off] : v[k];
-      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
-}
-// Same for 16 values per lane: on return every lane l holds the sum over all 32 lanes of their v[l & 15] (v is clobbered).
+// Transposing reduction of 16 values per lane across the warp (16 shuffles instead of 16 x 5): on return every lane l holds
+// the sum over all 32 lanes of their v[l & 15] (v is clobbered).
 UV_DEVINL float warp_colsum16(float (&v)[16], int lane) {
 #pragma unroll
   for (int off = 8; off >= 1; off >>= 1) {

@@ -35,8 +35,6 @@ int setup_gemm(GemmProblem& p, Mat16 A, int a_mn, Mat16 B, int b_mn, int M, int 
   return rc;
 }
 
-inline int pick_bn(int N) { return (N % 256 == 0) ? 256 : 128; }
-
 // Tile width + split-K factor for one grouped launch (cost model: choose_tile, gemm.cu).  K in elements; step 64 when a B operand
 // is MN-major; max_split = 1 for launches whose epilogue cannot accumulate.
 struct MNK {
