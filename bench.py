@@ -164,7 +164,7 @@ def run_reference_arm(args, wl, cfg):
                                    f"torch {torch.__version__} CPU, {cores} threads"},
         "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
 
 
 def pick_threads(fn):
@@ -217,7 +217,28 @@ def gemm_traffic_bytes():
         return None
 
 
+_REAL_STDOUT_FD = None
+
+
+def _quiet_stdout():
+    """stdout must carry exactly ONE JSON line: until it is printed, file descriptor 1 points at stderr so that banners written
+    by native libraries (e.g. "NCCL version ..." at communicator creation) cannot precede it."""
+    global _REAL_STDOUT_FD
+    if _REAL_STDOUT_FD is None:
+        sys.stdout.flush()
+        _REAL_STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json_line(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT_FD is not None:
+        os.dup2(_REAL_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -536,7 +557,7 @@ def main():
             line["postproc"] = postproc_line
         if n_gpus == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cfg, wl, args.workload)
-        print(json.dumps(line), flush=True)
+        emit_json_line(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -2,6 +2,7 @@
 // bias-gradient column sums, the last conv layer of the heads, weighted-pool backward and stream-gradient assembly.
 // Gradients that feed tensor-core GEMMs are emitted as bf16 (fp16 would underflow), statistics stay fp32.
 #include <math.h>
+#include <stdlib.h>
 
 #include "backward.h"
 #include "kernels.h"
@@ -219,7 +220,12 @@ int launch_layernorm_bwd(const LnBwdArgs& a, cudaStream_t stream) {
     if (e != cudaSuccess) set_error("layernorm_bwd launch failed: %s", cudaGetErrorString(e));
     return (int)e;
   }
-  const int grid = a.rows < 592 ? a.rows : 592;  // 4 blocks per SM; each block keeps register partials over its rows
+  static int max_blocks = 0;  // 4 blocks per SM by default; each block keeps register partials over its rows (UNIVTG_LNB_GRID overrides)
+  if (max_blocks == 0) {
+    const char* e = getenv("UNIVTG_LNB_GRID");
+    max_blocks = (e != nullptr && atoi(e) > 0) ? atoi(e) : 592;
+  }
+  const int grid = a.rows < max_blocks ? a.rows : max_blocks;
   const bool vec = a.d % 4 == 0 && a.ld_dout % 4 == 0 && a.ld_y % 4 == 0 && (!a.dbr16 || a.ld16 % 4 == 0) &&
                    (((uintptr_t)a.dout | (uintptr_t)a.y | (uintptr_t)a.gamma | (uintptr_t)a.dy32 | (uintptr_t)a.dout_mul) & 15) == 0 &&
                    (((uintptr_t)a.dgamma | (uintptr_t)a.dbeta | (uintptr_t)a.colsum) & 15) == 0 && ((uintptr_t)a.dbr16 & 7) == 0;
