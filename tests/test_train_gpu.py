@@ -111,15 +111,26 @@ def test_droppath_and_input_dropout_masks_flow_through_backward():
     model.to("cuda:0").train()
     crit.to("cuda:0")
     B = inp["src_vid"].shape[0]
+    keep = 0.7
+    # (1) reference call order: one torch.rand((B, 1, 1)) per DropPath site, as transformer_encoder_droppath.py:154-167 draws them
+    model.reference_rng_order = True
+    torch.manual_seed(5)
+    out_ref_order = model(**{k: v.cuda() for k, v in inp.items()})
+    torch.manual_seed(5)
+    scales_ref = torch.stack([torch.floor(keep + torch.rand((B, 1, 1), device="cuda")).flatten() / keep
+                              for _ in range(2 * cfg["enc_layers"])]).cpu()
+    model.reference_rng_order = False
+    # (2) default: one batched draw for all sites
     torch.manual_seed(5)
     out = model(**{k: v.cuda() for k, v in inp.items()})
     loss = crit(out, {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in tgt.items()})
     sum(loss[k] * crit.weight_dict[k] for k in loss).backward()
     torch.manual_seed(5)
-    keep = 0.7
-    scales = torch.stack([torch.floor(keep + torch.rand((B, 1, 1), device="cuda")).flatten() / keep
-                          for _ in range(2 * cfg["enc_layers"])]).cpu()
+    scales = (torch.floor(keep + torch.rand((2 * cfg["enc_layers"], B), device="cuda")) / keep).cpu()
     assert (scales == 0).any() and (scales > 1).any()
+    from oracle import univtg_oracle as O
+    oref = O.forward({k: v.double() for k, v in sd.items()}, cfg, **inp, dp_scale=scales_ref)
+    torch.testing.assert_close(out_ref_order["pred_spans"].detach().double().cpu(), oref["pred_spans"], rtol=2e-2, atol=2e-3)
     _, oloss, ograd = _oracle_grads(cfg, sd, inp, tgt, dp_scale=scales)
     for k in oloss:
         assert abs(float(loss[k]) - float(oloss[k])) <= 1e-3 * max(1.0, abs(float(oloss[k]))), k

@@ -12,27 +12,36 @@ from . import _lib
 
 
 def _draw_randomness(model, B, Lv, Lt, dev):
-    """Draw DropPath scales and input-dropout multipliers with the same torch calls, in the same order, as the reference's
-    forward (input_vid_proj dropouts, input_txt_proj dropouts, then per layer droppath1, droppath2), so a seeded run sees
-    the same masks (reference model/univtg.py:107-108,394; transformer_encoder_droppath.py:154-167)."""
+    """DropPath scales [2 * enc_layers, B] and input-dropout multipliers (one per projector layer and modality), drawn with
+    torch's generator (reference model/univtg.py:107-108,394; transformer_encoder_droppath.py:154-167).
+
+    Default: batched draws - one uniform tensor for all DropPath scales and a Bernoulli fill per dropout mask - a handful of
+    launches per step.  `model.reference_rng_order = True` issues the reference's own calls in the reference's order instead
+    (F.dropout on ones per projector layer, then one torch.rand((B, 1, 1)) per DropPath site: ~45 tiny launches per step)."""
     n = model.n_input_proj
     masks = [None] * (2 * n)
     p = model.input_dropout
+    ref_order = bool(getattr(model, "reference_rng_order", False))
     if p > 0.0:
         dims_v = [model.vid_dim] + [model.hidden_dim] * 3
         dims_t = [model.txt_dim] + [model.hidden_dim] * 3
-        for i in range(n):
-            masks[i] = torch.nn.functional.dropout(torch.ones(B, Lv, dims_v[i], device=dev), p, True).contiguous()
-        for i in range(n):
-            masks[n + i] = torch.nn.functional.dropout(torch.ones(B, Lt, dims_t[i], device=dev), p, True).contiguous()
+        shapes = [(B, Lv, dims_v[i]) for i in range(n)] + [(B, Lt, dims_t[i]) for i in range(n)]
+        for i, shp in enumerate(shapes):
+            if ref_order:
+                masks[i] = torch.nn.functional.dropout(torch.ones(shp, device=dev), p, True).contiguous()
+            else:
+                masks[i] = torch.empty(shp, dtype=torch.float32, device=dev).bernoulli_(1.0 - p).mul_(1.0 / (1.0 - p))
     scales = None
     if model.droppath > 0.0:
         keep = 1.0 - model.droppath
-        rows = []
-        for _ in range(2 * model.enc_layers):
-            m = keep + torch.rand((B, 1, 1), dtype=torch.float32, device=dev)
-            rows.append(m.floor_().flatten() / keep)
-        scales = torch.stack(rows).contiguous()
+        if ref_order:
+            rows = []
+            for _ in range(2 * model.enc_layers):
+                m = keep + torch.rand((B, 1, 1), dtype=torch.float32, device=dev)
+                rows.append(m.floor_().flatten() / keep)
+            scales = torch.stack(rows).contiguous()
+        else:
+            scales = torch.rand((2 * model.enc_layers, B), dtype=torch.float32, device=dev).add_(keep).floor_().div_(keep)
     if model.attn_dropout > 0.0:
         raise NotImplementedError("attention dropout > 0 is not supported (every reference script sets --dropout 0)")
     return scales, masks
