@@ -158,6 +158,10 @@ int univtg_op_gemm_cluster(const void* a, const void* b, int32_t M, int32_t N, i
  * [0] entry, [1] setup done, [2] all TMA issued, [3] first stage landed, [4] last MMA issued, [5] accumulator ready,
  * [6] epilogue done, [7] exit.  Pass NULL to switch it off. */
 int univtg_debug_gemm_timeline(void* buf);
+/* Host-only: the tile width / split-K factor the GEMM launcher's cost model picks for a grouped launch (num <= 4 problems of
+ * M x N with kblocks 64-wide k-blocks each; step 16 for K-major B, 64 for MN-major B).  Testing / tuning aid. */
+int univtg_debug_choose_tile(const int32_t* Ms, const int32_t* Ns, const int32_t* kblocks, int32_t num, int32_t num_sms, int32_t step,
+                             int32_t max_split, int32_t* bn, int32_t* ksplit);
 /* tcgen05.ld rate probe with the GEMM epilogue's access pattern: out_ns[block] = ns per 16-column step.  Profiling aid only. */
 int univtg_debug_tmem_ld_rate(int32_t iters, int32_t mode, int32_t blocks, float* out_ns, float* sink, void* stream);
 /* tcgen05.mma issue-rate probe (M=128, N=n, K=16 from resident smem): out_ns[block] = ns per MMA.  Profiling aid only. */

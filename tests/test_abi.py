@@ -40,3 +40,40 @@ def test_bad_config_is_rejected_with_message():
     cfg = _lib.Config(1000, 8, 1024, 4, 2, 2818, 512, 0)
     assert lib.univtg_packed_bytes(ctypes.byref(cfg)) == 0
     assert "hidden_dim" in _lib.last_error()
+
+
+def test_tile_cost_model_choices_are_legal_and_sensible():
+    """Host-side launch planning (choose_tile, gemm.cu): legal tile widths / split factors, single-round tilings when they
+    exist, split-K for weight-gradient shapes (few output tiles, long K)."""
+    import ctypes
+
+    from univtg_b200 import _lib
+
+    lib = _lib.load_library()
+
+    def choose(problems, step, max_split, sms=148):
+        n = len(problems)
+        Ms = (ctypes.c_int32 * n)(*[p[0] for p in problems])
+        Ns = (ctypes.c_int32 * n)(*[p[1] for p in problems])
+        kb = (ctypes.c_int32 * n)(*[(p[2] + 63) // 64 for p in problems])
+        bn, ks = ctypes.c_int32(0), ctypes.c_int32(0)
+        assert lib.univtg_debug_choose_tile(Ms, Ns, kb, n, sms, step, max_split, ctypes.byref(bn), ctypes.byref(ks)) == 0
+        return bn.value, ks.value
+
+    M, d, Mh = 3424, 1024, 2432
+    for problems, step, max_split in ([[(M, d, d)], 16, 1], [[(M, 2 * d, d), (M, d, d)], 16, 1], [[(Mh, 2 * d, 3 * d)], 16, 1],
+                                      [[(d, d, M)], 64, 16], [[(2 * d, d, M), (d, d, M)], 64, 16], [[(d, d, Mh)] * 3, 64, 8],
+                                      [[(300, 384, 200)], 16, 1], [[(64, 64, 64)], 64, 16]):
+        bn, ks = choose(problems, step, max_split)
+        assert 64 <= bn <= 256 and bn % step == 0
+        assert 1 <= ks <= max_split and (ks & (ks - 1)) == 0
+        assert ks == 1 or all(ks * 4 <= (p[2] + 63) // 64 for p in problems)
+    # N = 1024 over 27 row tiles: a single round exists (<= 148 tiles) and must be chosen
+    bn, ks = choose([(M, d, d)], 16, 1)
+    assert ((M + 127) // 128) * ((d + bn - 1) // bn) <= 148 and ks == 1
+    # weight gradient d x d with K = 3424: 32 output tiles -> split-K so that most SMs work
+    bn, ks = choose([(d, d, M)], 64, 16)
+    assert bn == 256 and ks >= 2 and 8 * 4 * ks <= 148
+    # bad arguments are rejected
+    z = ctypes.c_int32(0)
+    assert lib.univtg_debug_choose_tile(None, None, None, 1, 148, 16, 1, ctypes.byref(z), ctypes.byref(z)) != 0

@@ -72,6 +72,7 @@ SIGNATURES = {
     "univtg_op_gemm_cluster": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                        c_float, c_void_p, c_void_p, c_void_p]),
     "univtg_debug_gemm_timeline": (c_int, [c_void_p]),
+    "univtg_debug_choose_tile": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "univtg_debug_tmem_ld_rate": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "univtg_debug_mma_rate": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "univtg_op_layernorm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_int,

@@ -633,6 +633,18 @@ int univtg_debug_tmem_ld_rate(int32_t iters, int32_t mode, int32_t blocks, float
   return uv::debug_tmem_ld_rate(iters, mode, blocks, out_ns, sink, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int univtg_debug_choose_tile(const int32_t* Ms, const int32_t* Ns, const int32_t* kblocks, int32_t num, int32_t num_sms, int32_t step,
+                              int32_t max_split, int32_t* bn, int32_t* ksplit) {
+  if (!Ms || !Ns || !kblocks || !bn || !ksplit || num < 1 || num > GEMM_MAX_GROUP || num_sms < 1 || (step != 16 && step != 64) || max_split < 1) {
+    set_error("univtg_debug_choose_tile: bad argument");
+    return 1;
+  }
+  const uv::TileChoice t = uv::choose_tile(Ms, Ns, kblocks, num, num_sms, step, max_split);
+  *bn = t.bn;
+  *ksplit = t.ksplit;
+  return 0;
+}
+
 int univtg_debug_gemm_timeline(void* buf) {
   uv::set_gemm_timeline_buffer(reinterpret_cast<unsigned long long*>(buf));
   return 0;
