@@ -60,3 +60,25 @@ def test_fp16_operand_emulation_meets_north_star_tolerance():
             torch.testing.assert_close(out[k].float(), golden_out(z, k), rtol=1e-3, atol=1e-4, msg=lambda m: f"{name}/{k}: {m}")
         assert torch.equal(out["pred_logits"].squeeze(-1).argmax(1), golden_out(z, "pred_logits").squeeze(-1).argmax(1))
         assert torch.equal(out["saliency_scores"].argmax(1), golden_out(z, "saliency_scores").argmax(1))
+
+
+def test_paired_giou_matches_the_reference_doctest_vectors():
+    """The only known-answer vectors the reference holds for this path: the doctests of utils/span_utils.py (temporal_iou
+    :55-61, generalized_temporal_iou :106-110).  The reference builds the N x M matrix and loss_spans keeps its diagonal
+    (model/univtg.py:207-211); the oracle evaluates pairs directly, so every (i, j) entry is checked as a pair."""
+    from oracle import univtg_oracle as O
+
+    s1 = torch.tensor([[0.0, 0.2], [0.5, 1.0]], dtype=torch.float64)
+    s2 = torch.tensor([[0.0, 0.3], [0.0, 1.0]], dtype=torch.float64)
+    want_giou = [[0.6667, 0.2000], [-0.2000, 0.5000]]
+    want_iou = [[0.6667, 0.2000], [0.0000, 0.5000]]
+    want_union = [[0.3000, 1.0000], [0.8000, 1.0000]]
+    for i in range(2):
+        for j in range(2):
+            g = float(O._giou_pairs(s1[i:i + 1], s2[j:j + 1])[0])
+            assert abs(g - want_giou[i][j]) < 5e-5, (i, j, g)
+            # the doctest of temporal_iou pins IoU and union separately; rebuild them the way _giou_pairs does
+            inter = max(0.0, min(float(s1[i, 1]), float(s2[j, 1])) - max(float(s1[i, 0]), float(s2[j, 0])))
+            union = float(s1[i, 1] - s1[i, 0]) + float(s2[j, 1] - s2[j, 0]) - inter
+            assert abs(union - want_union[i][j]) < 5e-5 and abs(inter / union - want_iou[i][j]) < 5e-5
+    # span conversions' doctests (:13-20, :32-39) are not on the univtg path (moment_detr only)
