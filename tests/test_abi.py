@@ -77,3 +77,34 @@ def test_tile_cost_model_choices_are_legal_and_sensible():
     # bad arguments are rejected
     z = ctypes.c_int32(0)
     assert lib.univtg_debug_choose_tile(None, None, None, 1, 148, 16, 1, ctypes.byref(z), ctypes.byref(z)) != 0
+
+
+def test_product_entry_points_fail_loudly_without_cuda():
+    """No CPU / eager fallback anywhere on the product path: every host-side entry point raises on CPU tensors / models."""
+    import pytest
+    import torch
+
+    from univtg_b200 import build_model, postproc, synth
+    from univtg_b200.optim import FlatAdamW
+
+    cfg = synth.CONFIGS["tiny"]
+    model, crit = build_model(synth.reference_args(cfg, device="cpu"))
+    inp = synth.make_inputs(cfg, seed=1, ragged=True, batch=2)
+    tgt = synth.make_targets(inp, seed=2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.eval()
+        model(**inp)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.train()
+        model(**inp)
+    B, Lv = inp["src_vid"].shape[:2]
+    fake = {"pred_logits": torch.rand(B, Lv, 1), "pred_spans": torch.rand(B, Lv, 2), "vid_mem_proj": torch.rand(B, Lv, cfg["hidden_dim"]),
+            "txt_mem_proj": torch.rand(B, 1, cfg["hidden_dim"]), "saliency_scores": torch.rand(B, Lv), "src_vid_mask": inp["src_vid_mask"]}
+    with pytest.raises(RuntimeError, match="CUDA"):
+        crit(fake, tgt)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        postproc.decode_mr(fake, {"timestamp": tgt["timestamp"], "timestamp_mask": tgt["timestamp_mask"]}, [10.0] * B)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        postproc.temporal_nms(torch.zeros(B, 4, 3, dtype=torch.float64), 0.5)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        FlatAdamW(model)

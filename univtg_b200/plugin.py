@@ -339,6 +339,8 @@ class Model(nn.Module):
         dev = self._device()
         if src_vid.device != dev:
             raise RuntimeError(f"inputs on {src_vid.device}, model on {dev}")
+        if dev.type != "cuda":
+            raise RuntimeError("univtg_b200: the model must live on a CUDA device (no CPU path); call model.to('cuda')")
         B, Lv, _ = src_vid.shape
         Lt = src_txt.shape[1]
         if tuple(src_vid_mask.shape) != (B, Lv) or tuple(src_txt_mask.shape) != (B, Lt):
