@@ -121,10 +121,14 @@ def conv_head(x, sd, pre, opq):
     return conv1d_k3(h, sd[pre + "layers.2.weight"], sd[pre + "layers.2.bias"], opq, _ident)
 
 
-def input_proj(x, sd, pre, n_proj, opq):
+def input_proj(x, sd, pre, n_proj, opq, masks=None):
+    """LinearLayer stack (model/univtg.py:399-406): LayerNorm -> Dropout -> Linear [-> ReLU].  masks[i]: the train-mode
+    nn.Dropout multiplier of layer i (0 or 1/(1-p), same shape as the layer input) or None (eval / p = 0)."""
     for i in range(n_proj):
         p = f"{pre}{i}."
         x = layer_norm(x, sd[p + "LayerNorm.weight"], sd[p + "LayerNorm.bias"])
+        if masks is not None and masks[i] is not None:
+            x = x * masks[i].to(x.dtype)
         x = mm(x, sd[p + "net.1.weight"], opq, sd[p + "net.1.bias"])
         if i < n_proj - 1:
             x = torch.relu(x)
@@ -144,9 +148,10 @@ def cosine(a, b, eps=1e-8):
 
 
 def forward(sd, cfg, src_txt, src_txt_mask, src_vid, src_vid_mask, dp_scale=None, dtype=torch.float64, opq=None,
-            keep_intermediates=False):
-    """Restatement of Model.forward (eval mode unless dp_scale [2*N, B] is given).
+            keep_intermediates=False, drop_masks=None):
+    """Restatement of Model.forward (eval mode unless dp_scale [2*N, B] / drop_masks are given).
 
+    drop_masks: train-mode input-dropout multipliers, [video layer 0..n-1, text layer 0..n-1] (model/univtg.py:394,401).
     sd: reference-named state dict; cfg: dict with hidden_dim, nheads, enc_layers, n_input_proj."""
     opq = opq or _ident
     sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}  # differentiable cast (autograd oracle)
@@ -155,8 +160,10 @@ def forward(sd, cfg, src_txt, src_txt_mask, src_vid, src_vid_mask, dp_scale=None
     tmask, vmask = src_txt_mask.to(dtype), src_vid_mask.to(dtype)
     B, Lv = src_vid.shape[:2]
     Lt = src_txt.shape[1]
-    x_v = input_proj(src_vid, sd, "input_vid_proj.", n_proj, opq) + sd["token_type_embeddings.weight"][1]
-    x_t = input_proj(src_txt, sd, "input_txt_proj.", n_proj, opq) + sd["token_type_embeddings.weight"][0]
+    mv = drop_masks[:n_proj] if drop_masks is not None else None
+    mt = drop_masks[n_proj:2 * n_proj] if drop_masks is not None else None
+    x_v = input_proj(src_vid, sd, "input_vid_proj.", n_proj, opq, mv) + sd["token_type_embeddings.weight"][1]
+    x_t = input_proj(src_txt, sd, "input_txt_proj.", n_proj, opq, mt) + sd["token_type_embeddings.weight"][0]
     x = torch.cat([x_v, x_t], dim=1)
     key_valid = torch.cat([vmask, tmask], dim=1) != 0
     pos = torch.cat([sine_position(vmask, d, dtype), torch.zeros(B, Lt, d, dtype=dtype)], dim=1)

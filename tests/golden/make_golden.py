@@ -88,4 +88,5 @@ if __name__ == "__main__":
     run_case("tiny_full", "tiny", seed=20, ragged=False, head_gain=4.0)
     run_case("cfg1_demo", "cfg1", seed=30, ragged=False, demo=True)
     run_case("cfg2_b4_ragged", "cfg2", seed=40, ragged=True, batch=4)
-    run_case("cfg2_full", "cfg2", seed=50, ragged=False, with_grads=False)
+    run_case("cfg2_full", "cfg2", seed=50, ragged=False)  # the benchmarked B=32 shape, with gradient summaries
+    run_case("cfg4_b4_ragged", "cfg4", seed=60, ragged=True, batch=4)  # L = 182: two key tiles in attention

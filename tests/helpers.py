@@ -9,7 +9,7 @@ from univtg_b200 import synth
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 OUT_KEYS = ("pred_logits", "pred_spans", "saliency_scores", "vid_mem_proj", "txt_mem_proj")
-GOLDEN_CASES = ("tiny_ragged", "tiny_full", "cfg1_demo", "cfg2_b4_ragged", "cfg2_full")
+GOLDEN_CASES = ("tiny_ragged", "tiny_full", "cfg1_demo", "cfg2_b4_ragged", "cfg2_full", "cfg4_b4_ragged")
 
 
 def load_golden(name):

@@ -8,7 +8,7 @@ exact gradients by 1-3.5 % (ReLU / LayerNorm / InfoNCE with temperature 0.07 amp
 import pytest
 import torch
 
-from tests.helpers import load_golden
+from tests.helpers import golden_out, load_golden
 from univtg_b200 import build_model, synth
 
 pytestmark = pytest.mark.gpu
@@ -63,8 +63,34 @@ def test_criterion_kernels_match_oracle(name):
         assert _rel(g, v.grad) < 2e-4, (name, k, _rel(g, v.grad))
 
 
-@pytest.mark.parametrize("name", ["tiny_ragged", "tiny_full", "cfg2_b4_ragged"])
+def _record(name, payload):
+    """Measured parity numbers are also written to gpurun_out/parity_<name>.json (scratch; summarised in profiles/)."""
+    import json
+    import os
+
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, f"parity_{name}.json"), "w") as f:
+            json.dump(payload, f, indent=1)
+    except OSError:
+        pass
+
+
+# Gradient acceptance (per parameter tensor, against fp64 autograd through the oracle):
+#   exact oracle     rel-L2 <= 5e-2 and cosine >= 0.998: 16-bit operand rounding of the FORWARD alone moves exact gradients by
+#                    1 - 3.5 % (DESIGN.md section 3), so this bound is about the format, not the kernels
+#   emulating oracle rel-L2 <= EMU_TOL: same fp16 operand rounding in the forward (straight-through in its backward), so what
+#                    is left is the fp16 loss-scaled backward + accumulation order - the kernels' own error.  Tiny batches
+#                    (B = 3) get a wider bound: a single ReLU / argmax flip between two 16-bit forwards moves a tensor by percents.
+EMU_TOL = {"tiny_ragged": 6e-2, "tiny_full": 6e-2, "cfg2_b4_ragged": 3e-2, "cfg2_full": 2.5e-2, "cfg4_b4_ragged": 3e-2}
+
+
+@pytest.mark.parametrize("name", ["tiny_ragged", "tiny_full", "cfg2_b4_ragged", "cfg4_b4_ragged", "cfg2_full"])
 def test_full_training_step_gradients(name):
+    """Forward + criterion + backward of one batch against the oracle's autograd.  cfg2_full is the benchmarked shape (B = 32,
+    M = 3424: split-K weight gradients with fp32 reductions, 3-D-TMA MN-major operands); cfg4_b4_ragged has L = 182, i.e. two
+    key tiles in the attention forward and the atomic dQ path in its backward."""
     cfg, sd, inp, tgt, z = load_golden(name)
     model, crit = _models(cfg, sd)
     model.train()
@@ -75,10 +101,15 @@ def test_full_training_step_gradients(name):
     total.backward()
     torch.cuda.synchronize()
     _, oloss, ograd = _oracle_grads(cfg, sd, inp, tgt)
-    _, eloss, egrad = _oracle_grads(cfg, sd, inp, tgt, emulate=True)
+    eout, eloss, egrad = _oracle_grads(cfg, sd, inp, tgt, emulate=True)
     for k in oloss:
         assert abs(float(loss[k]) - float(oloss[k])) <= 1e-3 * max(1.0, abs(float(oloss[k]))), (name, k)
         assert abs(float(loss[k]) - float(eloss[k])) <= 1e-4 * max(1.0, abs(float(eloss[k]))), (name, k)
+        assert abs(float(loss[k]) - float(z["loss_" + k])) <= 1e-3 * max(1.0, abs(float(z["loss_" + k]))), (name, k)
+    # train-mode forward (droppath = input_dropout = 0) against the emulating oracle and the reference fixture
+    for k in ("pred_logits", "pred_spans"):
+        torch.testing.assert_close(out[k].detach().double().cpu(), eout[k].detach(), rtol=2e-4, atol=5e-5)
+        torch.testing.assert_close(out[k].detach().float().cpu(), golden_out(z, k), rtol=1e-3, atol=1e-4)
     worst = {}
     for n_, p in model.named_parameters():
         og = ograd[n_]
@@ -87,68 +118,144 @@ def test_full_training_step_gradients(name):
             continue
         assert p.grad is not None, f"{n_} got no gradient"
         g = p.grad.double().cpu()
+        assert bool(torch.isfinite(g).all()), n_
         worst[n_] = (_rel(g, og), _cos(g, og), _rel(g, egrad[n_]))
-        # reference golden: gradient norm of the fp32 reference
-        gn = float(z["gnorm_" + n_]) if ("gnorm_" + n_) in z else None
-        if gn is not None and gn > 1e-8:
+        # fixtures from the live reference (fp32): gradient norm and the first 16 entries of every parameter gradient
+        gn = float(z["gnorm_" + n_])
+        if gn > 1e-8:
             assert abs(float(g.norm()) - gn) <= 5e-2 * gn, (name, n_, float(g.norm()), gn)
-    # (the emulating oracle is reported for diagnosis only: on tiny batches a single ReLU / argmax flip between two 16-bit
-    #  forwards moves individual tensors by a few percent either way)
+        gh = torch.from_numpy(z["ghead_" + n_]).double()
+        assert float((g.flatten()[:16] - gh).norm()) <= 8e-2 * float(gh.norm()) + 2e-3 * gn / max(1.0, g.numel() ** 0.5), (name, n_)
+    _record("grads_" + name, {k: {"rel_exact": v[0], "cos_exact": v[1], "rel_emulating": v[2]} for k, v in worst.items()})
     bad = {k: v for k, v in worst.items() if v[0] > 5e-2 or v[1] < 0.998}
-    assert not bad, f"{name}: gradient mismatch {bad}"
+    assert not bad, f"{name}: gradient mismatch vs exact oracle {bad}"
+    bad_e = {k: v for k, v in worst.items() if v[2] > EMU_TOL[name]}
+    assert not bad_e, f"{name}: gradient mismatch vs fp16-emulating oracle (tol {EMU_TOL[name]}) {bad_e}"
 
 
-def test_droppath_and_input_dropout_masks_flow_through_backward():
-    """Train mode with DropPath + input dropout: the masks drawn by the glue are applied in forward and backward.  The oracle
-    gets the same DropPath scales; input dropout is emulated by scaling the LayerNorm affine terms is impossible, so only
-    DropPath is compared numerically and dropout is checked for determinism + non-identity."""
-    cfg = synth.CONFIGS["tiny"]
+def _train_inputs(cfg, batch, seed):
+    raw = synth.make_inputs(cfg, seed=seed, ragged=True, batch=batch)
+    tgt = synth.make_targets(raw, seed=seed + 1)
+    return raw, tgt, {k: v.cuda() for k, v in raw.items()}, {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in tgt.items()}
+
+
+@pytest.mark.parametrize("cfg_name,batch", [("tiny", 6), ("cfg2", 4)])
+def test_input_dropout_and_droppath_match_oracle_fed_the_same_draws(cfg_name, batch):
+    """The benchmarked arm: train mode with input_dropout = 0.5 and droppath = 0.1 (reference defaults).  The glue keeps the
+    multipliers it drew (reference call order: F.dropout per projector layer - model/univtg.py:394 -, then one torch.rand((B,1,1))
+    per DropPath site - transformer_encoder_droppath.py:154-167); the oracle is fed the same tensors (its mask semantics are
+    pinned to the live reference by tests/test_oracle_vs_reference.py), so forward, losses and gradients must agree."""
+    from oracle import univtg_oracle as O
+
+    cfg = synth.CONFIGS[cfg_name]
     sd = synth.make_state_dict(cfg, seed=77)
-    inp = synth.make_inputs(cfg, seed=78, ragged=True, batch=6)
-    tgt = synth.make_targets(inp, seed=79)
-    model, crit = build_model(synth.reference_args(cfg, device="cuda:0", droppath=0.3, input_dropout=0.0))
+    raw, tgt, inp, tgt_c = _train_inputs(cfg, batch, 78)
+    model, crit = build_model(synth.reference_args(cfg, device="cuda:0", droppath=0.3 if cfg_name == "tiny" else 0.1, input_dropout=0.5))
     model.load_state_dict(sd, strict=True)
     model.to("cuda:0").train()
     crit.to("cuda:0")
-    B = inp["src_vid"].shape[0]
-    keep = 0.7
-    # (1) reference call order: one torch.rand((B, 1, 1)) per DropPath site, as transformer_encoder_droppath.py:154-167 draws them
     model.reference_rng_order = True
+    model.keep_last_draw = True
     torch.manual_seed(5)
-    out_ref_order = model(**{k: v.cuda() for k, v in inp.items()})
-    torch.manual_seed(5)
-    scales_ref = torch.stack([torch.floor(keep + torch.rand((B, 1, 1), device="cuda")).flatten() / keep
-                              for _ in range(2 * cfg["enc_layers"])]).cpu()
-    model.reference_rng_order = False
-    # (2) default: one batched draw for all sites
-    torch.manual_seed(5)
-    out = model(**{k: v.cuda() for k, v in inp.items()})
-    loss = crit(out, {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in tgt.items()})
+    out = model(**inp)
+    scales, masks = model._last_draw
+    loss = crit(out, tgt_c)
     sum(loss[k] * crit.weight_dict[k] for k in loss).backward()
+    torch.cuda.synchronize()
+    # the draws are the reference's own calls in the reference's order
     torch.manual_seed(5)
-    scales = (torch.floor(keep + torch.rand((2 * cfg["enc_layers"], B), device="cuda")) / keep).cpu()
-    assert (scales == 0).any() and (scales > 1).any()
+    B, Lv, Lt, d = batch, raw["src_vid"].shape[1], raw["src_txt"].shape[1], cfg["hidden_dim"]
+    shapes = [(B, Lv, cfg["v_feat_dim"]), (B, Lv, d), (B, Lt, cfg["t_feat_dim"]), (B, Lt, d)]
+    redrawn = [torch.nn.functional.dropout(torch.ones(s, device="cuda"), 0.5, True) for s in shapes]
+    keep = 1.0 - model.droppath
+    redrawn_s = torch.stack([torch.floor(keep + torch.rand((B, 1, 1), device="cuda")).flatten() / keep for _ in range(2 * cfg["enc_layers"])])
+    assert all(torch.equal(a, b) for a, b in zip(masks, redrawn)) and torch.equal(scales, redrawn_s)
+    assert (scales == 0).any() or cfg_name != "tiny"
+    masks_c, scales_c = [m.cpu() for m in masks], scales.cpu()
+
+    def run(emulate):
+        leaves = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+        o = O.forward(leaves, cfg, **raw, dp_scale=scales_c, drop_masks=masks_c, opq=O.round_fp16 if emulate else None)
+        ls = O.criterion(o, tgt)
+        O.weighted_total(ls, WD).backward()
+        return o, ls, {k: v.grad for k, v in leaves.items()}
+
+    eout, eloss, egrad = run(True)
+    xout, xloss, xgrad = run(False)
+    for k in ("pred_logits", "pred_spans", "vid_mem_proj", "txt_mem_proj"):
+        got = out[k].detach().double().cpu()
+        torch.testing.assert_close(got, eout[k].detach(), rtol=2e-4, atol=5e-5, msg=lambda m: f"{k} vs emulating oracle: {m}")
+        torch.testing.assert_close(got, xout[k].detach(), rtol=1e-3, atol=1e-4 if k.startswith("pred") else 2e-3,
+                                   msg=lambda m: f"{k} vs exact oracle: {m}")
+    for k in xloss:
+        assert abs(float(loss[k]) - float(eloss[k])) <= 1e-4 * max(1.0, abs(float(eloss[k]))), k
+        assert abs(float(loss[k]) - float(xloss[k])) <= 1e-3 * max(1.0, abs(float(xloss[k]))), k
+    worst = {}
+    for n_, p in model.named_parameters():
+        if xgrad[n_] is None or float(xgrad[n_].abs().max()) == 0.0:
+            continue
+        g = p.grad.double().cpu()
+        worst[n_] = (_rel(g, xgrad[n_]), _cos(g, xgrad[n_]), _rel(g, egrad[n_]))
+    _record(f"dropout_{cfg_name}", {k: {"rel_exact": v[0], "cos_exact": v[1], "rel_emulating": v[2]} for k, v in worst.items()})
+    tol_e = 6e-2 if cfg_name == "tiny" else 3e-2
+    bad = {k: v for k, v in worst.items() if v[0] > 6e-2 or v[1] < 0.998 or v[2] > tol_e}
+    assert not bad, f"{cfg_name}: gradient mismatch with dropout + DropPath on {bad}"
+    # the default (batched) draws: deterministic under a seed, different from eval
+    model.reference_rng_order = False
+    torch.manual_seed(9)
+    a = model(**inp)["pred_spans"].detach().clone()
+    torch.manual_seed(9)
+    b = model(**inp)["pred_spans"].detach().clone()
+    model.eval()
+    with torch.no_grad():
+        c = model(**inp)["pred_spans"]
+    assert torch.equal(a, b) and not torch.allclose(a, c)
+
+
+def test_hl_loss_list_and_missing_saliency_labels():
+    """dset_type 'hl': losses = ['labels', 'saliency'], targets without timestamp / span_labels_nn (model/univtg.py:438-439,
+    main/dataset.py:1118-1126).  Also the branch without saliency_pos_labels: both saliency losses are the constant 0 and the
+    backward must deliver exact zeros (not uninitialised scratch) to vid_mem_proj / txt_mem_proj."""
     from oracle import univtg_oracle as O
-    oref = O.forward({k: v.double() for k, v in sd.items()}, cfg, **inp, dp_scale=scales_ref)
-    torch.testing.assert_close(out_ref_order["pred_spans"].detach().double().cpu(), oref["pred_spans"], rtol=2e-2, atol=2e-3)
-    _, oloss, ograd = _oracle_grads(cfg, sd, inp, tgt, dp_scale=scales)
+
+    cfg = synth.CONFIGS["tiny"]
+    sd = synth.make_state_dict(cfg, seed=5)
+    raw, full, inp, _ = _train_inputs(cfg, 6, 9)
+    model, crit = build_model(synth.reference_args(cfg, device="cuda:0", droppath=0.0, input_dropout=0.0, dset_type="hl"))
+    assert crit.losses == ["labels", "saliency"]
+    model.load_state_dict(sd, strict=True)
+    model.to("cuda:0").train()
+    crit.to("cuda:0")
+    tgt = {"saliency_scores": full["saliency_scores"], "saliency_pos_labels": full["saliency_pos_labels"],
+           "timestamp_mask": full["timestamp_mask"], "timestamp_window": 1 * (full["saliency_scores"] > 0)}
+    out = model(**inp)
+    loss = crit(out, {k: v.cuda() for k, v in tgt.items()})
+    assert sorted(loss) == ["loss_f", "loss_s_inter", "loss_s_intra"]
+    sum(loss[k] * crit.weight_dict[k] for k in loss).backward()
+    leaves = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    oloss = O.criterion(O.forward(leaves, cfg, **raw), tgt, losses=("labels", "saliency"))
+    O.weighted_total(oloss, WD).backward()
     for k in oloss:
         assert abs(float(loss[k]) - float(oloss[k])) <= 1e-3 * max(1.0, abs(float(oloss[k]))), k
-    for n_ in ("transformer.encoder.layers.0.linear1.weight", "input_vid_proj.0.net.1.weight", "span_embed.layers.0.weight"):
+    for n_ in ("transformer.encoder.layers.0.linear1.weight", "input_vid_proj.0.net.1.weight", "class_embed.layers.0.weight",
+               "weightedpool.weight"):
         g = dict(model.named_parameters())[n_].grad.double().cpu()
-        assert _rel(g, ograd[n_]) < 5e-2, (n_, _rel(g, ograd[n_]))
-    # input dropout: deterministic under a seed, different from the no-dropout output
-    model2, _ = build_model(synth.reference_args(cfg, device="cuda:0", droppath=0.0, input_dropout=0.5))
-    model2.load_state_dict(sd, strict=True)
-    model2.to("cuda:0").train()
-    torch.manual_seed(9)
-    a = model2(**{k: v.cuda() for k, v in inp.items()})["pred_spans"].detach()
-    torch.manual_seed(9)
-    b = model2(**{k: v.cuda() for k, v in inp.items()})["pred_spans"].detach()
-    model2.eval()
-    with torch.no_grad():
-        c = model2(**{k: v.cuda() for k, v in inp.items()})["pred_spans"]
-    assert torch.equal(a, b) and not torch.allclose(a, c)
+        assert _rel(g, leaves[n_].grad) < 6e-2, (n_, _rel(g, leaves[n_].grad))
+    g_span = dict(model.named_parameters())["span_embed.layers.0.weight"].grad
+    assert g_span is None or float(g_span.abs().max()) == 0.0  # no 'spans' loss -> no gradient into span_embed
+    # no saliency_pos_labels: reference returns 0. for both saliency losses (model/univtg.py:236-237)
+    for p in model.parameters():
+        p.grad = None
+    tgt2 = {k: v.cuda() for k, v in tgt.items() if k != "saliency_pos_labels"}
+    out = model(**inp)
+    torch.empty(64 << 20, dtype=torch.uint8, device="cuda").fill_(0xFF)  # poison the allocator's free blocks (NaN patterns)
+    loss = crit(out, tgt2)
+    assert float(loss["loss_s_inter"]) == 0.0 and float(loss["loss_s_intra"]) == 0.0
+    sum(loss[k] * crit.weight_dict[k] for k in loss).backward()
+    for n_, p in model.named_parameters():
+        if p.grad is not None:
+            assert bool(torch.isfinite(p.grad).all()), n_
+    assert float(dict(model.named_parameters())["weightedpool.weight"].grad.abs().max()) == 0.0
 
 
 def test_optimizer_step_decreases_loss():

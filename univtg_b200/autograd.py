@@ -64,6 +64,8 @@ class _UniVTGFunction(torch.autograd.Function):
             tmask = src_txt_mask.detach().to(torch.float32).contiguous()
             vmask = src_vid_mask.detach().to(torch.float32).contiguous()
             scales, masks = _draw_randomness(model, B, Lv, Lt, dev)
+            if getattr(model, "keep_last_draw", False):  # parity tests hand the same multipliers to the oracle
+                model.__dict__["_last_draw"] = (scales, masks)
             mask_arr = None
             if any(m is not None for m in masks):
                 mask_arr = (ctypes.c_void_p * len(masks))(*[m.data_ptr() if m is not None else None for m in masks])

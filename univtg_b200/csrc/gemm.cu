@@ -151,7 +151,10 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
 
   if (warp == 0) {
     // ======================================= TMA producer =======================================
-    if (lane == 0) {
+    // The whole warp walks the schedule convergently and ONE elected lane issues (elect.sync): inside a plain `if (lane == 0)`
+    // region ptxas cannot prove the TMA / MMA operands warp-uniform and wraps every UTMALDG / UTCHMMA / UTCBAR in an
+    // ELECT + BRA.U.ANY "waterfall" loop (measured in round 2: that, not the tensor pipe, set the ~90 ns per MMA of round 1).
+    {
       int stage = 0;
       uint32_t phase = 0;
       TileInfo ti;
@@ -169,7 +172,8 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           const int a1 = pr.ca.base1 + m0 * pr.ca.mn1s + tap * pr.ca.tap1 + kk * pr.ca.k1s;
           const int b0 = pr.cb.base0 + n0 * pr.cb.mn0s + tap * pr.cb.tap0 + kk * pr.cb.k0s;
           const int b1 = pr.cb.base1 + n0 * pr.cb.mn1s + tap * pr.cb.tap1 + kk * pr.cb.k1s;
-          if (CL == 1) {
+          if (!elect_one()) {
+          } else if (CL == 1) {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kABytes + BN * 128);
             if (!pr.a_mn) {
               tma_load_2d(sa, &pr.tm_a, &full_bar[stage], a0, a1);
@@ -202,17 +206,18 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
               for (int j = 0; j < nb; ++j) tma_load_2d_2sm(sb + j * 8192, &pr.tm_b, lead_bar, b0 + 64 * (crank * nb + j), b1);
             }
           }
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
       }
-      stamp(g.dbg, 2);  // all TMA loads issued
+      if (lane == 0) stamp(g.dbg, 2);  // all TMA loads issued
     }
   } else if (warp == 1) {
     // ======================================== MMA issuer ========================================
-    if (lane == 0 && (CL == 1 || crank == 0)) {  // CTA pair: the leader issues for both
+    if (CL == 1 || crank == 0) {  // CTA pair: the leader issues for both; convergent warp, one elected lane issues
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -224,33 +229,39 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * Cfg::kAccStride;
+        // descriptor = constant high part (layout, LBO/SBO) + start address; one k-step of 16 elements advances the address by
+        // 32 B inside the 128 B swizzle span (K-major) or by two 1024 B swizzle atoms (MN-major), in 16-byte units
+        const uint64_t da_hi = pr.a_mn ? make_smem_desc_sw128(0, 8192, 1024) : make_smem_desc_sw128(0, 16, 1024);
+        const uint64_t db_hi = pr.b_mn ? make_smem_desc_sw128(0, 8192, 1024) : make_smem_desc_sw128(0, 16, 1024);
+        const uint32_t a_step = pr.a_mn ? 128u : 2u, b_step = pr.b_mn ? 128u : 2u;
         for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
-          if (kb == ti.kb0 && t == tile0) stamp(g.dbg, 3);  // first operand stage landed
+          if (lane == 0 && kb == ti.kb0 && t == tile0) stamp(g.dbg, 3);  // first operand stage landed
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t da = da_hi + (uint64_t)(sa >> 4);
+          const uint64_t db = db_hi + (uint64_t)((sa + Cfg::kABytes) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            // K-major: advance 16 elements (32 B) inside the 128 B swizzle span.
-            // MN-major: advance 16 k-rows = two 1024 B swizzle atoms.
-            const uint64_t da = pr.a_mn ? make_smem_desc_sw128(sa + k * 2048, 8192, 1024)
-                                        : make_smem_desc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t db = pr.b_mn ? make_smem_desc_sw128(sb + k * 2048, 8192, 1024)
-                                        : make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            if (CL == 1) umma_f16_ss(d_tmem, da, db, idesc, (kb > ti.kb0 || k > 0) ? 1u : 0u);
-            else umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb > ti.kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              if (CL == 1) umma_f16_ss(d_tmem, da + k * a_step, db + k * b_step, idesc, (kb > ti.kb0 || k > 0) ? 1u : 0u);
+              else umma_f16_ss_2sm(d_tmem, da + k * a_step, db + k * b_step, idesc, (kb > ti.kb0 || k > 0) ? 1u : 0u);
+            }
+            if (CL == 1) umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            else umma_commit_2sm(&empty_bar[stage], (uint16_t)0x3);  // ... in both CTAs of the pair
           }
-          if (CL == 1) umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          else umma_commit_2sm(&empty_bar[stage], (uint16_t)0x3);  // ... in both CTAs of the pair
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        if (CL == 1) umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
-        else umma_commit_2sm(&tmem_full[as], (uint16_t)0x3);
-        stamp(g.dbg, 4);              // last MMA of the tile issued
+        if (elect_one()) {
+          if (CL == 1) umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+          else umma_commit_2sm(&tmem_full[as], (uint16_t)0x3);
+        }
+        __syncwarp();
+        if (lane == 0) stamp(g.dbg, 4);  // last MMA of the tile issued
         if (++as == 2) {
           as = 0;
           aphase ^= 1;

@@ -105,17 +105,19 @@ __global__ void __launch_bounds__(1024) loss_finish_kernel(const LossArgs a) {
     const float w = a.window[i];
     const bool fg = w != 0.f;
     float gb0 = 0.f, gb1 = 0.f, gg0 = 0.f, gg1 = 0.f;
-    const float s1 = a.timestamp[2 * i] + a.pred_spans[2 * i];
-    const float e1 = a.timestamp[2 * i + 1] + a.pred_spans[2 * i + 1];
-    const float s2 = a.span_gt[2 * i], e2 = a.span_gt[2 * i + 1];
-    {  // smooth L1 (beta = 1) * window, normalised by the foreground count
+    // loss list without 'spans' (dset_type hl / vs, model/univtg.py:438-439): the targets carry no timestamp / span_labels_nn
+    const bool spans = a.span_gt != nullptr && a.timestamp != nullptr;
+    const float s1 = spans ? a.timestamp[2 * i] + a.pred_spans[2 * i] : 0.f;
+    const float e1 = spans ? a.timestamp[2 * i + 1] + a.pred_spans[2 * i + 1] : 0.f;
+    const float s2 = spans ? a.span_gt[2 * i] : 0.f, e2 = spans ? a.span_gt[2 * i + 1] : 0.f;
+    if (spans) {  // smooth L1 (beta = 1) * window, normalised by the foreground count
       const float d0 = s1 - s2, d1 = e1 - e2;
       const float a0 = fabsf(d0), a1 = fabsf(d1);
       lb += ((a0 < 1.f ? 0.5f * d0 * d0 : a0 - 0.5f) + (a1 < 1.f ? 0.5f * d1 * d1 : a1 - 0.5f)) * w;
       gb0 = (a0 < 1.f ? d0 : (d0 > 0.f ? 1.f : -1.f)) * w / n_fg;
       gb1 = (a1 < 1.f ? d1 : (d1 > 0.f ? 1.f : -1.f)) * w / n_fg;
     }
-    if (fg) {  // generalised IoU of (s1, e1) vs (s2, e2)
+    if (spans && fg) {  // generalised IoU of (s1, e1) vs (s2, e2)
       const float lo_i = fmaxf(s1, s2), hi_i = fminf(e1, e2);
       const float inter_raw = hi_i - lo_i;
       const float inter = fmaxf(inter_raw, 0.f);
@@ -163,8 +165,9 @@ __global__ void __launch_bounds__(1024) loss_finish_kernel(const LossArgs a) {
   lg = block_sum(lg, s_red);
   lf = block_sum(lf, s_red);
   if (tid == 0) {
-    a.losses[0] = lb / n_fg;
-    a.losses[1] = lg / n_fg;
+    const bool spans = a.span_gt != nullptr && a.timestamp != nullptr;
+    a.losses[0] = spans ? lb / n_fg : 0.f;
+    a.losses[1] = spans ? lg / n_fg : 0.f;
     a.losses[2] = lf / n_valid;
   }
 
@@ -365,6 +368,16 @@ __global__ void __launch_bounds__(128) loss_bwd_txt_kernel(const LossBwdArgs a) 
 int launch_loss_backward(const LossBwdArgs& a, cudaStream_t stream) {
   const int n = a.B * a.Lv;
   launch_k(loss_bwd_small_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, a);
+  if (a.pos_idx == nullptr) {
+    // targets without saliency_pos_labels: the reference returns the constant 0. for both saliency losses
+    // (model/univtg.py:236-237), so nothing flows into vid_mem_proj / txt_mem_proj; the forward skipped loss_cos_kernel and
+    // the cosine scratch is unwritten - do not read it.
+    cudaMemsetAsync(a.d_xv, 0, (size_t)n * a.d * sizeof(float), stream);
+    cudaMemsetAsync(a.d_xt, 0, (size_t)a.B * a.d * sizeof(float), stream);
+    cudaError_t e0 = cudaGetLastError();
+    if (e0 != cudaSuccess) set_error("loss backward launch failed: %s", cudaGetErrorString(e0));
+    return (int)e0;
+  }
   launch_k(loss_bwd_vid_kernel, dim3((n * 32 + 255) / 256), dim3(256), (size_t)8 * a.B * sizeof(float), stream, a);
   launch_k(loss_bwd_txt_kernel, dim3(a.B, (a.d + 127) / 128), dim3(128), (size_t)(a.Lv + 2 * a.B) * sizeof(float), stream, a);
   cudaError_t e = cudaGetLastError();

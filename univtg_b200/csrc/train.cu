@@ -1080,8 +1080,8 @@ int univtg_loss_forward(const float* pred_logits, const float* pred_spans, const
                         const float* timestamp, const float* timestamp_mask, const float* timestamp_window,
                         const float* span_labels_nn, const float* saliency_scores, const int64_t* saliency_pos_idx, int32_t B,
                         int32_t Lv, int32_t d, float eos_coef, float temperature, float* losses5, void* scratch, void* stream) {
-  if (!pred_logits || !pred_spans || !vid_mem_proj || !txt_mem_proj || !timestamp || !timestamp_mask || !timestamp_window ||
-      !span_labels_nn || !saliency_scores || !losses5 || !scratch) {
+  if (!pred_logits || !pred_spans || !vid_mem_proj || !txt_mem_proj || !timestamp_mask || !timestamp_window || !saliency_scores ||
+      !losses5 || !scratch || ((timestamp == nullptr) != (span_labels_nn == nullptr))) {
     set_error("univtg_loss_forward: null argument");
     return 1;
   }

@@ -26,9 +26,9 @@ class _LossFunction(torch.autograd.Function):
             xt = txt_mem_proj.detach().to(torch.float32).contiguous()
             scratch = torch.empty(lib.univtg_loss_scratch_bytes(B, Lv), dtype=torch.uint8, device=dev)
             losses = torch.zeros(5, device=dev)
-            _lib.check(lib.univtg_loss_forward(_lib.ptr(pl), _lib.ptr(ps), _lib.ptr(xv), _lib.ptr(xt), _lib.ptr(tg["timestamp"]),
+            _lib.check(lib.univtg_loss_forward(_lib.ptr(pl), _lib.ptr(ps), _lib.ptr(xv), _lib.ptr(xt), _lib.ptr(tg.get("timestamp")),
                                                _lib.ptr(tg["timestamp_mask"]), _lib.ptr(tg["timestamp_window"]),
-                                               _lib.ptr(tg["span_labels_nn"]), _lib.ptr(tg["saliency_scores"]), _lib.ptr(tg["pos"]),
+                                               _lib.ptr(tg.get("span_labels_nn")), _lib.ptr(tg["saliency_scores"]), _lib.ptr(tg["pos"]),
                                                B, Lv, d, float(crit.eos_coef), float(crit.temperature), _lib.ptr(losses),
                                                _lib.ptr(scratch), _lib.stream_ptr()), "univtg_loss_forward")
         ctx.saved = (xv, xt, tg["pos"], scratch, B, Lv, d)
@@ -64,7 +64,10 @@ def criterion_forward(crit, outputs, targets):
     if dev.type != "cuda":
         raise RuntimeError("univtg_b200: the criterion runs on CUDA tensors only (no CPU path)")
     B, Lv = outputs["pred_logits"].shape[:2]
-    tg = {k: _f32(targets[k], dev) for k in ("timestamp", "timestamp_mask", "timestamp_window", "span_labels_nn")}
+    tg = {k: _f32(targets[k], dev) for k in ("timestamp_mask", "timestamp_window")}
+    if "spans" in crit.losses:  # the hl / vs targets carry neither timestamp nor span_labels_nn (main/dataset.py:1118-1126)
+        tg["timestamp"] = _f32(targets["timestamp"], dev)
+        tg["span_labels_nn"] = _f32(targets["span_labels_nn"], dev)
     if "saliency" in crit.losses and "saliency_pos_labels" in targets and "saliency_scores" in targets:
         tg["saliency_scores"] = _f32(targets["saliency_scores"], dev)
         tg["pos"] = targets["saliency_pos_labels"][:, 0].detach().to(device=dev, dtype=torch.int64).contiguous()
