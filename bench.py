@@ -110,32 +110,162 @@ def gemm_flops_forward(cfg):
     return B * (enc + proj + conv)
 
 
-def oracle_step_fn(cfg, mode, batch):
+def workload_config(workload, wl, cfg, n_gpus):
+    """The `config` object of the JSON line: names the workload only, and is IDENTICAL for --impl b200 and --impl reference (arm
+    specific details live in `impl_details`)."""
+    return {"workload": workload, "mode": wl["mode"], "batch_per_gpu": cfg["batch"], "global_batch": cfg["batch"] * n_gpus,
+            "l_vid": cfg["l_vid"], "l_txt": cfg["l_txt"], "hidden_dim": cfg["hidden_dim"], "nheads": cfg["nheads"],
+            "dim_feedforward": cfg["dim_feedforward"], "enc_layers": cfg["enc_layers"], "v_feat_dim": cfg["v_feat_dim"],
+            "t_feat_dim": cfg["t_feat_dim"],
+            "step": ("forward + criterion + backward + clip_grad_norm(0.1) + AdamW, input_dropout 0.5, droppath 0.1"
+                     if wl["mode"] == "train" else "inference forward"),
+            "l2_policy": "rotating input batches larger than the 126 MB L2 in total"}
+
+
+def oracle_step_fn(cfg, mode, batch, device="cpu", dtype=None, autocast=None):
     """One CPU step of the oracle port: forward (mode fwd) or forward + criterion + backward + grad-clip + AdamW (mode train)."""
     from oracle import univtg_oracle as O  # bench.py may execute oracle/ only in the CPU legs
 
-    sd = {k: v.float() for k, v in synth.make_state_dict(cfg, seed=0).items()}
-    inp = synth.make_inputs(cfg, seed=1, batch=batch)
+    import contextlib
+
+    sd = {k: v.float().to(device) for k, v in synth.make_state_dict(cfg, seed=0).items()}
+    inp = {k: v.to(device) for k, v in synth.make_inputs(cfg, seed=1, batch=batch).items()}
+    ctx = (lambda: torch.autocast(device_type="cuda", dtype=autocast)) if autocast is not None else contextlib.nullcontext
     if mode == "fwd":
         def step():
-            with torch.no_grad():
-                O.forward(sd, cfg, **inp, dtype=torch.float32)
+            with torch.no_grad(), ctx():
+                return O.forward(sd, cfg, **inp, dtype=torch.float32)["pred_spans"]
         return step
-    tgt = synth.make_targets(inp, seed=2)
+    tgt = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in synth.make_targets(synth.make_inputs(cfg, seed=1, batch=batch), seed=2).items()}
     leaves = {k: v.clone().requires_grad_(not k.startswith("txt_position_embed")) for k, v in sd.items()}
     params = [v for v in leaves.values() if v.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-4)
     wd = {"loss_b": 10.0, "loss_g": 1.0, "loss_f": 10.0, "loss_s_intra": 0.1, "loss_s_inter": 0.1}
 
     def step():
-        out = O.forward(leaves, cfg, **inp, dtype=torch.float32)
-        total = O.weighted_total(O.criterion(out, tgt), wd)
+        with ctx():
+            out = O.forward(leaves, cfg, **inp, dtype=torch.float32)
+            total = O.weighted_total(O.criterion({k: (v.float() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in out.items()}, tgt), wd)
         opt.zero_grad()
         total.backward()
         torch.nn.utils.clip_grad_norm_(params, 0.1)
         opt.step()
-        return float(total)
+        return total
     return step
+
+
+def gpu_eager_baseline(cfg, wl, dev, steps=10):
+    """The "second bar" of SURVEY.md section 8(d) / BASELINE.md section 3: the reference's fp32 PyTorch path run on the SAME B200
+    through torch eager (cuBLAS / ATen kernels) - here the oracle port of that path (oracle/univtg_oracle.py is device-agnostic
+    tensor algebra; the reference itself cannot travel to the GPU box).  Three precisions: strict fp32, TF32 matmuls, bf16 autocast.
+    A baseline beside the product, never part of it."""
+    res = {"what": "oracle port of the reference PyTorch path on this GPU via torch eager", "unit": "pairs/s", "steps": steps}
+    B = cfg["batch"]
+    old_tf32 = torch.backends.cuda.matmul.allow_tf32
+    try:
+        for name, tf32, ac in (("fp32", False, None), ("tf32", True, None), ("bf16_autocast", True, torch.bfloat16)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            step = oracle_step_fn(cfg, wl["mode"], B, device=dev, autocast=ac)
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            res[name] = {"value": B / (ms * 1e-3), "ms_per_step": ms}
+            del step
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old_tf32
+    return res
+
+
+def attention_work(cfg, train):
+    """Algorithmic work of the attention core per step: flops 4 L^2 d per sample and layer forward (+ 10 L^2 d backward: five
+    contractions), bytes = Q, K, V read + O written as 16-bit (forward; backward reads Q, K, V, dO and writes dQ, dK, dV)."""
+    B, L, d, N = cfg["batch"], cfg["l_vid"] + cfg["l_txt"], cfg["hidden_dim"], cfg["enc_layers"]
+    fl = 4.0 * L * L * d * B * N
+    by = 4.0 * B * L * d * 2 * N
+    if train:
+        fl += 10.0 * L * L * d * B * N
+        by += 7.0 * B * L * d * 2 * N
+    return fl, by
+
+
+def sub_workload(name, dev, operand_format, steps, peaks):
+    """A few steps of another BASELINE.json config inside the default run (configs[3] = cfg4_train, configs[4] = cfg5_fwd), with
+    the attention kernel's achieved TFLOP/s and HBM GB/s (CUDA events around its launches)."""
+    from univtg_b200 import build_model
+    from univtg_b200.optim import FlatAdamW
+
+    wl = WORKLOADS[name]
+    cfg = synth.CONFIGS[wl["cfg"]]
+    train = wl["mode"] == "train"
+    model, crit = build_model(synth.reference_args(cfg, device=str(dev), operand_format=operand_format))
+    model.load_state_dict(synth.make_state_dict(cfg, seed=0), strict=True)
+    model.to(dev)
+    crit.to(dev)
+    B, Lv, Lt = cfg["batch"], cfg["l_vid"], cfg["l_txt"]
+    raw = [synth.make_inputs(cfg, seed=11 + i) for i in range(3)]
+    inps = [{k: v.to(dev) for k, v in r.items()} for r in raw]
+    if train:
+        model.train()
+        crit.train()
+        opt = FlatAdamW(model, lr=1e-4, weight_decay=1e-4, max_grad_norm=0.1)
+        tgts = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in synth.make_targets(r, seed=21 + i).items()} for i, r in enumerate(raw)]
+
+        def step(i):
+            out = model(**inps[i % 3])
+            total = crit.weighted_total(crit(out, tgts[i % 3]))
+            opt.zero_grad()
+            total.backward()
+            opt.step()
+    else:
+        model.eval()
+
+        def step(i):
+            with torch.no_grad():
+                model(**inps[i % 3])
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if train:
+        def run():
+            out = model(**inps[0])
+            crit.weighted_total(crit(out, tgts[0])).backward()
+        tl = model.profile_train_step(B, Lv, Lt, run)
+    else:
+        with torch.no_grad():
+            tl = model.profile_forward(inps[0])
+    attn_ms = sum(m for k, m in tl if k == 2)
+    n_attn = sum(1 for k, m in tl if k == 2)
+    gemm_ms = sum(m for k, m in tl if k == 1)
+    fl, by = attention_work(cfg, train)
+    total_flops, enc_flops = synth.flops_forward(cfg)
+    mult = 3 if train else 1
+    res = {"workload": name, "ms_per_step": ms, "value": B / (ms * 1e-3), "unit": "pairs/s", "steps": steps,
+           "clips_per_s": B * Lv / (ms * 1e-3), "tflops_algorithmic": mult * total_flops / (ms * 1e-3) / 1e12,
+           "encoder_tflops_pct_of_sustained_peak": 100.0 * mult * enc_flops / (ms * 1e-3) / 1e12 / peaks["tflops_sustained"],
+           "attention": {"launches": n_attn, "ms": attn_ms, "tflops": fl / (attn_ms * 1e-3) / 1e12 if attn_ms > 0 else None,
+                         "hbm_gbs_algorithmic": by / (attn_ms * 1e-3) / 1e9 if attn_ms > 0 else None,
+                         "frac_of_tensor_peak": fl / (attn_ms * 1e-3) / 1e12 / peaks["tflops_sustained"] if attn_ms > 0 else None,
+                         "frac_of_hbm_peak": by / (attn_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if attn_ms > 0 else None,
+                         "flop_per_byte": fl / by},
+           "gemm_ms": gemm_ms}
+    del model, crit
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_reference_arm(args, wl, cfg):
@@ -157,8 +287,9 @@ def run_reference_arm(args, wl, cfg):
         "impl": "reference", "metric": "video-query pairs/sec" + (" (fwd+bwd)" if wl["mode"] == "train" else " (fwd)"), "value": val, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "mode": wl["mode"], "batch": B, "l_vid": cfg["l_vid"], "l_txt": cfg["l_txt"],
-                   "hidden_dim": cfg["hidden_dim"], "enc_layers": cfg["enc_layers"]},
+        "config": workload_config(args.workload, wl, cfg, args.gpus),
+        "impl_details": {"what": "oracle port of the reference fp32 PyTorch path on the host cores (one process, rank 0)",
+                         "batch": B, "threads": cores},
         "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} full steps (B={B}) of {args.workload}, oracle/univtg_oracle.py fp32, "
                                    f"torch {torch.__version__} CPU, {cores} threads"},
@@ -217,6 +348,88 @@ def gemm_traffic_bytes():
         return None
 
 
+def grad_sync_check(dist, dev, rank, world, operand_format, overlap):
+    """Hardware check of the data-parallel exchange (every loss is a LOCAL-batch mean, so the reference semantics is
+    DDP's average of the ranks' gradients): on a small config every rank back-propagates its own batch through the overlapped
+    exchange; rank r then recomputes all `world` batches alone (no exchange) and averages.  Reports the relative L2 difference."""
+    from univtg_b200 import build_model, ddp
+
+    cfg = dict(synth.CONFIGS["tiny"], nheads=2)
+    results = []
+    for mode in ("exchange", "local"):
+        model, crit = build_model(synth.reference_args(cfg, device=str(dev), operand_format=operand_format, droppath=0.0, input_dropout=0.0))
+        model.load_state_dict(synth.make_state_dict(cfg, seed=5), strict=True)
+        model.to(dev).train()
+        crit.to(dev).train()
+        model.direct_grad = True
+        if mode == "exchange":
+            ddp.attach_flat_allreduce(model, overlap=overlap)
+        acc = None
+        for r in ([rank] if mode == "exchange" else range(world)):
+            raw = synth.make_inputs(cfg, seed=900 + r, ragged=True, batch=4)
+            tgt = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in synth.make_targets(raw, seed=950 + r).items()}
+            model.__dict__["_flat_grad_dirty"] = False
+            out = model(**{k: v.to(dev) for k, v in raw.items()})
+            crit.weighted_total(crit(out, tgt)).backward()
+            torch.cuda.synchronize()
+            flat = model._grad_buffer()[0].clone()
+            acc = flat if acc is None else acc + flat
+        results.append(acc / (1 if mode == "exchange" else world))
+        ddp.detach_flat_allreduce(model)
+        del model, crit
+    rel = float((results[0] - results[1]).norm() / results[1].norm().clamp_min(1e-30))
+    t = torch.tensor([rel], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # fp32 atomics in split-K reductions + NCCL's reduction order: a few 1e-4 relative at most
+    return {"what": "all-reduced gradient vs the average of the ranks' gradients recomputed on one GPU (tiny config, B=4 per rank)",
+            "grad_rel_err": float(t[0]), "tolerance": 2e-3, "world": world}
+
+
+def ddp_cfg4_point(dist, dev, rank, world, operand_format, overlap, steps=10):
+    """BASELINE.json configs[3]: the vlp_ddp pre-training shape (B = 32 per rank, L_v = 150) through the same exchange; a few steps."""
+    from univtg_b200 import build_model, ddp
+    from univtg_b200.optim import FlatAdamW
+
+    cfg = synth.CONFIGS["cfg4"]
+    model, crit = build_model(synth.reference_args(cfg, device=str(dev), operand_format=operand_format))
+    model.load_state_dict(synth.make_state_dict(cfg, seed=0), strict=True)
+    model.to(dev).train()
+    crit.to(dev).train()
+    opt = FlatAdamW(model, lr=1e-4, weight_decay=1e-4, max_grad_norm=0.1)
+    ddp.broadcast_parameters(model)
+    ddp.attach_flat_allreduce(model, overlap=overlap)
+    raws = [synth.make_inputs(cfg, seed=31 + 7 * rank + i) for i in range(3)]
+    inps = [{k: v.to(dev) for k, v in r.items()} for r in raws]
+    tgts = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in synth.make_targets(r, seed=61 + i).items()} for i, r in enumerate(raws)]
+
+    def step(i):
+        out = model(**inps[i % 3])
+        total = crit.weighted_total(crit(out, tgts[i % 3]))
+        opt.zero_grad()
+        total.backward()
+        opt.step()
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / steps
+    B = cfg["batch"]
+    del model, crit, opt
+    torch.cuda.empty_cache()
+    return {"workload": "cfg4_train", "global_batch": B * world, "l_vid": cfg["l_vid"], "ms_per_step": ms,
+            "value": B * world / (ms * 1e-3), "unit": "pairs/s", "steps": steps, "timing": "CUDA events, max over ranks"}
+
+
 _REAL_STDOUT_FD = None
 
 
@@ -251,6 +464,8 @@ def main():
                     help="inference workloads: replay the forward from a CUDA graph (default: eager launches chained by "
                          "programmatic dependent launch, which measured faster: 0.712 vs 0.735 ms at cfg2)")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one all-reduce after the backward instead of stage slices")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra legs of the default line (cfg4_train / cfg5_fwd sub-results, GPU torch-eager baseline)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     wl = WORKLOADS[args.workload]
@@ -275,6 +490,10 @@ def main():
         dist = dist_mod
         # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed when NCCL_DEBUG is set) goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # the gradient all-reduce overlaps the backward: cap the SMs its kernels take (the backward's persistent GEMM grids are
+        # sized for what is left, univtg_b200/ddp.py: UNIVTG_DDP_SM_RESERVE)
+        os.environ.setdefault("NCCL_MAX_CTAS", "16")
+        os.environ.setdefault("UNIVTG_DDP_SM_RESERVE", "16")
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
@@ -312,7 +531,8 @@ def main():
             host_targets.append({k: v.pin_memory() for k, v in synth.make_targets(inp, seed=100 + 7 * rank + i).items()})
     dev_batches = [{k: v.to(dev) for k, v in hb.items()} for hb in host_batches]
     dev_targets = [{k: v.to(dev) for k, v in ht.items()} for ht in host_targets]
-    launches_per_step = model.num_forward_launches(B, Lv, Lt)
+    from univtg_b200 import _lib as uvlib
+    lib = uvlib.load_library()
 
     def sync_all():
         torch.cuda.synchronize()
@@ -344,12 +564,14 @@ def main():
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    launches0 = int(lib.univtg_launch_count())
     e0.record()
     for i in range(args.steps):
         device_step(i)
     e1.record()
     sync_all()
     ms_total = e0.elapsed_time(e1)
+    gpu_launches = int(lib.univtg_launch_count()) - launches0  # kernels of THIS library launched inside the timed region
 
     # -------------------------------------------- end-to-end through the public API ------------------------------------
     # Every step copies ITS inputs from pinned host memory and reads ITS result back on the host.  The H2D copy of step
@@ -478,25 +700,74 @@ def main():
         postproc_line = {"what": "decode_mr + temporal_nms(0.7, 10, 10) on one batch", "gpu_us_per_batch": gpu_us,
                          "cpu_port_ms_per_batch": cpu_ms, "bit_exact_vs_port": bool(dec["windows_r4"].cpu().tolist() == rows)}
 
-    # ------------------- per-kernel-class durations of the forward (CUDA events between launches) ---------------------
-    kind_ms = {0: [], 1: [], 2: []}
-    n_kind = {0: 0, 1: 0, 2: 0}
-    was_training = model.training
-    model.eval()
-    with torch.no_grad():
+    # ------------------- per-kernel-class durations (CUDA events around the launches of the measured step) ---------------------
+    # train workloads: the WHOLE step's GEMM launches (forward + dgrad + wgrad), inference workloads: the forward's
+    kind_ms = {0: [], 1: [], 2: [], 3: []}
+    n_kind = {0: 0, 1: 0, 2: 0, 3: 0}
+    if train:
         for i in range(5):
-            tl = model.profile_forward(dev_batches[i % n_rot])
-            acc = {0: 0.0, 1: 0.0, 2: 0.0}
-            n_kind = {0: 0, 1: 0, 2: 0}
+            def run(i=i):
+                out = model(**dev_batches[i % n_rot])
+                total = crit.weighted_total(crit(out, dev_targets[i % n_rot]))
+                opt.zero_grad(set_to_none=True)
+                total.backward()
+            tl = model.profile_train_step(B, Lv, Lt, run)
+            acc = {0: 0.0, 1: 0.0, 2: 0.0, 3: 0.0}
+            n_kind = {0: 0, 1: 0, 2: 0, 3: 0}
             for kind, ms in tl:
                 acc[kind] += ms
                 n_kind[kind] += 1
             for k in acc:
                 kind_ms[k].append(acc[k])
-    model.train(was_training)
+    else:
+        was_training = model.training
+        model.eval()
+        with torch.no_grad():
+            for i in range(5):
+                tl = model.profile_forward(dev_batches[i % n_rot])
+                acc = {0: 0.0, 1: 0.0, 2: 0.0, 3: 0.0}
+                n_kind = {0: 0, 1: 0, 2: 0, 3: 0}
+                for kind, ms in tl:
+                    acc[kind] += ms
+                    n_kind[kind] += 1
+                for k in acc:
+                    kind_ms[k].append(acc[k])
+        model.train(was_training)
     gemm_ms = statistics.median(kind_ms[1])
     attn_ms = statistics.median(kind_ms[2])
-    row_ms = statistics.median(kind_ms[0])
+    row_ms = statistics.median(kind_ms[0]) + statistics.median(kind_ms[3])
+
+    # ------------------- extra legs of the default line (rank 0 of a single-GPU run) --------------------------------------------
+    extras = {}
+    if n_gpus == 1 and not args.no_extras and args.workload == DEFAULT_WORKLOAD:
+        peaks_x = load_peaks()
+        dev_batches.clear()
+        dev_targets.clear()
+        torch.cuda.empty_cache()
+        try:
+            extras["cfg4_train"] = sub_workload("cfg4_train", dev, args.operand_format, 10, peaks_x)
+            extras["cfg5_fwd"] = sub_workload("cfg5_fwd", dev, args.operand_format, 10, peaks_x)
+        except Exception as ex:  # never lose the headline to an extra leg
+            extras["error"] = repr(ex)[:300]
+        try:
+            extras["gpu_eager_baseline"] = gpu_eager_baseline(cfg, wl, dev)
+        except Exception as ex:
+            extras["gpu_eager_baseline"] = {"error": repr(ex)[:300]}
+
+    # ------------------- N > 1: is the exchanged gradient the average of the ranks' gradients, and did the replicas stay equal? ----
+    sync_check = None
+    cfg4_line = None
+    if dist is not None and train:
+        sync_check = grad_sync_check(dist, dev, rank, world, args.operand_format, not args.no_overlap)
+        flat_p = opt._flat_p
+        cs = torch.stack([flat_p.double().sum(), flat_p.double().abs().sum()])
+        gathered = [torch.zeros_like(cs) for _ in range(world)]
+        dist.all_gather(gathered, cs)
+        same = all(bool(torch.equal(gathered[0], g_)) for g_ in gathered)
+        sync_check["param_checksum_equal_across_ranks"] = same
+        sync_check["status"] = "ok" if (same and sync_check["grad_rel_err"] <= sync_check["tolerance"]) else "MISMATCH"
+        if args.workload == DEFAULT_WORKLOAD and not args.no_extras:
+            cfg4_line = ddp_cfg4_point(dist, dev, rank, world, args.operand_format, not args.no_overlap)
 
     # max over ranks
     t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
@@ -512,7 +783,7 @@ def main():
         total_flops, enc_flops = synth.flops_forward(cfg)
         if train:
             total_flops, enc_flops = 3 * total_flops, 3 * enc_flops  # dgrad + wgrad
-        gflops = gemm_flops_forward(cfg)
+        gflops = gemm_flops_forward(cfg) * (3 if train else 1)  # train: forward + dgrad + wgrad launches of the same kernel
         n_gemm = max(1, n_kind[1])
         achieved_tf = gflops / (gemm_ms * 1e-3) / 1e12
         h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
@@ -525,28 +796,30 @@ def main():
             "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.operand_format == "fp16" else "bf16",
             "data": "synthetic",
-            "config": {"workload": args.workload, "mode": wl["mode"], "batch_per_gpu": B, "global_batch": B * n_gpus, "l_vid": Lv,
-                       "l_txt": Lt, "hidden_dim": d, "nheads": cfg["nheads"], "dim_feedforward": cfg["dim_feedforward"],
-                       "enc_layers": cfg["enc_layers"], "v_feat_dim": cfg["v_feat_dim"], "t_feat_dim": cfg["t_feat_dim"],
-                       "operands": "fp16 activations/weights/gradients (gradients under a 2^10 loss scale), f32 accumulate + statistics + master weights",
-                       "step": ("forward + criterion + backward + clip_grad_norm(0.1) + AdamW" if train
-                                else ("forward (41 launches chained by programmatic dependent launch)" if (not args.graphs)
-                                      else "forward (CUDA-graph replay of the 41 launches)")),
-                       "parallelism": (f"dp{n_gpus}: shard by sample; flat fp32 gradient buffer NCCL all-reduced (AVG) in backward-stage slices on a side stream" if train
-                                       else f"replicas x{n_gpus} (shard by sample, no collective)"),
-                       "l2_policy": f"{n_rot} rotating input batches ({n_rot * per_batch / 1e6:.0f} MB > 126 MB L2)",
-                       "clips_per_s": value * Lv},
+            "config": workload_config(args.workload, wl, cfg, n_gpus),
+            "impl_details": {
+                "operands": "fp16 activations/weights/gradients (gradients under a 2^10 loss scale), f32 accumulate + statistics + master weights",
+                "step": ("forward + criterion + backward + clip_grad_norm(0.1) + AdamW; dropout / DropPath multipliers generated in-kernel (Philox)" if train
+                         else ("forward (launches chained by programmatic dependent launch)" if (not args.graphs)
+                               else "forward (CUDA-graph replay)")),
+                "parallelism": (f"dp{n_gpus}: shard by sample; flat fp32 gradient buffer NCCL all-reduced (AVG) in backward-stage slices on a side stream" if train
+                                else f"replicas x{n_gpus} (shard by sample, no collective)"),
+                "l2_policy": f"{n_rot} rotating input batches ({n_rot * per_batch / 1e6:.0f} MB > 126 MB L2)",
+                "clips_per_s": value * Lv},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches_per_step * args.steps * (3 if train else 1),
-            "launches_per_step": launches_per_step * (3 if train else 1),
+            "gpu_launches": gpu_launches,
+            "launches_per_step": gpu_launches / args.steps,
             "clocks": clocks,
             "tflops_algorithmic": total_flops / (step_ms * 1e-3) / 1e12,
             "encoder_tflops_pct_of_sustained_peak": 100.0 * enc_flops / (step_ms * 1e-3) / 1e12 / peaks["tflops_sustained"],
             "roofline": {"kernel": "gemm_tcgen05_kernel", "bound": "tensor", "achieved": achieved_tf,
                          "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["tflops_sustained"],
-                         "traffic": gemm_traffic_bytes(), "peak_source": peaks["source"] + ", sustained (kernel timed inside a step)",
-                         "scope": "forward launches of the kernel (CUDA events between launches)",
+                         "traffic": gemm_traffic_bytes(),
+                         "traffic_source": "static: mean DRAM read+write bytes per launch of one encoder layer's four forward launches in the committed ncu --set full capture (profiles/gemm_traffic.json), not measured in this run",
+                         "peak_source": peaks["source"] + ", sustained (kernel timed inside a step)",
+                         "scope": ("every launch of the kernel in the train step: forward + dgrad + wgrad (CUDA events around each launch)" if train
+                                   else "forward launches of the kernel (CUDA events between launches)"),
                          "launches_per_step": n_gemm, "avg_launch_us": gemm_ms / n_gemm * 1e3,
                          "flops_per_launch": gflops / n_gemm,
                          "step_share": {"gemm_ms": gemm_ms, "attention_ms": attn_ms, "row_kernels_ms": row_ms}},
@@ -555,6 +828,13 @@ def main():
             line["forward_only"] = fwd_only
         if postproc_line is not None:
             line["postproc"] = postproc_line
+        for k_, v_ in extras.items():
+            line[k_] = v_
+        if sync_check is not None:
+            line["grad_sync_check"] = sync_check["status"]
+            line["grad_sync_detail"] = sync_check
+        if cfg4_line is not None:
+            line["cfg4_train"] = cfg4_line
         if n_gpus == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cfg, wl, args.workload)
         emit_json_line(line)

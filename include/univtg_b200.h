@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define UNIVTG_ABI_VERSION 1
+#define UNIVTG_ABI_VERSION 2
 
 /* Model hyper-parameters: the fields of `args` that reference model/univtg.py:409-450 (build_model),
  * model/transformer_encoder_droppath.py:141-152 (build_transformer) and model/position_encoding.py:113-126 read. */
@@ -45,6 +45,16 @@ typedef struct univtg_shape {
   int32_t training; /* 1: keep the activations backward needs (larger workspace) */
 } univtg_shape;
 
+/* Train-mode randomness generated inside the kernels (Philox4x32-10 keyed by (seed, mask index); csrc/philox.cuh): input
+ * dropout of every LinearLayer (reference model/univtg.py:394,401) and DropPath (transformer_encoder_droppath.py:154-167).
+ * The same struct passed to univtg_forward_train and univtg_backward reproduces the same draws; explicit multiplier tensors
+ * (droppath_scale / drop_masks arguments) take precedence where given. */
+typedef struct univtg_rng {
+  uint64_t seed;        /* one value per training forward */
+  float input_dropout;  /* args.input_dropout (p of nn.Dropout); 0 = off */
+  float droppath;       /* args.droppath (drop probability); 0 = off */
+} univtg_rng;
+
 typedef struct univtg_plan univtg_plan; /* opaque; host memory only (tensor maps + pointer table) */
 
 const char* univtg_last_error(void);
@@ -66,9 +76,15 @@ int univtg_pack_weights(const univtg_config* cfg, const float* const* params, in
 
 /* Workspace bytes for one (config, shape). */
 size_t univtg_workspace_bytes(const univtg_config* cfg, const univtg_shape* shape);
+/* Zero the few regions of a workspace that kernels rely on reading as zeros (the separator rows of the conv-head buffers that
+ * implement Conv1d's zero padding, reference model/univtg.py:375-377); everything else is written before it is read.  Call it
+ * when a workspace buffer is used for the first time or handed over from another shape (workspaces may be pooled and shared
+ * between shapes: size them for the largest shape).  training_ws: 0 = workspace of univtg_plan_create (univtg_workspace_bytes),
+ * 1 = training workspace (univtg_train_workspace_bytes). */
+int univtg_prepare_workspace(const univtg_config* cfg, const univtg_shape* shape, void* workspace, int32_t training_ws, void* stream);
 /* Build a plan: tensor maps over `packed` and `workspace` (both must stay alive and must not move).
  * `dim_t`: device fp32 [hidden_dim], the sine-embedding denominators temperature**(2*(j//2)/d)
- * (reference model/position_encoding.py:75) evaluated by the caller.  Zero-fills the workspace on `stream`. */
+ * (reference model/position_encoding.py:75) evaluated by the caller.  Calls univtg_prepare_workspace on `stream`. */
 int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, const void* packed, void* workspace,
                        const float* dim_t, void* stream, univtg_plan** out);
 void univtg_plan_destroy(univtg_plan* plan);
@@ -91,11 +107,16 @@ size_t univtg_train_workspace_bytes(const univtg_config* cfg, const univtg_shape
 
  *   droppath_scale: NULL or [2*enc_layers, B] (see univtg_forward)
  *   drop_masks: NULL or HOST array of 2*n_input_proj device pointers (video layers, then text layers): fp32 [rows, din_i]
- *               input-dropout multipliers (0 or 1/(1-p)) drawn by the caller in the reference's order; entries may be NULL. */
+ *               input-dropout multipliers (0 or 1/(1-p)) drawn by the caller in the reference's order; entries may be NULL.
+ *   rng: NULL or in-kernel randomness for whichever of the two is not given explicitly (mask index = position in drop_masks). */
 int univtg_forward_train(univtg_plan* plan, void* train_ws, const float* src_txt, const float* src_txt_mask,
                          const float* src_vid, const float* src_vid_mask, const float* droppath_scale,
-                         const float* const* drop_masks, float* pred_logits, float* pred_spans, float* vid_mem_proj,
-                         float* txt_mem_proj, float* saliency_scores, void* stream);
+                         const float* const* drop_masks, const univtg_rng* rng, float* pred_logits, float* pred_spans,
+                         float* vid_mem_proj, float* txt_mem_proj, float* saliency_scores, void* stream);
+/* The multipliers univtg_forward_train draws for `rng`: mask `mask_index` ([rows, din] row-major, n elements) and the DropPath
+ * scales [n_sites = 2*enc_layers, batch].  Parity tests hand them to the oracle. */
+int univtg_dropout_mask(const univtg_rng* rng, int32_t mask_index, size_t n, float* out, void* stream);
+int univtg_droppath_scales(const univtg_rng* rng, int32_t n_sites, int32_t batch, float* out, void* stream);
 /* Backward of the last univtg_forward_train on (plan, train_ws).  g_*: upstream gradients of pred_logits [B,Lv,1],
  * pred_spans [B,Lv,2], vid_mem_proj [B,Lv,d], txt_mem_proj [B,1,d] (NULL = zero).  grads: HOST array of device pointers,
  * one ZERO-FILLED fp32 tensor per parameter in univtg_pack_weights order and in the parameter's own layout.
@@ -104,8 +125,9 @@ int univtg_forward_train(univtg_plan* plan, void* train_ws, const float* src_txt
  * underflow, and every parameter gradient is multiplied by 1/S where it is written (the results are unscaled).  Use 1 for
  * bf16 plans. */
 int univtg_backward(univtg_plan* plan, void* train_ws, const float* src_txt, const float* src_vid, const float* droppath_scale,
-                    const float* const* drop_masks, const float* g_logits, const float* g_spans, const float* g_vid_mem_proj,
-                    const float* g_txt_mem_proj, float grad_scale, float* const* grads, int32_t n_grads, void* stream);
+                    const float* const* drop_masks, const univtg_rng* rng, const float* g_logits, const float* g_spans,
+                    const float* g_vid_mem_proj, const float* g_txt_mem_proj, float grad_scale, float* const* grads,
+                    int32_t n_grads, void* stream);
 
 /* Gradient-exchange overlap (the reference relies on DistributedDataParallel's bucketed all-reduce overlapping backward,
  * main/train_vlp_ddp.py:272-275).  univtg_backward finalises parameter gradients in n = enc_layers + 2 stages:
@@ -116,6 +138,9 @@ int univtg_backward(univtg_plan* plan, void* train_ws, const float* src_txt, con
  * k's gradients are final, so a communication stream can wait on it and reduce that slice while the backward continues.
  * n = 0 removes them.  (enc_layers <= 16, so n <= 18.) */
 int univtg_backward_stages(const univtg_config* cfg, int32_t* ranges, int32_t max_stages);
+/* The GEMM launches of univtg_backward are persistent grids of one CTA per SM.  When a collective (NCCL) runs beside the backward
+ * its CTAs occupy some SMs; give the backward the number of SMs that are left (0 = all) so that its grids stay single-wave. */
+int univtg_plan_set_backward_sm_budget(univtg_plan* plan, int32_t num_sms);
 int univtg_plan_set_grad_events(univtg_plan* plan, void* const* events, int32_t n);
 
 /* SetCriterion for model_id=univtg (reference model/univtg.py:195-282): losses5 = {loss_b, loss_g, loss_f, loss_s_inter,
@@ -133,6 +158,8 @@ int univtg_loss_backward(const float* w5, const float* vid_mem_proj, const float
 
 /* Number of kernels one univtg_forward launches (for bench accounting). */
 int univtg_forward_num_launches(const univtg_plan* plan);
+/* Kernels this library has launched since it was loaded (every launch of every entry point; memsets / memcpys not counted). */
+int64_t univtg_launch_count(void);
 
 /* Optional per-launch CUDA-event timeline of univtg_forward (bench / profiling only; adds event records to the stream).
  * read_profile returns the number of launches of the last forward and fills ms[i] / kinds[i]
@@ -173,11 +200,19 @@ int univtg_debug_mma_rate(int32_t n, int32_t iters, int32_t per_commit, int32_t 
  *   total_norm = ||grads||_2;  if max_grad_norm > 0: g *= min(1, max_grad_norm / (total_norm + 1e-6))   (clip_grad_norm_)
  *   p *= 1 - lr*wd;  m = m + (1-beta1)(g - m);  v = beta2 v + (1-beta2) g^2;
  *   p -= lr/(1-beta1^step) * m / (sqrt(v)/sqrt(1-beta2^step) + eps)                                      (AdamW, step >= 1)
- * scratch2: device fp32 [2]; on return [1] holds total_norm (what clip_grad_norm_ returns).  write_clipped_grads != 0
- * also stores the clipped gradients back (clip_grad_norm_ scales .grad in place). */
+ * scratch3: device fp32 [3]; on return [1] holds total_norm (what clip_grad_norm_ returns) and [2] is 1.0 when total_norm was not
+ * finite - then NOTHING was updated (the skipped step of dynamic loss scaling; the fp16 gradient operands of univtg_backward can
+ * overflow when grad_scale is too large), else 0.0.  write_clipped_grads != 0 also stores the clipped gradients back
+ * (clip_grad_norm_ scales .grad in place).
+ * cfg + packed (both non-NULL; the flat buffers must then hold exactly the config's parameters in univtg_pack_weights order, each
+ * padded to a multiple of 4 floats): the kernel also refreshes the 16-bit copies of the GEMM weight matrices inside `packed` from the
+ * values it has just computed, so no separate re-packing pass re-reads the weights; call univtg_pack_vectors afterwards for the
+ * fp32 vectors (LayerNorm terms, biases, token-type rows - a few hundred KB). */
 int univtg_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
                       float beta2, float eps, float weight_decay, int32_t step, float max_grad_norm,
-                      int32_t write_clipped_grads, float* scratch2, void* stream);
+                      int32_t write_clipped_grads, float* scratch3, const univtg_config* cfg, void* packed, void* stream);
+/* univtg_pack_weights restricted to the fp32 vectors and the two tiny last-conv tensors (everything that is not a 16-bit matrix). */
+int univtg_pack_vectors(const univtg_config* cfg, const float* const* params, int32_t n_params, void* packed, void* stream);
 
 /* Post-forward decode of the reference's MR evaluation loop, on the device.
  * univtg_decode_mr = main/inference_mr.py:112-120,146-157 (and main_gradio.py:100-106 with duration == NULL):

@@ -1,4 +1,6 @@
 """CPU oracle of the UniVTG hot path -- TEST INFRASTRUCTURE ONLY.
+(Device-agnostic tensor algebra: bench.py's `gpu_eager_baseline` leg also runs it on the GPU through torch eager / cuBLAS as the
+"reference on the same GPU" baseline of SURVEY.md section 8(d) - a baseline beside the product, never inside it.)
 
 This file is a from-scratch restatement (explicit tensor algebra on torch CPU tensors, fp64 by default) of what the
 reference computes on the path named in BASELINE.json; it is the *checker* for the CUDA kernels.  Only tests/,
@@ -65,10 +67,10 @@ def sine_position(vid_mask, d, dtype):
     m = vid_mask.to(dtype)
     c = torch.cumsum(m, dim=1)
     e = c / (c[:, -1:] + 1e-6) * (2.0 * math.pi)
-    j = torch.arange(d, dtype=dtype)
+    j = torch.arange(d, dtype=dtype, device=vid_mask.device)
     dim_t = 10000.0 ** (2.0 * torch.floor(j / 2.0) / d)
     arg = e[:, :, None] / dim_t
-    pos = torch.where((torch.arange(d) % 2 == 0)[None, None, :], torch.sin(arg), torch.cos(arg))
+    pos = torch.where((torch.arange(d, device=vid_mask.device) % 2 == 0)[None, None, :], torch.sin(arg), torch.cos(arg))
     return pos
 
 
@@ -107,7 +109,7 @@ def conv1d_k3(x, w, b, opq_x, opq_w):
     """x [B, L, C]; w [N, C, 3]; cross-correlation, zero padding 1:  y[l] = sum_t W[:, :, t] x[l + t - 1] + b."""
     B, L, C = x.shape
     xq = opq_x(x)
-    z = torch.zeros(B, 1, C, dtype=x.dtype)
+    z = torch.zeros(B, 1, C, dtype=x.dtype, device=x.device)
     # taps t = 0, 1, 2 read x[l-1], x[l], x[l+1]; one [B*L, 3C] x [3C, N] product
     taps = torch.cat([torch.cat([z, xq[:, :-1]], 1), xq, torch.cat([xq[:, 1:], z], 1)], dim=-1)
     w2 = opq_w(w).permute(0, 2, 1).reshape(w.shape[0], 3 * C)  # w2[n, t*C + c] = w[n, c, t]
@@ -166,8 +168,8 @@ def forward(sd, cfg, src_txt, src_txt_mask, src_vid, src_vid_mask, dp_scale=None
     x_t = input_proj(src_txt, sd, "input_txt_proj.", n_proj, opq, mt) + sd["token_type_embeddings.weight"][0]
     x = torch.cat([x_v, x_t], dim=1)
     key_valid = torch.cat([vmask, tmask], dim=1) != 0
-    pos = torch.cat([sine_position(vmask, d, dtype), torch.zeros(B, Lt, d, dtype=dtype)], dim=1)
-    ones = torch.ones(B, dtype=dtype)
+    pos = torch.cat([sine_position(vmask, d, dtype), torch.zeros(B, Lt, d, dtype=dtype, device=src_vid.device)], dim=1)
+    ones = torch.ones(B, dtype=dtype, device=src_vid.device)
     inter = {}
     for l in range(N):
         s1 = dp_scale[2 * l].to(dtype) if dp_scale is not None else ones
@@ -177,10 +179,10 @@ def forward(sd, cfg, src_txt, src_txt_mask, src_vid, src_vid_mask, dp_scale=None
     vid_mem = x[:, :Lv]
     pred_logits = torch.sigmoid(conv_head(vid_mem, sd, "class_embed.", opq))
     spans = torch.sigmoid(conv_head(vid_mem, sd, "span_embed.", opq))
-    pred_spans = spans * torch.tensor([-1.0, 1.0], dtype=dtype)
+    pred_spans = spans * torch.tensor([-1.0, 1.0], dtype=dtype, device=src_vid.device)
     pooled, alpha = weighted_pool(x_t, tmask, sd["weightedpool.weight"])
     # log(mask + 1e-45): 1e-45 rounds to the smallest fp32 denormal 2**-149 in the reference
-    tiny = torch.tensor(2.0 ** -149, dtype=dtype)
+    tiny = torch.tensor(2.0 ** -149, dtype=dtype, device=src_vid.device)
     sal = cosine(x_v, pooled[:, None, :]) + torch.log(vmask + tiny)
     out = {"pred_logits": pred_logits, "pred_spans": pred_spans, "src_vid_mask": src_vid_mask, "vid_mem_proj": x_v,
            "txt_mem_proj": pooled[:, None, :], "saliency_scores": sal}
@@ -236,13 +238,13 @@ def criterion(outputs, targets, eos_coef=0.1, temperature=0.07, losses=("spans",
     if "saliency" in losses:
         sal = t["saliency_scores"]
         if "saliency_pos_labels" not in t or float(sal.sum()) == 0.0:
-            res["loss_s_inter"] = torch.zeros((), dtype=dtype)
-            res["loss_s_intra"] = torch.zeros((), dtype=dtype)
+            res["loss_s_inter"] = torch.zeros((), dtype=dtype, device=sal.device)
+            res["loss_s_intra"] = torch.zeros((), dtype=dtype, device=sal.device)
         else:
             xv = outputs["vid_mem_proj"]
             xt = outputs["txt_mem_proj"].squeeze(1)
             B = xv.shape[0]
-            bi = torch.arange(B)
+            bi = torch.arange(B, device=xv.device)
             pi = t["saliency_pos_labels"][:, 0].long()
             vf = xv[bi, pi]
             a_n = vf / vf.norm(dim=1, keepdim=True).clamp_min(1e-8)
@@ -255,7 +257,7 @@ def criterion(outputs, targets, eos_coef=0.1, temperature=0.07, losses=("spans",
             neg = sal < sel
             neg[bi, pi] = True
             keep = (neg & (t["timestamp_mask"] != 0)).to(dtype)
-            tiny = torch.tensor(2.0 ** -149, dtype=dtype)
+            tiny = torch.tensor(2.0 ** -149, dtype=dtype, device=xv.device)
             sim_in = cosine(xv, xt[:, None, :]) + torch.log(keep + tiny)
             ls_i = _log_softmax(sim_in / temperature, 1)
             ls_j = _log_softmax(sim_in.t() / temperature, 1)

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_sizes():
     lib = _lib.load_library()
-    assert lib.univtg_abi_version() == 1
+    assert lib.univtg_abi_version() == 2
     cfg = _lib.Config(1024, 8, 1024, 4, 2, 2818, 512, 0)
     assert lib.univtg_num_params(ctypes.byref(cfg)) == 8 * 2 + 1 + 12 * 4 + 12 + 1
     pb = lib.univtg_packed_bytes(ctypes.byref(cfg))

@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libunivtg_b200.so")
+# UNIVTG_LIB: A/B-test another build of the same ABI (profiling only)
+LIB_PATH = os.environ.get("UNIVTG_LIB") or os.path.join(_HERE, "lib", "libunivtg_b200.so")
 _lib = None
 
 c_int = ctypes.c_int32
@@ -36,6 +37,12 @@ class Shape(ctypes.Structure):
     _fields_ = [("batch", c_int), ("l_vid", c_int), ("l_txt", c_int), ("training", c_int)]
 
 
+class Rng(ctypes.Structure):
+    """univtg_rng."""
+
+    _fields_ = [("seed", ctypes.c_uint64), ("input_dropout", c_float), ("droppath", c_float)]
+
+
 # symbol -> (restype, argtypes); every symbol declared in include/univtg_b200.h must be listed here
 SIGNATURES = {
     "univtg_last_error": (ctypes.c_char_p, []),
@@ -44,27 +51,34 @@ SIGNATURES = {
     "univtg_packed_bytes": (c_size_t, [ctypes.POINTER(Config)]),
     "univtg_pack_weights": (c_int, [ctypes.POINTER(Config), ctypes.POINTER(c_void_p), c_int, c_void_p, c_void_p]),
     "univtg_workspace_bytes": (c_size_t, [ctypes.POINTER(Config), ctypes.POINTER(Shape)]),
+    "univtg_prepare_workspace": (c_int, [ctypes.POINTER(Config), ctypes.POINTER(Shape), c_void_p, c_int, c_void_p]),
     "univtg_plan_create": (c_int, [ctypes.POINTER(Config), ctypes.POINTER(Shape), c_void_p, c_void_p, c_void_p, c_void_p,
                                    ctypes.POINTER(c_void_p)]),
     "univtg_plan_destroy": (None, [c_void_p]),
     "univtg_forward": (c_int, [c_void_p] * 12),
     "univtg_forward_num_launches": (c_int, [c_void_p]),
+    "univtg_launch_count": (ctypes.c_int64, []),
     "univtg_train_workspace_bytes": (c_size_t, [ctypes.POINTER(Config), ctypes.POINTER(Shape)]),
     "univtg_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                     ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "univtg_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_void_p, c_void_p,
-                                c_void_p, c_void_p, c_float, ctypes.POINTER(c_void_p), c_int, c_void_p]),
+                                     ctypes.POINTER(c_void_p), ctypes.POINTER(Rng), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p]),
+    "univtg_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(Rng),
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_float, ctypes.POINTER(c_void_p), c_int, c_void_p]),
+    "univtg_dropout_mask": (c_int, [ctypes.POINTER(Rng), c_int, c_size_t, c_void_p, c_void_p]),
+    "univtg_droppath_scales": (c_int, [ctypes.POINTER(Rng), c_int, c_int, c_void_p, c_void_p]),
     "univtg_loss_scratch_bytes": (c_size_t, [c_int, c_int]),
     "univtg_loss_forward": (c_int, [c_void_p] * 10 + [c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "univtg_loss_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p]),
     "univtg_backward_stages": (c_int, [ctypes.POINTER(Config), c_void_p, c_int]),
     "univtg_plan_set_grad_events": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_int]),
+    "univtg_plan_set_backward_sm_budget": (c_int, [c_void_p, c_int]),
     "univtg_decode_mr": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p]),
     "univtg_temporal_nms": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "univtg_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_size_t, c_float, c_float, c_float, c_float,
-                                  c_float, c_int, c_float, c_int, c_void_p, c_void_p]),
+                                  c_float, c_int, c_float, c_int, c_void_p, ctypes.POINTER(Config), c_void_p, c_void_p]),
+    "univtg_pack_vectors": (c_int, [ctypes.POINTER(Config), ctypes.POINTER(c_void_p), c_int, c_void_p, c_void_p]),
     "univtg_plan_set_profiling": (c_int, [c_void_p, c_int]),
     "univtg_plan_read_profile": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "univtg_op_gemm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
@@ -97,7 +111,7 @@ def load_library():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.univtg_abi_version() != 1:
+    if lib.univtg_abi_version() != 2:
         raise RuntimeError("univtg_b200: ABI version mismatch between header and library")
     _lib = lib
     return lib

@@ -25,7 +25,8 @@ size_t univtg_packed_bytes(const univtg_config* cfg) {
   return make_layout(*cfg).total;
 }
 
-int univtg_pack_weights(const univtg_config* cfg, const float* const* params, int32_t n_params, void* packed, void* stream) {
+// mode 0: everything; mode 1: only the fp32 vectors / small fp32 tensors (the 16-bit matrices are kept current by univtg_adamw_step)
+static int pack_impl(const univtg_config* cfg, const float* const* params, int32_t n_params, void* packed, void* stream, int mode) {
   if (!check_cfg(cfg)) return 1;
   const int expect = univtg_num_params(cfg);
   if (n_params != expect || !params || !packed) {
@@ -44,6 +45,7 @@ int univtg_pack_weights(const univtg_config* cfg, const float* const* params, in
   pk.fmt = cfg->operand_format;
   pk.st = (cudaStream_t)stream;
   pk.tab.n = 0;
+  pk.skip_matrices = mode == 1;
   int idx = 0;
   const int type_idx = 8 * cfg->n_input_proj;  // token_type_embeddings.weight [2, d]
   const float* type_emb = params[type_idx];
@@ -103,6 +105,98 @@ int univtg_pack_weights(const univtg_config* cfg, const float* const* params, in
   return 0;
 }
 
+int univtg_pack_weights(const univtg_config* cfg, const float* const* params, int32_t n_params, void* packed, void* stream) {
+  return pack_impl(cfg, params, n_params, packed, stream, 0);
+}
+int univtg_pack_vectors(const univtg_config* cfg, const float* const* params, int32_t n_params, void* packed, void* stream) {
+  return pack_impl(cfg, params, n_params, packed, stream, 1);
+}
+
+// Segments of the flat parameter buffer (univtg_pack_weights order, every tensor padded to a multiple of 4 floats) that are GEMM
+// weight matrices, with their place in `packed`.
+static int make_pack_segments(const univtg_config& c, void* packed, PackSegTable& t) {
+  const PackedLayout L = make_layout(c);
+  uint8_t* base = reinterpret_cast<uint8_t*>(packed);
+  const long long d = c.hidden_dim, ff = c.dim_feedforward;
+  t.n = 0;
+  t.fmt = c.operand_format;
+  long long off = 0;  // floats
+  auto skip = [&](long long numel) { off += (numel + 3) / 4 * 4; };
+  auto seg = [&](long long numel, size_t dst, int kind, int rows, int cols, int ld) {
+    if (t.n >= kMaxPackSegs) return 1;
+    PackSeg& s = t.s[t.n++];
+    s.start4 = off / 4;
+    s.end4 = (off + numel + 3) / 4;
+    s.dst = base + dst;
+    s.kind = kind;
+    s.rows = rows;
+    s.cols = cols;
+    s.ld = ld;
+    skip(numel);
+    return 0;
+  };
+  int rc = 0;
+  for (int sdx = 0; sdx < 2; ++sdx) {
+    const ProjPacked* pp = sdx == 0 ? L.vid : L.txt;
+    for (int i = 0; i < c.n_input_proj; ++i) {
+      skip(pp[i].din);
+      skip(pp[i].din);
+      rc |= seg(d * pp[i].din, pp[i].w16, 0, (int)d, pp[i].din, pp[i].kpad);
+      skip(d);
+    }
+  }
+  skip(2 * d);  // token_type_embeddings
+  for (int l = 0; l < c.enc_layers; ++l) {
+    const LayerPacked& lp = L.layer[l];
+    rc |= seg(3 * d * d, lp.w_in, 0, (int)(3 * d), (int)d, (int)d);
+    skip(3 * d);
+    rc |= seg(d * d, lp.w_out, 0, (int)d, (int)d, (int)d);
+    skip(d);
+    rc |= seg(ff * d, lp.w1, 0, (int)ff, (int)d, (int)d);
+    skip(ff);
+    rc |= seg(d * ff, lp.w2, 0, (int)d, (int)ff, (int)ff);
+    skip(d);
+    skip(d); skip(d); skip(d); skip(d);
+  }
+  // span_embed.layers.{0,1,2} then class_embed.layers.{0,1,2}; fused first conv: rows [0,d) class, [d,2d) span
+  rc |= seg(d * d * 3, L.conv1_w + (size_t)d * 3 * d * 2, 1, (int)d, (int)d, 0);
+  skip(d);
+  rc |= seg(d * d * 3, L.conv2s_w, 1, (int)d, (int)d, 0);
+  skip(d);
+  skip(2 * d * 3);
+  skip(2);
+  rc |= seg(d * d * 3, L.conv1_w, 1, (int)d, (int)d, 0);
+  skip(d);
+  rc |= seg(d * d * 3, L.conv2c_w, 1, (int)d, (int)d, 0);
+  skip(d);
+  skip(1 * d * 3);
+  skip(1);
+  skip(d);  // weightedpool.weight
+  if (rc) {
+    set_error("univtg_adamw_step: too many weight matrices for the pack-segment table");
+    return -1;
+  }
+  return (int)(off);  // total floats of the flat buffer
+}
+
+int univtg_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, int32_t step, float max_grad_norm, int32_t write_clipped_grads,
+                      float* scratch3, const univtg_config* cfg, void* packed, void* stream) {
+  if (cfg == nullptr || packed == nullptr)
+    return uv::adamw_step_impl(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, max_grad_norm,
+                               write_clipped_grads, scratch3, nullptr, stream);
+  if (!check_cfg(cfg)) return 1;
+  PackSegTable t;
+  const int total = make_pack_segments(*cfg, packed, t);
+  if (total < 0) return 1;
+  if ((size_t)total != n) {
+    set_error("univtg_adamw_step: flat buffer has %zu floats, the config's parameters need %d", n, total);
+    return 1;
+  }
+  return uv::adamw_step_impl(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, max_grad_norm,
+                             write_clipped_grads, scratch3, &t, stream);
+}
+
 }  // extern "C"
 
 extern "C" {
@@ -149,9 +243,7 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
   P->Mt = P->B * P->Lt;
   P->Mh = P->B * (P->Lv + 1);
   const WsLayout w = make_ws(*cfg, *shape, P->lay);
-  cudaError_t ce = cudaMemsetAsync(workspace, 0, w.total, (cudaStream_t)stream);
-  if (ce != cudaSuccess) {
-    set_error("workspace memset: %s", cudaGetErrorString(ce));
+  if (univtg_prepare_workspace(cfg, shape, workspace, 0, stream) != 0) {  // zero rows of the conv-head buffers
     delete P;
     return 1;
   }
@@ -360,7 +452,7 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
 
 void univtg_plan_destroy(univtg_plan* plan) {
   if (!plan) return;
-  for (int i = 0; i < 160; ++i)
+  for (int i = 0; i < kMaxMarks; ++i)
     if (plan->marks[i]) cudaEventDestroy(plan->marks[i]);
   delete plan;
 }
@@ -389,6 +481,7 @@ int univtg_plan_read_profile(univtg_plan* plan, float* ms, int32_t* kinds, int32
 }
 
 int univtg_forward_num_launches(const univtg_plan* plan) { return plan ? plan->launches : -1; }
+int64_t univtg_launch_count(void) { return (int64_t)*uv::launch_counter(); }
 
 int univtg_forward(univtg_plan* P, const float* src_txt, const float* src_txt_mask, const float* src_vid,
                    const float* src_vid_mask, const float* droppath_scale, float* pred_logits, float* pred_spans,

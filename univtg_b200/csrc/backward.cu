@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const LnBwdArgs a) {
       if (j < a.d) {
         float dj = dout[j];
         if (a.dout_mul) dj *= a.dout_mul[(size_t)row * a.d + j];
+        else if (a.drop.on) dj *= drop_mul1(a.drop, (unsigned long long)row * a.d + j);
         xh[i] = (y[j] - mean) * rstd;
         g[i] = dj * a.gamma[j];
         acc_g[i] += dj * xh[i];
@@ -110,6 +111,9 @@ __global__ void __launch_bounds__(128) layernorm_bwd_vec_kernel(const LnBwdArgs 
         ny[i] = __ldg(reinterpret_cast<const float4*>(a.y + (size_t)row * a.ld_y + j));
         if (a.dout_mul) {
           const float4 m = __ldg(reinterpret_cast<const float4*>(a.dout_mul + (size_t)row * a.d + j));
+          nd[i].x *= m.x, nd[i].y *= m.y, nd[i].z *= m.z, nd[i].w *= m.w;
+        } else if (a.drop.on) {
+          const float4 m = drop_mul4(a.drop, (unsigned long long)row * a.d + j);
           nd[i].x *= m.x, nd[i].y *= m.y, nd[i].z *= m.z, nd[i].w *= m.w;
         }
       }
@@ -204,6 +208,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_params_kernel(const LnBwdAr
   for (int r = r0; r < r1; ++r) {
     float dj = __ldg(a.dout + (size_t)r * a.ld_dout + j);
     if (a.dout_mul) dj *= __ldg(a.dout_mul + (size_t)r * a.d + j);
+    else if (a.drop.on) dj *= drop_mul1(a.drop, (unsigned long long)r * a.d + j);
     const float xh = (__ldg(a.y + (size_t)r * a.ld_y + j) - __ldg(a.mean + r)) * __ldg(a.rstd + r);
     ag += dj * xh;
     ab += dj;

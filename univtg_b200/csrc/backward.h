@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "philox.cuh"
+
 namespace uv {
 
 // LayerNorm backward over rows:  xhat = (y - mean) * rstd,  g = dout * gamma,
@@ -29,6 +31,7 @@ struct LnBwdArgs {
   float* colsum;           // [d] atomically accumulated column sums of the values written to dbr16 (bias gradient), or null
   float pgrad_scale;       // factor on dgamma / dbeta / colsum (1 / loss-scale: parameter gradients leave unscaled)
   const float* dout_mul;   // optional [rows, d] multiplier applied to dout on load (input-dropout mask incl. 1/(1-p))
+  DropSpec drop;           // in-kernel regeneration of the forward's input-dropout multipliers (drop.on; ignored with dout_mul)
 };
 int launch_layernorm_bwd(const LnBwdArgs& a, cudaStream_t stream);
 

@@ -153,7 +153,11 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
     // ======================================= TMA producer =======================================
     // The whole warp walks the schedule convergently and ONE elected lane issues (elect.sync): inside a plain `if (lane == 0)`
     // region ptxas cannot prove the TMA / MMA operands warp-uniform and wraps every UTMALDG / UTCHMMA / UTCBAR in an
-    // ELECT + BRA.U.ANY "waterfall" loop (measured in round 2: that, not the tensor pipe, set the ~90 ns per MMA of round 1).
+    // ELECT + BRA.U.ANY "waterfall" loop (round 2: -10 % GEMM time).  What paces the mainloop now is tcgen05.commit: two commits are
+    // at least ~615 SM cycles apart (tools/probes/mma_probe.cu), so a 64-wide k-block (4 MMAs, one commit to free its stage)
+    // costs ~0.33 us whatever the tile width.  Releasing stages in pairs with one commit was tried and measured SLOWER here
+    // (profiles/README.md, r2c/r2d): with a 192 KB ring of 42-48 KB stages only two groups fit, and the commit -> refill -> landed
+    // round trip (~1 us) then stalls the MMA warp; the same holds for requesting weight tiles before griddepcontrol.wait.
     {
       int stage = 0;
       uint32_t phase = 0;
@@ -736,6 +740,10 @@ bool pdl_enabled() {
   }
   return on == 1;
 }
+long long* launch_counter() {
+  static long long n = 0;
+  return &n;
+}
 static thread_local char g_err[512] = "";
 const char* last_error() { return g_err; }
 void set_error(const char* fmt, ...) {
@@ -915,6 +923,7 @@ int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    ++*launch_counter();
     e = full ? cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, true>, g) : cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, false>, g);
   }
   if (e != cudaSuccess) {

@@ -111,8 +111,10 @@ void set_error(const char* fmt, ...);
 // griddepcontrol.wait until this grid has completed and flushed - the launch latency and the next kernel's prologue
 // (barrier init, TMEM allocation, tensor-map prefetch) disappear under the current kernel's tail.  UNIVTG_PDL=0 disables it.
 bool pdl_enabled();
+long long* launch_counter();  // kernels launched by this library since it was loaded (bench accounting: gpu_launches)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  ++*launch_counter();
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
@@ -126,6 +128,24 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
+
+// 16-bit operand copies written by the fused AdamW step itself (optim.cu): the big GEMM weight matrices, described as ranges of the
+// flat parameter buffer.  kind 0: [rows, cols] -> 16-bit [rows, ld] (K padding beyond cols stays zero); kind 1: Conv1d weight
+// [N = rows, C = cols, 3] -> 16-bit [N, 3C] with w2[n, t*C + c] = w[n, c, t].
+struct PackSeg {
+  long long start4, end4;  // float4 index range inside the flat buffer
+  void* dst;
+  int kind, rows, cols, ld;
+};
+constexpr int kMaxPackSegs = 40;
+struct PackSegTable {
+  int n, fmt;
+  PackSeg s[kMaxPackSegs];
+};
+
+int adamw_step_impl(float* params, float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int32_t step, float max_grad_norm, int32_t write_clipped_grads, float* scratch3,
+                    const PackSegTable* segs, void* stream);
 
 int debug_tmem_ld_rate(int iters, int mode, int blocks, float* out, float* sink, cudaStream_t stream);
 int debug_mma_rate(int n, int iters, int per_commit, int kstep_bytes, int blocks, float* out, cudaStream_t stream, int a_mn = 0, int b_mn = 0);

@@ -38,16 +38,69 @@ struct AdamArgs {
   float* v;
   size_t n4;
   float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, max_norm;
-  float* scratch;  // [0] = sum of squares of g (in), [1] = total norm (out)
+  float* scratch;  // [0] = sum of squares of g (in), [1] = total norm (out), [2] = 1 when the step was skipped (non-finite gradients)
   float* g_out;    // clipped gradients written back (clip_grad_norm_ scales .grad in place) or null
 };
 
-__global__ void __launch_bounds__(256) adamw_kernel(const AdamArgs a) {
+// 16-bit operand copy of the four freshly updated parameters at flat float4 index i (see PackSeg)
+__device__ __forceinline__ void pack_updated(const PackSegTable& t, size_t i, const float4& p) {
+  int lo = 0, hi = t.n;  // first segment with start4 > i
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((size_t)t.s[mid].start4 <= i) lo = mid + 1;
+    else hi = mid;
+  }
+  if (lo == 0) return;
+  const PackSeg& sg = t.s[lo - 1];
+  if (i >= (size_t)sg.end4) return;
+  const size_t e = (i - (size_t)sg.start4) * 4;
+  uint16_t* dst = reinterpret_cast<uint16_t*>(sg.dst);
+  const float v[4] = {p.x, p.y, p.z, p.w};
+  if (sg.kind == 0) {
+    const size_t r = e / (size_t)sg.cols;
+    const int c = (int)(e - r * (size_t)sg.cols);
+    if ((sg.cols & 3) == 0) {  // four columns of one row, 8-byte aligned (ld % 4 == 0)
+      *reinterpret_cast<uint2*>(dst + r * (size_t)sg.ld + c) = make_uint2(cvt16x2(p.x, p.y, t.fmt), cvt16x2(p.z, p.w, t.fmt));
+    } else {
+      size_t rr = r;
+      int cc = c;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (rr < (size_t)sg.rows) dst[rr * (size_t)sg.ld + cc] = cvt16(v[q], t.fmt);
+        if (++cc == sg.cols) {
+          cc = 0;
+          ++rr;
+        }
+      }
+    }
+  } else {
+    const size_t C3 = (size_t)3 * sg.cols;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const size_t eq = e + q;
+      const size_t n = eq / C3;
+      const int rem = (int)(eq - n * C3);
+      const int c = rem / 3, tap = rem - 3 * c;
+      if (n < (size_t)sg.rows) dst[n * C3 + (size_t)tap * sg.cols + c] = cvt16(v[q], t.fmt);
+    }
+  }
+}
+
+template <bool PACK>
+__global__ void __launch_bounds__(256) adamw_kernel(const AdamArgs a, const __grid_constant__ PackSegTable segs) {
   pdl_prologue();
   const float norm = sqrtf(a.scratch[0]);
   float clip = 1.f;
   if (a.max_norm > 0.f) clip = fminf(a.max_norm / (norm + 1e-6f), 1.f);
-  if (blockIdx.x == 0 && threadIdx.x == 0) a.scratch[1] = norm;
+  // fp16 loss-scaled backward: an overflow in a 16-bit gradient operand shows up as inf / NaN in the gradient buffer, hence in its
+  // norm.  Such a step must leave weights and moments untouched (what torch.cuda.amp.GradScaler.step does); the caller reads
+  // scratch[2] later (no synchronisation here) and backs the loss scale off.
+  const bool skip = !isfinite(norm);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.scratch[1] = norm;
+    a.scratch[2] = skip ? 1.f : 0.f;
+  }
+  if (skip) return;
   float4* p4 = reinterpret_cast<float4*>(a.p);
   const float4* g4 = reinterpret_cast<const float4*>(a.g);
   float4* m4 = reinterpret_cast<float4*>(a.m);
@@ -66,6 +119,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamArgs a) {
     p4[i] = p;
     m4[i] = m;
     v4[i] = v;
+    if (PACK) pack_updated(segs, i, p);
     if (a.g_out) reinterpret_cast<float4*>(a.g_out)[i] = g;
   }
 }
@@ -73,9 +127,10 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamArgs a) {
 }  // namespace
 }  // namespace uv
 
-extern "C" int univtg_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
-                                 float beta2, float eps, float weight_decay, int32_t step, float max_grad_norm,
-                                 int32_t write_clipped_grads, float* scratch2, void* stream) {
+namespace uv {
+int adamw_step_impl(float* params, float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int32_t step, float max_grad_norm, int32_t write_clipped_grads, float* scratch2,
+                    const PackSegTable* segs, void* stream) {
   using namespace uv;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (n == 0) return 0;
@@ -90,7 +145,7 @@ extern "C" int univtg_adamw_step(float* params, float* grads, float* exp_avg, fl
   const size_t n4 = n / 4;
   size_t blocks = (n4 + 255) / 256;
   if (blocks > (size_t)sms * 8) blocks = (size_t)sms * 8;
-  cudaMemsetAsync(scratch2, 0, 2 * sizeof(float), st);
+  cudaMemsetAsync(scratch2, 0, 3 * sizeof(float), st);
   launch_k(sumsq_kernel, dim3((unsigned)blocks), dim3(256), 0, st, grads, n4, scratch2);
   AdamArgs a;
   a.p = params;
@@ -108,8 +163,16 @@ extern "C" int univtg_adamw_step(float* params, float* grads, float* exp_avg, fl
   a.max_norm = max_grad_norm;
   a.scratch = scratch2;
   a.g_out = write_clipped_grads ? grads : nullptr;
-  launch_k(adamw_kernel, dim3((unsigned)blocks), dim3(256), 0, st, a);
+  if (segs != nullptr && segs->n > 0) {
+    launch_k(adamw_kernel<true>, dim3((unsigned)blocks), dim3(256), 0, st, a, *segs);
+  } else {
+    PackSegTable none;
+    none.n = 0;
+    none.fmt = 0;
+    launch_k(adamw_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, st, a, none);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("univtg_adamw_step launch failed: %s", cudaGetErrorString(e));
   return (int)e;
 }
+}  // namespace uv

@@ -233,7 +233,9 @@ struct Packer {
   int fmt;
   cudaStream_t st;
   PackTable tab;
+  bool skip_matrices = false;  // only the fp32 vectors / small tensors (kinds 2, 3)
   void push(const PackTask& t) {
+    if (skip_matrices && (t.kind == 0 || t.kind == 1)) return;
     if (tab.n == kPackTasksPerLaunch) flush();
     tab.t[tab.n++] = t;
   }
@@ -259,6 +261,7 @@ struct Packer {
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
+constexpr int kMaxMarks = 640;
 struct univtg_plan {
   univtg_config cfg;
   univtg_shape shp;
@@ -267,6 +270,7 @@ struct univtg_plan {
   uint8_t* ws;
   const float* dim_t;
   int num_sms;
+  int num_sms_bwd;  // SM budget of the backward's GEMM launches (0: num_sms); see univtg_plan_set_backward_sm_budget
   int B, Lv, Lt, L, d, ff, H, dh, M, Mv, Mt, Mh;
   // workspace pointers
   uint16_t *a_vid[3], *a_txt[3];  // LN'd 16-bit projector inputs
@@ -292,8 +296,8 @@ struct univtg_plan {
   // optional per-launch CUDA-event timeline (bench / profiling only)
   int profiling;
   int n_marks;
-  cudaEvent_t marks[160];
-  int mark_kind[160];  // kind of the launch that ENDS at mark i (i >= 1): 0 row kernel, 1 tcgen05 GEMM, 2 attention
+  cudaEvent_t marks[kMaxMarks];
+  int mark_kind[kMaxMarks];  // kind of the interval that ENDS at mark i (i >= 1): 0 row kernel, 1 tcgen05 GEMM, 2 attention, 3 other work
 };
 
 namespace {
@@ -306,12 +310,20 @@ inline void prof_begin(univtg_plan* P, cudaStream_t st) {
   P->n_marks = 1;
 }
 inline void prof_mark(univtg_plan* P, cudaStream_t st, int kind) {
-  if (!P->profiling || P->n_marks >= 160) return;
+  if (!P->profiling || P->n_marks >= kMaxMarks) return;
   const int i = P->n_marks;
   if (!P->marks[i]) cudaEventCreate(&P->marks[i]);
   cudaEventRecord(P->marks[i], st);
   P->mark_kind[i] = kind;
   P->n_marks = i + 1;
+}
+// training path: a GEMM / attention launch bracketed by two marks, so that the interval ending at the second mark is that kernel
+// alone (the interval ending at the first one - kind 3 - collects whatever ran since the previous mark)
+inline int gemm_launch(univtg_plan* P, GemmGroup& g, int bn, int sms, cudaStream_t st) {
+  prof_mark(P, st, 3);
+  const int rc = launch_gemm_group(g, bn, sms, st);
+  prof_mark(P, st, 1);
+  return rc;
 }
 }  // namespace
 

@@ -37,6 +37,9 @@ struct LnStore {
     if (a.mul32) {
       const float4 m = *reinterpret_cast<const float4*>(a.mul32 + (size_t)row * a.d + j);
       v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+    } else if (a.drop.on) {
+      const float4 m = drop_mul4(a.drop, (unsigned long long)row * a.d + j);
+      v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
     }
     uint2 pk;
     pk.x = cvt16x2(v.x, v.y, a.fmt);
@@ -56,6 +59,7 @@ struct LnStore {
   __device__ __forceinline__ void store1(int j, float v) const {
     if (a.out32) a.out32[(size_t)row * a.d + j] = v;
     if (a.mul32) v *= a.mul32[(size_t)row * a.d + j];
+    else if (a.drop.on) v *= drop_mul1(a.drop, (unsigned long long)row * a.d + j);
     const uint16_t h = cvt16(v, a.fmt);
     if (a.out16) a.out16[(size_t)row * a.ld16 + j] = h;
     if (a.out16p) a.out16p[(size_t)row * a.ld16 + j] = has_pos ? cvt16(v + a.pos[prow * a.d + j], a.fmt) : h;
@@ -256,6 +260,10 @@ __global__ void __launch_bounds__(128) layernorm_rows_block2_kernel(const LnArgs
         const float2 m = *reinterpret_cast<const float2*>(a.mul32 + (size_t)row * a.d + j);
         ox *= m.x;
         oy *= m.y;
+      } else if (a.drop.on) {
+        const float2 m = drop_mul2(a.drop, (unsigned long long)row * a.d + j);
+        ox *= m.x;
+        oy *= m.y;
       }
       *reinterpret_cast<uint32_t*>(a.out16 + (size_t)row * a.ld16 + j) = cvt16x2(ox, oy, a.fmt);
     }
@@ -297,8 +305,11 @@ int launch_layernorm(const LnArgs& a, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sine_pos_table_kernel(const float* __restrict__ mask, const float* __restrict__ txt_mask,
                                                             const float* __restrict__ dim_t, float* __restrict__ pos,
-                                                            float* __restrict__ key_mask, int Lv, int Lt, int d) {
+                                                            float* __restrict__ key_mask, int Lv, int Lt, int d,
+                                                            float* __restrict__ dp_out, int dp_n, unsigned long long dp_seed, float dp_keep) {
   pdl_prologue();
+  if (dp_out != nullptr && blockIdx.x == 0 && blockIdx.y == 0)  // DropPath scales of this step ([sites, B], a few hundred values)
+    for (int i = threadIdx.x; i < dp_n; i += 256) dp_out[i] = droppath_scale(dp_seed, (unsigned int)i, dp_keep);
   extern __shared__ float s_e[];  // [Lv] cumulative position, then the normalised angle
   __shared__ float s_part[256];
   const int b = blockIdx.x;
@@ -350,13 +361,39 @@ __global__ void __launch_bounds__(256) sine_pos_table_kernel(const float* __rest
 }
 
 int launch_sine_pos(const float* mask, const float* txt_mask, const float* dim_t, float* pos, float* key_mask, int B, int Lv,
-                    int Lt, int d, cudaStream_t stream) {
+                    int Lt, int d, cudaStream_t stream, float* dp_out, int dp_sites, unsigned long long dp_seed, float dp_keep) {
   int chunks = (Lv * d + 4095) / 4096;
   if (chunks < 1) chunks = 1;
   if (chunks > 128) chunks = 128;
-  launch_k(sine_pos_table_kernel, dim3(dim3(B, chunks)), dim3(256), Lv * sizeof(float), stream, mask, txt_mask, dim_t, pos, key_mask, Lv, Lt, d);
+  launch_k(sine_pos_table_kernel, dim3(dim3(B, chunks)), dim3(256), Lv * sizeof(float), stream, mask, txt_mask, dim_t, pos, key_mask, Lv, Lt, d,
+           dp_out, dp_sites * B, dp_seed, dp_keep);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("sine_pos launch failed: %s", cudaGetErrorString(e));
+  return (int)e;
+}
+
+__global__ void __launch_bounds__(256) dropout_mask_kernel(const DropSpec spec, size_t n, float* __restrict__ out) {
+  pdl_prologue();
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = spec.on ? drop_mul1(spec, i) : 1.f;
+}
+__global__ void __launch_bounds__(256) droppath_scales_kernel(unsigned long long seed, int n, float keep, float* __restrict__ out) {
+  pdl_prologue();
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) out[i] = droppath_scale(seed, (unsigned int)i, keep);
+}
+int launch_dropout_mask(const DropSpec& spec, size_t n, float* out, cudaStream_t stream) {
+  if (n == 0) return 0;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  launch_k(dropout_mask_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, spec, n, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) set_error("dropout_mask launch failed: %s", cudaGetErrorString(e));
+  return (int)e;
+}
+int launch_droppath_scales(unsigned long long seed, int n, float keep, float* out, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  launch_k(droppath_scales_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, seed, n, keep, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) set_error("droppath_scales launch failed: %s", cudaGetErrorString(e));
   return (int)e;
 }
 

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "philox.cuh"
+
 namespace uv {
 
 struct LnArgs {
@@ -26,14 +28,20 @@ struct LnArgs {
   const float* pos;    // [B*Lv, d] fp32 sine table (row b*Lv + l)
   uint16_t* outc;      // conv-head layout: row 1 + b*(Lv+1) + l of a [B*(Lv+1)+2, d] buffer (video rows only)
   const float* mul32;  // [rows, d] multiplier applied to the 16-bit outputs only (input-dropout mask incl. 1/(1-p)), or null
+  DropSpec drop;       // in-kernel input dropout (drop.on; ignored when mul32 is given): same multiplier semantics
   float* mean_out;     // [rows] (training)
   float* rstd_out;     // [rows]
 };
 int launch_layernorm(const LnArgs& a, cudaStream_t stream);
 
 // pos [B*Lv, d] sine table + key_mask [B, Lv+Lt] = cat(vid_mask, txt_mask)
+// dp_out (optional): [dp_sites, B] DropPath scales floor(keep + u) / keep drawn in-kernel from (dp_seed, site * B + b)
 int launch_sine_pos(const float* mask, const float* txt_mask, const float* dim_t, float* pos, float* key_mask, int B, int Lv,
-                    int Lt, int d, cudaStream_t stream);
+                    int Lt, int d, cudaStream_t stream, float* dp_out = nullptr, int dp_sites = 0, unsigned long long dp_seed = 0,
+                    float dp_keep = 1.f);
+// standalone generators (parity tests read the in-kernel draws back through them)
+int launch_dropout_mask(const DropSpec& spec, size_t n, float* out, cudaStream_t stream);
+int launch_droppath_scales(unsigned long long seed, int n, float keep, float* out, cudaStream_t stream);
 
 struct PoolSalArgs {
   const float* x_txt;     // [B, Lt, d] projected text tokens (incl. token-type embedding)

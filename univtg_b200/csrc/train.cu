@@ -54,6 +54,7 @@ struct TrainWs {
   float *pmean_v[3], *prstd_v[3], *pmean_t[3], *prstd_t[3];
   float *p_vid32[3], *p_txt32[3];  // output of projector layer i (input of LayerNorm i+1)
   float *txtproj32, *pool_alpha, *pos, *key_mask, *pool_logits;
+  float* dp_scale;  // [2 * enc_layers, B] DropPath scales drawn in-kernel by the forward (univtg_rng), reused by the backward
   uint16_t *xin16[17], *xpos16[17];  // operands of layer l's in-projections (index enc_layers: unused tail)
   uint16_t *qkv16[16], *attn16[16], *x1_16[16], *h16[16];
   float *lse[16], *y1[16], *mean1[16], *rstd1[16], *hpre[16], *y2[16], *mean2[16], *rstd2[16];
@@ -93,6 +94,7 @@ TrainWs make_train_ws(const univtg_config& c, const univtg_shape& s, const Packe
   w.pool_logits = take32(B * Lt);
   w.pos = take32(Mv * d);
   w.key_mask = take32(B * Lc);
+  w.dp_scale = take32((size_t)2 * c.enc_layers * B);
   for (int l = 0; l <= c.enc_layers; ++l) {
     w.xin16[l] = take16(M * d);
     w.xpos16[l] = take16(M * d);
@@ -158,6 +160,45 @@ TrainWs make_train_ws(const univtg_config& c, const univtg_shape& s, const Packe
 
 extern "C" {
 
+// Buffers whose untouched rows must read as zeros (conv-head layout [B*(Lv+1)+2, C]: the separator rows that implement the
+// Conv1d zero padding, model/univtg.py:375-377).  Every other byte of a workspace is written by a kernel before it is read,
+// so a pooled workspace only needs this when it is handed to a different shape (or for the first time).
+int univtg_prepare_workspace(const univtg_config* cfg, const univtg_shape* shape, void* workspace, int32_t training_ws, void* stream) {
+  if (!check_cfg(cfg) || !check_shape(shape) || !workspace) {
+    if (workspace == nullptr) set_error("univtg_prepare_workspace: null workspace");
+    return 1;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const PackedLayout L = make_layout(*cfg);
+  const size_t d = cfg->hidden_dim, Mh = (size_t)shape->batch * (shape->l_vid + 1);
+  uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+  cudaError_t e = cudaSuccess;
+  auto zero = [&](void* p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMemsetAsync(p, 0, bytes, st);
+  };
+  if (training_ws) {
+    const TrainWs T = make_train_ws(*cfg, *shape, L, base);
+    zero(T.hA, (Mh + 2) * d * 2);
+    zero(T.h1, (Mh + 2) * 2 * d * 2);
+    zero(T.hc2, (Mh + 2) * d * 2);
+    zero(T.hs2, (Mh + 2) * d * 2);
+    zero(T.dhc2, (Mh + 2) * d * 2);
+    zero(T.dhs2, (Mh + 2) * d * 2);
+    zero(T.dh1, (Mh + 2) * 2 * d * 2);
+  } else {
+    const WsLayout w = make_ws(*cfg, *shape, L);
+    zero(base + w.hA, (Mh + 2) * d * 2);
+    zero(base + w.h1, (Mh + 2) * 2 * d * 2);
+    zero(base + w.hc2, (Mh + 2) * d * 2);
+    zero(base + w.hs2, (Mh + 2) * d * 2);
+  }
+  if (e != cudaSuccess) {
+    set_error("univtg_prepare_workspace: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
 size_t univtg_train_workspace_bytes(const univtg_config* cfg, const univtg_shape* shape) {
   if (!check_cfg(cfg) || !check_shape(shape)) return 0;
   return make_train_ws(*cfg, *shape, make_layout(*cfg), nullptr).total;
@@ -168,7 +209,7 @@ size_t univtg_train_workspace_bytes(const univtg_config* cfg, const univtg_shape
 // multipliers (0 or 1/(1-p)) or NULL entries / NULL array when dropout is off.
 int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const float* src_txt_mask, const float* src_vid,
                          const float* src_vid_mask, const float* droppath_scale, const float* const* drop_masks,
-                         float* pred_logits, float* pred_spans, float* vid_mem_proj, float* txt_mem_proj,
+                         const univtg_rng* rng, float* pred_logits, float* pred_spans, float* vid_mem_proj, float* txt_mem_proj,
                          float* saliency_scores, void* stream) {
   if (!P || !ws || !src_txt || !src_txt_mask || !src_vid || !src_vid_mask || !pred_logits || !pred_spans || !vid_mem_proj ||
       !txt_mem_proj || !saliency_scores) {
@@ -187,8 +228,14 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
   int rc = 0;
   GemmGroup g;
 
-  rc = launch_sine_pos(src_vid_mask, src_txt_mask, P->dim_t, T.pos, T.key_mask, P->B, Lv, P->Lt, d, st);
+  // train-mode randomness: explicit tensors (the caller drew them, e.g. with the reference's torch calls) win over `rng`
+  prof_begin(P, st);
+  const bool dp_rng = droppath_scale == nullptr && rng != nullptr && rng->droppath > 0.f;
+  const bool drop_rng = drop_masks == nullptr && rng != nullptr && rng->input_dropout > 0.f;
+  rc = launch_sine_pos(src_vid_mask, src_txt_mask, P->dim_t, T.pos, T.key_mask, P->B, Lv, P->Lt, d, st, dp_rng ? T.dp_scale : nullptr,
+                       2 * c.enc_layers, rng ? rng->seed : 0ull, rng ? 1.0f - rng->droppath : 1.f);
   if (rc) return rc;
+  if (dp_rng) droppath_scale = T.dp_scale;
 
   // ---- input projectors ----
   for (int i = 0; i < c.n_input_proj; ++i) {
@@ -207,6 +254,7 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
       a.out16 = s == 0 ? T.a_vid[i] : T.a_txt[i];
       a.ld16 = pp.kpad;
       a.mul32 = drop_masks ? drop_masks[s * c.n_input_proj + i] : nullptr;
+      if (drop_rng) a.drop = make_drop_spec(rng->seed, (unsigned int)(s * c.n_input_proj + i), rng->input_dropout);
       a.mean_out = s == 0 ? T.pmean_v[i] : T.pmean_t[i];
       a.rstd_out = s == 0 ? T.prstd_v[i] : T.prstd_t[i];
       rc = launch_layernorm(a, st);
@@ -245,7 +293,7 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
       g.p[0].out32_id = vid_mem_proj;
       g.p[1].out32_id = T.txtproj32;
     }
-    rc = launch_gemm_group(g, P->bn_proj[i], sms, st);
+    rc = gemm_launch(P, g, P->bn_proj[i], sms, st);
     if (rc) return rc;
   }
 
@@ -264,7 +312,7 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
     g.p[1].bias = F32(lp.b_in) + 2 * d;
     g.p[1].out16 = T.qkv16[l] + 2 * d;
     g.p[1].ld16 = 3 * d;
-    rc = launch_gemm_group(g, P->bn_qkv, sms, st);
+    rc = gemm_launch(P, g, P->bn_qkv, sms, st);
     if (rc) return rc;
     {
       AttnArgs a;
@@ -281,7 +329,9 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
       a.fmt = fmt;
       if (P->dh == 64 || P->dh == 128) {
         if (make_tmap_2d(&a.tm_qkv, T.qkv16[l], (uint64_t)M, (uint64_t)3 * d, (uint64_t)3 * d, 128, 64)) return 1;
+        prof_mark(P, st, 3);
         rc = launch_attention(a, st);
+        prof_mark(P, st, 2);
       } else {
         rc = launch_attention_simt(a, T.qkv16[l], st);
       }
@@ -298,7 +348,7 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
     g.p[0].row_scale = droppath_scale ? droppath_scale + (size_t)(2 * l) * P->B : nullptr;
     g.p[0].out16 = T.br16;
     g.p[0].ld16 = d;
-    rc = launch_gemm_group(g, P->bn_out, sms, st);
+    rc = gemm_launch(P, g, P->bn_out, sms, st);
     if (rc) return rc;
     {
       LnArgs a;
@@ -333,7 +383,7 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
     g.p[0].ld16 = ff;
     g.p[0].pre32 = T.hpre[l];
     g.p[0].ld_pre = ff;
-    rc = launch_gemm_group(g, P->bn_ffn1, sms, st);
+    rc = gemm_launch(P, g, P->bn_ffn1, sms, st);
     if (rc) return rc;
     memset(&g, 0, sizeof(g));
     g.num = 1;
@@ -346,7 +396,7 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
     g.p[0].row_scale = droppath_scale ? droppath_scale + (size_t)(2 * l + 1) * P->B : nullptr;
     g.p[0].out16 = T.br16;
     g.p[0].ld16 = d;
-    rc = launch_gemm_group(g, P->bn_ffn2, sms, st);
+    rc = gemm_launch(P, g, P->bn_ffn2, sms, st);
     if (rc) return rc;
     {
       LnArgs a;
@@ -405,7 +455,7 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
   g.fmt = fmt;
   rc = conv_problem(g.p[0], T.hA, d, W16(Lw.conv1_w), 2 * d, F32(Lw.conv1_b), T.h1, 2 * d, P->bn_conv1);
   if (rc) return rc;
-  rc = launch_gemm_group(g, P->bn_conv1, sms, st);
+  rc = gemm_launch(P, g, P->bn_conv1, sms, st);
   if (rc) return rc;
   memset(&g, 0, sizeof(g));
   g.num = 2;
@@ -413,7 +463,7 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
   rc |= conv_problem(g.p[0], T.h1, 2 * d, W16(Lw.conv2c_w), d, F32(Lw.conv2c_b), T.hc2, d, P->bn_conv2);
   rc |= conv_problem(g.p[1], T.h1 + d, 2 * d, W16(Lw.conv2s_w), d, F32(Lw.conv2s_b), T.hs2, d, P->bn_conv2);
   if (rc) return rc;
-  rc = launch_gemm_group(g, P->bn_conv2, sms, st);
+  rc = gemm_launch(P, g, P->bn_conv2, sms, st);
   if (rc) return rc;
   {
     HeadFinalArgs a;
@@ -466,8 +516,9 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
 // be zero-filled by the caller (several are accumulated atomically); they are written in the parameters' native layouts.
 // drop_masks / droppath_scale: the same arrays that were passed to the forward.
 int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float* src_vid, const float* droppath_scale,
-                    const float* const* drop_masks, const float* g_logits, const float* g_spans, const float* g_vid_mem_proj,
-                    const float* g_txt_mem_proj, float grad_scale, float* const* grads, int32_t n_grads, void* stream) {
+                    const float* const* drop_masks, const univtg_rng* rng, const float* g_logits, const float* g_spans,
+                    const float* g_vid_mem_proj, const float* g_txt_mem_proj, float grad_scale, float* const* grads,
+                    int32_t n_grads, void* stream) {
   if (!P || !ws || !grads || !src_txt || !src_vid || !(grad_scale > 0.f)) {
     set_error("univtg_backward: null argument");
     return 1;
@@ -483,9 +534,13 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
   auto F32 = [&](size_t off) { return reinterpret_cast<const float*>(pk + off); };
   auto W16 = [&](size_t off) { return reinterpret_cast<const uint16_t*>(pk + off); };
   const TrainWs T = make_train_ws(c, P->shp, Lw, reinterpret_cast<uint8_t*>(ws));
+  if (droppath_scale == nullptr && rng != nullptr && rng->droppath > 0.f) droppath_scale = T.dp_scale;  // drawn by the forward
+  const bool drop_rng = drop_masks == nullptr && rng != nullptr && rng->input_dropout > 0.f;
   const int d = P->d, ff = P->ff, fmt = c.operand_format, M = P->M, Mv = P->Mv, Mt = P->Mt, Mh = P->Mh, L = P->L, Lv = P->Lv,
             Lt = P->Lt, B = P->B;
-  const int sms = P->num_sms;
+  // persistent GEMM grids assume every CTA is resident at once; when a gradient all-reduce runs beside the backward its CTAs
+  // hold some SMs, and a 148-CTA grid would wait for them (a second wave): launch on the SMs that are left
+  const int sms = (P->num_sms_bwd > 0 && P->num_sms_bwd < P->num_sms) ? P->num_sms_bwd : P->num_sms;
   const int FMT_G = fmt;                 // gradient operand format == activation operand format
   const float GS = grad_scale;           // loss scale carried by every intermediate gradient
   const float INV = 1.0f / grad_scale;   // applied wherever a parameter gradient is written
@@ -600,7 +655,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       p.colsum = s == 0 ? G_cls(1) : G_span(1);  // bias gradient of conv layer 0
       p.colsum_scale = INV;
     }
-    rc = launch_gemm_group(g, bn_c2d, sms, st);
+    rc = gemm_launch(P, g, bn_c2d, sms, st);
     if (rc) return rc;
     // wgrad conv layer 2: 2 heads x 3 taps
     for (int s = 0; s < 2; ++s) {
@@ -611,7 +666,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
         rc |= conv_wgrad(g.p[t], s == 0 ? T.dhc2 : T.dhs2, d, d, T.h1 + s * d, 2 * d, d, t, s == 0 ? G_cls(2) : G_span(2));
       if (rc) return rc;
       if (t_cw.ksplit > 1) cudaMemsetAsync(T.wtap, 0, (size_t)3 * d * d * 4, st);  // split-K accumulates into the planes
-      rc = launch_gemm_group(g, bn_cw, sms, st);
+      rc = gemm_launch(P, g, bn_cw, sms, st);
       if (rc) return rc;
       rc = launch_tap_interleave(T.wtap, s == 0 ? G_cls(2) : G_span(2), d, d, st);
       if (rc) return rc;
@@ -628,7 +683,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.p[0].skip_sep = 1;
     g.p[0].out32 = T.dx;
     g.p[0].ld32 = d;
-    rc = launch_gemm_group(g, bn_c1d, sms, st);
+    rc = gemm_launch(P, g, bn_c1d, sms, st);
     if (rc) return rc;
     // wgrad conv layer 1: class rows [0,d) and span rows [d,2d) of the fused weight
     for (int s = 0; s < 2; ++s) {
@@ -638,7 +693,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       for (int t = 0; t < 3; ++t) rc |= conv_wgrad(g.p[t], T.dh1 + s * d, 2 * d, d, T.hA, d, d, t, s == 0 ? G_cls(0) : G_span(0));
       if (rc) return rc;
       if (t_cw.ksplit > 1) cudaMemsetAsync(T.wtap, 0, (size_t)3 * d * d * 4, st);
-      rc = launch_gemm_group(g, bn_cw, sms, st);
+      rc = gemm_launch(P, g, bn_cw, sms, st);
       if (rc) return rc;
       rc = launch_tap_interleave(T.wtap, s == 0 ? G_cls(0) : G_span(0), d, d, st);
       if (rc) return rc;
@@ -703,7 +758,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.p[0].out_fmt = FMT_G;
     g.p[0].colsum = G_layer(l, 5);  // linear1.bias
     g.p[0].colsum_scale = INV;
-    rc = launch_gemm_group(g, bn_dff, sms, st);
+    rc = gemm_launch(P, g, bn_dff, sms, st);
     if (rc) return rc;
     memset(&g, 0, sizeof(g));
     g.num = 2;
@@ -721,7 +776,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       g.p[1].ld32 = d;
       g.p[0].alpha = g.p[1].alpha = INV;
       g.p[0].ksplit = g.p[1].ksplit = t_wf.ksplit;
-      rc = launch_gemm_group(g, bnw, sms, st);
+      rc = gemm_launch(P, g, bnw, sms, st);
       if (rc) return rc;
     }
     // ---- FFN1 dgrad: d(x1) = dhpre W1 + dy (residual) ----
@@ -736,7 +791,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.p[0].ld_resid = d;
     g.p[0].out32 = T.dx;
     g.p[0].ld32 = d;
-    rc = launch_gemm_group(g, bn_dd1, sms, st);
+    rc = gemm_launch(P, g, bn_dd1, sms, st);
     if (rc) return rc;
     // ---- LN1 backward ----
     {
@@ -775,7 +830,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.p[0].out16 = T.dO16;
     g.p[0].ld16 = d;
     g.p[0].out_fmt = FMT_G;
-    rc = launch_gemm_group(g, bn_ddo, sms, st);
+    rc = gemm_launch(P, g, bn_ddo, sms, st);
     if (rc) return rc;
     memset(&g, 0, sizeof(g));
     g.num = 1;
@@ -788,7 +843,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.p[0].ld32 = d;
     g.p[0].alpha = INV;
     g.p[0].ksplit = t_wo.ksplit;
-    rc = launch_gemm_group(g, bn_wo, sms, st);
+    rc = gemm_launch(P, g, bn_wo, sms, st);
     if (rc) return rc;
     // ---- attention core backward -> dqkv32 -> dqkv16 (+ in_proj_bias gradient) ----
     rc = launch_attn_delta(T.dO16, FMT_G, T.attn16[l], fmt, T.delta, B, L, P->H, P->dh, st);
@@ -820,7 +875,9 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       if (tc) {
         if (make_tmap_2d(&a.tm_qkv, T.qkv16[l], (uint64_t)M, (uint64_t)3 * d, (uint64_t)3 * d, 128, 64)) return 1;
         if (make_tmap_2d(&a.tm_do, T.dO16, (uint64_t)M, (uint64_t)d, (uint64_t)d, 128, 64)) return 1;
+        prof_mark(P, st, 3);
         rc = launch_attention_bwd(a, st);
+        prof_mark(P, st, 2);
       } else {
         rc = launch_attention_bwd_simt(a, st);
       }
@@ -841,7 +898,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.p[0].ld_resid = d;
     g.p[0].out32 = T.dx;
     g.p[0].ld32 = d;
-    rc = launch_gemm_group(g, bn_ddq, sms, st);
+    rc = gemm_launch(P, g, bn_ddq, sms, st);
     if (rc) return rc;
     memset(&g, 0, sizeof(g));
     g.num = 2;
@@ -857,7 +914,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.p[1].ld32 = d;
     g.p[0].alpha = g.p[1].alpha = INV;
     g.p[0].ksplit = g.p[1].ksplit = t_wq.ksplit;
-    rc = launch_gemm_group(g, bn_wq, sms, st);
+    rc = gemm_launch(P, g, bn_wq, sms, st);
     if (rc) return rc;
     stage_done(1 + (c.enc_layers - 1 - l));  // encoder layer l
   }
@@ -910,7 +967,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.p[0].alpha = g.p[1].alpha = INV;
     g.p[0].ksplit = g.p[1].ksplit = t_pw.ksplit;
     if (pad_v && t_pw.ksplit > 1) cudaMemsetAsync(T.wtap, 0, (size_t)d * kpv * 4, st);  // split-K accumulates into the padded copy
-    rc = launch_gemm_group(g, bn, sms, st);
+    rc = gemm_launch(P, g, bn, sms, st);
     if (rc) return rc;
     if (pad_v)
       cudaMemcpy2DAsync(G_vid(i, 2), (size_t)dinv * 4, T.wtap, (size_t)kpv * 4, (size_t)dinv * 4, (size_t)d, cudaMemcpyDeviceToDevice, st);
@@ -929,7 +986,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     g.p[0].ld32 = kpv;
     g.p[1].out32 = T.dA_t;
     g.p[1].ld32 = kpt;
-    rc = launch_gemm_group(g, bn_pd, sms, st);
+    rc = gemm_launch(P, g, bn_pd, sms, st);
     if (rc) return rc;
     // LayerNorm_i backward: parameter gradients; for i > 0 also the gradient of the previous layer's ReLU output
     for (int s = 0; s < 2; ++s) {
@@ -939,6 +996,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       a.dout = s == 0 ? T.dA_v : T.dA_t;
       a.ld_dout = pp.kpad;
       a.dout_mul = drop_masks ? drop_masks[s * np + i] : nullptr;
+      if (drop_rng) a.drop = make_drop_spec(rng->seed, (unsigned int)(s * np + i), rng->input_dropout);
       a.y = i == 0 ? (s == 0 ? src_vid : src_txt) : (s == 0 ? T.p_vid32[i - 1] : T.p_txt32[i - 1]);
       a.ld_y = pp.din;
       a.mean = s == 0 ? T.pmean_v[i] : T.pmean_t[i];
@@ -961,6 +1019,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     }
   }
   stage_done(c.enc_layers + 1);  // projectors, token-type embedding, pooling weight
+  prof_mark(P, st, 3);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("univtg_backward: %s", cudaGetErrorString(e));
@@ -993,6 +1052,15 @@ int univtg_backward_stages(const univtg_config* cfg, int32_t* ranges, int32_t ma
   }
   put(nl + 1, 0, 8 * np + 1, hb + 12, hb + 13);  // both projectors + token_type_embeddings, weightedpool.weight
   return n;
+}
+
+int univtg_plan_set_backward_sm_budget(univtg_plan* plan, int32_t num_sms) {
+  if (!plan || num_sms < 0) {
+    set_error("univtg_plan_set_backward_sm_budget: bad argument");
+    return 1;
+  }
+  plan->num_sms_bwd = num_sms;
+  return 0;
 }
 
 int univtg_plan_set_grad_events(univtg_plan* plan, void* const* events, int32_t n) {
@@ -1072,6 +1140,22 @@ int univtg_op_attention_bwd(const void* qkv, const void* dO, const void* O, cons
   if (make_tmap_2d(&a.tm_qkv, qkv, (uint64_t)M, (uint64_t)3 * d, (uint64_t)3 * d, 128, 64)) return 1;
   if (make_tmap_2d(&a.tm_do, dO, (uint64_t)M, (uint64_t)d, (uint64_t)d, 128, 64)) return 1;
   return launch_attention_bwd(a, st);
+}
+
+int univtg_dropout_mask(const univtg_rng* rng, int32_t mask_index, size_t n, float* out, void* stream) {
+  if (!rng || !out || mask_index < 0) {
+    set_error("univtg_dropout_mask: bad argument");
+    return 1;
+  }
+  return launch_dropout_mask(make_drop_spec(rng->seed, (unsigned int)mask_index, rng->input_dropout), n, out, (cudaStream_t)stream);
+}
+
+int univtg_droppath_scales(const univtg_rng* rng, int32_t n_sites, int32_t batch, float* out, void* stream) {
+  if (!rng || !out || n_sites < 1 || batch < 1) {
+    set_error("univtg_droppath_scales: bad argument");
+    return 1;
+  }
+  return launch_droppath_scales(rng->seed, n_sites * batch, 1.0f - rng->droppath, out, (cudaStream_t)stream);
 }
 
 size_t univtg_loss_scratch_bytes(int32_t B, int32_t Lv) { return make_loss_scratch(B, Lv, nullptr).total; }

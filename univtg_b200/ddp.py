@@ -12,6 +12,8 @@ Usage (one process per GPU, torchrun):
 The reference's own script wraps the model in torch DistributedDataParallel(find_unused_parameters=True); that also works
 unchanged with this model (gradients reach param.grad through autograd), with DDP's 25 MB buckets instead of one buffer.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -79,7 +81,8 @@ class OverlappedGradExchange:
         self.stages = grad_stage_slices(model)
         self.events = None
         self.comm_stream = None
-        self._armed = set()
+        # SMs left to the collective's CTAs while it overlaps the backward (NCCL_MAX_CTAS caps what NCCL takes)
+        self.sm_reserve = int(os.environ.get("UNIVTG_DDP_SM_RESERVE", "16")) if self.backend == "nccl" else 0
 
     def _reduce(self, t):
         if self.backend == "nccl":
@@ -101,11 +104,17 @@ class OverlappedGradExchange:
             self.events = [torch.cuda.Event() for _ in self.stages]
             for e in self.events:
                 e.record()  # materialises the cudaEvent_t handle
-        if id(plan) not in self._armed:
+        # the armed state lives on the plan entry itself: id(plan) of an evicted entry is recycled by CPython for the next one,
+        # which would then run its backward without stage events while the exchange waits on stale, already-completed ones
+        if plan.grad_events_owner is not self:
             arr = (ctypes.c_void_p * len(self.events))(*[e.cuda_event for e in self.events])
-            _lib.check(_lib.load_library().univtg_plan_set_grad_events(plan.handle, arr, len(self.events)),
-                       "univtg_plan_set_grad_events")
-            self._armed.add(id(plan))
+            lib = _lib.load_library()
+            _lib.check(lib.univtg_plan_set_grad_events(plan.handle, arr, len(self.events)), "univtg_plan_set_grad_events")
+            if getattr(self, "sm_reserve", 0) > 0:  # the all-reduce kernels hold SMs while the backward's persistent GEMM grids run
+                sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+                _lib.check(lib.univtg_plan_set_backward_sm_budget(plan.handle, max(8, sms - self.sm_reserve)),
+                           "univtg_plan_set_backward_sm_budget")
+            plan.grad_events_owner = self
 
     def after_backward(self, flat):
         """All launches of the backward are enqueued: chain one all-reduce per stage behind its event."""

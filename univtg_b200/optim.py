@@ -10,6 +10,8 @@ The reference does, per step (main/train_vlp_ddp.py:63-68 = main/train_mr.py:61-
 buffer laid out like the flat gradient buffer the backward kernels write (and the DDP hook all-reduces), so clipping and AdamW
 are two kernel launches (univtg_adamw_step) instead of ~90 per-parameter launches.  CUDA only - there is no CPU path.
 """
+import ctypes
+
 import torch
 
 from . import _lib
@@ -17,12 +19,19 @@ from . import _lib
 
 class FlatAdamW:
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, max_grad_norm=0.1,
-                 write_clipped_grads=False):
+                 write_clipped_grads=False, dynamic_loss_scale=True, growth_interval=2000, max_loss_scale=65536.0):
         self.model = model
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
         self.max_grad_norm = float(max_grad_norm) if max_grad_norm is not None else 0.0
         self.write_clipped_grads = bool(write_clipped_grads)
         self.step_count = 0
+        # dynamic loss scale of the fp16 backward (model.grad_scale): a step whose gradients are not finite is skipped ON THE
+        # DEVICE (univtg_adamw_step); the flag is read back one step later (no host synchronisation in the step), the scale is
+        # halved and the step counter corrected; after `growth_interval` good steps in a row the scale doubles again.
+        self.dynamic_loss_scale = bool(dynamic_loss_scale) and model.operand_format == 0
+        self.growth_interval, self.max_loss_scale = int(growth_interval), float(max_loss_scale)
+        self.skipped_steps, self._good_streak = 0, 0
+        self._flag_host, self._flag_event = None, None
         self._flat_p = None
         self._views = None
         self._m = self._v = self._scratch = None
@@ -56,14 +65,16 @@ class FlatAdamW:
         if not keep:
             self._m = torch.zeros_like(flat_p)
             self._v = torch.zeros_like(flat_p)
-            self._scratch = torch.zeros(2, dtype=torch.float32, device=dev)
+            self._scratch = torch.zeros(4, dtype=torch.float32, device=dev)
 
     def _seated(self):
         return all(p.data_ptr() == v.data_ptr() for p, v in zip(self.model._abi_params(), self._views))
 
     # -- torch.optim-like surface ---------------------------------------------------------------------------------------
     def zero_grad(self, set_to_none=True):
-        # the backward zero-fills the flat gradient buffer itself; nothing to do per parameter
+        """The next backward writes the flat gradient buffer from scratch (it zero-fills it itself); without a zero_grad() in
+        between, further backwards accumulate into it like torch's .grad (univtg_b200/autograd.py)."""
+        self.model.__dict__["_flat_grad_dirty"] = False
         return None
 
     @torch.no_grad()
@@ -76,14 +87,53 @@ class FlatAdamW:
         if flat_g.numel() != self._flat_p.numel():
             raise RuntimeError("FlatAdamW: gradient / parameter buffer size mismatch")
         lib = _lib.load_library()
+        self._consume_overflow_flag()
         self.step_count += 1
         with torch.cuda.device(flat_g.device):
+            # The update kernel also refreshes the 16-bit GEMM operand copies of the weight matrices it has just computed (the
+            # packed buffer of the training format), so the next forward needs no re-packing pass over the 43 M fp32 weights;
+            # only the fp32 vectors (LayerNorm terms, biases, token-type rows) are re-copied by one small launch.
+            model._ensure_packed(training=True)  # allocates / fully packs once; a no-op afterwards (see below)
+            fmt = model._fmt(True)
+            cfg = model._cfgs[fmt]
+            packed = model._packed[fmt]
             _lib.check(lib.univtg_adamw_step(_lib.ptr(self._flat_p), _lib.ptr(flat_g), _lib.ptr(self._m), _lib.ptr(self._v),
                                              flat_g.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
                                              self.step_count, self.max_grad_norm, int(self.write_clipped_grads),
-                                             _lib.ptr(self._scratch), _lib.stream_ptr()), "univtg_adamw_step")
-        model._packed_key = {}  # parameters changed behind autograd's version counters: repack the 16-bit operands
+                                             _lib.ptr(self._scratch), ctypes.byref(cfg), _lib.ptr(packed), _lib.stream_ptr()),
+                       "univtg_adamw_step")
+            params = model._abi_params()
+            arr = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
+            _lib.check(lib.univtg_pack_vectors(ctypes.byref(cfg), arr, len(params), _lib.ptr(packed), _lib.stream_ptr()),
+                       "univtg_pack_vectors")
+            # the raw-pointer update does not bump autograd's version counters, so the packed-buffer key of this format is still
+            # current; a second operand format (if ever packed) is stale
+            for other in list(model._packed_key):
+                if other != fmt:
+                    model._packed_key.pop(other)
+            if self.dynamic_loss_scale:
+                if self._flag_host is None:
+                    self._flag_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+                    self._flag_event = torch.cuda.Event()
+                self._flag_host.copy_(self._scratch[2:3], non_blocking=True)
+                self._flag_event.record()
         return self._scratch[1]
+
+    def _consume_overflow_flag(self):
+        """Outcome of the PREVIOUS step (its flag copy finished long ago: no stall): back off / grow the loss scale."""
+        if not self.dynamic_loss_scale or self._flag_event is None:
+            return
+        self._flag_event.synchronize()
+        if float(self._flag_host[0]) != 0.0:
+            self.step_count -= 1  # that update never happened
+            self.skipped_steps += 1
+            self._good_streak = 0
+            self.model.grad_scale = max(1.0, self.model.grad_scale * 0.5)
+        else:
+            self._good_streak += 1
+            if self._good_streak >= self.growth_interval and self.model.grad_scale < self.max_loss_scale:
+                self.model.grad_scale *= 2.0
+                self._good_streak = 0
 
     def state_dict(self):
         return {"step": self.step_count, "exp_avg": self._m, "exp_avg_sq": self._v,

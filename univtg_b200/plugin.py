@@ -88,7 +88,37 @@ def _uniform_(t, bound):
 
 
 class _PlanEntry:
-    __slots__ = ("handle", "workspace", "shape")
+    """One (B, Lv, Lt, training) shape bucket: the C plan (tensor maps + launch descriptors over the shared workspace)."""
+    __slots__ = ("handle", "shape", "key", "pins", "grad_events_owner")
+
+    def __init__(self):
+        self.handle = None
+        self.shape = None
+        self.key = None
+        self.pins = 0                  # live autograd contexts holding this plan: a pinned plan is never evicted
+        self.grad_events_owner = None  # the gradient exchange whose stage events are installed on the C plan (ddp.py)
+
+
+class _WorkspaceLease:
+    """A training workspace (saved activations + backward scratch) checked out of the model's pool for ONE forward; it goes back
+    when the backward has run or when the autograd context is dropped without one.  Two training forwards before a backward
+    (micro-batches, two views summed into one loss) therefore get two buffers instead of overwriting each other."""
+
+    def __init__(self, pool, buf, plan):
+        self.pool, self.buf, self.plan = pool, buf, plan
+        plan.pins += 1
+
+    def release(self):
+        if self.buf is not None:
+            self.pool.append(self.buf)
+            self.buf = None
+            self.plan.pins -= 1
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 class Model(nn.Module):
@@ -230,12 +260,23 @@ class Model(nn.Module):
                    "univtg_pack_weights")
         self._packed_key[fmt] = key
 
-    def _drop_plans(self):
+    PLAN_CACHE = 32  # shape buckets kept (LRU); collate pads to the batch maximum, so a corpus produces many (B, Lv, Lt)
+
+    def _drop_plans(self, keep_training=False):
+        """Destroy the cached plans (their tensor maps point into the packed-weight buffer and the shared workspace).
+        keep_training: the shared workspace is being re-allocated - training plans never touch it (univtg_forward_train /
+        univtg_backward work in a leased buffer) and may be held by live autograd contexts, so they stay."""
         lib = _lib.load_library()
         self.__dict__["_graphs"] = {}  # captured graphs reference the plans' workspaces and tensor maps
-        for e in self._plans.values():
-            lib.univtg_plan_destroy(e.handle)
-        self._plans = {}
+        kept = {}
+        for k, e in self._plans.items():
+            if keep_training and k[3] == 1:
+                kept[k] = e
+            elif e.handle is not None:
+                lib.univtg_plan_destroy(e.handle)
+                e.handle = None  # a live autograd ctx that still holds this entry fails loudly instead of using a freed plan
+        self._plans = kept
+        self.__dict__["_ws_owner"] = None
 
     def __del__(self):
         try:
@@ -243,22 +284,44 @@ class Model(nn.Module):
         except Exception:
             pass
 
-    def _get_train_ws(self, B, Lv, Lt):
-        """Training workspace (saved activations + backward scratch), one per shape bucket, zero-filled once."""
-        lib = _lib.load_library()
-        key = (B, Lv, Lt)
-        cache = self.__dict__.setdefault("_train_ws", {})
-        ws = cache.get(key)
-        if ws is None:
-            if len(cache) >= 4:
-                cache.pop(next(iter(cache)))
-            shp = _lib.Shape(B, Lv, Lt, 1)
-            nbytes = lib.univtg_train_workspace_bytes(ctypes.byref(self._cfg), ctypes.byref(shp))
-            if nbytes == 0:
-                raise RuntimeError("univtg_b200: " + _lib.last_error())
-            ws = torch.zeros(nbytes, dtype=torch.uint8, device=self._device())
-            cache[key] = ws
+    def _shared_workspace(self, nbytes):
+        """ONE inference workspace for all shape buckets, sized for the largest shape seen (grown geometrically; growing drops
+        the plans, whose tensor maps point into the old buffer)."""
+        ws = self.__dict__.get("_ws_infer")
+        if ws is None or ws.device != self._device() or ws.numel() < nbytes:
+            self._drop_plans(keep_training=ws is not None and ws.device == self._device())
+            cap = nbytes if ws is None or ws.device != self._device() else max(nbytes, int(ws.numel() * 1.5))
+            ws = torch.empty(cap, dtype=torch.uint8, device=self._device())
+            self.__dict__["_ws_infer"] = ws
         return ws
+
+    def _lease_train_ws(self, plan):
+        """Check a training workspace out of the pool (univtg_b200.plugin._WorkspaceLease).  Buffers are sized for the largest
+        shape seen so far and shared between shapes; a buffer that last served another shape gets its zero rows re-established
+        (univtg_prepare_workspace) - no per-shape allocation and no full-buffer memset in steady state."""
+        lib = _lib.load_library()
+        dev = self._device()
+        nbytes = lib.univtg_train_workspace_bytes(ctypes.byref(self._cfg), ctypes.byref(plan.shape))
+        if nbytes == 0:
+            raise RuntimeError("univtg_b200: " + _lib.last_error())
+        pool = self.__dict__.setdefault("_train_pool", [])
+        owners = self.__dict__.setdefault("_train_ws_shape", {})
+        buf = None
+        for i, cand in enumerate(pool):
+            if cand.device == dev and cand.numel() >= nbytes:
+                buf = pool.pop(i)
+                break
+        if buf is None:
+            if pool:  # too small for this shape: let the allocator recycle it
+                owners.pop(pool.pop().data_ptr(), None)
+            grow = max([nbytes] + [int(k[1]) for k in owners.values()])
+            buf = torch.empty(grow, dtype=torch.uint8, device=dev)
+        key = (plan.key[:3], buf.numel())
+        if owners.get(buf.data_ptr()) != key:
+            _lib.check(lib.univtg_prepare_workspace(ctypes.byref(self._cfg), ctypes.byref(plan.shape), _lib.ptr(buf), 1,
+                                                    _lib.stream_ptr()), "univtg_prepare_workspace")
+            owners[buf.data_ptr()] = key
+        return _WorkspaceLease(pool, buf, plan)
 
     def _grad_buffer(self):
         """One flat fp32 gradient buffer with a view per parameter (C-ABI order); also the all-reduce payload."""
@@ -294,31 +357,52 @@ class Model(nn.Module):
         return self._dim_t
 
     def _get_plan(self, B, Lv, Lt, training):
+        """Plan of a shape bucket (LRU cache).  Inference plans share ONE workspace; before a forward the caller passes the plan
+        through _activate(), which re-establishes the workspace's zero rows when the previous forward had another shape."""
         key = (B, Lv, Lt, int(training))
-        e = self._plans.get(key)
+        e = self._plans.pop(key, None)
         if e is not None:
+            self._plans[key] = e  # most recently used last
             return e
         lib = _lib.load_library()
-        if len(self._plans) >= 8:  # bounded cache of shape buckets (collate pads to the batch maximum, so shapes vary)
-            old = next(iter(self._plans))
-            lib.univtg_plan_destroy(self._plans.pop(old).handle)
+        if len(self._plans) >= self.PLAN_CACHE:
+            for old_key, old in list(self._plans.items()):  # least recently used first; never a plan a live autograd ctx holds
+                if old.pins == 0:
+                    del self._plans[old_key]
+                    self.__dict__.get("_graphs", {}).pop(old_key[:3], None)  # a captured graph replays this plan's tensor maps
+                    if self.__dict__.get("_ws_owner") is old:
+                        self.__dict__["_ws_owner"] = None
+                    lib.univtg_plan_destroy(old.handle)
+                    old.handle = None
+                    break
         dev = self._device()
         cfg = self._cfgs[self._fmt(training)]
         shp = _lib.Shape(B, Lv, Lt, int(training))
         nbytes = lib.univtg_workspace_bytes(ctypes.byref(cfg), ctypes.byref(shp))
         if nbytes == 0:
             raise RuntimeError("univtg_b200: " + _lib.last_error())
+        ws = self._shared_workspace(nbytes)
         e = _PlanEntry()
         e.shape = shp
-        e.workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        e.key = key
         handle = ctypes.c_void_p()
+        # (a training plan never touches the plan workspace: univtg_forward_train / univtg_backward work in a leased buffer)
         _lib.check(lib.univtg_plan_create(ctypes.byref(cfg), ctypes.byref(shp), _lib.ptr(self._packed[self._fmt(training)]),
-                                          _lib.ptr(e.workspace),
-                                          _lib.ptr(self._get_dim_t(dev)), _lib.stream_ptr(), ctypes.byref(handle)),
+                                          _lib.ptr(ws), _lib.ptr(self._get_dim_t(dev)), _lib.stream_ptr(), ctypes.byref(handle)),
                    "univtg_plan_create")
         e.handle = handle
         self._plans[key] = e
+        self.__dict__["_ws_owner"] = e if not training else None  # plan_create prepared the workspace for THIS shape
         return e
+
+    def _activate(self, plan):
+        """The shared inference workspace is about to be used by `plan`."""
+        if self.__dict__.get("_ws_owner") is not plan:
+            lib = _lib.load_library()
+            cfg = self._cfgs[self._fmt(False)]
+            _lib.check(lib.univtg_prepare_workspace(ctypes.byref(cfg), ctypes.byref(plan.shape), _lib.ptr(self._ws_infer), 0,
+                                                    _lib.stream_ptr()), "univtg_prepare_workspace")
+            self.__dict__["_ws_owner"] = plan
 
     # ---- forward ------------------------------------------------------------------------------------------------------
     def forward(self, src_txt, src_txt_mask, src_vid, src_vid_mask, src_cls=None, src_cls_mask=None):
@@ -404,6 +488,7 @@ class Model(nn.Module):
         with torch.cuda.device(dev):
             self._ensure_packed()
             plan = self._get_plan(B, Lv, Lt, False)
+            self._activate(plan)
             txt = src_txt.detach().to(torch.float32).contiguous()
             vid = src_vid.detach().to(torch.float32).contiguous()
             tmask = src_txt_mask.detach().to(torch.float32).contiguous()
@@ -429,12 +514,34 @@ class Model(nn.Module):
         with torch.cuda.device(self._device()):
             self._ensure_packed()
             plan = self._get_plan(B, Lv, Lt, False)
+            self._activate(plan)
             lib.univtg_plan_set_profiling(plan.handle, 1)
             try:
                 self._forward_inference(**inputs)
                 ms = (ctypes.c_float * 160)()
                 kinds = (ctypes.c_int32 * 160)()
                 n = lib.univtg_plan_read_profile(plan.handle, ms, kinds, 160)
+            finally:
+                lib.univtg_plan_set_profiling(plan.handle, 0)
+        if n < 0:
+            raise RuntimeError("univtg_b200: " + _lib.last_error())
+        return [(int(kinds[i]), float(ms[i])) for i in range(n)]
+
+    def profile_train_step(self, B, Lv, Lt, run):
+        """CUDA-event timeline of ONE training step of shape (B, Lv, Lt): `run()` must execute forward + criterion + backward.
+        Returns [(kind, ms), ...]: kind 1 = one tcgen05 GEMM launch, 2 = one attention launch (forward or backward), 3 = whatever
+        ran between two of those (row kernels, criterion, launch gaps)."""
+        lib = _lib.load_library()
+        with torch.cuda.device(self._device()):
+            self._ensure_packed(training=True)
+            plan = self._get_plan(B, Lv, Lt, True)
+            lib.univtg_plan_set_profiling(plan.handle, 1)
+            try:
+                run()
+                cap = 640
+                ms = (ctypes.c_float * cap)()
+                kinds = (ctypes.c_int32 * cap)()
+                n = lib.univtg_plan_read_profile(plan.handle, ms, kinds, cap)
             finally:
                 lib.univtg_plan_set_profiling(plan.handle, 0)
         if n < 0:
