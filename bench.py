@@ -184,6 +184,54 @@ def gpu_eager_baseline(cfg, wl, dev, steps=10):
     return res
 
 
+def shard_e2e_forward(model, cfg, dev, steps):
+    """Inference end to end from a packed fp16 feature shard (univtg_b200/data.py): the loader assembles
+    every padded batch from the memory-mapped shard into pinned buffers and copies it on a side stream one batch ahead; the
+    model reads the fp16 features directly; results are read back on the host every step."""
+    import tempfile
+
+    import numpy as np
+
+    from univtg_b200 import data as D
+
+    B, Lv, Lt = cfg["batch"], cfg["l_vid"], cfg["l_txt"]
+    n_batches = steps + 4
+    path = os.path.join(tempfile.gettempdir(), f"univtg_bench_{os.getpid()}.uvshard")
+    rng = np.random.default_rng(0)
+    vids = [rng.standard_normal((Lv, cfg["v_feat_dim"])).astype(np.float16) * np.float16(0.02) for _ in range(64)]
+    qs = [rng.standard_normal((Lt, cfg["t_feat_dim"])).astype(np.float16) * np.float16(0.04) for _ in range(64)]
+    samples = [(int(rng.integers(0, 64)), int(rng.integers(0, 64))) for _ in range(B * n_batches)]
+    D.write_shard(path, vids, qs, samples)
+    try:
+        loader = D.ShardLoader(path, batch_size=B, device=dev, slots=3, workers=8)
+        out_host = [torch.empty(B, Lv).pin_memory() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        model.eval()
+        t_ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+        seen = 0.0
+        with torch.no_grad():
+            for i, (batch, _) in enumerate(loader):
+                if i == 4:
+                    torch.cuda.synchronize()
+                    t_ev[0].record()
+                out = model(**batch)
+                out_host[i % 2].copy_(out["saliency_scores"], non_blocking=True)
+                done[i % 2].record()
+                if i >= 1:
+                    done[(i - 1) % 2].synchronize()
+                    seen += float(out_host[(i - 1) % 2][0, 0])
+            t_ev[1].record()
+            torch.cuda.synchronize()
+        ms = t_ev[0].elapsed_time(t_ev[1]) / steps
+        return {"value": B / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "h2d_bytes_per_step": loader.h2d_bytes(B, Lv, Lt),
+                "d2h_bytes_per_step": B * Lv * 4, "what": "forward fed by ShardLoader (packed fp16 shard -> pinned staging -> side-stream H2D)"}
+    finally:
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
+
+
 def attention_work(cfg, train):
     """Algorithmic work of the attention core per step: flops 4 L^2 d per sample and layer forward (+ 10 L^2 d backward: five
     contractions), bytes = Q, K, V read + O written as 16-bit (forward; backward reads Q, K, V, dO and writes dQ, dK, dV)."""
@@ -572,6 +620,14 @@ def main():
     sync_all()
     ms_total = e0.elapsed_time(e1)
     gpu_launches = int(lib.univtg_launch_count()) - launches0  # kernels of THIS library launched inside the timed region
+    # host side of the same loop: how long the CPU needs to ENQUEUE a step (5 steps = ~600 launches stay below the driver's launch
+    # queue depth, so the host is not throttled by the GPU here).  enqueue time ~ ms_per_step means the step is host-bound.
+    sync_all()
+    t_h0 = time.perf_counter()
+    for i in range(5):
+        device_step(i)
+    host_enqueue_ms = (time.perf_counter() - t_h0) * 1e3 / 5
+    sync_all()
 
     # -------------------------------------------- end-to-end through the public API ------------------------------------
     # Every step copies ITS inputs from pinned host memory and reads ITS result back on the host.  The H2D copy of step
@@ -665,6 +721,11 @@ def main():
         ms_fwd = g0.elapsed_time(g1)
         fwd_only = {"value": B * args.steps * n_gpus / (ms_fwd * 1e-3), "unit": "pairs/s", "ms_per_step": ms_fwd / args.steps,
                     "note": "BASELINE configs[1]: inference forward on the same shapes (max over ranks not applied)"}
+        if n_gpus == 1 and not args.no_extras:
+            try:
+                fwd_only["e2e_from_feature_shard"] = shard_e2e_forward(model, cfg, dev, args.steps)
+            except Exception as ex:
+                fwd_only["e2e_from_feature_shard"] = {"error": repr(ex)[:300]}
         model.use_cuda_graphs = False
         model.train()
 
@@ -808,6 +869,7 @@ def main():
                 "clips_per_s": value * Lv},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
+            "host_enqueue_ms_per_step": host_enqueue_ms,
             "gpu_launches": gpu_launches,
             "launches_per_step": gpu_launches / args.steps,
             "clocks": clocks,

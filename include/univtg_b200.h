@@ -89,6 +89,11 @@ int univtg_plan_create(const univtg_config* cfg, const univtg_shape* shape, cons
                        const float* dim_t, void* stream, univtg_plan** out);
 void univtg_plan_destroy(univtg_plan* plan);
 
+/* Element type of the src_txt / src_vid pointers the forward entry points (and univtg_backward) receive for this plan:
+ * 0 = f32 (what the reference collate produces, default), 1 = fp16, 2 = bf16 (packed feature shards, univtg_b200/data.py: the CLIP /
+ * SlowFast features are stored as 16-bit on disk, so the H2D copy and the first LayerNorm's read halve).  Masks stay f32. */
+int univtg_plan_set_input_format(univtg_plan* plan, int32_t fmt);
+
 /* Model.forward (reference model/univtg.py:105-155).
  *   src_txt [B,Lt,Dt] f32, src_txt_mask [B,Lt] f32 (1 = valid), src_vid [B,Lv,Dv] f32, src_vid_mask [B,Lv] f32
  *   droppath_scale: NULL (eval) or [2*enc_layers, B] f32 per-sample residual-branch scales
@@ -113,9 +118,9 @@ int univtg_forward_train(univtg_plan* plan, void* train_ws, const float* src_txt
                          const float* src_vid, const float* src_vid_mask, const float* droppath_scale,
                          const float* const* drop_masks, const univtg_rng* rng, float* pred_logits, float* pred_spans,
                          float* vid_mem_proj, float* txt_mem_proj, float* saliency_scores, void* stream);
-/* The multipliers univtg_forward_train draws for `rng`: mask `mask_index` ([rows, din] row-major, n elements) and the DropPath
+/* The multipliers univtg_forward_train draws for `rng`: mask `mask_index` ([rows, cols = din] row-major) and the DropPath
  * scales [n_sites = 2*enc_layers, batch].  Parity tests hand them to the oracle. */
-int univtg_dropout_mask(const univtg_rng* rng, int32_t mask_index, size_t n, float* out, void* stream);
+int univtg_dropout_mask(const univtg_rng* rng, int32_t mask_index, size_t rows, size_t cols, float* out, void* stream);
 int univtg_droppath_scales(const univtg_rng* rng, int32_t n_sites, int32_t batch, float* out, void* stream);
 /* Backward of the last univtg_forward_train on (plan, train_ws).  g_*: upstream gradients of pred_logits [B,Lv,1],
  * pred_spans [B,Lv,2], vid_mem_proj [B,Lv,d], txt_mem_proj [B,1,d] (NULL = zero).  grads: HOST array of device pointers,

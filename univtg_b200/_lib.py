@@ -64,7 +64,7 @@ SIGNATURES = {
                                      c_void_p]),
     "univtg_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(Rng),
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_float, ctypes.POINTER(c_void_p), c_int, c_void_p]),
-    "univtg_dropout_mask": (c_int, [ctypes.POINTER(Rng), c_int, c_size_t, c_void_p, c_void_p]),
+    "univtg_dropout_mask": (c_int, [ctypes.POINTER(Rng), c_int, c_size_t, c_size_t, c_void_p, c_void_p]),
     "univtg_droppath_scales": (c_int, [ctypes.POINTER(Rng), c_int, c_int, c_void_p, c_void_p]),
     "univtg_loss_scratch_bytes": (c_size_t, [c_int, c_int]),
     "univtg_loss_forward": (c_int, [c_void_p] * 10 + [c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]),
@@ -80,6 +80,7 @@ SIGNATURES = {
                                   c_float, c_int, c_float, c_int, c_void_p, ctypes.POINTER(Config), c_void_p, c_void_p]),
     "univtg_pack_vectors": (c_int, [ctypes.POINTER(Config), ctypes.POINTER(c_void_p), c_int, c_void_p, c_void_p]),
     "univtg_plan_set_profiling": (c_int, [c_void_p, c_int]),
+    "univtg_plan_set_input_format": (c_int, [c_void_p, c_int]),
     "univtg_plan_read_profile": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "univtg_op_gemm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                c_float, c_void_p, c_void_p, c_void_p]),

@@ -457,6 +457,15 @@ void univtg_plan_destroy(univtg_plan* plan) {
   delete plan;
 }
 
+int univtg_plan_set_input_format(univtg_plan* plan, int32_t fmt) {
+  if (!plan || fmt < 0 || fmt > 2) {
+    set_error("univtg_plan_set_input_format: format must be 0 (f32), 1 (fp16) or 2 (bf16)");
+    return 1;
+  }
+  plan->in_fmt = fmt;
+  return 0;
+}
+
 int univtg_plan_set_profiling(univtg_plan* plan, int32_t enable) {
   if (!plan) return 1;
   plan->profiling = enable ? 1 : 0;
@@ -511,6 +520,10 @@ int univtg_forward(univtg_plan* P, const float* src_txt, const float* src_txt_ma
       LnArgs a;
       memset(&a, 0, sizeof(a));
       a.in = i == 0 ? (s == 0 ? src_vid : src_txt) : (s == 0 ? P->p_vid32 : P->p_txt32);
+      if (i == 0 && P->in_fmt != 0) {
+        a.in16 = reinterpret_cast<const uint16_t*>(a.in);
+        a.in_fmt = P->in_fmt - 1;
+      }
       a.ld_in = pp.din;
       a.rows = s == 0 ? P->Mv : P->Mt;
       a.d = pp.din;

@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const LnBwdArgs a) {
       if (j < a.d) {
         float dj = dout[j];
         if (a.dout_mul) dj *= a.dout_mul[(size_t)row * a.d + j];
-        else if (a.drop.on) dj *= drop_mul1(a.drop, (unsigned long long)row * a.d + j);
+        else if (a.drop.on) dj *= drop_mul1(a.drop, (unsigned int)row, (unsigned int)j);
         xh[i] = (y[j] - mean) * rstd;
         g[i] = dj * a.gamma[j];
         acc_g[i] += dj * xh[i];
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(128) layernorm_bwd_vec_kernel(const LnBwdArgs 
           const float4 m = __ldg(reinterpret_cast<const float4*>(a.dout_mul + (size_t)row * a.d + j));
           nd[i].x *= m.x, nd[i].y *= m.y, nd[i].z *= m.z, nd[i].w *= m.w;
         } else if (a.drop.on) {
-          const float4 m = drop_mul4(a.drop, (unsigned long long)row * a.d + j);
+          const float4 m = drop_mul4(a.drop, (unsigned int)row, (unsigned int)j);
           nd[i].x *= m.x, nd[i].y *= m.y, nd[i].z *= m.z, nd[i].w *= m.w;
         }
       }
@@ -194,13 +194,109 @@ __global__ void __launch_bounds__(128) layernorm_bwd_vec_kernel(const LnBwdArgs 
   }
 }
 
+// Warp-per-row variant for d == NV * 128 (256 / 512 / 1024: every LayerNorm of the encoder and the inner projector layers).  A warp
+// holds its whole row in registers, so the two row statistics are warp shuffles - no block barrier per row (the block-per-row
+// kernel above spends two __syncthreads per 1024-element row and measured 45 % of the HBM roofline).  Column partials (dgamma,
+// dbeta, bias column sums) stay in registers over the rows a warp visits, are combined across the block's 8 warps through
+// shared memory and leave as ONE vector reduction per block and column group.
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_bwd_warp_kernel(const LnBwdArgs a) {
+  pdl_prologue();
+  extern __shared__ float s_part[];  // [8 warps][NV * 128] floats, reused for the three column accumulators
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int D = NV * 128;
+  float4 acc_g[NV], acc_b[NV], acc_c[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc_g[i] = acc_b[i] = acc_c[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float inv_d = 1.0f / (float)D;
+  for (int row = blockIdx.x * 8 + warp; row < a.rows; row += gridDim.x * 8) {
+    float4 g[NV], xh[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int j = (i * 32 + lane) * 4;
+      g[i] = __ldg(reinterpret_cast<const float4*>(a.dout + (size_t)row * a.ld_dout + j));
+      xh[i] = __ldg(reinterpret_cast<const float4*>(a.y + (size_t)row * a.ld_y + j));
+    }
+    const float mean = a.mean[row], rstd = a.rstd[row];
+    float rs = 1.f;
+    if (a.row_scale != nullptr) rs = a.row_scale[a.L > 0 ? row / a.L : 0];
+    float s1 = 0.f, s2 = 0.f;
+    unsigned int relu = 0u;  // bit 4 i + c: y > 0 (ReLU mask of the projector chain)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int j = (i * 32 + lane) * 4;
+      if (a.dout_mul) {
+        const float4 m = __ldg(reinterpret_cast<const float4*>(a.dout_mul + (size_t)row * D + j));
+        g[i].x *= m.x, g[i].y *= m.y, g[i].z *= m.z, g[i].w *= m.w;
+      } else if (a.drop.on) {
+        const float4 m = drop_mul4(a.drop, (unsigned int)row, (unsigned int)j);
+        g[i].x *= m.x, g[i].y *= m.y, g[i].z *= m.z, g[i].w *= m.w;
+      }
+      const float4 gam = __ldg(reinterpret_cast<const float4*>(a.gamma + j));
+#define UV_LNW(c, bit)                                  \
+  if (xh[i].c > 0.f) relu |= 1u << (4 * i + bit);       \
+  xh[i].c = (xh[i].c - mean) * rstd;                    \
+  acc_g[i].c += g[i].c * xh[i].c;                       \
+  acc_b[i].c += g[i].c;                                 \
+  g[i].c *= gam.c;                                      \
+  s1 += g[i].c;                                         \
+  s2 += g[i].c * xh[i].c;
+      UV_LNW(x, 0) UV_LNW(y, 1) UV_LNW(z, 2) UV_LNW(w, 3)
+#undef UV_LNW
+    }
+    const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int j = (i * 32 + lane) * 4;
+      float4 dy;
+      dy.x = rstd * (g[i].x - c1 - xh[i].x * c2);
+      dy.y = rstd * (g[i].y - c1 - xh[i].y * c2);
+      dy.z = rstd * (g[i].z - c1 - xh[i].z * c2);
+      dy.w = rstd * (g[i].w - c1 - xh[i].w * c2);
+      if (a.relu_mask_y) {
+        if (!(relu & (1u << (4 * i + 0)))) dy.x = 0.f;
+        if (!(relu & (1u << (4 * i + 1)))) dy.y = 0.f;
+        if (!(relu & (1u << (4 * i + 2)))) dy.z = 0.f;
+        if (!(relu & (1u << (4 * i + 3)))) dy.w = 0.f;
+      }
+      if (a.dy32) *reinterpret_cast<float4*>(a.dy32 + (size_t)row * D + j) = dy;
+      const float4 br = make_float4(dy.x * rs, dy.y * rs, dy.z * rs, dy.w * rs);
+      acc_c[i].x += br.x, acc_c[i].y += br.y, acc_c[i].z += br.z, acc_c[i].w += br.w;
+      if (a.dbr16)
+        *reinterpret_cast<uint2*>(a.dbr16 + (size_t)row * a.ld16 + j) = make_uint2(cvt16x2(br.x, br.y, a.fmt16), cvt16x2(br.z, br.w, a.fmt16));
+    }
+  }
+  // block-level combination of the column partials: warp w parks its slice, 256 threads sum the 8 slices of 4 columns each
+  auto flush = [&](const float4 (&acc)[NV], float* dst) {
+    if (dst == nullptr) return;  // uniform over the block
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(s_part + (size_t)warp * D + (i * 32 + lane) * 4) = acc[i];
+    __syncthreads();
+    for (int j = tid * 4; j < D; j += 256 * 4) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const float4 v = *reinterpret_cast<const float4*>(s_part + (size_t)w * D + j);
+        t.x += v.x, t.y += v.y, t.z += v.z, t.w += v.w;
+      }
+      const float ps = a.pgrad_scale;
+      red_add_f32x4(dst + j, make_float4(t.x * ps, t.y * ps, t.z * ps, t.w * ps));
+    }
+  };
+  flush(acc_g, a.dgamma);
+  flush(acc_b, a.dbeta);
+  flush(acc_c, a.colsum);
+}
+
 // Parameter gradients only (no dy requested): a pure column reduction, no per-row statistics of the gradient are needed.
 // Thread = one column, block = 256 columns x kRowsPerBlock rows.
 constexpr int kLnParamRows = 32;
 __global__ void __launch_bounds__(256) layernorm_bwd_params_kernel(const LnBwdArgs a) {
   pdl_prologue();
-  const int j = blockIdx.x * 256 + threadIdx.x;
-  if (j >= a.d) return;
+  const int jj = blockIdx.x * 256 + threadIdx.x;
+  const bool in = jj < a.d;         // threads past the row end stay in the loop: the Philox words travel by warp shuffle
+  const int j = in ? jj : a.d - 1;  // (their loads hit a valid column, their sums are dropped)
   const int r0 = blockIdx.y * kLnParamRows;
   const int r1 = min(a.rows, r0 + kLnParamRows);
   float ag = 0.f, ab = 0.f;
@@ -208,13 +304,23 @@ __global__ void __launch_bounds__(256) layernorm_bwd_params_kernel(const LnBwdAr
   for (int r = r0; r < r1; ++r) {
     float dj = __ldg(a.dout + (size_t)r * a.ld_dout + j);
     if (a.dout_mul) dj *= __ldg(a.dout_mul + (size_t)r * a.d + j);
-    else if (a.drop.on) dj *= drop_mul1(a.drop, (unsigned long long)r * a.d + j);
-    const float xh = (__ldg(a.y + (size_t)r * a.ld_y + j) - __ldg(a.mean + r)) * __ldg(a.rstd + r);
+    else if (a.drop.on) {  // the eight threads of an aligned column group share ONE Philox call (thread = column here)
+      uint4 blk = make_uint4(0u, 0u, 0u, 0u);
+      if ((threadIdx.x & 7) == 0) blk = drop_block(a.drop, (unsigned int)r, (unsigned int)(jj >> 3));
+      const int src = (threadIdx.x & 31) & ~7;
+      blk.x = __shfl_sync(0xffffffffu, blk.x, src);
+      blk.y = __shfl_sync(0xffffffffu, blk.y, src);
+      blk.z = __shfl_sync(0xffffffffu, blk.z, src);
+      blk.w = __shfl_sync(0xffffffffu, blk.w, src);
+      dj *= drop_pick(a.drop, blk, (unsigned int)(j & 7));
+    }
+    const float yv = a.y16 ? ld16(__ldg(a.y16 + (size_t)r * a.ld_y + j), a.y_fmt) : __ldg(a.y + (size_t)r * a.ld_y + j);
+    const float xh = (yv - __ldg(a.mean + r)) * __ldg(a.rstd + r);
     ag += dj * xh;
     ab += dj;
   }
-  if (a.dgamma) atomicAdd(a.dgamma + j, ag * a.pgrad_scale);
-  if (a.dbeta) atomicAdd(a.dbeta + j, ab * a.pgrad_scale);
+  if (in && a.dgamma) atomicAdd(a.dgamma + j, ag * a.pgrad_scale);
+  if (in && a.dbeta) atomicAdd(a.dbeta + j, ab * a.pgrad_scale);
 }
 
 int launch_layernorm_bwd(const LnBwdArgs& a, cudaStream_t stream) {
@@ -225,6 +331,10 @@ int launch_layernorm_bwd(const LnBwdArgs& a, cudaStream_t stream) {
     if (e != cudaSuccess) set_error("layernorm_bwd launch failed: %s", cudaGetErrorString(e));
     return (int)e;
   }
+  if (a.y16 != nullptr) {
+    set_error("layernorm_bwd: a 16-bit LayerNorm input is only supported for the first projector layer (parameter gradients only)");
+    return (int)cudaErrorInvalidValue;
+  }
   static int max_blocks = 0;  // 4 blocks per SM by default; each block keeps register partials over its rows (UNIVTG_LNB_GRID overrides)
   if (max_blocks == 0) {
     const char* e = getenv("UNIVTG_LNB_GRID");
@@ -234,7 +344,24 @@ int launch_layernorm_bwd(const LnBwdArgs& a, cudaStream_t stream) {
   const bool vec = a.d % 4 == 0 && a.ld_dout % 4 == 0 && a.ld_y % 4 == 0 && (!a.dbr16 || a.ld16 % 4 == 0) &&
                    (((uintptr_t)a.dout | (uintptr_t)a.y | (uintptr_t)a.gamma | (uintptr_t)a.dy32 | (uintptr_t)a.dout_mul) & 15) == 0 &&
                    (((uintptr_t)a.dgamma | (uintptr_t)a.dbeta | (uintptr_t)a.colsum) & 15) == 0 && ((uintptr_t)a.dbr16 & 7) == 0;
-  if (vec && a.d <= 512) launch_k(layernorm_bwd_vec_kernel<1>, dim3(grid), dim3(128), 0, stream, a);
+  // warp-per-row kernel: d in {256, 512, 1024}, no K padding in the 16-bit output
+  static int use_warp = -1;
+  if (use_warp < 0) {
+    const char* e = getenv("UNIVTG_LNB_WARP");
+    use_warp = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  const bool warp_ok = use_warp && vec && (a.d == 256 || a.d == 512 || a.d == 1024) && (!a.dbr16 || a.ld16 == a.d);
+  if (warp_ok) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int wgrid = (a.rows + 7) / 8;
+    if (wgrid > sms) wgrid = sms;  // one 8-warp block per SM (253 registers per thread at d = 1024): a single wave
+    const size_t smem = (size_t)8 * a.d * sizeof(float);
+    if (a.d == 1024) launch_k(layernorm_bwd_warp_kernel<8>, dim3(wgrid), dim3(256), smem, stream, a);
+    else if (a.d == 512) launch_k(layernorm_bwd_warp_kernel<4>, dim3(wgrid), dim3(256), smem, stream, a);
+    else launch_k(layernorm_bwd_warp_kernel<2>, dim3(wgrid), dim3(256), smem, stream, a);
+  } else if (vec && a.d <= 512) launch_k(layernorm_bwd_vec_kernel<1>, dim3(grid), dim3(128), 0, stream, a);
   else if (vec && a.d <= 1024) launch_k(layernorm_bwd_vec_kernel<2>, dim3(grid), dim3(128), 0, stream, a);
   else if (a.d <= 128 * 8) launch_k(layernorm_bwd_kernel<8>, dim3(grid), dim3(128), 0, stream, a);
   else if (a.d <= 128 * 24) launch_k(layernorm_bwd_kernel<24>, dim3(grid), dim3(128), 0, stream, a);
@@ -297,17 +424,22 @@ int launch_tap_interleave(const float* src, float* dst, int N, int C, cudaStream
 
 // colsum[c] += scale * sum_r in16[r, c]: column sums of a 16-bit matrix (bias gradient of a GEMM whose output gradient was
 // written directly in 16-bit).  thread = 8 columns (128-bit loads), block = 1024 columns x 64 rows.
+constexpr int kColsumRows = 16;  // rows per block: all 16 loads of a thread are in flight at once (the first version walked 64
+                                 // rows four loads at a time and sat at 13 us for 21 MB - latency, not bandwidth)
 __global__ void __launch_bounds__(128) colsum16_kernel(const uint16_t* __restrict__ in16, int ld, int rows, int cols, int fmt,
                                                       float* __restrict__ colsum, float scale) {
   pdl_prologue();
   const int c = (blockIdx.x * 128 + threadIdx.x) * 8;
   if (c >= cols) return;
-  const int r0 = blockIdx.y * 64, r1 = min(rows, r0 + 64);
+  const int r0 = blockIdx.y * kColsumRows;
+  uint4 q[kColsumRows];
+#pragma unroll
+  for (int k = 0; k < kColsumRows; ++k)
+    q[k] = (r0 + k < rows) ? __ldg(reinterpret_cast<const uint4*>(in16 + (size_t)(r0 + k) * ld + c)) : make_uint4(0u, 0u, 0u, 0u);
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-  for (int r = r0; r < r1; ++r) {
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(in16 + (size_t)r * ld + c));
-    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int k = 0; k < kColsumRows; ++k) {
+    const uint32_t w[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       s[2 * i] += ld16((uint16_t)(w[i] & 0xffff), fmt);
@@ -323,7 +455,8 @@ int launch_colsum16(const uint16_t* in16, int ld, int rows, int cols, int fmt, f
     set_error("colsum16: columns / leading dimension must be multiples of 8 and the pointers 16-byte aligned");
     return (int)cudaErrorInvalidValue;
   }
-  launch_k(colsum16_kernel, dim3((cols / 8 + 127) / 128, (rows + 63) / 64), dim3(128), 0, stream, in16, ld, rows, cols, fmt, colsum, scale);
+  launch_k(colsum16_kernel, dim3((cols / 8 + 127) / 128, (rows + kColsumRows - 1) / kColsumRows), dim3(128), 0, stream, in16, ld, rows, cols,
+           fmt, colsum, scale);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("colsum16 launch failed: %s", cudaGetErrorString(e));
   return (int)e;
@@ -345,14 +478,34 @@ int launch_cvt16_colsum(const float* in32, int ld_in, uint16_t* out16, int ld_ou
 // ------------------------------------------------------------------------------------------------
 // delta[b,h,i] = rowsum(dO * O) per head.  One warp per token row.
 // ------------------------------------------------------------------------------------------------
+// vec = 1 (dh % 8 == 0, 16-byte aligned rows): a lane owns 8 consecutive channels per step (128-bit loads of dO and O), dh / 8
+// consecutive lanes cover one head and reduce among themselves - the scalar version moved 2 bytes per lane and load.
 __global__ void __launch_bounds__(256) attn_delta_kernel(const uint16_t* __restrict__ dO, int fmt_do, const uint16_t* __restrict__ O,
-                                                        int fmt_o, float* __restrict__ delta, int B, int L, int H, int dh) {
+                                                        int fmt_o, float* __restrict__ delta, int B, int L, int H, int dh, int vec) {
   pdl_prologue();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= B * L) return;
   const int b = row / L, i = row - b * L;
   const int d = H * dh;
+  if (vec) {
+    const int lph = dh / 8;  // lanes per head: 16 (dh 128), 8 (dh 64), 4 (dh 32)
+    for (int base = 0; base < d; base += 256) {  // warp-uniform trip count: the shuffles below need every lane
+      const int c0 = base + lane * 8;
+      const bool in = c0 < d;
+      const uint4 x = in ? __ldg(reinterpret_cast<const uint4*>(dO + (size_t)row * d + c0)) : make_uint4(0u, 0u, 0u, 0u);
+      const uint4 y = in ? __ldg(reinterpret_cast<const uint4*>(O + (size_t)row * d + c0)) : make_uint4(0u, 0u, 0u, 0u);
+      const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        s += ld16((uint16_t)(xw[k] & 0xffff), fmt_do) * ld16((uint16_t)(yw[k] & 0xffff), fmt_o) +
+             ld16((uint16_t)(xw[k] >> 16), fmt_do) * ld16((uint16_t)(yw[k] >> 16), fmt_o);
+      for (int o = lph >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (in && (lane & (lph - 1)) == 0) delta[((size_t)b * H + c0 / dh) * L + i] = s;
+    }
+    return;
+  }
   for (int h = 0; h < H; ++h) {
     float s = 0.f;
     for (int c = lane; c < dh; c += 32) {
@@ -367,7 +520,11 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const uint16_t* __restr
 int launch_attn_delta(const uint16_t* dO, int fmt_do, const uint16_t* O, int fmt_o, float* delta, int B, int L, int H, int dh,
                       cudaStream_t stream) {
   const int rows = B * L;
-  launch_k(attn_delta_kernel, dim3((rows * 32 + 255) / 256), dim3(256), 0, stream, dO, fmt_do, O, fmt_o, delta, B, L, H, dh);
+  const int d = H * dh;
+  // vector path: 8 channels per lane, 2^k lanes per head, every 256-channel step of a warp covers whole heads
+  const int vec = (dh % 8 == 0) && ((dh / 8) & (dh / 8 - 1)) == 0 && dh <= 256 && (d % 8 == 0) && (256 % dh == 0 || dh == 256) &&
+                  ((reinterpret_cast<uintptr_t>(dO) | reinterpret_cast<uintptr_t>(O)) & 15) == 0;
+  launch_k(attn_delta_kernel, dim3((rows * 32 + 255) / 256), dim3(256), 0, stream, dO, fmt_do, O, fmt_o, delta, B, L, H, dh, vec ? 1 : 0);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("attn_delta launch failed: %s", cudaGetErrorString(e));
   return (int)e;

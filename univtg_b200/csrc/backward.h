@@ -15,6 +15,8 @@ struct LnBwdArgs {
   int ld_dout;
   const float* y;     // [rows, ld_y] LayerNorm input saved by the forward pass
   int ld_y;
+  const uint16_t* y16;  // alternative: the LayerNorm input as 16-bit (first projector layer fed from a 16-bit feature shard)
+  int y_fmt;
   const float* mean;  // [rows]
   const float* rstd;  // [rows]
   const float* gamma; // [d]

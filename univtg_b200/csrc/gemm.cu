@@ -757,6 +757,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+int make_tmap_2d_uncached(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
+                          uint32_t box_cols);
+
 static EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   if (fn) return fn;
@@ -771,8 +774,51 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Tensor maps are pure functions of (base, extents, pitch, box): the training path describes ~250 operand views per step and, with
+// pooled workspaces, describes the SAME views every step - a small direct-mapped cache turns ~250 driver calls per step
+// (cuTensorMapEncodeTiled, ~1.5 us each on the host) into hash look-ups.  Thread-local: one process per GPU, one host thread.
+struct TmapKey {
+  const void* base;
+  uint64_t rows, cols, ld;
+  uint32_t box_rows, box_cols, kind;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols && kind == o.kind;
+  }
+};
+struct TmapSlot {
+  TmapKey key;
+  CUtensorMap map;
+  bool used;
+};
+constexpr int kTmapCacheSlots = 4096;
+static thread_local TmapSlot* g_tmap_cache = nullptr;
+static inline TmapSlot* tmap_slot(const TmapKey& k) {
+  if (g_tmap_cache == nullptr) g_tmap_cache = static_cast<TmapSlot*>(calloc(kTmapCacheSlots, sizeof(TmapSlot)));
+  uint64_t h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
+  h ^= (k.rows * 0xC2B2AE3D27D4EB4Full) ^ (k.cols << 17) ^ (k.ld << 29) ^ ((uint64_t)k.box_rows << 41) ^ ((uint64_t)k.box_cols << 47) ^ ((uint64_t)k.kind << 55);
+  h ^= h >> 29;
+  return g_tmap_cache ? &g_tmap_cache[h & (kTmapCacheSlots - 1)] : nullptr;
+}
+
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
                  uint32_t box_cols) {
+  const TmapKey key{base, rows, cols, ld_elems, box_rows, box_cols, 2u};
+  TmapSlot* slot = tmap_slot(key);
+  if (slot != nullptr && slot->used && slot->key == key) {
+    *out = slot->map;
+    return 0;
+  }
+  const int rc = make_tmap_2d_uncached(out, base, rows, cols, ld_elems, box_rows, box_cols);
+  if (rc == 0 && slot != nullptr) {
+    slot->key = key;
+    slot->map = *out;
+    slot->used = true;
+  }
+  return rc;
+}
+
+int make_tmap_2d_uncached(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
+                          uint32_t box_cols) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return 1;
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld_elems * 2) % 16 != 0) {
@@ -797,6 +843,13 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 int make_tmap_b_mn(GemmProblem& p, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, int bn, bool allow_3d) {
   p.b_3d = 0;
   if (!allow_3d || cols % 64 != 0 || bn % 64 != 0 || bn < 64) return make_tmap_2d(&p.tm_b, base, rows, cols, ld_elems, 64, 64);
+  const TmapKey key{base, rows, cols, ld_elems, (uint32_t)bn, 64u, 3u};
+  TmapSlot* slot = tmap_slot(key);
+  if (slot != nullptr && slot->used && slot->key == key) {
+    p.tm_b = slot->map;
+    p.b_3d = bn / 64;
+    return 0;
+  }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return 1;
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld_elems * 2) % 16 != 0) {
@@ -816,6 +869,11 @@ int make_tmap_b_mn(GemmProblem& p, const void* base, uint64_t rows, uint64_t col
     return 3;
   }
   p.b_3d = bn / 64;
+  if (slot != nullptr) {
+    slot->key = key;
+    slot->map = p.tm_b;
+    slot->used = true;
+  }
   return 0;
 }
 

@@ -270,6 +270,7 @@ struct univtg_plan {
   uint8_t* ws;
   const float* dim_t;
   int num_sms;
+  int in_fmt;       // src_vid / src_txt element type: 0 f32 (reference collate), 1 fp16, 2 bf16 (packed feature shards)
   int num_sms_bwd;  // SM budget of the backward's GEMM launches (0: num_sms); see univtg_plan_set_backward_sm_budget
   int B, Lv, Lt, L, d, ff, H, dh, M, Mv, Mt, Mh;
   // workspace pointers

@@ -38,7 +38,7 @@ struct LnStore {
       const float4 m = *reinterpret_cast<const float4*>(a.mul32 + (size_t)row * a.d + j);
       v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
     } else if (a.drop.on) {
-      const float4 m = drop_mul4(a.drop, (unsigned long long)row * a.d + j);
+      const float4 m = drop_mul4(a.drop, (unsigned int)row, (unsigned int)j);
       v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
     }
     uint2 pk;
@@ -59,7 +59,7 @@ struct LnStore {
   __device__ __forceinline__ void store1(int j, float v) const {
     if (a.out32) a.out32[(size_t)row * a.d + j] = v;
     if (a.mul32) v *= a.mul32[(size_t)row * a.d + j];
-    else if (a.drop.on) v *= drop_mul1(a.drop, (unsigned long long)row * a.d + j);
+    else if (a.drop.on) v *= drop_mul1(a.drop, (unsigned int)row, (unsigned int)j);
     const uint16_t h = cvt16(v, a.fmt);
     if (a.out16) a.out16[(size_t)row * a.ld16 + j] = h;
     if (a.out16p) a.out16p[(size_t)row * a.ld16 + j] = has_pos ? cvt16(v + a.pos[prow * a.d + j], a.fmt) : h;
@@ -80,6 +80,11 @@ __global__ void __launch_bounds__(256) layernorm_rows_vec_kernel(const LnArgs a)
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int j = (i * 32 + lane) * 4;
+    if (a.in16 != nullptr) {  // 16-bit feature shard: 64-bit load = four features
+      const uint2 w = *reinterpret_cast<const uint2*>(a.in16 + (size_t)warp * a.ld_in + j);
+      v[i] = make_float4(ld16((uint16_t)(w.x & 0xffff), a.in_fmt), ld16((uint16_t)(w.x >> 16), a.in_fmt),
+                         ld16((uint16_t)(w.y & 0xffff), a.in_fmt), ld16((uint16_t)(w.y >> 16), a.in_fmt));
+    } else
     v[i] = *reinterpret_cast<const float4*>(x + j);
     if (a.add16) {
       const uint2 h = *reinterpret_cast<const uint2*>(a.add16 + (size_t)warp * a.ld_add16 + j);
@@ -126,12 +131,14 @@ __global__ void __launch_bounds__(256) layernorm_rows_generic_kernel(const LnArg
   const int lane = threadIdx.x & 31;
   if (warp >= a.rows) return;
   const float* x = a.in + (size_t)warp * a.ld_in;
+  const uint16_t* x16 = a.in16 ? a.in16 + (size_t)warp * a.ld_in : nullptr;
+  auto X = [&](int j) { return x16 ? ld16(x16[j], a.in_fmt) : x[j]; };
   float s = 0.f;
-  for (int j = lane; j < a.d; j += 32) s += x[j];
+  for (int j = lane; j < a.d; j += 32) s += X(j);
   const float mean = warp_sum(s) / (float)a.d;
   float q = 0.f;
   for (int j = lane; j < a.d; j += 32) {
-    const float dx = x[j] - mean;
+    const float dx = X(j) - mean;
     q += dx * dx;
   }
   const float var = warp_sum(q) / (float)a.d;
@@ -141,7 +148,7 @@ __global__ void __launch_bounds__(256) layernorm_rows_generic_kernel(const LnArg
     if (a.rstd_out) a.rstd_out[warp] = rstd;
   }
   const LnStore st(a, warp);
-  for (int j = lane; j < a.d; j += 32) st.store1(j, (x[j] - mean) * rstd * a.gamma[j] + a.beta[j]);
+  for (int j = lane; j < a.d; j += 32) st.store1(j, (X(j) - mean) * rstd * a.gamma[j] + a.beta[j]);
   // zero the K padding of the 16-bit operand row (columns d .. ld16)
   if (a.out16)
     for (int j = a.d + lane; j < a.ld16; j += 32) a.out16[(size_t)warp * a.ld16 + j] = 0;
@@ -156,12 +163,13 @@ __global__ void __launch_bounds__(128) layernorm_rows_block_kernel(const LnArgs 
   const int row = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* x = a.in + (size_t)row * a.ld_in;
+  const uint16_t* x16 = a.in16 ? a.in16 + (size_t)row * a.ld_in : nullptr;
   float v[EPT];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < EPT; ++i) {
     const int j = tid + 128 * i;
-    v[i] = j < a.d ? x[j] : 0.f;
+    v[i] = j < a.d ? (x16 ? ld16(x16[j], a.in_fmt) : x[j]) : 0.f;
     if (a.add16 && j < a.d) {
       v[i] += ld16(a.add16[(size_t)row * a.ld_add16 + j], a.fmt);
       if (a.sum_out) a.sum_out[(size_t)row * a.d + j] = v[i];
@@ -213,12 +221,20 @@ __global__ void __launch_bounds__(128) layernorm_rows_block2_kernel(const LnArgs
   const int row = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* x = a.in + (size_t)row * a.ld_in;
+  const uint16_t* x16 = a.in16 ? a.in16 + (size_t)row * a.ld_in : nullptr;
+  // a thread owns 8 consecutive columns per step (four 64-bit loads): one Philox call decides all eight dropout multipliers
+  constexpr int STEPS = EPT2 / 4;
   float2 v[EPT2];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < EPT2; ++i) {
-    const int j = 2 * (tid + 128 * i);
-    v[i] = j < a.d ? *reinterpret_cast<const float2*>(x + j) : make_float2(0.f, 0.f);
+    const int j = 8 * (tid + 128 * (i / 4)) + 2 * (i % 4);
+    if (x16 != nullptr) {  // 16-bit feature shard: one 32-bit load = two features
+      const uint32_t w = j < a.d ? *reinterpret_cast<const uint32_t*>(x16 + j) : 0u;
+      v[i] = make_float2(ld16((uint16_t)(w & 0xffff), a.in_fmt), ld16((uint16_t)(w >> 16), a.in_fmt));
+    } else {
+      v[i] = j < a.d ? *reinterpret_cast<const float2*>(x + j) : make_float2(0.f, 0.f);
+    }
     s += v[i].x + v[i].y;
   }
   s = warp_sum(s);
@@ -230,7 +246,7 @@ __global__ void __launch_bounds__(128) layernorm_rows_block2_kernel(const LnArgs
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < EPT2; ++i) {
-    const int j = 2 * (tid + 128 * i);
+    const int j = 8 * (tid + 128 * (i / 4)) + 2 * (i % 4);
     if (j < a.d) {
       const float dx = v[i].x - mean, dy = v[i].y - mean;
       q += dx * dx + dy * dy;
@@ -249,23 +265,29 @@ __global__ void __launch_bounds__(128) layernorm_rows_block2_kernel(const LnArgs
   __syncthreads();
   const float rstd = s_stat[1];
 #pragma unroll
-  for (int i = 0; i < EPT2; ++i) {
-    const int j = 2 * (tid + 128 * i);
-    if (j < a.d) {
-      const float2 g = *reinterpret_cast<const float2*>(a.gamma + j);
-      const float2 be = *reinterpret_cast<const float2*>(a.beta + j);
-      float ox = (v[i].x - mean) * rstd * g.x + be.x;
-      float oy = (v[i].y - mean) * rstd * g.y + be.y;
-      if (a.mul32) {
-        const float2 m = *reinterpret_cast<const float2*>(a.mul32 + (size_t)row * a.d + j);
-        ox *= m.x;
-        oy *= m.y;
-      } else if (a.drop.on) {
-        const float2 m = drop_mul2(a.drop, (unsigned long long)row * a.d + j);
-        ox *= m.x;
-        oy *= m.y;
+  for (int st = 0; st < STEPS; ++st) {
+    const int j0 = 8 * (tid + 128 * st);
+    float m8[8];
+    const bool rnd = a.mul32 == nullptr && a.drop.on && j0 < a.d;
+    if (rnd) drop_mul8(a.drop, (unsigned int)row, (unsigned int)(j0 >> 3), m8);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = st * 4 + k, j = j0 + 2 * k;
+      if (j < a.d) {
+        const float2 g = *reinterpret_cast<const float2*>(a.gamma + j);
+        const float2 be = *reinterpret_cast<const float2*>(a.beta + j);
+        float ox = (v[i].x - mean) * rstd * g.x + be.x;
+        float oy = (v[i].y - mean) * rstd * g.y + be.y;
+        if (a.mul32) {
+          const float2 m = *reinterpret_cast<const float2*>(a.mul32 + (size_t)row * a.d + j);
+          ox *= m.x;
+          oy *= m.y;
+        } else if (rnd) {
+          ox *= m8[2 * k];
+          oy *= m8[2 * k + 1];
+        }
+        *reinterpret_cast<uint32_t*>(a.out16 + (size_t)row * a.ld16 + j) = cvt16x2(ox, oy, a.fmt);
       }
-      *reinterpret_cast<uint32_t*>(a.out16 + (size_t)row * a.ld16 + j) = cvt16x2(ox, oy, a.fmt);
     }
   }
   for (int j = a.d + 2 * tid; j < a.ld16; j += 256) *reinterpret_cast<uint32_t*>(a.out16 + (size_t)row * a.ld16 + j) = 0u;
@@ -275,12 +297,13 @@ int launch_layernorm(const LnArgs& a, cudaStream_t stream) {
   if (a.rows <= 0) return 0;
   const int threads = 256;
   const int blocks = (a.rows * 32 + threads - 1) / threads;
-  const bool vec_ok = (a.ld_in % 4 == 0) && (a.ld16 == a.d) && ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0);
+  const bool vec_ok = (a.ld_in % 4 == 0) && (a.ld16 == a.d) &&
+                      (a.in16 ? (reinterpret_cast<uintptr_t>(a.in16) & 7) == 0 : (reinterpret_cast<uintptr_t>(a.in) & 15) == 0);
   if (vec_ok && a.d == 1024) launch_k(layernorm_rows_vec_kernel<8>, dim3(blocks), dim3(threads), 0, stream, a);
   else if (vec_ok && a.d == 512) launch_k(layernorm_rows_vec_kernel<4>, dim3(blocks), dim3(threads), 0, stream, a);
   else if (vec_ok && a.d == 256) launch_k(layernorm_rows_vec_kernel<2>, dim3(blocks), dim3(threads), 0, stream, a);
-  else if (a.d > 1024 && a.d <= 256 * 12 && a.d % 2 == 0 && a.ld_in % 2 == 0 && a.ld16 % 2 == 0 && a.out16 && !a.out32 &&
-           !a.out16p && !a.outc && !a.add16 && (reinterpret_cast<uintptr_t>(a.in) & 7) == 0 &&
+  else if (a.d > 1024 && a.d <= 1024 * 3 && a.d % 2 == 0 && a.ld_in % 2 == 0 && a.ld16 % 2 == 0 && a.out16 && !a.out32 &&
+           !a.out16p && !a.outc && !a.add16 && (a.in16 ? (reinterpret_cast<uintptr_t>(a.in16) & 3) == 0 : (reinterpret_cast<uintptr_t>(a.in) & 7) == 0) &&
            (reinterpret_cast<uintptr_t>(a.gamma) & 7) == 0 && (reinterpret_cast<uintptr_t>(a.beta) & 7) == 0 &&
            (!a.mul32 || (reinterpret_cast<uintptr_t>(a.mul32) & 7) == 0))
     launch_k(layernorm_rows_block2_kernel<12>, dim3(a.rows), dim3(128), 0, stream, a);
@@ -372,19 +395,20 @@ int launch_sine_pos(const float* mask, const float* txt_mask, const float* dim_t
   return (int)e;
 }
 
-__global__ void __launch_bounds__(256) dropout_mask_kernel(const DropSpec spec, size_t n, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) dropout_mask_kernel(const DropSpec spec, size_t n, size_t cols, float* __restrict__ out) {
   pdl_prologue();
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = spec.on ? drop_mul1(spec, i) : 1.f;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+    out[i] = spec.on ? drop_mul1(spec, (unsigned int)(i / cols), (unsigned int)(i % cols)) : 1.f;
 }
 __global__ void __launch_bounds__(256) droppath_scales_kernel(unsigned long long seed, int n, float keep, float* __restrict__ out) {
   pdl_prologue();
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) out[i] = droppath_scale(seed, (unsigned int)i, keep);
 }
-int launch_dropout_mask(const DropSpec& spec, size_t n, float* out, cudaStream_t stream) {
+int launch_dropout_mask(const DropSpec& spec, size_t n, size_t cols, float* out, cudaStream_t stream) {
   if (n == 0) return 0;
   size_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  launch_k(dropout_mask_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, spec, n, out);
+  launch_k(dropout_mask_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, spec, n, cols, out);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) set_error("dropout_mask launch failed: %s", cudaGetErrorString(e));
   return (int)e;

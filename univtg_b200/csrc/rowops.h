@@ -11,6 +11,8 @@ namespace uv {
 struct LnArgs {
   const float* in;  // [rows, ld_in] fp32
   int ld_in;
+  const uint16_t* in16;  // alternative 16-bit input [rows, ld_in] (packed feature shards: fp16 / bf16 per in_fmt); `in` is then unused
+  int in_fmt;
   const uint16_t* add16;  // optional 16-bit [rows, ld_add16] branch added to `in` before normalising (x + DropPath(branch))
   int ld_add16;
   float* sum_out;         // optional fp32 [rows, d]: the pre-normalisation sum (saved for LayerNorm backward)
@@ -40,7 +42,7 @@ int launch_sine_pos(const float* mask, const float* txt_mask, const float* dim_t
                     int Lt, int d, cudaStream_t stream, float* dp_out = nullptr, int dp_sites = 0, unsigned long long dp_seed = 0,
                     float dp_keep = 1.f);
 // standalone generators (parity tests read the in-kernel draws back through them)
-int launch_dropout_mask(const DropSpec& spec, size_t n, float* out, cudaStream_t stream);
+int launch_dropout_mask(const DropSpec& spec, size_t n, size_t cols, float* out, cudaStream_t stream);  // [n / cols, cols] row-major
 int launch_droppath_scales(unsigned long long seed, int n, float keep, float* out, cudaStream_t stream);
 
 struct PoolSalArgs {

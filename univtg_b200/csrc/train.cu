@@ -1,6 +1,8 @@
 // Training path of the C-ABI: forward that keeps what backward needs, the backward pass (reference
 // main/train_vlp_ddp.py:56-64: outputs = model(...); losses.backward()) and the criterion entry points.
 // GEMM descriptors (tensor maps) are built per call here; shapes vary per training batch anyway (collate pads to the batch max).
+#include <stdlib.h>
+
 #include "plan.h"
 
 namespace {
@@ -46,7 +48,6 @@ inline TileChoice tile_for(int sms, int step, int max_split, MNK a, MNK b = MNK{
   return choose_tile(Ms, Ns, kb, num, sms, step, max_split);
 }
 inline int bn_for(int sms, int step, MNK a, MNK b = MNK{0, 0, 0}) { return tile_for(sms, step, 1, a, b).bn; }
-
 
 struct TrainWs {
   // ---- saved by the forward ----
@@ -244,6 +245,10 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
       LnArgs a;
       memset(&a, 0, sizeof(a));
       a.in = i == 0 ? (s == 0 ? src_vid : src_txt) : (s == 0 ? T.p_vid32[i - 1] : T.p_txt32[i - 1]);
+      if (i == 0 && P->in_fmt != 0) {
+        a.in16 = reinterpret_cast<const uint16_t*>(a.in);
+        a.in_fmt = P->in_fmt - 1;
+      }
       a.ld_in = pp.din;
       a.rows = s == 0 ? Mv : Mt;
       a.d = pp.din;
@@ -743,56 +748,78 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       if (rc) return rc;
     }
     // ---- FFN2: dgrad -> d(hpre) = (dF W2) * gelu'(hpre);  wgrad dW2 = dF^T h ----
-    memset(&g, 0, sizeof(g));
-    g.num = 1;
-    g.fmt = fmt;
-    rc = setup_gemm(g.p[0], Mat16{T.dbr16, M, d, d}, 0, Mat16{W16(lp.w2), d, ff, ff}, 1, M, ff, d, bn_dff);
-    if (rc) return rc;
-    g.p[0].a_fmt = FMT_G;
-    g.p[0].b_fmt = fmt;
-    g.p[0].aux32 = T.hpre[l];
-    g.p[0].ld_aux = ff;
-    g.p[0].aux_mode = 1;
-    g.p[0].out16 = T.dhpre16;
-    g.p[0].ld16 = ff;
-    g.p[0].out_fmt = FMT_G;
-    g.p[0].colsum = G_layer(l, 5);  // linear1.bias
-    g.p[0].colsum_scale = INV;
-    rc = gemm_launch(P, g, bn_dff, sms, st);
-    if (rc) return rc;
-    memset(&g, 0, sizeof(g));
-    g.num = 2;
-    g.fmt = fmt;
+    // ---- FFN1: dgrad d(x1) = dhpre W1 + dy (residual);          wgrad dW1 = dhpre^T x1 ----
+    // (sharing one launch between a data-gradient GEMM and the weight-gradient GEMM that reads the same dY was measured: fewer
+    //  launches and 10 % less event-timed GEMM time, but the pipelined step got 50 us SLOWER - profiles/README.md round 2 - so the
+    //  launches stay separate and are chained by programmatic dependent launch)
+    auto ffn2_dgrad = [&](GemmProblem& p, int bnn) -> int {
+      int r = setup_gemm(p, Mat16{T.dbr16, M, d, d}, 0, Mat16{W16(lp.w2), d, ff, ff}, 1, M, ff, d, bnn);
+      p.a_fmt = FMT_G;
+      p.b_fmt = fmt;
+      p.aux32 = T.hpre[l];
+      p.ld_aux = ff;
+      p.aux_mode = 1;
+      p.out16 = T.dhpre16;
+      p.ld16 = ff;
+      p.out_fmt = FMT_G;
+      p.colsum = G_layer(l, 5);  // linear1.bias
+      p.colsum_scale = INV;
+      return r;
+    };
+    auto ffn2_wgrad = [&](GemmProblem& p, int bnn, int ks) -> int {
+      int r = setup_gemm(p, Mat16{T.dbr16, M, d, d}, 1, Mat16{T.h16[l], M, ff, ff}, 1, d, ff, M, bnn);
+      p.a_fmt = FMT_G;
+      p.b_fmt = fmt;
+      p.out32 = G_layer(l, 6);  // linear2.weight [d, ff]
+      p.ld32 = ff;
+      p.alpha = INV;
+      p.ksplit = ks;
+      return r;
+    };
+    auto ffn1_dgrad = [&](GemmProblem& p, int bnn) -> int {
+      int r = setup_gemm(p, Mat16{T.dhpre16, M, ff, ff}, 0, Mat16{W16(lp.w1), ff, d, d}, 1, M, d, ff, bnn);
+      p.a_fmt = FMT_G;
+      p.b_fmt = fmt;
+      p.resid = T.dy;
+      p.ld_resid = d;
+      p.out32 = T.dx;
+      p.ld32 = d;
+      return r;
+    };
+    auto ffn1_wgrad = [&](GemmProblem& p, int bnn, int ks) -> int {
+      int r = setup_gemm(p, Mat16{T.dhpre16, M, ff, ff}, 1, Mat16{T.x1_16[l], M, d, d}, 1, ff, d, M, bnn);
+      p.a_fmt = FMT_G;
+      p.b_fmt = fmt;
+      p.out32 = G_layer(l, 4);  // linear1.weight [ff, d]
+      p.ld32 = d;
+      p.alpha = INV;
+      p.ksplit = ks;
+      return r;
+    };
     {
-      const int bnw = t_wf.bn;
-      rc |= setup_gemm(g.p[0], Mat16{T.dbr16, M, d, d}, 1, Mat16{T.h16[l], M, ff, ff}, 1, d, ff, M, bnw);
-      rc |= setup_gemm(g.p[1], Mat16{T.dhpre16, M, ff, ff}, 1, Mat16{T.x1_16[l], M, d, d}, 1, ff, d, M, bnw);
+      memset(&g, 0, sizeof(g));
+      g.num = 1;
+      g.fmt = fmt;
+      rc = ffn2_dgrad(g.p[0], bn_dff);
       if (rc) return rc;
-      g.p[0].a_fmt = g.p[1].a_fmt = FMT_G;
-      g.p[0].b_fmt = g.p[1].b_fmt = fmt;
-      g.p[0].out32 = G_layer(l, 6);  // linear2.weight [d, ff]
-      g.p[0].ld32 = ff;
-      g.p[1].out32 = G_layer(l, 4);  // linear1.weight [ff, d]
-      g.p[1].ld32 = d;
-      g.p[0].alpha = g.p[1].alpha = INV;
-      g.p[0].ksplit = g.p[1].ksplit = t_wf.ksplit;
-      rc = gemm_launch(P, g, bnw, sms, st);
+      rc = gemm_launch(P, g, bn_dff, sms, st);
+      if (rc) return rc;
+      memset(&g, 0, sizeof(g));
+      g.num = 2;
+      g.fmt = fmt;
+      rc |= ffn2_wgrad(g.p[0], t_wf.bn, t_wf.ksplit);
+      rc |= ffn1_wgrad(g.p[1], t_wf.bn, t_wf.ksplit);
+      if (rc) return rc;
+      rc = gemm_launch(P, g, t_wf.bn, sms, st);
+      if (rc) return rc;
+      memset(&g, 0, sizeof(g));
+      g.num = 1;
+      g.fmt = fmt;
+      rc = ffn1_dgrad(g.p[0], bn_dd1);
+      if (rc) return rc;
+      rc = gemm_launch(P, g, bn_dd1, sms, st);
       if (rc) return rc;
     }
-    // ---- FFN1 dgrad: d(x1) = dhpre W1 + dy (residual) ----
-    memset(&g, 0, sizeof(g));
-    g.num = 1;
-    g.fmt = fmt;
-    rc = setup_gemm(g.p[0], Mat16{T.dhpre16, M, ff, ff}, 0, Mat16{W16(lp.w1), ff, d, d}, 1, M, d, ff, bn_dd1);
-    if (rc) return rc;
-    g.p[0].a_fmt = FMT_G;
-    g.p[0].b_fmt = fmt;
-    g.p[0].resid = T.dy;
-    g.p[0].ld_resid = d;
-    g.p[0].out32 = T.dx;
-    g.p[0].ld32 = d;
-    rc = gemm_launch(P, g, bn_dd1, sms, st);
-    if (rc) return rc;
     // ---- LN1 backward ----
     {
       LnBwdArgs a;
@@ -819,32 +846,42 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       rc = launch_layernorm_bwd(a, st);
       if (rc) return rc;
     }
-    // ---- out-proj: dgrad -> dO (bf16); wgrad dWo = dA^T attn ----
-    memset(&g, 0, sizeof(g));
-    g.num = 1;
-    g.fmt = fmt;
-    rc = setup_gemm(g.p[0], Mat16{T.dbr16, M, d, d}, 0, Mat16{W16(lp.w_out), d, d, d}, 1, M, d, d, bn_ddo);
-    if (rc) return rc;
-    g.p[0].a_fmt = FMT_G;
-    g.p[0].b_fmt = fmt;
-    g.p[0].out16 = T.dO16;
-    g.p[0].ld16 = d;
-    g.p[0].out_fmt = FMT_G;
-    rc = gemm_launch(P, g, bn_ddo, sms, st);
-    if (rc) return rc;
-    memset(&g, 0, sizeof(g));
-    g.num = 1;
-    g.fmt = fmt;
-    rc = setup_gemm(g.p[0], Mat16{T.dbr16, M, d, d}, 1, Mat16{T.attn16[l], M, d, d}, 1, d, d, M, bn_wo);
-    if (rc) return rc;
-    g.p[0].a_fmt = FMT_G;
-    g.p[0].b_fmt = fmt;
-    g.p[0].out32 = G_layer(l, 2);
-    g.p[0].ld32 = d;
-    g.p[0].alpha = INV;
-    g.p[0].ksplit = t_wo.ksplit;
-    rc = gemm_launch(P, g, bn_wo, sms, st);
-    if (rc) return rc;
+    // ---- out-proj: dgrad -> dO (16-bit); wgrad dWo = dA^T attn ----
+    auto out_dgrad = [&](GemmProblem& p, int bnn) -> int {
+      int r = setup_gemm(p, Mat16{T.dbr16, M, d, d}, 0, Mat16{W16(lp.w_out), d, d, d}, 1, M, d, d, bnn);
+      p.a_fmt = FMT_G;
+      p.b_fmt = fmt;
+      p.out16 = T.dO16;
+      p.ld16 = d;
+      p.out_fmt = FMT_G;
+      return r;
+    };
+    auto out_wgrad = [&](GemmProblem& p, int bnn, int ks) -> int {
+      int r = setup_gemm(p, Mat16{T.dbr16, M, d, d}, 1, Mat16{T.attn16[l], M, d, d}, 1, d, d, M, bnn);
+      p.a_fmt = FMT_G;
+      p.b_fmt = fmt;
+      p.out32 = G_layer(l, 2);
+      p.ld32 = d;
+      p.alpha = INV;
+      p.ksplit = ks;
+      return r;
+    };
+    {
+      memset(&g, 0, sizeof(g));
+      g.num = 1;
+      g.fmt = fmt;
+      rc = out_dgrad(g.p[0], bn_ddo);
+      if (rc) return rc;
+      rc = gemm_launch(P, g, bn_ddo, sms, st);
+      if (rc) return rc;
+      memset(&g, 0, sizeof(g));
+      g.num = 1;
+      g.fmt = fmt;
+      rc = out_wgrad(g.p[0], bn_wo, t_wo.ksplit);
+      if (rc) return rc;
+      rc = gemm_launch(P, g, bn_wo, sms, st);
+      if (rc) return rc;
+    }
     // ---- attention core backward -> dqkv32 -> dqkv16 (+ in_proj_bias gradient) ----
     rc = launch_attn_delta(T.dO16, FMT_G, T.attn16[l], fmt, T.delta, B, L, P->H, P->dh, st);
     if (rc) return rc;
@@ -887,35 +924,45 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     else rc = launch_colsum16(T.dqkv16, 3 * d, M, 3 * d, FMT_G, G_layer(l, 1), INV, st);  // in_proj_bias gradient
     if (rc) return rc;
     // ---- in-projections: dgrad dx = dy + [dq|dk|dv] [Wq;Wk;Wv]; wgrad dWqk = [dq|dk]^T (x+pos), dWv = dv^T x ----
-    memset(&g, 0, sizeof(g));
-    g.num = 1;
-    g.fmt = fmt;
-    rc = setup_gemm(g.p[0], Mat16{T.dqkv16, M, 3 * d, 3 * d}, 0, Mat16{W16(lp.w_in), 3 * d, d, d}, 1, M, d, 3 * d, bn_ddq);
-    if (rc) return rc;
-    g.p[0].a_fmt = FMT_G;
-    g.p[0].b_fmt = fmt;
-    g.p[0].resid = T.dy;
-    g.p[0].ld_resid = d;
-    g.p[0].out32 = T.dx;
-    g.p[0].ld32 = d;
-    rc = gemm_launch(P, g, bn_ddq, sms, st);
-    if (rc) return rc;
-    memset(&g, 0, sizeof(g));
-    g.num = 2;
-    g.fmt = fmt;
-    rc |= setup_gemm(g.p[0], Mat16{T.dqkv16, M, 2 * d, 3 * d}, 1, Mat16{T.xpos16[l], M, d, d}, 1, 2 * d, d, M, bn_wq);
-    rc |= setup_gemm(g.p[1], Mat16{T.dqkv16 + 2 * d, M, d, 3 * d}, 1, Mat16{T.xin16[l], M, d, d}, 1, d, d, M, bn_wq);
-    if (rc) return rc;
-    g.p[0].a_fmt = g.p[1].a_fmt = FMT_G;
-    g.p[0].b_fmt = g.p[1].b_fmt = fmt;
-    g.p[0].out32 = G_layer(l, 0);
-    g.p[0].ld32 = d;
-    g.p[1].out32 = G_layer(l, 0) + (size_t)2 * d * d;
-    g.p[1].ld32 = d;
-    g.p[0].alpha = g.p[1].alpha = INV;
-    g.p[0].ksplit = g.p[1].ksplit = t_wq.ksplit;
-    rc = gemm_launch(P, g, bn_wq, sms, st);
-    if (rc) return rc;
+    auto qkv_dgrad = [&](GemmProblem& p, int bnn) -> int {
+      int r = setup_gemm(p, Mat16{T.dqkv16, M, 3 * d, 3 * d}, 0, Mat16{W16(lp.w_in), 3 * d, d, d}, 1, M, d, 3 * d, bnn);
+      p.a_fmt = FMT_G;
+      p.b_fmt = fmt;
+      p.resid = T.dy;
+      p.ld_resid = d;
+      p.out32 = T.dx;
+      p.ld32 = d;
+      return r;
+    };
+    auto qkv_wgrads = [&](GemmProblem& pqk, GemmProblem& pv, int bnn, int ks) -> int {
+      int r = setup_gemm(pqk, Mat16{T.dqkv16, M, 2 * d, 3 * d}, 1, Mat16{T.xpos16[l], M, d, d}, 1, 2 * d, d, M, bnn);
+      r |= setup_gemm(pv, Mat16{T.dqkv16 + 2 * d, M, d, 3 * d}, 1, Mat16{T.xin16[l], M, d, d}, 1, d, d, M, bnn);
+      pqk.a_fmt = pv.a_fmt = FMT_G;
+      pqk.b_fmt = pv.b_fmt = fmt;
+      pqk.out32 = G_layer(l, 0);
+      pqk.ld32 = d;
+      pv.out32 = G_layer(l, 0) + (size_t)2 * d * d;
+      pv.ld32 = d;
+      pqk.alpha = pv.alpha = INV;
+      pqk.ksplit = pv.ksplit = ks;
+      return r;
+    };
+    {
+      memset(&g, 0, sizeof(g));
+      g.num = 1;
+      g.fmt = fmt;
+      rc = qkv_dgrad(g.p[0], bn_ddq);
+      if (rc) return rc;
+      rc = gemm_launch(P, g, bn_ddq, sms, st);
+      if (rc) return rc;
+      memset(&g, 0, sizeof(g));
+      g.num = 2;
+      g.fmt = fmt;
+      rc = qkv_wgrads(g.p[0], g.p[1], bn_wq, t_wq.ksplit);
+      if (rc) return rc;
+      rc = gemm_launch(P, g, bn_wq, sms, st);
+      if (rc) return rc;
+    }
     stage_done(1 + (c.enc_layers - 1 - l));  // encoder layer l
   }
 
@@ -998,6 +1045,10 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       a.dout_mul = drop_masks ? drop_masks[s * np + i] : nullptr;
       if (drop_rng) a.drop = make_drop_spec(rng->seed, (unsigned int)(s * np + i), rng->input_dropout);
       a.y = i == 0 ? (s == 0 ? src_vid : src_txt) : (s == 0 ? T.p_vid32[i - 1] : T.p_txt32[i - 1]);
+      if (i == 0 && P->in_fmt != 0) {
+        a.y16 = reinterpret_cast<const uint16_t*>(a.y);
+        a.y_fmt = P->in_fmt - 1;
+      }
       a.ld_y = pp.din;
       a.mean = s == 0 ? T.pmean_v[i] : T.pmean_t[i];
       a.rstd = s == 0 ? T.prstd_v[i] : T.prstd_t[i];
@@ -1142,12 +1193,13 @@ int univtg_op_attention_bwd(const void* qkv, const void* dO, const void* O, cons
   return launch_attention_bwd(a, st);
 }
 
-int univtg_dropout_mask(const univtg_rng* rng, int32_t mask_index, size_t n, float* out, void* stream) {
-  if (!rng || !out || mask_index < 0) {
+int univtg_dropout_mask(const univtg_rng* rng, int32_t mask_index, size_t rows, size_t cols, float* out, void* stream) {
+  if (!rng || !out || mask_index < 0 || cols == 0) {
     set_error("univtg_dropout_mask: bad argument");
     return 1;
   }
-  return launch_dropout_mask(make_drop_spec(rng->seed, (unsigned int)mask_index, rng->input_dropout), n, out, (cudaStream_t)stream);
+  return launch_dropout_mask(make_drop_spec(rng->seed, (unsigned int)mask_index, rng->input_dropout), rows * cols, cols, out,
+                             (cudaStream_t)stream);
 }
 
 int univtg_droppath_scales(const univtg_rng* rng, int32_t n_sites, int32_t batch, float* out, void* stream) {

@@ -68,7 +68,8 @@ class FlatAdamW:
             self._scratch = torch.zeros(4, dtype=torch.float32, device=dev)
 
     def _seated(self):
-        return all(p.data_ptr() == v.data_ptr() for p, v in zip(self.model._abi_params(), self._views))
+        ps = self.model._abi_params()  # model.to() / load_state_dict(assign=True) move every parameter: two sentinels suffice per step
+        return ps[0].data_ptr() == self._views[0].data_ptr() and ps[-1].data_ptr() == self._views[-1].data_ptr()
 
     # -- torch.optim-like surface ---------------------------------------------------------------------------------------
     def zero_grad(self, set_to_none=True):
@@ -102,9 +103,12 @@ class FlatAdamW:
                                              self.step_count, self.max_grad_norm, int(self.write_clipped_grads),
                                              _lib.ptr(self._scratch), ctypes.byref(cfg), _lib.ptr(packed), _lib.stream_ptr()),
                        "univtg_adamw_step")
-            params = model._abi_params()
-            arr = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
-            _lib.check(lib.univtg_pack_vectors(ctypes.byref(cfg), arr, len(params), _lib.ptr(packed), _lib.stream_ptr()),
+            arr = self.__dict__.get("_ptr_array")
+            if arr is None or self.__dict__.get("_ptr_array_base") != self._flat_p.data_ptr():
+                params = model._abi_params()
+                arr = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
+                self.__dict__["_ptr_array"], self.__dict__["_ptr_array_base"] = arr, self._flat_p.data_ptr()
+            _lib.check(lib.univtg_pack_vectors(ctypes.byref(cfg), arr, len(arr), _lib.ptr(packed), _lib.stream_ptr()),
                        "univtg_pack_vectors")
             # the raw-pointer update does not bump autograd's version counters, so the packed-buffer key of this format is still
             # current; a second operand format (if ever packed) is stale

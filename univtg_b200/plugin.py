@@ -210,8 +210,16 @@ class Model(nn.Module):
                     _uniform_(p, 1.0 / math.sqrt(fan_in))
 
     # ---- C-ABI plumbing -----------------------------------------------------------------------------------------------
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .float(): parameter storage moves
+        self.__dict__.pop("_abi_cache", None)
+        return super()._apply(fn, *args, **kwargs)
+
     def _abi_params(self):
-        """Parameters in the order include/univtg_b200.h documents for univtg_pack_weights."""
+        """Parameters in the order include/univtg_b200.h documents for univtg_pack_weights (the list is cached: the Parameter
+        objects of this module never change identity; the hot loop asks for it several times per step)."""
+        cached = self.__dict__.get("_abi_cache")
+        if cached is not None:
+            return cached
         ps = []
         for proj in (self.input_vid_proj, self.input_txt_proj):
             for layer in proj:
@@ -225,6 +233,7 @@ class Model(nn.Module):
             for c in head.layers:
                 ps += [c.weight, c.bias]
         ps.append(self.weightedpool.weight)
+        self.__dict__["_abi_cache"] = ps
         return ps
 
     def _device(self):
@@ -395,6 +404,22 @@ class Model(nn.Module):
         self.__dict__["_ws_owner"] = e if not training else None  # plan_create prepared the workspace for THIS shape
         return e
 
+    @staticmethod
+    def _feature_inputs(lib, plan, src_txt, src_vid):
+        """Feature tensors as the kernels read them.  16-bit features (fp16 / bf16 - the packed shards of univtg_b200/data.py) are
+        consumed as they are (the first LayerNorm reads 2 bytes per element; the H2D copy of a batch halves); anything else
+        becomes contiguous float32 like the reference's collate output.  Both modalities must use the same element type."""
+        kinds = {torch.float16: 1, torch.bfloat16: 2}
+        kt, kv = kinds.get(src_txt.dtype, 0), kinds.get(src_vid.dtype, 0)
+        if kt != kv or kt == 0:
+            kt = 0
+            txt = src_txt.detach().to(torch.float32).contiguous()
+            vid = src_vid.detach().to(torch.float32).contiguous()
+        else:
+            txt, vid = src_txt.detach().contiguous(), src_vid.detach().contiguous()
+        _lib.check(lib.univtg_plan_set_input_format(plan.handle, kt), "univtg_plan_set_input_format")
+        return txt, vid
+
     def _activate(self, plan):
         """The shared inference workspace is about to be used by `plan`."""
         if self.__dict__.get("_ws_owner") is not plan:
@@ -489,8 +514,7 @@ class Model(nn.Module):
             self._ensure_packed()
             plan = self._get_plan(B, Lv, Lt, False)
             self._activate(plan)
-            txt = src_txt.detach().to(torch.float32).contiguous()
-            vid = src_vid.detach().to(torch.float32).contiguous()
+            txt, vid = self._feature_inputs(lib, plan, src_txt, src_vid)
             tmask = src_txt_mask.detach().to(torch.float32).contiguous()
             vmask = src_vid_mask.detach().to(torch.float32).contiguous()
             pred_logits = torch.empty(B, Lv, 1, device=dev)
