@@ -203,7 +203,8 @@ def shard_e2e_forward(model, cfg, dev, steps):
     samples = [(int(rng.integers(0, 64)), int(rng.integers(0, 64))) for _ in range(B * n_batches)]
     D.write_shard(path, vids, qs, samples)
     try:
-        loader = D.ShardLoader(path, batch_size=B, device=dev, slots=3, workers=8)
+        loader = D.ShardLoader(path, batch_size=B, device=dev, slots=3, workers=8)  # direct DMA from the page-locked mapping if allowed
+        direct_used = bool(loader.direct)
         out_host = [torch.empty(B, Lv).pin_memory() for _ in range(2)]
         done = [torch.cuda.Event() for _ in range(2)]
         model.eval()
@@ -223,7 +224,9 @@ def shard_e2e_forward(model, cfg, dev, steps):
             t_ev[1].record()
             torch.cuda.synchronize()
         ms = t_ev[0].elapsed_time(t_ev[1]) / steps
+        loader.close()
         return {"value": B / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "h2d_bytes_per_step": loader.h2d_bytes(B, Lv, Lt),
+                "path": ("copy engines read the page-locked shard mapping directly" if direct_used else "native gather into pinned staging, one H2D per tensor"),
                 "d2h_bytes_per_step": B * Lv * 4, "what": "forward fed by ShardLoader (packed fp16 shard -> pinned staging -> side-stream H2D)"}
     finally:
         try:
@@ -512,6 +515,10 @@ def main():
                     help="inference workloads: replay the forward from a CUDA graph (default: eager launches chained by "
                          "programmatic dependent launch, which measured faster: 0.712 vs 0.735 ms at cfg2)")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one all-reduce after the backward instead of stage slices")
+    ap.add_argument("--train-graph-probe", action="store_true",
+                    help="experiment: also time the train step replayed from ONE CUDA graph (host launch cost removed; RNG seed and "
+                         "AdamW step count frozen at capture time, so this is a timing probe, not a training mode)")
+    ap.add_argument("--static-loss-scale", action="store_true", help="fixed fp16 loss scale (no overflow flag read-back)")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the extra legs of the default line (cfg4_train / cfg5_fwd sub-results, GPU torch-eager baseline)")
     args = ap.parse_args()
@@ -559,7 +566,7 @@ def main():
         # the reference's update (main/config.py:349-350 AdamW; train_vlp_ddp.py:66-68 clip 0.1 + step) fused over the flat
         # parameter / gradient buffers: univtg_adamw_step, two launches per step
         from univtg_b200.optim import FlatAdamW
-        opt = FlatAdamW(model, lr=1e-4, weight_decay=1e-4, max_grad_norm=0.1)
+        opt = FlatAdamW(model, lr=1e-4, weight_decay=1e-4, max_grad_norm=0.1, dynamic_loss_scale=not args.static_loss_scale)
         if dist is not None:
             ddp.broadcast_parameters(model)
             # NCCL all-reduce of the flat gradient buffer, issued in backward-stage slices on a side stream (overlaps backward)
@@ -815,6 +822,36 @@ def main():
         except Exception as ex:
             extras["gpu_eager_baseline"] = {"error": repr(ex)[:300]}
 
+    graph_probe = None
+    if train and args.train_graph_probe and dist is None:
+        try:
+            opt.dynamic_loss_scale = False  # its flag read-back synchronises with the host
+            inp0 = {k: v.to(dev) for k, v in host_batches[0].items()}
+            tgt0 = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host_targets[0].items()}
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    train_step(inp0, tgt0)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                train_step(inp0, tgt0)
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            for _ in range(args.steps):
+                graph.replay()
+            q1.record()
+            torch.cuda.synchronize()
+            ms_g = q0.elapsed_time(q1) / args.steps
+            graph_probe = {"ms_per_step": ms_g, "value": B / (ms_g * 1e-3), "note": "one CUDA graph per step, same batch every replay"}
+        except Exception as ex:
+            graph_probe = {"error": repr(ex)[:400]}
+
     # ------------------- N > 1: is the exchanged gradient the average of the ranks' gradients, and did the replicas stay equal? ----
     sync_check = None
     cfg4_line = None
@@ -892,6 +929,8 @@ def main():
             line["postproc"] = postproc_line
         for k_, v_ in extras.items():
             line[k_] = v_
+        if graph_probe is not None:
+            line["train_graph_probe"] = graph_probe
         if sync_check is not None:
             line["grad_sync_check"] = sync_check["status"]
             line["grad_sync_detail"] = sync_check

@@ -23,6 +23,7 @@ extern "C" {
 #endif
 
 #define UNIVTG_ABI_VERSION 2
+#define UNIVTG_ADAMW_SCRATCH_FLOATS 2048
 
 /* Model hyper-parameters: the fields of `args` that reference model/univtg.py:409-450 (build_model),
  * model/transformer_encoder_droppath.py:141-152 (build_transformer) and model/position_encoding.py:113-126 read. */
@@ -205,7 +206,9 @@ int univtg_debug_mma_rate(int32_t n, int32_t iters, int32_t per_commit, int32_t 
  *   total_norm = ||grads||_2;  if max_grad_norm > 0: g *= min(1, max_grad_norm / (total_norm + 1e-6))   (clip_grad_norm_)
  *   p *= 1 - lr*wd;  m = m + (1-beta1)(g - m);  v = beta2 v + (1-beta2) g^2;
  *   p -= lr/(1-beta1^step) * m / (sqrt(v)/sqrt(1-beta2^step) + eps)                                      (AdamW, step >= 1)
- * scratch3: device fp32 [3]; on return [1] holds total_norm (what clip_grad_norm_ returns) and [2] is 1.0 when total_norm was not
+ * scratch3: device fp32 [UNIVTG_ADAMW_SCRATCH_FLOATS] (per-block partial sums of squares live behind the first four floats: the
+ * norm is accumulated in a fixed order, without atomics, so the update is bit-reproducible and identical on every data-parallel
+ * rank); on return [1] holds total_norm (what clip_grad_norm_ returns) and [2] is 1.0 when total_norm was not
  * finite - then NOTHING was updated (the skipped step of dynamic loss scaling; the fp16 gradient operands of univtg_backward can
  * overflow when grad_scale is too large), else 0.0.  write_clipped_grads != 0 also stores the clipped gradients back
  * (clip_grad_norm_ scales .grad in place).
@@ -218,6 +221,23 @@ int univtg_adamw_step(float* params, float* grads, float* exp_avg, float* exp_av
                       int32_t write_clipped_grads, float* scratch3, const univtg_config* cfg, void* packed, void* stream);
 /* univtg_pack_weights restricted to the fp32 vectors and the two tiny last-conv tensors (everything that is not a 16-bit matrix). */
 int univtg_pack_vectors(const univtg_config* cfg, const float* const* params, int32_t n_params, void* packed, void* stream);
+
+/* HOST function (no device work): assemble one padded batch from a memory-mapped 16-bit feature shard into (pinned) staging
+ * buffers - what the reference's per-sample loads + pad_sequences_1d collate do (main/dataset.py:644-696, 1037-1052,
+ * utils/tensor_utils.py:6-53).  src_vid [rows, Dv] / src_txt [rows, Dt]: the shard's 16-bit matrices; sample b copies vid_len[b]
+ * rows starting at vid_row0[b] (txt likewise) into dst_vid [B, Lv, Dv] / dst_txt [B, Lt, Dt], zero-fills the rest and writes the
+ * float masks dst_vmask [B, Lv] / dst_tmask [B, Lt] (1 = valid).  threads > 1 uses a persistent worker pool. */
+int univtg_host_assemble_batch(void* dst_vid, void* dst_txt, float* dst_vmask, float* dst_tmask, const void* src_vid,
+                               const void* src_txt, const int64_t* vid_row0, const int64_t* txt_row0, const int32_t* vid_len,
+                               const int32_t* txt_len, int32_t B, int32_t Lv, int32_t Lt, int32_t Dv, int32_t Dt, int32_t threads);
+
+/* Direct variant: page-lock the shard's memory mapping once (univtg_host_register; enable = 0 undoes it) and let the copy engines
+ * pull every sample's rows straight from it into the device batch on `stream` - no CPU staging copy.  mask_stage: pinned host
+ * scratch of B * (Lv + Lt) floats that must stay untouched until the stream has passed this call. */
+int univtg_host_register(void* base, size_t bytes, int32_t enable);
+int univtg_h2d_gather_batch(void* dev_vid, void* dev_txt, float* dev_vmask, float* dev_tmask, float* mask_stage, const void* src_vid,
+                            const void* src_txt, const int64_t* vid_row0, const int64_t* txt_row0, const int32_t* vid_len,
+                            const int32_t* txt_len, int32_t B, int32_t Lv, int32_t Lt, int32_t Dv, int32_t Dt, void* stream);
 
 /* Post-forward decode of the reference's MR evaluation loop, on the device.
  * univtg_decode_mr = main/inference_mr.py:112-120,146-157 (and main_gradio.py:100-106 with duration == NULL):

@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 WD = {"loss_b": 10.0, "loss_g": 1.0, "loss_f": 10.0, "loss_s_intra": 0.1, "loss_s_inter": 0.1}
 
 
-def test_shard_loader_feeds_fp16_features_to_the_model(tmp_path):
+@pytest.mark.parametrize("direct", [True, False])
+def test_shard_loader_feeds_fp16_features_to_the_model(tmp_path, direct):
     from oracle import univtg_oracle as O
 
     cfg = dict(synth.CONFIGS["tiny"], nheads=2)
@@ -27,7 +28,9 @@ def test_shard_loader_feeds_fp16_features_to_the_model(tmp_path):
     model.load_state_dict(sd, strict=True)
     model.to("cuda:0")
     crit.to("cuda:0")
-    loader = D.ShardLoader(path, batch_size=4, device="cuda:0", slots=3, workers=2)
+    # direct: the copy engines read the page-locked shard mapping; else: native gather into pinned staging + one H2D per tensor
+    loader = D.ShardLoader(path, batch_size=4, device="cuda:0", slots=3, workers=2, direct=direct)
+    assert loader.direct in (direct, False)
     n = 0
     for batch, idx in loader:
         assert batch["src_vid"].dtype == torch.float16 and batch["src_vid"].is_cuda

@@ -58,6 +58,10 @@ SIGNATURES = {
     "univtg_forward": (c_int, [c_void_p] * 12),
     "univtg_forward_num_launches": (c_int, [c_void_p]),
     "univtg_launch_count": (ctypes.c_int64, []),
+    "univtg_host_register": (c_int, [c_void_p, c_size_t, c_int]),
+    "univtg_h2d_gather_batch": (c_int, [c_void_p] * 11 + [c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "univtg_host_assemble_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_int, c_int, c_int, c_int, c_int, c_int]),
     "univtg_train_workspace_bytes": (c_size_t, [ctypes.POINTER(Config), ctypes.POINTER(Shape)]),
     "univtg_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      ctypes.POINTER(c_void_p), ctypes.POINTER(Rng), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

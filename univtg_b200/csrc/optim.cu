@@ -12,7 +12,10 @@
 namespace uv {
 namespace {
 
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n4, float* __restrict__ out) {
+// Per-block partial sums of squares, written to partial[blockIdx.x] (no atomics): the update kernel adds them in a fixed order, so
+// the gradient norm - and with it the clip factor and every updated weight - is bit-reproducible and bit-identical on every
+// data-parallel rank (an atomicAdd accumulation differs in the last bits from GPU to GPU, and the replicas then drift apart).
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n4, float* __restrict__ partial) {
   pdl_prologue();
   __shared__ float s_red[8];
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -27,8 +30,21 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += s_red[i];
-    atomicAdd(out, t);
+    partial[blockIdx.x] = t;
   }
+}
+
+// fixed-order total of the per-block partials (every block of the update kernel computes the same value)
+__device__ __forceinline__ float ordered_total(const float* __restrict__ partial, int n, float* s_red) {
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < 8; ++i) t += s_red[i];
+  __syncthreads();
+  return t;
 }
 
 struct AdamArgs {
@@ -38,7 +54,8 @@ struct AdamArgs {
   float* v;
   size_t n4;
   float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, max_norm;
-  float* scratch;  // [0] = sum of squares of g (in), [1] = total norm (out), [2] = 1 when the step was skipped (non-finite gradients)
+  float* scratch;  // [1] = total norm (out), [2] = 1 when the step was skipped (non-finite gradients), [4 ..) = per-block partial sums (in)
+  int n_partial;
   float* g_out;    // clipped gradients written back (clip_grad_norm_ scales .grad in place) or null
 };
 
@@ -89,7 +106,8 @@ __device__ __forceinline__ void pack_updated(const PackSegTable& t, size_t i, co
 template <bool PACK>
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamArgs a, const __grid_constant__ PackSegTable segs) {
   pdl_prologue();
-  const float norm = sqrtf(a.scratch[0]);
+  __shared__ float s_red[8];
+  const float norm = sqrtf(ordered_total(a.scratch + 4, a.n_partial, s_red));
   float clip = 1.f;
   if (a.max_norm > 0.f) clip = fminf(a.max_norm / (norm + 1e-6f), 1.f);
   // fp16 loss-scaled backward: an overflow in a 16-bit gradient operand shows up as inf / NaN in the gradient buffer, hence in its
@@ -145,8 +163,8 @@ int adamw_step_impl(float* params, float* grads, float* exp_avg, float* exp_avg_
   const size_t n4 = n / 4;
   size_t blocks = (n4 + 255) / 256;
   if (blocks > (size_t)sms * 8) blocks = (size_t)sms * 8;
-  cudaMemsetAsync(scratch2, 0, 3 * sizeof(float), st);
-  launch_k(sumsq_kernel, dim3((unsigned)blocks), dim3(256), 0, st, grads, n4, scratch2);
+  if (blocks > UNIVTG_ADAMW_SCRATCH_FLOATS - 4) blocks = UNIVTG_ADAMW_SCRATCH_FLOATS - 4;
+  launch_k(sumsq_kernel, dim3((unsigned)blocks), dim3(256), 0, st, grads, n4, scratch2 + 4);
   AdamArgs a;
   a.p = params;
   a.g = grads;
@@ -162,6 +180,7 @@ int adamw_step_impl(float* params, float* grads, float* exp_avg, float* exp_avg_
   a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   a.max_norm = max_grad_norm;
   a.scratch = scratch2;
+  a.n_partial = (int)blocks;
   a.g_out = write_clipped_grads ? grads : nullptr;
   if (segs != nullptr && segs->n > 0) {
     launch_k(adamw_kernel<true>, dim3((unsigned)blocks), dim3(256), 0, st, a, *segs);

@@ -23,7 +23,6 @@ vid f16 [rows_v, Dv], txt f16 [rows_t, Dt].
 import json
 import os
 import threading
-from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import torch
@@ -134,7 +133,10 @@ class Shard:
             base = f.tell()
         self.path = path
         a = self.header["arrays"]
-        mm = np.memmap(path, dtype=np.uint8, mode="r")
+        # mode "c" = private copy-on-write mapping: never written by this module, but a writable mapping is what cudaHostRegister
+        # accepts (ShardLoader's direct mode page-locks it; read-only mappings need cudaHostRegisterReadOnly, which this platform
+        # refuses).  Page-locking a private mapping makes the kernel materialise its pages: direct mode wants shards that fit in RAM.
+        mm = np.memmap(path, dtype=np.uint8, mode="c")
 
         def arr(name, dtype, shape):
             o = base + a[name]["offset"]
@@ -170,18 +172,48 @@ class ShardLoader:
     device=None keeps everything on the host (pinned tensors when CUDA is available) - used by the CPU tests."""
 
     def __init__(self, shard, batch_size, device=None, shuffle=False, seed=0, rank=0, world=1, drop_last=False, slots=3, workers=4,
-                 max_v_l=None, max_q_l=None):
+                 max_v_l=None, max_q_l=None, direct=True):
         self.shard = shard if isinstance(shard, Shard) else Shard(shard)
         self.batch_size, self.device = int(batch_size), (torch.device(device) if device is not None else None)
         self.shuffle, self.seed, self.rank, self.world, self.drop_last = bool(shuffle), int(seed), int(rank), int(world), bool(drop_last)
         self.slots, self.workers = max(2, int(slots)), max(1, int(workers))
         self.max_v_l, self.max_q_l = max_v_l, max_q_l
         self.epoch = 0
-        self._pool = ThreadPoolExecutor(max_workers=self.workers)
         self._host, self._dev = [None] * self.slots, [None] * self.slots
         self._h2d_done = [None] * self.slots   # the slot's pinned buffers may be rewritten once its last H2D copy has finished
         self._consumed = [None] * self.slots   # the slot's device buffers may be overwritten once the consumer's stream got here
         self._stream = torch.cuda.Stream(device=self.device) if self.device is not None and self.device.type == "cuda" else None
+        # direct=True: page-lock the shard's mapping once and let the copy engines pull every sample's rows straight from the page
+        # cache (univtg_h2d_gather_batch) - no CPU staging copy.  Falls back to the staged path when the driver refuses.
+        self.direct = False
+        if direct and self._stream is not None:
+            from . import _lib
+            lib = _lib.load_library()
+            sh = self.shard
+            regions = [(sh.vid.ctypes.data, sh.vid.nbytes), (sh.txt.ctypes.data, sh.txt.nbytes)]
+            done = []
+            with torch.cuda.device(self.device):
+                for base, nbytes in regions:
+                    lo = base // 4096 * 4096
+                    hi = (base + nbytes + 4095) // 4096 * 4096
+                    if lib.univtg_host_register(lo, hi - lo, 1) != 0:
+                        for b_, _ in done:
+                            lib.univtg_host_register(b_, 0, 0)
+                        done = None
+                        break
+                    done.append((lo, hi - lo))
+            self._registered = done
+            self.direct = done is not None
+
+    def close(self):
+        """Undo the page-locking of the shard mapping (direct mode)."""
+        if getattr(self, "_registered", None):
+            from . import _lib
+            lib = _lib.load_library()
+            for base, _ in self._registered:
+                lib.univtg_host_register(base, 0, 0)
+            self._registered = None
+            self.direct = False
 
     def set_epoch(self, epoch):
         self.epoch = int(epoch)
@@ -225,25 +257,25 @@ class ShardLoader:
             self._h2d_done[slot].synchronize()
         h, _ = self._buffers(slot, B, Lv, Lt)
         Dv, Dt = sh.v_feat_dim, sh.t_feat_dim
+        if self.direct:
+            return self._assemble_direct(slot, idx, lv, lt, B, Lv, Lt)
         vid = h["vid"][:B * Lv * Dv].view(B, Lv, Dv)
         txt = h["txt"][:B * Lt * Dt].view(B, Lt, Dt)
         vmask = h["vmask"][:B * Lv].view(B, Lv)
         tmask = h["tmask"][:B * Lt].view(B, Lt)
-        vid_np, txt_np, vm_np, tm_np = vid.numpy(), txt.numpy(), vmask.numpy(), tmask.numpy()
-
-        def one(b):
-            v, q = sh.samples[idx[b]]
-            nv, nt = int(lv[b]), int(lt[b])
-            vid_np[b, :nv] = sh.vid[sh.vid_off[v]:sh.vid_off[v] + nv]
-            vid_np[b, nv:] = 0
-            txt_np[b, :nt] = sh.txt[sh.txt_off[q]:sh.txt_off[q] + nt]
-            txt_np[b, nt:] = 0
-            vm_np[b, :nv] = 1
-            vm_np[b, nv:] = 0
-            tm_np[b, :nt] = 1
-            tm_np[b, nt:] = 0
-
-        list(self._pool.map(one, range(B)))
+        # the gather itself is native (csrc/hostio.cu: one memcpy per sample and modality on a persistent thread pool, GIL released
+        # by ctypes) - per-sample numpy statements cost more interpreter time than the 13 MB they move
+        smp = sh.samples[idx]
+        vrow0 = np.ascontiguousarray(sh.vid_off[smp[:, 0]], dtype=np.int64)
+        trow0 = np.ascontiguousarray(sh.txt_off[smp[:, 1]], dtype=np.int64)
+        vlen = np.ascontiguousarray(lv, dtype=np.int32)
+        tlen = np.ascontiguousarray(lt, dtype=np.int32)
+        from . import _lib
+        lib = _lib.load_library()
+        _lib.check(lib.univtg_host_assemble_batch(vid.data_ptr(), txt.data_ptr(), vmask.data_ptr(), tmask.data_ptr(),
+                                                  sh.vid.ctypes.data, sh.txt.ctypes.data, vrow0.ctypes.data, trow0.ctypes.data,
+                                                  vlen.ctypes.data, tlen.ctypes.data, B, Lv, Lt, Dv, Dt, self.workers),
+                   "univtg_host_assemble_batch")
         out = {"src_vid": vid, "src_vid_mask": vmask, "src_txt": txt, "src_txt_mask": tmask}
         if self._stream is None:
             return out, None
@@ -255,6 +287,35 @@ class ShardLoader:
                 self._stream.wait_event(self._consumed[slot])  # kernels still reading this slot's previous batch
             for k in out:
                 dev_out[k].copy_(out[k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._stream)
+        self._h2d_done[slot] = ev
+        return dev_out, ev
+
+    def _assemble_direct(self, slot, idx, lv, lt, B, Lv, Lt):
+        from . import _lib
+        lib = _lib.load_library()
+        sh = self.shard
+        Dv, Dt = sh.v_feat_dim, sh.t_feat_dim
+        smp = sh.samples[idx]
+        vrow0 = np.ascontiguousarray(sh.vid_off[smp[:, 0]], dtype=np.int64)
+        trow0 = np.ascontiguousarray(sh.txt_off[smp[:, 1]], dtype=np.int64)
+        vlen = np.ascontiguousarray(lv, dtype=np.int32)
+        tlen = np.ascontiguousarray(lt, dtype=np.int32)
+        d = self._dev[slot]
+        h = self._host[slot]
+        dev_out = {"src_vid": d["vid"][:B * Lv * Dv].view(B, Lv, Dv), "src_vid_mask": d["vmask"][:B * Lv].view(B, Lv),
+                   "src_txt": d["txt"][:B * Lt * Dt].view(B, Lt, Dt), "src_txt_mask": d["tmask"][:B * Lt].view(B, Lt)}
+        # mask staging: the pinned vmask / tmask buffers of the slot, laid out back to back in one scratch tensor
+        stage = h.setdefault("mask_stage", torch.empty(h["cap"][0] * (h["cap"][1] + h["cap"][2]), dtype=torch.float32).pin_memory())
+        with torch.cuda.device(self.device), torch.cuda.stream(self._stream):
+            if self._consumed[slot] is not None:
+                self._stream.wait_event(self._consumed[slot])
+            _lib.check(lib.univtg_h2d_gather_batch(dev_out["src_vid"].data_ptr(), dev_out["src_txt"].data_ptr(),
+                                                   dev_out["src_vid_mask"].data_ptr(), dev_out["src_txt_mask"].data_ptr(), stage.data_ptr(),
+                                                   sh.vid.ctypes.data, sh.txt.ctypes.data, vrow0.ctypes.data, trow0.ctypes.data,
+                                                   vlen.ctypes.data, tlen.ctypes.data, B, Lv, Lt, Dv, Dt,
+                                                   self._stream.cuda_stream), "univtg_h2d_gather_batch")
             ev = torch.cuda.Event()
             ev.record(self._stream)
         self._h2d_done[slot] = ev

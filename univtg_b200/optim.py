@@ -65,7 +65,7 @@ class FlatAdamW:
         if not keep:
             self._m = torch.zeros_like(flat_p)
             self._v = torch.zeros_like(flat_p)
-            self._scratch = torch.zeros(4, dtype=torch.float32, device=dev)
+            self._scratch = torch.zeros(2048, dtype=torch.float32, device=dev)  # UNIVTG_ADAMW_SCRATCH_FLOATS
 
     def _seated(self):
         ps = self.model._abi_params()  # model.to() / load_state_dict(assign=True) move every parameter: two sentinels suffice per step
