@@ -204,7 +204,7 @@ def shard_e2e_forward(model, cfg, dev, steps):
     D.write_shard(path, vids, qs, samples)
     try:
         loader = D.ShardLoader(path, batch_size=B, device=dev, slots=3, workers=8)  # direct DMA from the page-locked mapping if allowed
-        direct_used = bool(loader.direct)
+        direct_used, direct_error = bool(loader.direct), getattr(loader, "direct_error", None)
         out_host = [torch.empty(B, Lv).pin_memory() for _ in range(2)]
         done = [torch.cuda.Event() for _ in range(2)]
         model.eval()
@@ -227,7 +227,8 @@ def shard_e2e_forward(model, cfg, dev, steps):
         loader.close()
         return {"value": B / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "h2d_bytes_per_step": loader.h2d_bytes(B, Lv, Lt),
                 "path": ("copy engines read the page-locked shard mapping directly" if direct_used else "native gather into pinned staging, one H2D per tensor"),
-                "d2h_bytes_per_step": B * Lv * 4, "what": "forward fed by ShardLoader (packed fp16 shard -> pinned staging -> side-stream H2D)"}
+                "direct_refused": direct_error,
+                "d2h_bytes_per_step": B * Lv * 4, "what": "forward fed by ShardLoader (packed fp16 shard -> side-stream H2D, one batch ahead)"}
     finally:
         try:
             os.unlink(path)

@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_warp_kernel(const LnBwdArgs
 
 // Parameter gradients only (no dy requested): a pure column reduction, no per-row statistics of the gradient are needed.
 // Thread = one column, block = 256 columns x kRowsPerBlock rows.
-constexpr int kLnParamRows = 32;
+constexpr int kLnParamRows = 16;  // all 2 x 16 loads of a thread are issued before the first use (the loop is fully unrolled)
 __global__ void __launch_bounds__(256) layernorm_bwd_params_kernel(const LnBwdArgs a) {
   pdl_prologue();
   const int jj = blockIdx.x * 256 + threadIdx.x;
@@ -300,8 +300,10 @@ __global__ void __launch_bounds__(256) layernorm_bwd_params_kernel(const LnBwdAr
   const int r0 = blockIdx.y * kLnParamRows;
   const int r1 = min(a.rows, r0 + kLnParamRows);
   float ag = 0.f, ab = 0.f;
-#pragma unroll 8
-  for (int r = r0; r < r1; ++r) {
+#pragma unroll
+  for (int rr = 0; rr < kLnParamRows; ++rr) {
+    const int r = r0 + rr;
+    if (r >= r1) break;  // warp-uniform
     float dj = __ldg(a.dout + (size_t)r * a.ld_dout + j);
     if (a.dout_mul) dj *= __ldg(a.dout_mul + (size_t)r * a.d + j);
     else if (a.drop.on) {  // the eight threads of an aligned column group share ONE Philox call (thread = column here)

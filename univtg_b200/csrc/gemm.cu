@@ -307,6 +307,8 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       float* __restrict__ colsum = pr.colsum;
       const int cs32 = pr.cs32 > 1 ? pr.cs32 : 1;
       float* __restrict__ pre32 = pr.pre32;
+      uint16_t* __restrict__ dact16 = FULL ? pr.dact16 : nullptr;
+      const bool mask_mul = FULL && pr.mask_mul != 0;
 
       const int m0 = ti.m_blk * GEMM_BM + wq * 32;
       // the BN/16 column steps of the tile are split between the two warps of this lane quarter (first warp gets the extra one)
@@ -336,6 +338,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       uint16_t* o16_row = out16 ? out16 + orow * pr.ld16 : nullptr;
       uint16_t* o16p_row = out16p ? out16p + orow * pr.ld16 : nullptr;
       float* pre_row = pre32 ? pre32 + orow * pr.ld_pre : nullptr;
+      uint16_t* dact_row = dact16 ? dact16 + orow * pr.ld_dact : nullptr;
 
       // bias slice of this warp's columns -> smem (broadcast reads in the column loop)
       __syncwarp();
@@ -426,7 +429,27 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
                 *reinterpret_cast<float4*>(pre_row + n0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
         }
-        if (act == ACT_GELU) {
+        if (FULL && act == ACT_GELU && dact_row != nullptr) {  // training forward: activation and its derivative in one pass
+          float dg[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float gj;
+            gelu_erf_both(v[j], gj, dg[j]);
+            v[j] = gj * rsc;
+          }
+          if (valid) {
+            if (v256) {
+              uint32_t w8[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) w8[q] = cvt16x2(dg[2 * q], dg[2 * q + 1], ofmt);
+              st_global_256(dact_row + n0, w8);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (n0 + j < pN) dact_row[n0 + j] = cvt16(dg[j], ofmt);
+            }
+          }
+        } else if (act == ACT_GELU) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]) * rsc;
         } else if (act == ACT_RELU) {
@@ -469,8 +492,13 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
                 const uint32_t w4[4] = {mk.x, mk.y, mk.z, mk.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  if (!pos16((uint16_t)(w4[e] & 0xffff))) v[8 * q + 2 * e] = 0.f;
-                  if (!pos16((uint16_t)(w4[e] >> 16))) v[8 * q + 2 * e + 1] = 0.f;
+                  if (mask_mul) {  // saved activation derivative (GELU'): multiply
+                    v[8 * q + 2 * e] *= ld16((uint16_t)(w4[e] & 0xffff), fmt);
+                    v[8 * q + 2 * e + 1] *= ld16((uint16_t)(w4[e] >> 16), fmt);
+                  } else {         // ReLU mask: zero where the saved activation is <= 0
+                    if (!pos16((uint16_t)(w4[e] & 0xffff))) v[8 * q + 2 * e] = 0.f;
+                    if (!pos16((uint16_t)(w4[e] >> 16))) v[8 * q + 2 * e + 1] = 0.f;
+                  }
                 }
               }
             }
@@ -552,7 +580,10 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
             if (valid && n < pN) {
               if (resid_row != nullptr) x += resid_row[n];
               if (aux_row != nullptr) x *= (aux_mode == 1) ? gelu_erf_grad(aux_row[n]) : aux_row[n];
-              if (mask_row != nullptr && !pos16(mask_row[n])) x = 0.f;
+              if (mask_row != nullptr) {
+                if (mask_mul) x *= ld16(mask_row[n], fmt);
+                else if (!pos16(mask_row[n])) x = 0.f;
+              }
               if (o32_row != nullptr) {
                 float* dst = o32_row + (size_t)n * cs32;
                 if (atomic) atomicAdd(dst, x);
@@ -938,13 +969,13 @@ int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
     GemmProblem& w = g.p[p];
     // epilogue (thread = row, 16 columns per step): 128-bit accesses need N % 16 == 0 and aligned leading dimensions
     w.vec_ok = (pr.N % 16 == 0) && (pr.cs32 <= 1) && (!pr.aux32 || (al16(pr.aux32) && pr.ld_aux % 4 == 0)) &&
-               (!pr.pre32 || (al16(pr.pre32) && pr.ld_pre % 4 == 0)) && (!pr.mask16 || (al16(pr.mask16) && pr.ld_mask % 8 == 0)) &&
+               (!pr.pre32 || (al16(pr.pre32) && pr.ld_pre % 4 == 0)) && (!pr.dact16 || (al16(pr.dact16) && pr.ld_dact % 8 == 0)) && (!pr.mask16 || (al16(pr.mask16) && pr.ld_mask % 8 == 0)) &&
                (!pr.resid || (al16(pr.resid) && pr.ld_resid % 4 == 0)) && (!pr.addtab || (al16(pr.addtab) && pr.ld_addtab % 4 == 0)) &&
                (!pr.out32 || (al16(pr.out32) && pr.ld32 % 4 == 0)) && (!pr.out32_id || (al16(pr.out32_id) && pr.ld32_id % 4 == 0)) &&
                ((!pr.out16 && !pr.out16p) || (pr.ld16 % 8 == 0 && al16(pr.out16) && al16(pr.out16p)));
     auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
     // 256-bit accesses (one whole 32-byte sector per thread and instruction) when every leading dimension keeps rows 32-byte aligned
-    if (w.vec_ok && (!pr.pre32 || (al32(pr.pre32) && pr.ld_pre % 8 == 0)) && (!pr.aux32 || (al32(pr.aux32) && pr.ld_aux % 8 == 0)) && (!pr.addtab || (al32(pr.addtab) && pr.ld_addtab % 8 == 0)) && (!pr.resid || (al32(pr.resid) && pr.ld_resid % 8 == 0)) &&
+    if (w.vec_ok && (!pr.pre32 || (al32(pr.pre32) && pr.ld_pre % 8 == 0)) && (!pr.dact16 || (al32(pr.dact16) && pr.ld_dact % 16 == 0)) && (!pr.aux32 || (al32(pr.aux32) && pr.ld_aux % 8 == 0)) && (!pr.addtab || (al32(pr.addtab) && pr.ld_addtab % 8 == 0)) && (!pr.resid || (al32(pr.resid) && pr.ld_resid % 8 == 0)) &&
         (!pr.out32 || (al32(pr.out32) && pr.ld32 % 8 == 0)) && (!pr.out32_id || (al32(pr.out32_id) && pr.ld32_id % 8 == 0)) &&
         ((!pr.out16 && !pr.out16p) || (pr.ld16 % 16 == 0 && al32(pr.out16) && al32(pr.out16p))))
       w.vec_ok = 2;
@@ -953,7 +984,7 @@ int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
   bool full = false;  // does any problem of the group need an epilogue option only the FULL variant compiles in?
   for (int p = 0; p < g.num; ++p) {
     const GemmProblem& pr = g.p[p];
-    full = full || pr.vec_ok != 2 || pr.pre32 || pr.aux32 || pr.mask16 || pr.accumulate || pr.ksplit > 1 || pr.out32_id || pr.colsum || pr.cs32 > 1;
+    full = full || pr.vec_ok != 2 || pr.pre32 || pr.dact16 || pr.aux32 || pr.mask16 || pr.accumulate || pr.ksplit > 1 || pr.out32_id || pr.colsum || pr.cs32 > 1;
   }
   g.bn = bn;
   g.dbg = g_timeline;
@@ -992,8 +1023,8 @@ int launch_gemm_group(GemmGroup& g, int bn, int num_sms, cudaStream_t stream) {
 }
 
 // Tile width (and split-K factor) that minimise the modelled time of one grouped launch.  Constants are measurements on B200
-// (profiles/README.md): a 64-wide k-block costs ~0.41 us per CTA WHATEVER the tile width (tcgen05.mma M128 x N x K16 retires
-// every ~95 ns for any N <= 256), ~2 us from kernel entry to the first MMA, an epilogue of ~0.5 us + 2.5 us x bn/256 (4 us x
+// (profiles/README.md, round 2): a 64-wide k-block (4 MMAs + one tcgen05.commit) costs ~0.33 us per CTA WHATEVER the tile width
+// (two commits are never closer than ~615 cycles, which hides the N/2-cycle cost of the MMAs in between), ~2 us from kernel entry to the first MMA, an epilogue of ~0.5 us + 2.5 us x bn/256 (4 us x
 // bn/256 with split-K reductions), of which only a fraction is exposed when a CTA has further tiles to run.
 //   kblocks[p] = 64-wide k-blocks of problem p (taps included); max_split = 1 disables split-K.
 TileChoice choose_tile(const int* Ms, const int* Ns, const int* kblocks, int num, int num_sms, int step, int max_split) {
@@ -1019,7 +1050,7 @@ TileChoice choose_tile(const int* Ms, const int* Ns, const int* kblocks, int num
       for (int i = 0; i < ncta; ++i) kb_cta = load[i] > kb_cta ? load[i] : kb_cta;
       const long rounds = (tiles + ncta - 1) / ncta;
       const double epi = 0.5 + bn * (ks > 1 ? 4.0 : 2.5) / 256.0;
-      const double t = 2.0 + 0.41 * (double)kb_cta + epi * (1.0 + 0.3 * (double)(rounds - 1));
+      const double t = 2.0 + 0.33 * (double)kb_cta + epi * (1.0 + 0.3 * (double)(rounds - 1));
       if (best_t < 0 || t < best_t - 1e-9) {
         best_t = t;
         best = TileChoice{bn, ks};

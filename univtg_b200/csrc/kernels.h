@@ -66,8 +66,11 @@ struct GemmProblem {
   int aux_mode;            // 1: v *= gelu'(aux)   2: v *= aux (e.g. a dropout mask incl. its 1/(1-p) scale)
   const uint16_t* mask16;  // 16-bit activation indexed like out16: v = 0 where mask16 <= 0 (ReLU backward)
   int ld_mask;
-  float* pre32;            // fp32 (acc + bias) BEFORE the activation, indexed like out32 (saved for GELU backward)
+  float* pre32;            // fp32 (acc + bias) BEFORE the activation, indexed like out32
   int ld_pre;
+  uint16_t* dact16;        // 16-bit d act / d pre-activation at (acc + bias), indexed like out16 (ACT_GELU: saved for the backward, which
+  int ld_dact;             //   then multiplies by it - mask16 + mask_mul - instead of re-evaluating erf / exp on an fp32 copy)
+  int mask_mul;            // 1: v *= mask16 (an activation derivative) instead of zeroing where mask16 <= 0
   float colsum_scale;      // factor applied to the column sums (1/loss-scale for bias gradients)
   float* colsum;           // fp32 [N]: atomically accumulates the column sums of the stored values (bias gradients)
   int cs32;                // column stride of out32 (0/1: dense); 3 writes a Conv1d weight-gradient tap in [n, c, 3] layout

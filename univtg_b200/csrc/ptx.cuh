@@ -334,6 +334,20 @@ UV_DEVINL float gelu_erf_grad(float x) {
   const float r = fmaf(-y, e, 1.0f);  // erf(|x| / sqrt 2)
   return fmaf(0.5f, copysignf(r, x), 0.5f) + x * 0.3989422804014327f * e;
 }
+// gelu(x) and d/dx gelu(x) together (they share the reciprocal, the polynomial and the exponential)
+UV_DEVINL void gelu_erf_both(float x, float& g, float& dg) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f));
+  float y = fmaf(1.061405429f, t, -1.453152027f);
+  y = fmaf(y, t, 1.421413741f);
+  y = fmaf(y, t, -0.284496736f);
+  y = fmaf(y, t, 0.254829592f);
+  y = y * t;
+  const float e = exp2f(ax * ax * (-0.5f * 1.4426950408889634f));  // exp(-x^2 / 2)
+  const float r = fmaf(-y, e, 1.0f);                                // erf(|x| / sqrt 2)
+  g = 0.5f * fmaf(ax, r, x);
+  dg = fmaf(0.5f, copysignf(r, x), 0.5f) + x * 0.3989422804014327f * e;
+}
 UV_DEVINL bool pos16(uint16_t h) { return (h & 0x8000u) == 0 && (h & 0x7fffu) != 0; }  // 16-bit float > 0 (fp16 or bf16)
 
 // 16-bit MMA operand storage.  fmt: 0 = fp16 (default; 11-bit significand), 1 = bf16 (8-bit).

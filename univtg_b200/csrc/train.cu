@@ -58,7 +58,8 @@ struct TrainWs {
   float* dp_scale;  // [2 * enc_layers, B] DropPath scales drawn in-kernel by the forward (univtg_rng), reused by the backward
   uint16_t *xin16[17], *xpos16[17];  // operands of layer l's in-projections (index enc_layers: unused tail)
   uint16_t *qkv16[16], *attn16[16], *x1_16[16], *h16[16];
-  float *lse[16], *y1[16], *mean1[16], *rstd1[16], *hpre[16], *y2[16], *mean2[16], *rstd2[16];
+  float *lse[16], *y1[16], *mean1[16], *rstd1[16], *y2[16], *mean2[16], *rstd2[16];
+  uint16_t* dgelu16[16];  // GELU'(pre-activation) of the FFN, written by FFN1's forward epilogue beside h16
   float *x32, *x1_32;
   uint16_t *hA, *h1, *hc2, *hs2, *br16;
   float *pred_logits, *pred_spans, *vid_mem_proj, *txt_mem_proj;  // copies of the outputs the backward needs
@@ -109,7 +110,7 @@ TrainWs make_train_ws(const univtg_config& c, const univtg_shape& s, const Packe
     w.y1[l] = take32(M * d);
     w.mean1[l] = take32(M);
     w.rstd1[l] = take32(M);
-    w.hpre[l] = take32(M * ff);
+    w.dgelu16[l] = take16(M * ff);
     w.y2[l] = take32(M * d);
     w.mean2[l] = take32(M);
     w.rstd2[l] = take32(M);
@@ -386,8 +387,8 @@ int univtg_forward_train(univtg_plan* P, void* ws, const float* src_txt, const f
     g.p[0].act = ACT_GELU;
     g.p[0].out16 = T.h16[l];
     g.p[0].ld16 = ff;
-    g.p[0].pre32 = T.hpre[l];
-    g.p[0].ld_pre = ff;
+    g.p[0].dact16 = T.dgelu16[l];
+    g.p[0].ld_dact = ff;
     rc = gemm_launch(P, g, P->bn_ffn1, sms, st);
     if (rc) return rc;
     memset(&g, 0, sizeof(g));
@@ -638,6 +639,8 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       return r;
     };
     const int bn_c2d = bn_for(sms, 64, MNK{Mh, d, 3 * d}, MNK{Mh, d, 3 * d}), bn_c1d = bn_for(sms, 64, MNK{Mh, d, 6 * d});
+    // (splitting the k-blocks of the layer-1 dgrad - 76 tiles of 96 k-blocks - over idle SMs saves ~8 us but reduces into the stream
+    // gradient with atomics, which makes every gradient upstream of the heads order-dependent in its last bits: not taken)
     const int bn_cw = t_cw.bn;
     const int bn = bn_c2d;
     // ---- conv layer 2 (two heads): dgrad -> dh1 [Mh+2, 2d] (class cols [0,d), span cols [d,2d)), ReLU mask of h1 ----
@@ -748,7 +751,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       rc = launch_layernorm_bwd(a, st);
       if (rc) return rc;
     }
-    // ---- FFN2: dgrad -> d(hpre) = (dF W2) * gelu'(hpre);  wgrad dW2 = dF^T h ----
+    // ---- FFN2: dgrad -> d(hpre) = (dF W2) * gelu'(hpre) (saved 16-bit derivative);  wgrad dW2 = dF^T h ----
     // ---- FFN1: dgrad d(x1) = dhpre W1 + dy (residual);          wgrad dW1 = dhpre^T x1 ----
     // (sharing one launch between a data-gradient GEMM and the weight-gradient GEMM that reads the same dY was measured: fewer
     //  launches and 10 % less event-timed GEMM time, but the pipelined step got 50 us SLOWER - profiles/README.md round 2 - so the
@@ -757,9 +760,9 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       int r = setup_gemm(p, Mat16{T.dbr16, M, d, d}, 0, Mat16{W16(lp.w2), d, ff, ff}, 1, M, ff, d, bnn);
       p.a_fmt = FMT_G;
       p.b_fmt = fmt;
-      p.aux32 = T.hpre[l];
-      p.ld_aux = ff;
-      p.aux_mode = 1;
+      p.mask16 = T.dgelu16[l];  // d(hpre) = (dF W2) * GELU'(hpre), the derivative saved by the forward as a 16-bit operand
+      p.ld_mask = ff;
+      p.mask_mul = 1;
       p.out16 = T.dhpre16;
       p.ld16 = ff;
       p.out_fmt = FMT_G;

@@ -190,13 +190,22 @@ class ShardLoader:
             from . import _lib
             lib = _lib.load_library()
             sh = self.shard
-            regions = [(sh.vid.ctypes.data, sh.vid.nbytes), (sh.txt.ctypes.data, sh.txt.nbytes)]
+            # page-rounded extents of the two feature arrays; they are neighbours in the file, so their end / start pages usually
+            # coincide and the extents are merged (a page can be registered once)
+            spans = sorted((b // 4096 * 4096, (b + n + 4095) // 4096 * 4096) for b, n in
+                           ((sh.vid.ctypes.data, sh.vid.nbytes), (sh.txt.ctypes.data, sh.txt.nbytes)) if n)
+            merged = []
+            for lo, hi in spans:
+                if merged and lo <= merged[-1][1]:
+                    merged[-1][1] = max(merged[-1][1], hi)
+                else:
+                    merged.append([lo, hi])
             done = []
+            self.direct_error = None
             with torch.cuda.device(self.device):
-                for base, nbytes in regions:
-                    lo = base // 4096 * 4096
-                    hi = (base + nbytes + 4095) // 4096 * 4096
+                for lo, hi in merged:
                     if lib.univtg_host_register(lo, hi - lo, 1) != 0:
+                        self.direct_error = lib.univtg_last_error().decode()
                         for b_, _ in done:
                             lib.univtg_host_register(b_, 0, 0)
                         done = None
