@@ -520,6 +520,8 @@ def main():
                     help="experiment: also time the train step replayed from ONE CUDA graph (host launch cost removed; RNG seed and "
                          "AdamW step count frozen at capture time, so this is a timing probe, not a training mode)")
     ap.add_argument("--static-loss-scale", action="store_true", help="fixed fp16 loss scale (no overflow flag read-back)")
+    ap.add_argument("--no-zero-after-step", action="store_true",
+                    help="zero the flat gradient buffer in front of the backward instead of on a side stream behind the optimizer step")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the extra legs of the default line (cfg4_train / cfg5_fwd sub-results, GPU torch-eager baseline)")
     args = ap.parse_args()
@@ -548,8 +550,8 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         # the gradient all-reduce overlaps the backward: cap the SMs its kernels take (the backward's persistent GEMM grids are
         # sized for what is left, univtg_b200/ddp.py: UNIVTG_DDP_SM_RESERVE)
-        os.environ.setdefault("NCCL_MAX_CTAS", "16")
-        os.environ.setdefault("UNIVTG_DDP_SM_RESERVE", "16")
+        os.environ.setdefault("NCCL_MAX_CTAS", "32")
+        os.environ.setdefault("UNIVTG_DDP_SM_RESERVE", os.environ["NCCL_MAX_CTAS"])
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
@@ -567,7 +569,8 @@ def main():
         # the reference's update (main/config.py:349-350 AdamW; train_vlp_ddp.py:66-68 clip 0.1 + step) fused over the flat
         # parameter / gradient buffers: univtg_adamw_step, two launches per step
         from univtg_b200.optim import FlatAdamW
-        opt = FlatAdamW(model, lr=1e-4, weight_decay=1e-4, max_grad_norm=0.1, dynamic_loss_scale=not args.static_loss_scale)
+        opt = FlatAdamW(model, lr=1e-4, weight_decay=1e-4, max_grad_norm=0.1, dynamic_loss_scale=not args.static_loss_scale,
+                        zero_grad_after_step=not args.no_zero_after_step)
         if dist is not None:
             ddp.broadcast_parameters(model)
             # NCCL all-reduce of the flat gradient buffer, issued in backward-stage slices on a side stream (overlaps backward)
@@ -827,6 +830,8 @@ def main():
     if train and args.train_graph_probe and dist is None:
         try:
             opt.dynamic_loss_scale = False  # its flag read-back synchronises with the host
+            opt.zero_grad_after_step = False  # a side-stream fill joined by the NEXT step cannot live inside a one-step capture
+            model.__dict__.pop("_flat_grad_prezeroed", None)
             inp0 = {k: v.to(dev) for k, v in host_batches[0].items()}
             tgt0 = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host_targets[0].items()}
             side = torch.cuda.Stream(device=dev)

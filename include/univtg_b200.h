@@ -136,13 +136,15 @@ int univtg_backward(univtg_plan* plan, void* train_ws, const float* src_txt, con
                     int32_t n_grads, void* stream);
 
 /* Gradient-exchange overlap (the reference relies on DistributedDataParallel's bucketed all-reduce overlapping backward,
- * main/train_vlp_ddp.py:272-275).  univtg_backward finalises parameter gradients in n = enc_layers + 2 stages:
- *   stage 0: conv heads; stage 1 + k: encoder layer enc_layers-1-k; stage n-1: projectors, token-type embedding, pooling weight.
+ * main/train_vlp_ddp.py:272-275).  univtg_backward finalises parameter gradients in n = enc_layers + 3 stages:
+ *   stage 0: conv heads + pooling weight; stage 1 + k: encoder layer enc_layers-1-k; stage n-2: projector weights / biases, the later
+ *   projector layers' LayerNorm terms, token-type embedding; stage n-1: LayerNorm terms of the first projector layers (a few KB: the
+ *   large input-projection gradients start their exchange before the backward's last kernels run).
  * univtg_backward_stages writes, per stage, two half-open parameter-index ranges {first0, last0, first1, last1}
  * (univtg_pack_weights order; an empty second range is 0,0) and returns n (ranges == NULL: just returns n).
  * univtg_plan_set_grad_events installs n cudaEvent_t handles; univtg_backward records event k on its stream as soon as stage
  * k's gradients are final, so a communication stream can wait on it and reduce that slice while the backward continues.
- * n = 0 removes them.  (enc_layers <= 16, so n <= 18.) */
+ * n = 0 removes them.  (enc_layers <= 16, so n <= 19.) */
 int univtg_backward_stages(const univtg_config* cfg, int32_t* ranges, int32_t max_stages);
 /* The GEMM launches of univtg_backward are persistent grids of one CTA per SM.  When a collective (NCCL) runs beside the backward
  * its CTAs occupy some SMs; give the backward the number of SMs that are left (0 = all) so that its grids stay single-wave. */

@@ -69,7 +69,7 @@ def test_backward_stage_slices_cover_the_flat_gradient_buffer_once():
         cfg = synth.CONFIGS[name]
         model, _ = build_model(synth.reference_args(cfg, device="cpu"))
         stages = ddp.grad_stage_slices(model)
-        assert len(stages) == cfg["enc_layers"] + 2
+        assert len(stages) == cfg["enc_layers"] + 3
         offs = model._grad_offsets()
         cover = torch.zeros(offs[-1], dtype=torch.int32)
         for _, sl in stages:

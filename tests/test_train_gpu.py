@@ -324,6 +324,121 @@ def test_flat_adamw_matches_torch_clip_plus_adamw(gscale):
             torch.testing.assert_close(p.detach(), rp.detach(), rtol=2e-5, atol=2e-7)
 
 
+def _fill_grads(model, ref_params, gen, gscale=1e-3):
+    """Same random gradients into the model's flat buffer and into `ref_params` (clones of named_parameters(), same order)."""
+    flat, views = model._grad_buffer()
+    flat.zero_()
+    pos = {id(p): i for i, (_, p) in enumerate(model.named_parameters())}
+    for v, p in zip(views, model._abi_params()):
+        g = torch.randn(v.shape, device="cuda", generator=gen) * gscale
+        v.copy_(g)
+        ref_params[pos[id(p)]].grad = g.clone()
+
+
+def test_flat_adamw_is_a_torch_optimizer_checkpoints_both_ways_and_follows_schedulers():
+    """The reference drives its optimizer through lr schedulers (main/config.py:352-360) and writes / resumes
+    optimizer.state_dict() (main/train_mr.py:151, main/config.py:371): FlatAdamW is a torch.optim.Optimizer whose checkpoints are
+    interchangeable with those of torch.optim.AdamW built the reference's way (all named_parameters(), one group), and whose lr
+    is the parameter group's."""
+    from univtg_b200.optim import FlatAdamW
+
+    cfg = synth.CONFIGS["tiny"]
+    sd0 = synth.make_state_dict(cfg, seed=3)
+    model, _ = _models(cfg, sd0)
+
+    def clones(m):
+        return [p.detach().clone().requires_grad_(True) for _, p in m.named_parameters()]
+
+    def check(m, ref):
+        for (n, p), rp in zip(m.named_parameters(), ref):
+            torch.testing.assert_close(p.detach(), rp.detach(), rtol=2e-5, atol=2e-7, msg=lambda s, n=n: f"{n}: {s}")
+
+    ref_params = clones(model)
+    opt_ref = torch.optim.AdamW(ref_params, lr=1e-3, weight_decay=1e-2)
+    opt = FlatAdamW(model, lr=1e-3, weight_decay=1e-2, max_grad_norm=0.0, dynamic_loss_scale=False)
+    assert isinstance(opt, torch.optim.Optimizer) and len(opt.param_groups) == 1
+    assert [id(p) for p in opt.param_groups[0]["params"]] == [id(p) for _, p in model.named_parameters()]
+    assert len(ref_params) > len(model._abi_params())  # txt_position_embed.*: in the group, never updated (no gradient)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for _ in range(3):
+        _fill_grads(model, ref_params, gen)
+        opt_ref.step()
+        opt.step()
+    check(model, ref_params)
+    # (1) this optimizer's checkpoint -> the reference's optimizer
+    ck = opt.state_dict()
+    assert set(ck["state"]) == set(opt_ref.state_dict()["state"]) and float(ck["state"][min(ck["state"])]["step"]) == 3.0
+    other = clones(model)
+    opt_t = torch.optim.AdamW(other, lr=5e-2, weight_decay=0.0)
+    opt_t.load_state_dict(ck)
+    assert opt_t.param_groups[0]["lr"] == 1e-3 and opt_t.param_groups[0]["weight_decay"] == 1e-2
+    # (2) the reference's checkpoint -> a fresh FlatAdamW on a fresh model holding the same weights
+    model2, _ = _models(cfg, sd0)
+    with torch.no_grad():
+        for p2, p in zip(model2.parameters(), model.parameters()):
+            p2.copy_(p)
+    opt2 = FlatAdamW(model2, lr=7e-2, weight_decay=0.0, max_grad_norm=0.0, dynamic_loss_scale=False)
+    opt2.load_state_dict(opt_ref.state_dict())
+    assert opt2.step_count == 3 and opt2.lr == 1e-3 and opt2.weight_decay == 1e-2
+    # one more step everywhere on identical gradients: four optimizers, one trajectory
+    _fill_grads(model, ref_params, torch.Generator(device="cuda").manual_seed(9))
+    for o, rp in zip(other, ref_params):
+        o.grad = None if rp.grad is None else rp.grad.clone()
+    _fill_grads(model2, clones(model2), torch.Generator(device="cuda").manual_seed(9))
+    opt_ref.step()
+    opt.step()
+    opt_t.step()
+    opt2.step()
+    check(model, ref_params)
+    check(model2, ref_params)
+    for o, rp in zip(other, ref_params):
+        torch.testing.assert_close(o.detach(), rp.detach(), rtol=2e-5, atol=2e-7)
+    # (3) schedulers write the group's lr and the kernel reads it: after the decay to 0 a step moves nothing
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=0.0)
+    assert opt.param_groups[0]["initial_lr"] == 1e-3
+    opt.param_groups[0]["weight_decay"] = 0.0
+    opt.step()  # (schedulers want an optimizer step before their own)
+    sched.step()
+    assert opt.lr == 0.0
+    before = [p.detach().clone() for p in model.parameters()]
+    _fill_grads(model, ref_params, gen)
+    opt.step()
+    for p, b in zip(model.parameters(), before):
+        assert torch.equal(p.detach(), b)
+    with pytest.raises(RuntimeError):
+        opt.add_param_group({"params": [torch.zeros(1, device="cuda", requires_grad=True)]})
+
+
+def test_zero_grad_after_step_is_the_same_training_run():
+    """FlatAdamW(zero_grad_after_step=True) moves the zero-fill of the flat gradient buffer from the front of the backward to a
+    side stream behind the update: same trajectory as the default, gradients read zero after step(), and a loop that never calls
+    zero_grad() is then the reference loop (train_vlp_ddp.py:63-68) too."""
+    from univtg_b200.optim import FlatAdamW
+
+    cfg = synth.CONFIGS["tiny"]
+    raw, tgt, inp, ctgt = _train_inputs(cfg, 6, 31)
+    runs = []
+    for pre, call_zero in ((False, True), (True, True), (True, False)):
+        model, crit = _models(cfg, synth.make_state_dict(cfg, seed=3))
+        model.train()
+        opt = FlatAdamW(model, lr=1e-3, weight_decay=1e-2, max_grad_norm=0.1, zero_grad_after_step=pre)
+        for _ in range(4):
+            torch.manual_seed(7)
+            out = model(**inp)
+            total = crit.weighted_total(crit(out, ctgt))
+            if call_zero:
+                opt.zero_grad()
+            total.backward()
+            opt.step()
+        torch.cuda.synchronize()
+        if pre:
+            assert float(model._grad_buffer()[0].abs().max()) == 0.0
+        runs.append([p.detach().clone() for p in model._abi_params()])
+    for other in runs[1:]:
+        for a, b in zip(runs[0], other):
+            torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-6)  # fp32 atomics in the backward are order-dependent
+
+
 def test_training_loop_with_flat_adamw_decreases_loss_and_repacks():
     from univtg_b200.optim import FlatAdamW
 
@@ -379,7 +494,7 @@ def test_stage_events_fire_only_after_their_gradients_are_final():
         sum(ld[k] * crit.weight_dict[k] for k in ld).backward()
     torch.cuda.synchronize()
     snaps = model._grad_sync.snaps
-    assert len(snaps) == cfg["enc_layers"] + 3  # the last stage has two slices
+    assert len(snaps) == cfg["enc_layers"] + 5  # heads, one per encoder layer, two slices for each of the two projector stages
     flat, _ = model._grad_buffer()
     assert sum(s.numel() for s, _ in snaps) == flat.numel()
     for i, (live, snap) in enumerate(snaps):

@@ -713,7 +713,24 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
   auto stage_done = [&](int k) {
     if (P->n_grad_events > 0 && k < P->n_grad_events) cudaEventRecord(P->grad_events[k], st);
   };
-  stage_done(0);  // conv heads
+  // attention pooling of the text tokens: needs only the loss gradient of the pooled vector, so it runs before the first stage
+  // event and its weight gradient travels with the heads' slice
+  if (g_txt_mem_proj) {
+    PoolBwdArgs a;
+    a.x_txt = T.txtproj32;
+    a.alpha = T.pool_alpha;
+    a.w = F32(Lw.pool_w);
+    a.g_pooled = g_txt_mem_proj;
+    a.dx_txt = T.dxt_pool;
+    a.gw = G_pool;
+    a.out_scale = GS;
+    a.B = B;
+    a.Lt = Lt;
+    a.d = d;
+    rc = launch_pool_bwd(a, st);
+    if (rc) return rc;
+  }
+  stage_done(0);  // conv heads + weightedpool.weight
 
   // ================================================ encoder ================================================
   for (int l = c.enc_layers - 1; l >= 0; --l) {
@@ -972,22 +989,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
   }
 
   // ================================================ projectors ================================================
-  // gradient w.r.t. the projected tokens = stream gradient rows + direct (saliency-loss) gradients
-  if (g_txt_mem_proj) {
-    PoolBwdArgs a;
-    a.x_txt = T.txtproj32;
-    a.alpha = T.pool_alpha;
-    a.w = F32(Lw.pool_w);
-    a.g_pooled = g_txt_mem_proj;
-    a.dx_txt = T.dxt_pool;
-    a.gw = G_pool;
-    a.out_scale = GS;
-    a.B = B;
-    a.Lt = Lt;
-    a.d = d;
-    rc = launch_pool_bwd(a, st);
-    if (rc) return rc;
-  }
+  // gradient w.r.t. the projected tokens = stream gradient rows + direct (saliency-loss) gradients (dxt_pool: written up front)
   // column sums = bias gradient of the last projector layer AND the token-type embedding rows
   rc = launch_stream_gather(T.dx, L, 0, g_vid_mem_proj, GS, T.dxv16, G_type + d, INV, B, Lv, d, FMT_G, st);
   if (rc) return rc;
@@ -1023,6 +1025,9 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
     if (rc) return rc;
     if (pad_v)
       cudaMemcpy2DAsync(G_vid(i, 2), (size_t)dinv * 4, T.wtap, (size_t)kpv * 4, (size_t)dinv * 4, (size_t)d, cudaMemcpyDeviceToDevice, st);
+    // every projector weight, the later layers' LayerNorm terms and all biases are final here; what follows only produces the
+    // first layer's LayerNorm terms - the 11.5 MB video weight gradient need not wait for it to start its exchange
+    if (i == 0) stage_done(c.enc_layers + 1);
     // dgrad: dA_i = dOut W_i  (fp32, [rows, kpad_i]: N is padded to the packed weight's K so the epilogue stays on its
     // 128-bit path even for the 2818-wide video features; the padded columns are zeros).  The input-dropout mask is applied
     // by the LayerNorm backward when it loads dA.
@@ -1074,7 +1079,7 @@ int univtg_backward(univtg_plan* P, void* ws, const float* src_txt, const float*
       if (rc) return rc;
     }
   }
-  stage_done(c.enc_layers + 1);  // projectors, token-type embedding, pooling weight
+  stage_done(c.enc_layers + 2);  // LayerNorm terms of the first projector layers
   prof_mark(P, st, 3);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -1088,7 +1093,7 @@ int univtg_backward_stages(const univtg_config* cfg, int32_t* ranges, int32_t ma
   const int n_params = univtg_num_params(cfg);
   if (n_params < 0) return -1;
   const int np = cfg->n_input_proj, nl = cfg->enc_layers;
-  const int n = nl + 2;
+  const int n = nl + 3;
   if (ranges == nullptr) return n;
   if (max_stages < n) {
     set_error("univtg_backward_stages: need room for %d stages", n);
@@ -1101,12 +1106,14 @@ int univtg_backward_stages(const univtg_config* cfg, int32_t* ranges, int32_t ma
     ranges[4 * k + 2] = b0;
     ranges[4 * k + 3] = b1;
   };
-  put(0, hb, hb + 12, 0, 0);  // span_embed + class_embed
+  put(0, hb, hb + 13, 0, 0);  // span_embed + class_embed, weightedpool.weight
   for (int k = 0; k < nl; ++k) {
     const int l = nl - 1 - k;
     put(1 + k, 8 * np + 1 + 12 * l, 8 * np + 1 + 12 * (l + 1), 0, 0);
   }
-  put(nl + 1, 0, 8 * np + 1, hb + 12, hb + 13);  // both projectors + token_type_embeddings, weightedpool.weight
+  // projector parameters are [ln.weight, ln.bias, W, b] per layer, video layers first, then text, then token_type_embeddings
+  put(nl + 1, 2, 4 * np, 4 * np + 2, 8 * np + 1);  // everything but the first layers' LayerNorm terms
+  put(nl + 2, 0, 2, 4 * np, 4 * np + 2);           // those (final only after the last LayerNorm backward)
   return n;
 }
 
@@ -1124,8 +1131,8 @@ int univtg_plan_set_grad_events(univtg_plan* plan, void* const* events, int32_t 
     set_error("univtg_plan_set_grad_events: bad argument");
     return 1;
   }
-  if (n > 0 && n != plan->cfg.enc_layers + 2) {
-    set_error("univtg_plan_set_grad_events: expected %d events (univtg_backward_stages), got %d", plan->cfg.enc_layers + 2, n);
+  if (n > 0 && n != plan->cfg.enc_layers + 3) {
+    set_error("univtg_plan_set_grad_events: expected %d events (univtg_backward_stages), got %d", plan->cfg.enc_layers + 3, n);
     return 1;
   }
   plan->n_grad_events = n;

@@ -69,7 +69,7 @@ def grad_stage_slices(model):
 
 
 class OverlappedGradExchange:
-    """Average the flat gradient buffer over the group in `enc_layers + 2` slices, each all-reduced on a side stream as soon
+    """Average the flat gradient buffer over the group in `enc_layers + 3` slices, each all-reduced on a side stream as soon
     as the fused backward has finished writing it (CUDA events recorded by univtg_backward), so the NVLink traffic of the
     heads / late encoder layers overlaps the backward of the earlier layers - what DDP's bucketed all-reduce does for the
     reference (main/train_vlp_ddp.py:272-275)."""
@@ -81,8 +81,11 @@ class OverlappedGradExchange:
         self.stages = grad_stage_slices(model)
         self.events = None
         self.comm_stream = None
-        # SMs left to the collective's CTAs while it overlaps the backward (NCCL_MAX_CTAS caps what NCCL takes)
-        self.sm_reserve = int(os.environ.get("UNIVTG_DDP_SM_RESERVE", "16")) if self.backend == "nccl" else 0
+        # SMs left to the collective's CTAs while it overlaps the backward: an NCCL CTA cannot share an SM with a GEMM CTA (registers),
+        # so the reserve follows NCCL_MAX_CTAS, the cap on what NCCL takes.  Measured at N=8 (profiles/README.md section 7): 8 / 16 /
+        # 24 / 32 CTAs -> 3.98 / 3.08 / 2.95 / 2.90 ms per step - the NVLS all-reduce is channel-bound below 32.
+        default_reserve = os.environ.get("NCCL_MAX_CTAS", "32")
+        self.sm_reserve = int(os.environ.get("UNIVTG_DDP_SM_RESERVE", default_reserve)) if self.backend == "nccl" else 0
 
     def _reduce(self, t):
         if self.backend == "nccl":

@@ -17,11 +17,21 @@ import torch
 from . import _lib
 
 
-class FlatAdamW:
+class FlatAdamW(torch.optim.Optimizer):
+    """A `torch.optim.Optimizer`: ONE parameter group whose `lr / betas / eps / weight_decay` are read at every step, so the
+    reference's schedulers (`WarmupStepLR`, `StepLR`, main/config.py:309-360) drive it unchanged, and `state_dict()` /
+    `load_state_dict()` speak torch.optim.AdamW's format, so `--resume_all` checkpoints (main/config.py:366-372,
+    main/train_mr.py:151) move between the reference's optimizer and this one in either direction."""
+
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, max_grad_norm=0.1,
-                 write_clipped_grads=False, dynamic_loss_scale=True, growth_interval=2000, max_loss_scale=65536.0):
+                 write_clipped_grads=False, dynamic_loss_scale=True, growth_interval=2000, max_loss_scale=65536.0,
+                 zero_grad_after_step=False):
         self.model = model
-        self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+        # zero_grad_after_step: step() ends by zero-filling the flat gradient buffer on a side stream (as if zero_grad() were called
+        # right after it - the reference loop calls it before the next backward anyway, train_vlp_ddp.py:63); the fill then runs
+        # under the next forward instead of in front of the next backward.  Off by default: torch leaves .grad readable after step().
+        self.zero_grad_after_step = bool(zero_grad_after_step) and not write_clipped_grads
+        self._zero_stream = self._zero_event = None
         self.max_grad_norm = float(max_grad_norm) if max_grad_norm is not None else 0.0
         self.write_clipped_grads = bool(write_clipped_grads)
         self.step_count = 0
@@ -37,6 +47,32 @@ class FlatAdamW:
         self._m = self._v = self._scratch = None
         model.direct_grad = True  # gradients stay in the flat buffer; param.grad are views of it
         self._flatten()
+        # the keys torch.optim.AdamW keeps in a group, so a state_dict written here loads into the reference's optimizer
+        defaults = dict(lr=float(lr), betas=(float(betas[0]), float(betas[1])), eps=float(eps), weight_decay=float(weight_decay),
+                        amsgrad=False, maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
+                        decoupled_weight_decay=True)
+        # the group lists what the reference hands its AdamW (main/config.py:345-350): every trainable parameter in
+        # named_parameters() order - state_dict() numbers parameters by their position in this list.  Parameters outside the
+        # C-ABI list (txt_position_embed.*: never used by the univtg path) receive no gradient here or there and keep no state.
+        torch.optim.Optimizer.__init__(self, [{"params": [p for _, p in model.named_parameters() if p.requires_grad]}], defaults)
+
+    # the hyper-parameters live in the (single) parameter group, where torch's lr schedulers write them
+    def _group(self):
+        if len(self.param_groups) != 1:
+            raise RuntimeError("FlatAdamW: one parameter group (the reference builds one, main/config.py:345-350)")
+        return self.param_groups[0]
+
+    lr = property(lambda self: float(self._group()["lr"]), lambda self, v: self._group().__setitem__("lr", float(v)))
+    eps = property(lambda self: float(self._group()["eps"]), lambda self, v: self._group().__setitem__("eps", float(v)))
+    weight_decay = property(lambda self: float(self._group()["weight_decay"]),
+                            lambda self, v: self._group().__setitem__("weight_decay", float(v)))
+    betas = property(lambda self: tuple(float(b) for b in self._group()["betas"]),
+                     lambda self, v: self._group().__setitem__("betas", (float(v[0]), float(v[1]))))
+
+    def add_param_group(self, group):
+        if getattr(self, "param_groups", None):
+            raise RuntimeError("FlatAdamW: one parameter group (the reference builds one, main/config.py:345-350)")
+        return super().add_param_group(group)
 
     # -- layout ---------------------------------------------------------------------------------------------------------
     def _flatten(self):
@@ -76,7 +112,7 @@ class FlatAdamW:
         """The next backward writes the flat gradient buffer from scratch (it zero-fills it itself); without a zero_grad() in
         between, further backwards accumulate into it like torch's .grad (univtg_b200/autograd.py)."""
         self.model.__dict__["_flat_grad_dirty"] = False
-        return None
+        return None  # (with zero_grad_after_step the buffer is already being cleared; the backward waits for that fill)
 
     @torch.no_grad()
     def step(self):
@@ -115,6 +151,15 @@ class FlatAdamW:
             for other in list(model._packed_key):
                 if other != fmt:
                     model._packed_key.pop(other)
+            if self.zero_grad_after_step:
+                if self._zero_stream is None:
+                    self._zero_stream, self._zero_event = torch.cuda.Stream(), torch.cuda.Event()
+                self._zero_stream.wait_stream(torch.cuda.current_stream())  # the update (and any exchange before it) has read the buffer
+                with torch.cuda.stream(self._zero_stream):
+                    flat_g.zero_()
+                    self._zero_event.record()
+                model.__dict__["_flat_grad_prezeroed"] = (flat_g.data_ptr(), self._zero_event)
+                model.__dict__["_flat_grad_dirty"] = False
             if self.dynamic_loss_scale:
                 if self._flag_host is None:
                     self._flag_host = torch.zeros(1, dtype=torch.float32).pin_memory()
@@ -139,18 +184,73 @@ class FlatAdamW:
                 self.model.grad_scale *= 2.0
                 self._good_streak = 0
 
-    def state_dict(self):
-        return {"step": self.step_count, "exp_avg": self._m, "exp_avg_sq": self._v,
-                "hyper": {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay,
-                          "max_grad_norm": self.max_grad_norm}}
+    # -- checkpoints in torch.optim.AdamW's format -----------------------------------------------------------------------
+    def _offsets(self):
+        offs, off = {}, 0
+        for p in self.model._abi_params():
+            offs[id(p)] = (off, p.numel())
+            off += (p.numel() + 3) // 4 * 4
+        return offs
 
+    @torch.no_grad()
+    def state_dict(self):
+        """{'state': {i: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_groups': [...]} exactly as torch.optim.AdamW writes it
+        (parameters numbered in group order = named_parameters() order), plus a 'loss_scale' entry torch ignores."""
+        group = self._group()
+        offs = self._offsets()
+        state = {}
+        if self.step_count > 0 or self.skipped_steps > 0:
+            for i, p in enumerate(group["params"]):
+                if id(p) not in offs:
+                    continue
+                off, n = offs[id(p)]
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self._m[off:off + n].view_as(p).clone(),
+                            "exp_avg_sq": self._v[off:off + n].view_as(p).clone()}
+        g = {k: v for k, v in group.items() if k != "params"}
+        g["params"] = list(range(len(group["params"])))
+        return {"state": state, "param_groups": [g],
+                "loss_scale": {"grad_scale": float(self.model.grad_scale), "good_streak": self._good_streak,
+                               "skipped_steps": self.skipped_steps, "max_grad_norm": self.max_grad_norm}}
+
+    @torch.no_grad()
     def load_state_dict(self, sd):
-        self.step_count = int(sd["step"])
-        self._m.copy_(sd["exp_avg"])
-        self._v.copy_(sd["exp_avg_sq"])
-        h = sd.get("hyper", {})
-        self.lr = float(h.get("lr", self.lr))
-        self.betas = tuple(h.get("betas", self.betas))
-        self.eps = float(h.get("eps", self.eps))
-        self.weight_decay = float(h.get("weight_decay", self.weight_decay))
-        self.max_grad_norm = float(h.get("max_grad_norm", self.max_grad_norm))
+        """Accepts what state_dict() above or torch.optim.AdamW.state_dict() wrote for the same parameter list."""
+        group = self._group()
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(group["params"]):
+            raise ValueError("FlatAdamW.load_state_dict: expected one parameter group of "
+                             f"{len(group['params'])} parameters, got {[len(g['params']) for g in groups]}")
+        if groups[0].get("amsgrad") or groups[0].get("maximize"):
+            raise ValueError("FlatAdamW.load_state_dict: amsgrad / maximize checkpoints are not supported")
+        if not self._seated():
+            self._flatten()
+        offs = self._offsets()
+        self._m.zero_()
+        self._v.zero_()
+        steps = set()
+        for key, p in zip(groups[0]["params"], group["params"]):
+            st = sd["state"].get(key)
+            if st is None:
+                continue
+            if id(p) not in offs:
+                raise ValueError("FlatAdamW.load_state_dict: the checkpoint holds moments for a parameter outside the univtg path")
+            off, n = offs[id(p)]
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError(f"FlatAdamW.load_state_dict: moment shape {tuple(st['exp_avg'].shape)} vs parameter {tuple(p.shape)}")
+            self._m[off:off + n].view_as(p).copy_(st["exp_avg"])
+            self._v[off:off + n].view_as(p).copy_(st["exp_avg_sq"])
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"FlatAdamW.load_state_dict: parameters at different step counts {sorted(steps)}")
+        self.step_count = steps.pop() if steps else 0
+        for k, v in groups[0].items():
+            if k != "params":
+                group[k] = v  # lr, betas, eps, weight_decay, initial_lr (schedulers), ...
+        ls = sd.get("loss_scale")
+        if ls:
+            self.model.grad_scale = float(ls.get("grad_scale", self.model.grad_scale))
+            self._good_streak = int(ls.get("good_streak", 0))
+            self.skipped_steps = int(ls.get("skipped_steps", 0))
+            self.max_grad_norm = float(ls.get("max_grad_norm", self.max_grad_norm))
+        self._flag_event = None  # a pending overflow flag belongs to the state that was just replaced
