@@ -267,7 +267,7 @@ def sub_workload(name, dev, operand_format, steps, peaks):
     if train:
         model.train()
         crit.train()
-        opt = FlatAdamW(model, lr=1e-4, weight_decay=1e-4, max_grad_norm=0.1)
+        opt = FlatAdamW(model, lr=1e-4, weight_decay=1e-4, max_grad_norm=0.1, zero_grad_after_step=True)
         tgts = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in synth.make_targets(r, seed=21 + i).items()} for i, r in enumerate(raw)]
 
         def step(i):
@@ -447,7 +447,7 @@ def ddp_cfg4_point(dist, dev, rank, world, operand_format, overlap, steps=10):
     model.load_state_dict(synth.make_state_dict(cfg, seed=0), strict=True)
     model.to(dev).train()
     crit.to(dev).train()
-    opt = FlatAdamW(model, lr=1e-4, weight_decay=1e-4, max_grad_norm=0.1)
+    opt = FlatAdamW(model, lr=1e-4, weight_decay=1e-4, max_grad_norm=0.1, zero_grad_after_step=True)
     ddp.broadcast_parameters(model)
     ddp.attach_flat_allreduce(model, overlap=overlap)
     raws = [synth.make_inputs(cfg, seed=31 + 7 * rank + i) for i in range(3)]
@@ -903,7 +903,7 @@ def main():
             "config": workload_config(args.workload, wl, cfg, n_gpus),
             "impl_details": {
                 "operands": "fp16 activations/weights/gradients (gradients under a 2^10 loss scale), f32 accumulate + statistics + master weights",
-                "step": ("forward + criterion + backward + clip_grad_norm(0.1) + AdamW; dropout / DropPath multipliers generated in-kernel (Philox)" if train
+                "step": ("forward + criterion + backward + clip_grad_norm(0.1) + AdamW; dropout / DropPath multipliers generated in-kernel (Philox); the flat gradient buffer is zero-filled on a side stream behind the update (FlatAdamW zero_grad_after_step)" if train
                          else ("forward (launches chained by programmatic dependent launch)" if (not args.graphs)
                                else "forward (CUDA-graph replay)")),
                 "parallelism": (f"dp{n_gpus}: shard by sample; flat fp32 gradient buffer NCCL all-reduced (AVG) in backward-stage slices on a side stream" if train

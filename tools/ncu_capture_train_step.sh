@@ -1,3 +1,6 @@
+#!/bin/bash
+# ncu captures of one cfg3_train step (run on the GPU box: gpurun -- bash tools/ncu_capture_train_step.sh).  Numbers printed by bench.py
+# under ncu are never bench values; the reports are summarised on the box because gpurun_out/ is limited to 64 MiB.
 mkdir -p gpurun_out
 T=/tmp/ncu_r2
 mkdir -p $T
