@@ -95,3 +95,14 @@ def test_prepared_features_and_collate_match_the_reference_code(tmp_path):
     assert torch.equal(batch["src_vid_mask"], mask_v) and torch.equal(batch["src_txt_mask"], mask_q)
     torch.testing.assert_close(batch["src_vid"].float(), pad_v.half().float(), rtol=0, atol=0)
     torch.testing.assert_close(batch["src_txt"].float(), pad_q.half().float(), rtol=0, atol=0)
+
+
+def test_page_extents_merge_neighbouring_arrays():
+    """Direct mode page-locks the shard's feature arrays: they are neighbours in the file, so the video array's last page is
+    usually the text array's first - one registration must cover both (found on the GPU box: the second cudaHostRegister failed)."""
+    from univtg_b200.data import page_extents
+
+    assert page_extents([(4096 * 3 + 100, 5000), (4096 * 3 + 5100, 300)]) == [[4096 * 3, 4096 * 5]]
+    assert page_extents([(8192, 4096), (12288, 10)]) == [[8192, 16384]]  # touching extents merge too
+    assert page_extents([(100, 10), (3 * 4096 + 1, 4096)]) == [[0, 4096], [3 * 4096, 5 * 4096]]
+    assert page_extents([(100, 0), (5000, 1)]) == [[4096, 8192]]  # empty arrays are skipped

@@ -163,6 +163,19 @@ class Shard:
         return self.vid_off[v + 1] - self.vid_off[v], self.txt_off[q + 1] - self.txt_off[q]
 
 
+def page_extents(regions, page=4096):
+    """Page-rounded [lo, hi) extents covering `regions` = [(address, nbytes), ...], overlapping or touching extents merged (a page
+    can be registered with the driver only once)."""
+    spans = sorted((b // page * page, (b + n + page - 1) // page * page) for b, n in regions if n)
+    merged = []
+    for lo, hi in spans:
+        if merged and lo <= merged[-1][1]:
+            merged[-1][1] = max(merged[-1][1], hi)
+        else:
+            merged.append([lo, hi])
+    return merged
+
+
 class ShardLoader:
     """Batches of model inputs straight from a shard: src_vid [B, Lv, Dv] / src_txt [B, Lt, Dt] as fp16, masks as float32 (1 = valid),
     zero right-padded to the batch maximum like start_end_collate_mr.  `slots` pinned staging buffers and device buffers are reused
@@ -192,14 +205,7 @@ class ShardLoader:
             sh = self.shard
             # page-rounded extents of the two feature arrays; they are neighbours in the file, so their end / start pages usually
             # coincide and the extents are merged (a page can be registered once)
-            spans = sorted((b // 4096 * 4096, (b + n + 4095) // 4096 * 4096) for b, n in
-                           ((sh.vid.ctypes.data, sh.vid.nbytes), (sh.txt.ctypes.data, sh.txt.nbytes)) if n)
-            merged = []
-            for lo, hi in spans:
-                if merged and lo <= merged[-1][1]:
-                    merged[-1][1] = max(merged[-1][1], hi)
-                else:
-                    merged.append([lo, hi])
+            merged = page_extents([(sh.vid.ctypes.data, sh.vid.nbytes), (sh.txt.ctypes.data, sh.txt.nbytes)])
             done = []
             self.direct_error = None
             with torch.cuda.device(self.device):
