@@ -391,8 +391,8 @@ def cpu_baseline(cfg, wl, workload):
 
 
 def gemm_traffic_bytes():
-    """DRAM bytes (read + write) per launch of the GEMM kernel from the committed `ncu --set full` capture (mean over one
-    encoder layer's four launches; profiles/gemm_traffic.json), or None when the file is absent."""
+    """DRAM bytes (read + write) per launch of the GEMM kernel from the committed `ncu --set full` capture (mean over the 58
+    launches of one train step; profiles/gemm_traffic.json), or None when the file is absent."""
     try:
         with open(os.path.join(ROOT, "profiles", "gemm_traffic.json")) as f:
             return int(json.load(f)["bytes_per_launch_mean"])
@@ -921,7 +921,7 @@ def main():
             "roofline": {"kernel": "gemm_tcgen05_kernel", "bound": "tensor", "achieved": achieved_tf,
                          "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["tflops_sustained"],
                          "traffic": gemm_traffic_bytes(),
-                         "traffic_source": "static: mean DRAM read+write bytes per launch of one encoder layer's four forward launches in the committed ncu --set full capture (profiles/gemm_traffic.json), not measured in this run",
+                         "traffic_source": "static: mean DRAM read+write bytes per launch over the 58 GEMM launches of one train step in the committed ncu --set full capture (profiles/gemm_traffic.json), not measured in this run",
                          "peak_source": peaks["source"] + ", sustained (kernel timed inside a step)",
                          "scope": ("every launch of the kernel in the train step: forward + dgrad + wgrad (CUDA events around each launch)" if train
                                    else "forward launches of the kernel (CUDA events between launches)"),
