@@ -41,6 +41,25 @@ def test_forward_and_losses(cfg_name, ragged, batch):
         assert abs(float(loss[k]) - float(v)) < 5e-6 * max(1.0, abs(float(v))), k
 
 
+def test_bool_masks_of_the_highlight_path_give_the_same_outputs():
+    """The HL collate hands the model bool masks (main/dataset.py:1104) where the MR collate hands float32 ones
+    (utils/tensor_utils.py:36-53): the reference and the restatement must not care."""
+    from oracle import univtg_oracle as O
+
+    cfg = synth.CONFIGS["tiny"]
+    sd = synth.make_state_dict(cfg, seed=11)
+    model, _ = _ref_model(cfg, sd)
+    model.eval()
+    inp = synth.make_inputs(cfg, seed=3, ragged=True, batch=4)
+    as_bool = dict(inp, src_vid_mask=inp["src_vid_mask"].bool(), src_txt_mask=inp["src_txt_mask"].bool())
+    with torch.no_grad():
+        ref_f, ref_b = model(**inp), model(**as_bool)
+    out = O.forward(sd, cfg, **as_bool)
+    for k in ("pred_logits", "pred_spans", "saliency_scores", "vid_mem_proj", "txt_mem_proj"):
+        torch.testing.assert_close(ref_b[k], ref_f[k], rtol=0, atol=0)
+        torch.testing.assert_close(out[k], ref_f[k].double(), rtol=2e-5, atol=2e-5)
+
+
 def test_droppath_scales_match_reference_train_mode():
     """Train mode with droppath: the reference draws floor(keep + U) per sample, per residual branch, in layer order;
     feeding the same draws to the oracle as scales reproduces its output."""
